@@ -1,0 +1,131 @@
+/* include/rnacode_cuda.h -- C ABI of libRNAcode_cuda, the B200 (sm_100a) implementation of RNAcode's
+ * scoring hot path.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * What it replaces in the reference (/root/reference, RNAcode v0.3.1):
+ *
+ *   segmentStats* scoreAln(const struct aln *alignment[], TTree*, float kappa, int backtrack)
+ *       src/score.h:116, src/score.c:1067-1147, called from src/RNAcode.c:171      -> rc_score_aln()
+ *   the scoring half of  int getExtremeValuePars(...)  i.e. the n calls of scoreAln() on the null
+ *   alignments and the max over their HSS,
+ *       src/score.h:103-104, src/score.c:1004-1044, called from src/RNAcode.c:180  -> rc_score_samples()
+ *   both at once for many alignment blocks (the reference processes one block per iteration of
+ *   main()'s while loop, src/RNAcode.c:115-221)                                    -> rc_batch_*()
+ *
+ * Everything that stays host C in the reference also stays outside this library: alignment
+ * parsing, PhyML tree + kappa (treeML), the background models (getModels -> scores[4] per species,
+ * which arrive here as plain float tables), seq-gen simulation in exact mode (null alignments
+ * arrive as bytes), the Gumbel fit (EVDMaxLikelyFit), the p-value formula and printing.
+ *
+ * Conventions
+ *   - rows are N*cols bytes, row-major, NOT NUL-terminated, exactly the bytes scoreAln() would see
+ *     (main() upper-cases them first, src/RNAcode.c:121-128).  Row 0 is the reference sequence.
+ *   - scores_fwd / scores_rev are models[k].scores[0..3] / modelsRev[k].scores[0..3]
+ *     (bgModel, src/score.h:34-44), N*4 floats each; entry k=0 is unused.
+ *   - blosum is the 24x24 int matrix of bgModel.matrix (src/code.c:39-88), row-major.
+ *   - null alignments ("samples") are n*N*cols bytes, sample-major, rows already permuted into
+ *     input order (sortAln, src/misc.c:150-171).  The native gap pattern is re-imposed by the
+ *     library (reintroduceGaps, src/misc.c:127-148), so callers may pass either form.
+ *   - every entry point returns RC_OK (0) or a negative rc_status; the library never exits or
+ *     prints.  rc_last_error() gives a message for the last failure on that context.
+ *   - there is NO CPU fallback: without a CUDA device rc_create() fails with RC_ERR_CUDA.
+ */
+#ifndef RNACODE_CUDA_H
+#define RNACODE_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RC_OK = 0,
+  RC_ERR_ARG = -1,      /* bad argument (N<2, cols<1, NULL pointer, ...) */
+  RC_ERR_CUDA = -2,     /* CUDA runtime failure, see rc_last_error() */
+  RC_ERR_NOMEM = -3,    /* host or device allocation failed */
+  RC_ERR_CAPACITY = -4, /* caller-provided output buffer too small (n_hss still reports the need) */
+  RC_ERR_STATE = -5     /* call sequence violated (e.g. results requested before run) */
+} rc_status;
+
+/* pars.Delta, .Omega, .omega, .stopPenalty_0, .stopPenalty_k  (src/RNAcode.h:29-35; defaults
+ * src/RNAcode.c:68-72: -10, -4, -2, -9999, -8) */
+typedef struct {
+  float Delta, Omega, omega, stopPenalty_0, stopPenalty_k;
+} rc_params;
+
+/* The fields of segmentStats (src/score.h:48-63) decided by the scoring core.  The caller derives
+ * start/end/startGenomic/endGenomic/name exactly as src/score.c:914-938 does. */
+typedef struct {
+  int strand; /* '+' or '-' */
+  int frame;  /* 0,1,2 */
+  int startSite, endSite; /* codon indices, 0-based, inclusive */
+  float score;
+} rc_hss;
+
+/* One alignment block and (optionally) its null alignments. */
+typedef struct {
+  int N;                   /* rows (species), >= 2 */
+  int cols;                /* alignment columns, >= 1 */
+  const char *rows;        /* N*cols bytes */
+  const float *scores_fwd; /* N*4 */
+  const float *scores_rev; /* N*4 */
+  int n_samples;           /* 0 if none */
+  const char *samples;     /* n_samples*N*cols bytes or NULL */
+} rc_block_desc;
+
+typedef struct rc_ctx rc_ctx;
+typedef struct rc_batch rc_batch;
+
+/* -- context ---------------------------------------------------------------------------------- */
+int rc_create(rc_ctx **ctx, int device);
+void rc_destroy(rc_ctx *ctx);
+const char *rc_last_error(const rc_ctx *ctx);
+void rc_default_params(rc_params *p);
+/* Use an existing CUDA stream (a cudaStream_t passed as void*) for all work of this context; NULL
+ * restores the context's own stream. */
+int rc_set_stream(rc_ctx *ctx, void *cuda_stream);
+/* Tunables / test hooks: "force_dense" (0/1: route every alignment through the dense-S fallback),
+ * "band_slots" (1..3: tie-band slots per row record before the dense fallback is taken),
+ * "scratch_mb" (device scratch budget per chunk). */
+int rc_set_option(rc_ctx *ctx, const char *key, long value);
+
+/* -- one block at a time (same call shape as the reference) ----------------------------------- */
+/* scoreAln(): native alignment, both strands.  HSS are returned '+' strand first, then '-', each in
+ * frame order and in order of discovery, like src/score.c:1107-1127.  *n_hss is always the full count. */
+int rc_score_aln(rc_ctx *ctx, const rc_block_desc *block, const rc_params *params, const int *blosum, rc_hss *out,
+                 int max_hss, int *n_hss);
+/* maxScores[i] of src/score.c:1044 for every null alignment i: best HSS score over both strands or
+ * -1.0 when the sample has none. */
+int rc_score_samples(rc_ctx *ctx, const rc_block_desc *block, const rc_params *params, const int *blosum,
+                     double *max_scores);
+
+/* -- many blocks at once ------------------------------------------------------------------------ */
+/* The descriptors (and the host memory they point to) must stay valid until rc_batch_upload() returns. */
+int rc_batch_create(rc_ctx *ctx, const rc_block_desc *blocks, int n_blocks, const rc_params *params, const int *blosum,
+                    rc_batch **batch);
+int rc_batch_upload(rc_batch *batch);   /* host -> device copies of rows, samples and score tables */
+int rc_batch_run(rc_batch *batch);      /* all kernels; inputs and outputs stay in HBM */
+int rc_batch_download(rc_batch *batch); /* device -> host copy of HSS records and per-sample maxima; synchronises */
+int rc_batch_native_hss(rc_batch *batch, int block, rc_hss *out, int max_hss, int *n_hss);
+int rc_batch_max_scores(rc_batch *batch, int block, double *max_scores /* n_samples of that block */);
+void rc_batch_destroy(rc_batch *batch);
+
+/* -- introspection for benchmarks and tests ------------------------------------------------------- */
+typedef struct {
+  double cells;        /* algorithmic DP cells of the batch: sum (n+1)*2*(N-1)*P(L) */
+  long long launches;  /* kernels launched by the last rc_batch_run() */
+  long long dense_fallbacks; /* alignments re-scored through the dense-S path in the last run */
+  float ms_pack, ms_sigma, ms_dp, ms_hss; /* CUDA-event time of each stage in the last run */
+  long long dp_launches;
+  size_t h2d_bytes, d2h_bytes; /* bytes moved by upload / download */
+  size_t device_bytes;         /* device memory held by the batch */
+} rc_batch_stats;
+int rc_batch_get_stats(rc_batch *batch, rc_batch_stats *stats);
+
+/* Library / build identification, e.g. "libRNAcode_cuda 0.1 sm_100a". */
+const char *rc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

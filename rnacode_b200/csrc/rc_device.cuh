@@ -1,0 +1,75 @@
+// rc_device.cuh -- device-side data layout shared by the kernels and the host planner of
+// libRNAcode_cuda (sm_100a only).  See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rc {
+
+constexpr int TILE = 16;          // codon steps per staged sigma/z tile
+constexpr int REC_SLOTS = 3;      // tie-band slots in a row record
+constexpr int DP_WARPS = 4;       // warps per DP CTA (each warp owns one task)
+
+// class byte of one alignment character (k_pack): what calculateSigma / getBlock / revAln need
+//   bits 0-1  ntMap[c]                 (forward strand code; anything but ACGTU -> 0, src/RNAcode.c:94-98)
+//   bits 2-3  ntMap[revcomp(c)]        (reverse strand code; revAln complements upper-case ACGTU only,
+//                                       src/rnaz_utils.c:327-333)
+//   bit  4    c == 'N'                 (src/score.c:400-404)
+//   bit  5    c == 'X'                 (the "XXX" guard, src/score.c:394-396)
+//   bit  6    c == '-'                 (gap; getBlock src/misc.c:214-227, calculateSigma src/score.c:385)
+constexpr unsigned CLS_N = 0x10, CLS_X = 0x20, CLS_GAP = 0x40;
+
+// One scored row (start codon i of one frame of one strand of one alignment): everything the
+// sequential part of getHSS (src/score.c:888-961) needs to know about the row.  32 bytes.
+struct __align__(16) RowRec {
+  float Emax;              // largest positive entry of the row (by the fresh lenient fold)
+  float vF;                // value of the last entry the fresh fold accepted
+  float be[REC_SLOTS];     // tie band: accepted entries within 1e-4 of Emax ...
+  unsigned short jF;       // end codon of the last accepted entry
+  unsigned short n;        // band entries in use | 0x8000 if the band overflowed; 0 = row has no positive entry
+  unsigned short bj[REC_SLOTS];  // ... and their end codons
+  unsigned short pad;
+};
+static_assert(sizeof(RowRec) == 32, "RowRec must be 32 bytes");
+
+struct HssDev {  // one emitted high-scoring segment of the native alignment
+  int startSite, endSite;
+  float score;
+};
+
+struct Params {
+  float Delta, Omega, omega, stop0, stopk;
+};
+
+// Per alignment block, resident for the life of a batch.
+struct BlockDev {
+  int N, cols, L, NK;       // NK = N-1 scored species
+  int n_inst;               // 1 (native) + n_samples
+  int inst_stride;          // bytes between consecutive instances in raw/cls (N*cols rounded up to 16)
+  int zstride;              // u32 words per z tile (NK rounded up to 4)
+  int sites[3], ntiles[3];  // codon sites / tiles per frame
+  long long raw_off, cls_off;   // byte offsets
+  long long cols0_off;          // int offset: [2][L+1], forward column (0-based) of position x (1-based) per strand
+  long long scores_off;         // float offset: [2][N][4]
+  long long z_off[2][3];        // u32 offset: [tile][zstride]
+  long long res_off;            // float offset: [n_inst][6]   best emitted score per (strand, frame), -1 none, -2 overflow
+  long long hss_off[2][3];      // HssDev offset, capacity sites/3+1 each
+  long long hsscnt_off;         // int offset: [6]
+  float fNK, rcpNK;
+};
+
+// A contiguous range of instances of one block whose sigma tiles and row records are in scratch.
+struct Item {
+  int block, inst0, ninst, pad;
+  long long sigma_off[2][3];  // float offset: [inst_local][tile][NK][TILE]
+  long long rec_off[2][3];    // RowRec offset: [inst_local][sites]
+  long long dense_off[2][3];  // float offset (dense fallback only): [inst_local][sites*(sites+1)/2]
+};
+
+struct CtaDesc {
+  int item;
+  int sf;     // strand*3 + frame
+  int task0;  // first task (warp) of this CTA inside the problem
+};
+
+}  // namespace rc

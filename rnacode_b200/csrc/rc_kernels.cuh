@@ -1,0 +1,662 @@
+// rc_kernels.cuh -- the CUDA kernels of libRNAcode_cuda (sm_100a).
+//
+//   k_pack   (a) alignment bytes -> class bytes (codes both strands + gap/N/X flags), 128-bit loads/stores
+//   k_prep   (a) per block: position->column maps of the reference row for both strands and the
+//                sample-invariant frameshift indicator z, packed per (tile, species)
+//   k_sigma  (b) codon-pair substitution scores sigma for every (instance, strand, species, position)
+//   k_dp     (c) 3-state frameshift DP over all (start, end) pairs + per-row digest of getHSS
+//   k_hss    (c) sequential part of getHSS over the row digests; per-sample maxima and native HSS list
+//   k_hss_dense  exact fallback of (c) on a materialised S matrix
+//
+// Reference semantics (all file:line relative to /root/reference): see SURVEY.md Appendix A/C.1.
+#pragma once
+#include "rc_device.cuh"
+
+namespace rc {
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP), 3-input max (SASS FMNMX3)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (a) k_pack: raw bytes -> class bytes for every instance of every block.
+// grid = (x: block, y: grid-stride over 16-byte chunks).  HBM-bound: reads 16 B sample + 16 B native
+// (L2 resident), writes 16 B.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack(const BlockDev* __restrict__ blocks, const unsigned char* __restrict__ raw,
+                                              unsigned char* __restrict__ cls, const unsigned char* __restrict__ lut) {
+  __shared__ unsigned char s_lut[256];
+  s_lut[threadIdx.x] = lut[threadIdx.x];
+  __syncthreads();
+  const BlockDev bd = blocks[blockIdx.x];
+  const int chunks_per_inst = bd.inst_stride >> 4;
+  const long long total = (long long)chunks_per_inst * bd.n_inst;
+  const uint4* raw4 = reinterpret_cast<const uint4*>(raw + bd.raw_off);
+  uint4* cls4 = reinterpret_cast<uint4*>(cls + bd.cls_off);
+  for (long long ch = (long long)blockIdx.y * blockDim.x + threadIdx.x; ch < total; ch += (long long)gridDim.y * blockDim.x) {
+    const int within = (int)(ch % chunks_per_inst);
+    uint4 v = raw4[ch];
+    uint4 g = raw4[within];  // native bytes: where the native alignment has '-', the sample gets '-' (src/misc.c:141-145)
+    unsigned vin[4] = {v.x, v.y, v.z, v.w}, gin[4] = {g.x, g.y, g.z, g.w}, out[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+      unsigned o = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        unsigned c = (vin[w] >> (8 * b)) & 0xffu, n = (gin[w] >> (8 * b)) & 0xffu;
+        unsigned k = (n == (unsigned)'-') ? CLS_GAP : (unsigned)s_lut[c];
+        o |= k << (8 * b);
+      }
+      out[w] = o;
+    }
+    cls4[ch] = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (a) k_prep: one CTA per block.
+//   cols0[strand][x], x = 1..L : forward 0-based column of the x-th non-gap character of the reference
+//   row when read in that strand's direction (pos2col, src/misc.c:250-269, as a prefix sum).
+//   z word per (strand, frame, tile, species): bit c = z != 0 at step c of the tile, bit 16+c = z == -1
+//   (getBlock, src/misc.c:198-244: |gaps_k - gaps_0| mod 3 over the columns of the codon ending at
+//   position x plus the reference-gap columns in front of it; from column 1 for x == 3).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prep(const BlockDev* __restrict__ blocks, const unsigned char* __restrict__ cls,
+                                              int* __restrict__ cols0, unsigned* __restrict__ ztiles) {
+  __shared__ int s_cnt[256];
+  const BlockDev bd = blocks[blockIdx.x];
+  const unsigned char* nat = cls + bd.cls_off;  // instance 0 = native
+  const int cols = bd.cols, L = bd.L;
+  int* c0f = cols0 + bd.cols0_off;
+  int* c0r = c0f + (L + 1);
+  // 1) prefix count of non-gap characters of row 0
+  const int per = (cols + 255) / 256;
+  const int lo = min(cols, (int)threadIdx.x * per), hi = min(cols, lo + per);
+  int cnt = 0;
+  for (int c = lo; c < hi; c++) cnt += !(nat[c] & CLS_GAP);
+  s_cnt[threadIdx.x] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < 256; i++) {
+      int t = s_cnt[i];
+      s_cnt[i] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+  int p = s_cnt[threadIdx.x];
+  for (int c = lo; c < hi; c++)
+    if (!(nat[c] & CLS_GAP)) {
+      ++p;
+      c0f[p] = c;
+      c0r[L + 1 - p] = c;
+    }
+  if (threadIdx.x == 0) c0f[0] = c0r[0] = -1;
+  __syncthreads();  // cols0 written by this CTA is visible to it below (global writes + barrier)
+  // 2) z words
+  const int NK = bd.NK;
+  for (int s = 0; s < 2; s++) {
+    const int* c0 = s ? c0r : c0f;
+    for (int f = 0; f < 3; f++) {
+      const int sites = bd.sites[f], nt = bd.ntiles[f];
+      unsigned* zt = ztiles + bd.z_off[s][f];
+      const int work = nt * bd.zstride;
+      for (int w = threadIdx.x; w < work; w += blockDim.x) {
+        const int tile = w / bd.zstride, k = w % bd.zstride;
+        unsigned word = 0;
+        if (k < NK) {
+          const unsigned char* rowk = nat + (size_t)(k + 1) * cols;
+          for (int c = 0; c < TILE; c++) {
+            const int j = tile * TILE + c;
+            if (j >= sites) break;
+            const int x = 3 * j + 3 + f;
+            // forward-column range covered by the block; on the reverse strand the range is mirrored,
+            // the gap counts are the same
+            int a, b;
+            if (s == 0) {
+              a = (x > 3) ? c0[x - 3] + 1 : 0;
+              b = c0[x];
+            } else {
+              a = c0[x];
+              b = (x > 3) ? c0[x - 3] - 1 : cols - 1;
+            }
+            int gk = 0;
+            for (int col = a; col <= b; col++) gk += (rowk[col] & CLS_GAP) ? 1 : 0;
+            const int g0 = (b - a + 1) - 3;
+            int diff = gk - g0;
+            diff = diff < 0 ? -diff : diff;
+            const int m = diff % 3;
+            if (m != 0) word |= 1u << c;
+            if (m == 2) word |= 1u << (16 + c);
+          }
+        }
+        zt[w] = word;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (b) k_sigma: sigma[k][x] of calculateSigma (src/score.c:375-426) for every instance / strand.
+// grid = (x: item, y: grid-stride over (inst, strand, position)).  Each thread owns one reference
+// position and walks the species, so the three column look-ups and the reference codon are shared.
+// Tables (BLOSUM as float, genetic code) are staged into shared memory with one TMA bulk copy.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) SigmaTables {
+  float blosum[576];
+  signed char transcode[64];
+};
+
+__global__ void __launch_bounds__(256)
+    k_sigma(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned char* __restrict__ cls,
+            const int* __restrict__ cols0, const float* __restrict__ scores, const SigmaTables* __restrict__ tables,
+            float* __restrict__ sigma, Params prm) {
+  __shared__ SigmaTables s_tab;
+  __shared__ __align__(8) uint64_t s_bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&s_bar, (unsigned)sizeof(SigmaTables));
+    bulk_g2s(&s_tab, tables, (unsigned)sizeof(SigmaTables), &s_bar);
+  }
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+
+  const Item it = items[blockIdx.x];
+  const BlockDev bd = blocks[it.block];
+  const int L = bd.L, N = bd.N, NK = bd.NK, cols = bd.cols;
+  const int npos = L - 2;
+  const long long total = (long long)it.ninst * 2 * npos;
+  for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.y * blockDim.x) {
+    const int xi = (int)(idx % npos);
+    const int rest = (int)(idx / npos);
+    const int s = rest & 1, inst_l = rest >> 1;
+    const int x = xi + 3;
+    const int* c0 = cols0 + bd.cols0_off + (size_t)s * (L + 1);
+    const int c1 = c0[x - 2], c2 = c0[x - 1], c3 = c0[x];
+    const unsigned char* base = cls + bd.cls_off + (size_t)(it.inst0 + inst_l) * bd.inst_stride;
+    const unsigned a1 = base[c1], a2 = base[c2], a3 = base[c3];
+    const int sh = s ? 2 : 0;
+    const unsigned qa = (((a1 >> sh) & 3u) << 4) | (((a2 >> sh) & 3u) << 2) | ((a3 >> sh) & 3u);
+    const unsigned nA = (a1 | a2 | a3) & CLS_N;
+    const int pepA = s_tab.transcode[qa];
+    const int f = xi % 3, j = xi / 3;
+    const int tile = j / TILE, c = j % TILE;
+    float* out = sigma + it.sigma_off[s][f] + ((size_t)inst_l * bd.ntiles[f] + tile) * NK * TILE + c;
+    const float* sc = scores + bd.scores_off + (size_t)s * N * 4;
+    for (int k = 0; k < NK; k++) {
+      const unsigned char* rowk = base + (size_t)(k + 1) * cols;
+      const unsigned b1 = rowk[c1], b2 = rowk[c2], b3 = rowk[c3];
+      const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
+      float v;
+      if (nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X)) {
+        v = 0.0f;  // src/score.c:394-404
+      } else if (qa == qb) {
+        v = 0.0f;  // Hamming distance 0, tested before the stop codons (:409)
+      } else {
+        const int pepB = s_tab.transcode[qb];
+        if (pepA < 0)
+          v = prm.stop0;  // :414-416
+        else if (pepB < 0)
+          v = prm.stopk;  // :418-420
+        else {
+          const unsigned d = qa ^ qb;
+          const int h = ((d & 0x30u) != 0) + ((d & 0x0cu) != 0) + ((d & 0x03u) != 0);
+          v = s_tab.blosum[pepA * 24 + pepB] - sc[(k + 1) * 4 + h];  // observed - expected, float32 (:422-425)
+        }
+      }
+      out[(size_t)k * TILE] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (c) k_dp
+// One warp = one task = (instance, strand, frame, group of 32*R consecutive start codons); lane l owns
+// the R rows  row_base + l*R + t.  All lanes walk the end codon j together, so sigma and z are
+// warp-uniform: they are staged per tile of 16 steps into the warp's shared-memory ring by TMA bulk
+// copies (2 stages, mbarrier complete_tx) and read back with broadcast LDS.128.  The 3-float state per
+// (species, row) lives in shared memory between tiles ([k][state][t][lane], conflict-free); inside a
+// tile it is in registers.  Float operations and their order are exactly the reference's
+// (src/score.c:506-533, :834-843): per species the recurrence advances left to right, the species sum
+// is accumulated in k order, then max(sum, Delta) / (N-1).
+//
+// getHSS digest (src/score.c:888-961).  While a row produces its entries S[b][i] in i order, the lane
+// folds them from a fresh state with the tie rule's length test dropped ("fresh lenient fold":
+// accept e iff e > last accepted or |e - last accepted| < 1e-4).  Whatever state the sequential scan
+// enters the row with, (1) every entry it can accept is accepted by the fresh fold, (2) after its
+// first acceptance it coincides with the fresh fold, so the row ends in the fresh fold's final
+// (value vF, end jF) or is left untouched, and (3) whether it accepts anything depends only on the row
+// maximum Emax and on the accepted entries within 1e-4 of Emax (the tie band).  RowRec keeps exactly
+// that; k_hss replays it.  Band overflow (> band_slots distinct near-ties) marks the row and the
+// alignment is re-scored through the dense path.
+// ---------------------------------------------------------------------------------------------
+struct RowSt {
+  float lb;  // last accepted value of the fresh fold (-inf before the first)
+  float M;   // row maximum so far (-inf before the first)
+  int jF;    // end codon of the last accepted entry
+  int nb;    // band entries in use | 0x8000 overflow
+};
+
+// fabs(e - cur) < 0.0001 is evaluated in double by the reference (src/score.c:953-954).  For a float
+// difference d this is |d| <= 0.0001f: (double)0.0001f < 0.0001 < (double)nextafterf(0.0001f, 1).
+__device__ __noinline__ RowSt hss_accept(RowSt s, float e, int j, RowRec* rec, int slots) {
+  const float d = e - s.lb;
+  if (!(d >= -0.0001f)) return s;  // e > lb  or  |e - lb| within tolerance
+  s.lb = e;
+  s.jF = j;
+  int nb = s.nb & 0xff, ovf = s.nb & 0x8000;
+  if (e > s.M) {
+    if (s.M - e < -0.0001f) nb = 0;  // everything seen so far is out of the band of the new maximum
+    s.M = e;
+  }
+  if (nb > 0 && rec->be[nb - 1] == e) {
+    rec->bj[nb - 1] = (unsigned short)j;  // exact tie: only the longest one can matter
+  } else {
+    if (nb == slots) {  // drop entries that fell out of the band
+      int w = 0;
+      for (int m = 0; m < nb; m++) {
+        const float b = rec->be[m];
+        if (!(b - s.M < -0.0001f)) {
+          rec->be[w] = b;
+          rec->bj[w] = rec->bj[m];
+          w++;
+        }
+      }
+      nb = w;
+    }
+    if (nb == slots) {
+      ovf = 0x8000;
+    } else {
+      rec->be[nb] = e;
+      rec->bj[nb] = (unsigned short)j;
+      nb++;
+    }
+  }
+  s.nb = nb | ovf;
+  return s;
+}
+
+template <int R>
+struct DpSmem {
+  static __host__ __device__ size_t state_bytes(int NK) { return (size_t)NK * 3 * R * 32 * sizeof(float); }
+  static __host__ __device__ size_t sig_bytes(int NK) { return (size_t)NK * TILE * sizeof(float); }
+  static __host__ __device__ size_t z_bytes(int zstride) { return (size_t)zstride * sizeof(unsigned); }
+  static __host__ __device__ size_t per_warp(int NK, int zstride) {
+    return state_bytes(NK) + 2 * (sig_bytes(NK) + z_bytes(zstride)) + 16;
+  }
+};
+
+template <int R, bool DENSE>
+__global__ void __launch_bounds__(DP_WARPS * 32)
+    k_dp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
+         const float* __restrict__ sigma, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs,
+         float* __restrict__ dense, Params prm, int band_slots, int smem_NK, int smem_zstride) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const CtaDesc cd = ctas[blockIdx.x];
+  const Item& it = items[cd.item];
+  const BlockDev& bd = blocks[it.block];
+  const int strand = cd.sf / 3, frame = cd.sf % 3;
+  const int sites = bd.sites[frame], ntiles = bd.ntiles[frame], NK = bd.NK, zstride = bd.zstride;
+  const int ngroups = (sites + 32 * R - 1) / (32 * R);
+  const int task = cd.task0 + warp;
+  if (task >= it.ninst * ngroups) return;  // warps are independent: no CTA-wide barrier below
+  const int inst_l = task / ngroups, g = task % ngroups;
+  const int row_base = g * 32 * R;
+  const int r0 = row_base + lane * R;  // first of this lane's R rows
+
+  unsigned char* wsm = smem + (size_t)warp * DpSmem<R>::per_warp(smem_NK, smem_zstride);
+  float* st = reinterpret_cast<float*>(wsm);
+  unsigned char* ring = wsm + DpSmem<R>::state_bytes(smem_NK);
+  const size_t stage_bytes = DpSmem<R>::sig_bytes(smem_NK) + DpSmem<R>::z_bytes(smem_zstride);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * stage_bytes);
+
+  const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * ntiles * NK * TILE;
+  const unsigned* z_src = ztiles + bd.z_off[strand][frame];
+  const unsigned sig_tx = (unsigned)(NK * TILE * sizeof(float)), z_tx = (unsigned)(zstride * sizeof(unsigned));
+
+  const int t0 = row_base / TILE;
+  const int t_last_diag = (row_base + 32 * R - 1) / TILE;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+    for (int s = 0; s < 2 && t0 + s < ntiles; s++) {
+      unsigned char* dst = ring + s * stage_bytes;
+      mbar_expect_tx(&bars[s], sig_tx + z_tx);
+      bulk_g2s(dst, sig_src + (size_t)(t0 + s) * NK * TILE, sig_tx, &bars[s]);
+      bulk_g2s(dst + DpSmem<R>::sig_bytes(smem_NK), z_src + (size_t)(t0 + s) * zstride, z_tx, &bars[s]);
+    }
+  }
+  for (int i = 0; i < NK * 3 * R; i++) st[i * 32 + lane] = 0.0f;
+  __syncwarp();
+
+  RowSt rs[R];
+  RowRec* rec0 = recs + it.rec_off[strand][frame] + (size_t)inst_l * sites + r0;
+#pragma unroll
+  for (int t = 0; t < R; t++) {
+    rs[t].lb = -INFINITY;
+    rs[t].M = -INFINITY;
+    rs[t].jF = 0;
+    rs[t].nb = 0;
+  }
+  float* dense_row[R];
+  if (DENSE) {
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+      const long long r = r0 + t;
+      // row r of the frame starts at offset r*sites - r(r-1)/2 and holds entries j = r..sites-1
+      dense_row[t] = dense + it.dense_off[strand][frame] + (size_t)inst_l * ((size_t)sites * (sites + 1) / 2) +
+                     (r * sites - r * (r - 1) / 2) - r;
+    }
+  }
+
+  const float Delta = prm.Delta, Omega = prm.Omega, omega = prm.omega;
+  const float fNK = bd.fNK, rcpNK = bd.rcpNK;
+
+  for (int tile = t0; tile < ntiles; tile++) {
+    const int s = (tile - t0) & 1;
+    const unsigned parity = ((tile - t0) >> 1) & 1;
+    const float* sg = reinterpret_cast<const float*>(ring + s * stage_bytes);
+    const unsigned* zt = reinterpret_cast<const unsigned*>(ring + s * stage_bytes + DpSmem<R>::sig_bytes(smem_NK));
+    const int j0 = tile * TILE;
+    const bool diag = tile <= t_last_diag;
+    mbar_wait(&bars[s], parity);
+
+    float sum[TILE][R];
+#pragma unroll
+    for (int c = 0; c < TILE; c++)
+#pragma unroll
+      for (int t = 0; t < R; t++) sum[c][t] = 0.0f;
+
+    for (int k = 0; k < NK; k++) {
+      const unsigned zz = zt[k];
+      const float4* sp = reinterpret_cast<const float4*>(sg + k * TILE);
+      const float4 q0 = sp[0], q1 = sp[1], q2 = sp[2], q3 = sp[3];
+      const float sv[TILE] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w,
+                              q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+      float S0[R], S1[R], S2[R];
+      float* stk = st + (size_t)k * 3 * R * 32 + lane;
+#pragma unroll
+      for (int t = 0; t < R; t++) {
+        S0[t] = stk[(0 * R + t) * 32];
+        S1[t] = stk[(1 * R + t) * 32];
+        S2[t] = stk[(2 * R + t) * 32];
+      }
+      if (zz == 0u && !diag) {
+        // no frameshift for this species anywhere in the tile and every row already started (src/score.c:506-510)
+#pragma unroll
+        for (int c = 0; c < TILE; c++) {
+#pragma unroll
+          for (int t = 0; t < R; t++) {
+            S0[t] += sv[c];
+            S1[t] += omega;
+            S2[t] += omega;
+            sum[c][t] += max3f(S0[t], S1[t], S2[t]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < TILE; c++) {
+          const int j = j0 + c;
+          const bool nz = (zz >> c) & 1u, neg = (zz >> (16 + c)) & 1u;
+#pragma unroll
+          for (int t = 0; t < R; t++) {
+            if (diag && j == r0 + t) {  // the row starts here from (0,0,0) (src/score.c:500-504)
+              S0[t] = 0.0f;
+              S1[t] = 0.0f;
+              S2[t] = 0.0f;
+            }
+            float n0, n1, n2;
+            if (!nz) {
+              n0 = S0[t] + sv[c];
+              n1 = S1[t] + omega;
+              n2 = S2[t] + omega;
+            } else if (!neg) {  // z = +1 (src/score.c:512-521)
+              n0 = fmaxf(S0[t] + Delta, S2[t] + Omega);
+              n1 = fmaxf(S0[t] + Omega, S1[t] + Delta);
+              n2 = fmaxf(S1[t] + Omega, S2[t] + Delta);
+            } else {  // z = -1 (src/score.c:523-533)
+              n0 = fmaxf(S0[t] + Delta, S1[t] + Omega);
+              n1 = fmaxf(S1[t] + Delta, S2[t] + Omega);
+              n2 = fmaxf(S2[t] + Delta, S0[t] + Omega);
+            }
+            S0[t] = n0;
+            S1[t] = n1;
+            S2[t] = n2;
+            sum[c][t] += max3f(n0, n1, n2);
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < R; t++) {
+        stk[(0 * R + t) * 32] = S0[t];
+        stk[(1 * R + t) * 32] = S1[t];
+        stk[(2 * R + t) * 32] = S2[t];
+      }
+    }
+    __syncwarp();  // every lane has consumed this stage
+    if (lane == 0 && tile + 2 < ntiles) {
+      unsigned char* dst = ring + s * stage_bytes;
+      mbar_expect_tx(&bars[s], sig_tx + z_tx);
+      bulk_g2s(dst, sig_src + (size_t)(tile + 2) * NK * TILE, sig_tx, &bars[s]);
+      bulk_g2s(dst + DpSmem<R>::sig_bytes(smem_NK), z_src + (size_t)(tile + 2) * zstride, z_tx, &bars[s]);
+    }
+
+    // S[b][i] = max(sum, Delta) / (N-1)  (src/score.c:841-843; S[b][i-1], S[b][i-2] are always 0) and the
+    // positive-entry filter of getHSS (:891).  The quotient is the correctly rounded IEEE one:
+    // q = m*rcp, r = fma(-d, q, m), q' = fma(r, rcp, q) with rcp = RN(1/d) (checked exhaustively on the host).
+    const bool chk = diag || (tile == ntiles - 1);
+#pragma unroll
+    for (int c = 0; c < TILE; c++) {
+      const int j = j0 + c;
+#pragma unroll
+      for (int t = 0; t < R; t++) {
+        const float m = fmaxf(sum[c][t], Delta);
+        bool live = true;
+        if (chk) live = (j >= r0 + t) && (j < sites);
+        if (DENSE) {
+          if (live) {
+            const float q = m * rcpNK;
+            const float e = __fmaf_rn(__fmaf_rn(-fNK, q, m), rcpNK, q);
+            dense_row[t][j] = e;
+          }
+        } else if (m > 0.0f && live) {
+          const float q = m * rcpNK;
+          const float e = __fmaf_rn(__fmaf_rn(-fNK, q, m), rcpNK, q);
+          rs[t] = hss_accept(rs[t], e, j, rec0 + t, band_slots);
+        }
+      }
+    }
+  }
+
+  if (!DENSE) {
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+      if (r0 + t < sites) {
+        RowRec* rec = rec0 + t;
+        rec->Emax = rs[t].M;
+        rec->vF = rs[t].lb;
+        rec->jF = (unsigned short)rs[t].jF;
+        rec->n = (unsigned short)rs[t].nb;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (c) k_hss: the sequential scan of getHSS (src/score.c:888-961) over row digests.
+// One thread per (instance, strand, frame).  grid = (x: item, y over ninst*6).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    k_hss(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const RowRec* __restrict__ recs,
+          float* __restrict__ res, HssDev* __restrict__ hss, int* __restrict__ hsscnt, int* __restrict__ ovf_counter) {
+  const Item it = items[blockIdx.x];
+  const BlockDev& bd = blocks[it.block];
+  const int idx = blockIdx.y * blockDim.x + threadIdx.x;
+  if (idx >= it.ninst * 6) return;
+  const int inst_l = idx / 6, sf = idx % 6;
+  const int strand = sf / 3, frame = sf % 3;
+  const int sites = bd.sites[frame];
+  const int inst = it.inst0 + inst_l;
+  const uint4* rp = reinterpret_cast<const uint4*>(recs + it.rec_off[strand][frame] + (size_t)inst_l * sites);
+  HssDev* out = hss + bd.hss_off[strand][frame];
+  int nout = 0;
+  float best = -1.0f;
+  bool overflow = false;
+  float cur = 0.0f;
+  int segS = -1, segE = -1;
+  for (int i = 0; i + 1 < sites; i++) {  // the last row only holds the frame's final entry, which never survives (:893-900)
+    const uint4 w0 = rp[2 * i], w1 = rp[2 * i + 1];
+    RowRec r;
+    *reinterpret_cast<uint4*>(&r) = w0;
+    *(reinterpret_cast<uint4*>(&r) + 1) = w1;
+    if (r.n == 0) continue;  // no positive entry in this row
+    if (r.n & 0x8000) overflow = true;
+    bool take;
+    if (cur > 0.0f && segE < i) {  // flush (:897-949)
+      if (segE - segS >= 2) {
+        if (inst == 0) {
+          out[nout].startSite = segS;
+          out[nout].endSite = segE;
+          out[nout].score = cur;
+        }
+        nout++;
+        best = fmaxf(best, cur);
+      }
+      take = true;
+    } else {  // overlap with the current segment (:953-959)
+      take = r.Emax > cur;
+      const int nb = r.n & 0xff;
+      for (int m = 0; m < nb && !take; m++) {
+        const float d = r.be[m] - cur;
+        if (d >= -0.0001f && d <= 0.0001f && ((int)r.bj[m] - i) >= (segE - segS)) take = true;
+      }
+    }
+    if (take) {
+      cur = r.vF;
+      segS = i;
+      segE = r.jF;
+    }
+  }
+  if (sites > 0 && segE - segS >= 2) {  // forced flush on the frame's last entry
+    if (inst == 0) {
+      out[nout].startSite = segS;
+      out[nout].endSite = segE;
+      out[nout].score = cur;
+    }
+    nout++;
+    best = fmaxf(best, cur);
+  }
+  if (overflow) {
+    best = -2.0f;
+    atomicAdd(ovf_counter, 1);
+  }
+  res[bd.res_off + (size_t)inst * 6 + sf] = best;
+  if (inst == 0) hsscnt[bd.hsscnt_off + sf] = overflow ? -1 : nout;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact fallback: getHSS on the materialised S entries of one frame.  One warp per
+// (instance, strand, frame); lanes fetch 32 entries at a time, only positive ones are replayed
+// (identically on every lane).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    k_hss_dense(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const float* __restrict__ dense,
+                float* __restrict__ res, HssDev* __restrict__ hss, int* __restrict__ hsscnt) {
+  const Item it = items[blockIdx.x];
+  const BlockDev& bd = blocks[it.block];
+  const int widx = (blockIdx.y * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (widx >= it.ninst * 6) return;
+  const int inst_l = widx / 6, sf = widx % 6;
+  const int strand = sf / 3, frame = sf % 3;
+  const int sites = bd.sites[frame];
+  const int inst = it.inst0 + inst_l;
+  const float* S = dense + it.dense_off[strand][frame] + (size_t)inst_l * ((size_t)sites * (sites + 1) / 2);
+  HssDev* out = hss + bd.hss_off[strand][frame];
+  int nout = 0;
+  float best = -1.0f, cur = 0.0f;
+  int segS = -1, segE = -1;
+  for (int i = 0; i < sites; i++) {
+    const float* row = S + ((long long)i * sites - (long long)i * (i - 1) / 2) - i;
+    for (int jb = i; jb < sites; jb += 32) {
+      const int j = jb + lane;
+      const float v = (j < sites) ? row[j] : 0.0f;
+      const bool last = (i == sites - 1 && j == sites - 1);
+      unsigned mask = __ballot_sync(0xffffffffu, (j < sites) && (v > 0.0f || last));
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float e = __shfl_sync(0xffffffffu, v, src);
+        const int jj = jb + src;
+        const bool lst = (i == sites - 1 && jj == sites - 1);
+        if ((cur > 0.0f && segE < i) || lst) {
+          if (segE - segS >= 2) {
+            if (inst == 0 && lane == 0) {
+              out[nout].startSite = segS;
+              out[nout].endSite = segE;
+              out[nout].score = cur;
+            }
+            nout++;
+            best = fmaxf(best, cur);
+          }
+          cur = e;
+          segS = i;
+          segE = jj;
+        } else {
+          const float d = e - cur;
+          if (e > cur || (d >= -0.0001f && d <= 0.0001f && (jj - i) >= (segE - segS))) {
+            cur = e;
+            segS = i;
+            segE = jj;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    res[bd.res_off + (size_t)inst * 6 + sf] = best;
+    if (inst == 0) hsscnt[bd.hsscnt_off + sf] = nout;
+  }
+}
+
+}  // namespace rc

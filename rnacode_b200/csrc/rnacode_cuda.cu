@@ -1,0 +1,787 @@
+// rnacode_cuda.cu -- libRNAcode_cuda: host-side planner + C ABI (include/rnacode_cuda.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+//
+// A batch is a list of alignment blocks.  Persistent per-batch device data: raw bytes, class bytes,
+// position->column maps, z tiles, score tables, results.  Scratch (sigma tiles + row records) is
+// sized per chunk; a chunk is a list of Items (block, instance range).  Per chunk: k_sigma -> k_dp
+// (one launch per register-blocking class) -> k_hss.  No CPU fallback exists anywhere in this file.
+#include "../../include/rnacode_cuda.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rc_kernels.cuh"
+
+using namespace rc;
+
+#define RC_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ctx_fail(ctx, std::string(#call) + ": " + cudaGetErrorString(_e));                       \
+      return RC_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+struct rc_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  unsigned char* d_lut = nullptr;
+  std::string err;
+  long force_dense = 0;
+  long band_slots = REC_SLOTS;
+  long scratch_mb = 2048;
+  int smem_optin = 0;
+  int sm_count = 0;
+};
+
+static void ctx_fail(rc_ctx* ctx, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+}
+
+namespace {
+
+struct Chunk {
+  size_t item0 = 0, nitems = 0;          // range in the batch's item array
+  size_t cta0[2] = {0, 0}, ncta[2] = {0, 0};  // per class (0: R=2, 1: R=1) range in the CTA array
+  int maxNK[2] = {0, 0}, maxZs[2] = {0, 0};
+  size_t sigma_floats = 0, rec_count = 0;
+  long long max_sigma_work = 0;  // largest ninst*2*(L-2) of an item, for the k_sigma grid
+  int max_ninst = 0;
+};
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int stage;  // 0 pack, 1 sigma, 2 dp, 3 hss
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int class_of(int NK) { return NK <= 24 ? 0 : 1; }
+
+}  // namespace
+
+struct rc_batch {
+  rc_ctx* ctx = nullptr;
+  int n_blocks = 0;
+  std::vector<rc_block_desc> descs;
+  std::vector<BlockDev> blocks;
+  std::vector<Item> items;
+  std::vector<CtaDesc> ctas;
+  std::vector<Chunk> chunks;
+  Params prm{};
+  SigmaTables tables{};
+  // device, persistent
+  BlockDev* d_blocks = nullptr;
+  Item* d_items = nullptr;
+  CtaDesc* d_ctas = nullptr;
+  unsigned char *d_raw = nullptr, *d_cls = nullptr;
+  int* d_cols0 = nullptr;
+  float* d_scores = nullptr;
+  unsigned* d_z = nullptr;
+  float* d_res = nullptr;
+  HssDev* d_hss = nullptr;
+  int* d_hsscnt = nullptr;
+  int* d_ovf = nullptr;
+  SigmaTables* d_tables = nullptr;
+  // device, scratch
+  float* d_sigma = nullptr;
+  RowRec* d_recs = nullptr;
+  float* d_dense = nullptr;
+  size_t dense_floats = 0;
+  // sizes
+  size_t raw_bytes = 0, cols0_ints = 0, scores_floats = 0, z_words = 0, res_floats = 0, hss_count = 0, hsscnt_ints = 0;
+  size_t sigma_floats = 0, rec_count = 0;
+  // host results
+  std::vector<float> h_res;
+  std::vector<HssDev> h_hss;
+  std::vector<int> h_hsscnt;
+  std::vector<float> h_scores;
+  bool uploaded = false, ran = false, downloaded = false;
+  rc_batch_stats stats{};
+  std::vector<EventPair> events;
+  size_t device_bytes = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* rc_version(void) { return "libRNAcode_cuda 0.1 (sm_100a)"; }
+
+extern "C" void rc_default_params(rc_params* p) {
+  if (!p) return;
+  p->Delta = -10.0f;  // src/RNAcode.c:68-72
+  p->Omega = -4.0f;
+  p->omega = -2.0f;
+  p->stopPenalty_k = -8.0f;
+  p->stopPenalty_0 = -9999.0f;
+}
+
+static void build_lut(unsigned char* lut) {
+  for (int c = 0; c < 256; c++) {
+    auto nt = [](int ch) -> unsigned {
+      switch (ch) {
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': case 'U': case 'u': return 3;
+        default: return 0;
+      }
+    };
+    int rcmp = c;
+    switch (c) {  // revAln, src/rnaz_utils.c:327-333
+      case 'T': rcmp = 'A'; break;
+      case 'U': rcmp = 'A'; break;
+      case 'C': rcmp = 'G'; break;
+      case 'G': rcmp = 'C'; break;
+      case 'A': rcmp = 'T'; break;
+      default: break;
+    }
+    unsigned v = nt(c) | (nt(rcmp) << 2);
+    if (c == 'N') v |= CLS_N;
+    if (c == 'X') v |= CLS_X;
+    if (c == '-') v |= CLS_GAP;
+    lut[c] = (unsigned char)v;
+  }
+}
+
+extern "C" int rc_create(rc_ctx** out, int device) {
+  if (!out) return RC_ERR_ARG;
+  *out = nullptr;
+  rc_ctx* ctx = new (std::nothrow) rc_ctx();
+  if (!ctx) return RC_ERR_NOMEM;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    // no CPU fallback: the product fails loudly without a usable CUDA device
+    delete ctx;
+    return RC_ERR_CUDA;
+  }
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return RC_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  unsigned char lut[256];
+  build_lut(lut);
+  if (cudaMalloc(&ctx->d_lut, 256) != cudaSuccess ||
+      cudaMemcpy(ctx->d_lut, lut, 256, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return RC_ERR_CUDA;
+  }
+  *out = ctx;
+  return RC_OK;
+}
+
+extern "C" void rc_destroy(rc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->d_lut) cudaFree(ctx->d_lut);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" const char* rc_last_error(const rc_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+extern "C" int rc_set_stream(rc_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return RC_ERR_ARG;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return RC_OK;
+}
+
+extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
+  if (!ctx || !key) return RC_ERR_ARG;
+  std::string k(key);
+  if (k == "force_dense") ctx->force_dense = value ? 1 : 0;
+  else if (k == "band_slots") {
+    if (value < 1 || value > REC_SLOTS) { ctx_fail(ctx, "band_slots must be 1..3"); return RC_ERR_ARG; }
+    ctx->band_slots = value;
+  } else if (k == "scratch_mb") {
+    if (value < 1) { ctx_fail(ctx, "scratch_mb must be >= 1"); return RC_ERR_ARG; }
+    ctx->scratch_mb = value;
+  } else {
+    ctx_fail(ctx, "unknown option " + k);
+    return RC_ERR_ARG;
+  }
+  return RC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// planning
+// ------------------------------------------------------------------------------------------------
+static void free_batch_device(rc_batch* b) {
+  cudaFree(b->d_blocks); cudaFree(b->d_items); cudaFree(b->d_ctas); cudaFree(b->d_raw); cudaFree(b->d_cls);
+  cudaFree(b->d_cols0); cudaFree(b->d_scores); cudaFree(b->d_z); cudaFree(b->d_res); cudaFree(b->d_hss);
+  cudaFree(b->d_hsscnt); cudaFree(b->d_ovf); cudaFree(b->d_tables); cudaFree(b->d_sigma); cudaFree(b->d_recs);
+  cudaFree(b->d_dense);
+  for (auto& e : b->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  b->events.clear();
+}
+
+// Append CTA descriptors for `items[i0..i0+n)` with row-group size 32*R.
+static void build_ctas(const std::vector<BlockDev>& blocks, const std::vector<Item>& items, size_t i0, size_t n, int R,
+                       int want_class, std::vector<CtaDesc>& out) {
+  for (size_t i = i0; i < i0 + n; i++) {
+    const Item& it = items[i];
+    const BlockDev& bd = blocks[it.block];
+    if (want_class >= 0 && class_of(bd.NK) != want_class) continue;
+    for (int sf = 0; sf < 6; sf++) {
+      const int sites = bd.sites[sf % 3];
+      if (sites <= 0) continue;
+      const long long ngroups = (sites + 32 * R - 1) / (32 * R);
+      const long long ntasks = ngroups * it.ninst;
+      for (long long t = 0; t < ntasks; t += DP_WARPS) out.push_back(CtaDesc{(int)i, sf, (int)t});
+    }
+  }
+}
+
+extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_blocks, const rc_params* params,
+                               const int* blosum, rc_batch** out) {
+  if (!ctx || !out) return RC_ERR_ARG;
+  *out = nullptr;
+  if (!descs || n_blocks < 1 || !params || !blosum) {
+    ctx_fail(ctx, "rc_batch_create: NULL argument or empty batch");
+    return RC_ERR_ARG;
+  }
+  rc_batch* b = new (std::nothrow) rc_batch();
+  if (!b) return RC_ERR_NOMEM;
+  b->ctx = ctx;
+  b->n_blocks = n_blocks;
+  b->descs.assign(descs, descs + n_blocks);
+  b->prm = Params{params->Delta, params->Omega, params->omega, params->stopPenalty_0, params->stopPenalty_k};
+  for (int i = 0; i < 576; i++) b->tables.blosum[i] = (float)blosum[i];
+  {
+    // standard genetic code in the reference's encoding (src/code.c:26-35): A,C,G,T = 0..3, amino acids in
+    // BLOSUM order ARNDCQEGHILKMFPSTWYV, stop = -1
+    static const char* tcag_aa = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    static const char* aa_order = "ARNDCQEGHILKMFPSTWYV";
+    static const int tcag_to_acgt[4] = {3, 1, 0, 2};
+    for (int i = 0; i < 64; i++) {
+      int b1 = tcag_to_acgt[i / 16], b2 = tcag_to_acgt[(i / 4) % 4], b3 = tcag_to_acgt[i % 4];
+      char aa = tcag_aa[i];
+      b->tables.transcode[b1 * 16 + b2 * 4 + b3] = (aa == '*') ? -1 : (signed char)(strchr(aa_order, aa) - aa_order);
+    }
+  }
+
+  b->blocks.resize(n_blocks);
+  double cells = 0;
+  for (int i = 0; i < n_blocks; i++) {
+    const rc_block_desc& d = descs[i];
+    if (d.N < 2 || d.N > 500 || d.cols < 1 || d.cols > 190000 || !d.rows || !d.scores_fwd || !d.scores_rev || d.n_samples < 0 ||
+        (d.n_samples > 0 && !d.samples)) {
+      ctx_fail(ctx, "rc_batch_create: invalid block descriptor " + std::to_string(i));
+      delete b;
+      return RC_ERR_ARG;
+    }
+    BlockDev& bd = b->blocks[i];
+    memset(&bd, 0, sizeof(bd));
+    bd.N = d.N;
+    bd.cols = d.cols;
+    int L = 0;
+    for (int c = 0; c < d.cols; c++) L += d.rows[c] != '-';  // getSeqLength, src/misc.c:272-289
+    bd.L = L;
+    bd.NK = d.N - 1;
+    bd.n_inst = 1 + d.n_samples;
+    bd.inst_stride = (int)align_up((size_t)d.N * d.cols, 16);
+    bd.zstride = (int)align_up((size_t)bd.NK, 4);
+    bd.fNK = (float)bd.NK;
+    bd.rcpNK = 1.0f / bd.fNK;
+    bd.raw_off = (long long)b->raw_bytes;
+    bd.cls_off = bd.raw_off;
+    b->raw_bytes += (size_t)bd.inst_stride * bd.n_inst;
+    bd.cols0_off = (long long)b->cols0_ints;
+    b->cols0_ints += 2 * (size_t)(L + 1);
+    bd.scores_off = (long long)b->scores_floats;
+    b->scores_floats += 2 * (size_t)d.N * 4;
+    double P = 0;
+    for (int f = 0; f < 3; f++) {
+      bd.sites[f] = L >= 3 ? (L - f) / 3 : 0;
+      bd.ntiles[f] = (bd.sites[f] + TILE - 1) / TILE;
+      P += (double)bd.sites[f] * (bd.sites[f] + 1) / 2;
+    }
+    cells += (double)bd.n_inst * 2.0 * bd.NK * P;
+    for (int s = 0; s < 2; s++)
+      for (int f = 0; f < 3; f++) {
+        bd.z_off[s][f] = (long long)b->z_words;
+        b->z_words += (size_t)bd.ntiles[f] * bd.zstride;
+        bd.hss_off[s][f] = (long long)b->hss_count;
+        b->hss_count += (size_t)bd.sites[f] / 3 + 1;
+      }
+    bd.res_off = (long long)b->res_floats;
+    b->res_floats += (size_t)bd.n_inst * 6;
+    bd.hsscnt_off = (long long)b->hsscnt_ints;
+    b->hsscnt_ints += 6;
+  }
+  b->stats.cells = cells;
+
+  // chunking: fill items until the scratch budget is reached
+  const size_t budget = (size_t)ctx->scratch_mb << 20;
+  Chunk cur;
+  size_t cur_bytes = 0;
+  auto close_chunk = [&]() {
+    if (cur.nitems == 0) return;
+    b->chunks.push_back(cur);
+    cur = Chunk();
+    cur.item0 = b->items.size();
+    cur_bytes = 0;
+  };
+  for (int i = 0; i < n_blocks; i++) {
+    const BlockDev& bd = b->blocks[i];
+    if (bd.L < 3) continue;  // nothing to score (the reference skips such blocks, src/RNAcode.c:147-150)
+    size_t sig_per_inst = 0, rec_per_inst = 0;
+    for (int f = 0; f < 3; f++) {
+      sig_per_inst += 2 * (size_t)bd.ntiles[f] * bd.NK * TILE;
+      rec_per_inst += 2 * (size_t)bd.sites[f];
+    }
+    const size_t bytes_per_inst = sig_per_inst * sizeof(float) + rec_per_inst * sizeof(RowRec);
+    int inst = 0;
+    while (inst < bd.n_inst) {
+      size_t room = budget > cur_bytes ? (budget - cur_bytes) / bytes_per_inst : 0;
+      if (room == 0) {
+        if (cur.nitems == 0) room = 1;  // a single instance always goes through
+        else { close_chunk(); continue; }
+      }
+      const int take = (int)std::min<size_t>(room, (size_t)(bd.n_inst - inst));
+      Item it;
+      memset(&it, 0, sizeof(it));
+      it.block = i;
+      it.inst0 = inst;
+      it.ninst = take;
+      for (int s = 0; s < 2; s++)
+        for (int f = 0; f < 3; f++) {
+          it.sigma_off[s][f] = (long long)cur.sigma_floats;
+          cur.sigma_floats += (size_t)take * bd.ntiles[f] * bd.NK * TILE;
+          it.rec_off[s][f] = (long long)cur.rec_count;
+          cur.rec_count += (size_t)take * bd.sites[f];
+        }
+      const int cl = class_of(bd.NK);
+      cur.maxNK[cl] = std::max(cur.maxNK[cl], bd.NK);
+      cur.maxZs[cl] = std::max(cur.maxZs[cl], bd.zstride);
+      cur.max_sigma_work = std::max(cur.max_sigma_work, (long long)take * 2 * (bd.L - 2));
+      cur.max_ninst = std::max(cur.max_ninst, take);
+      b->items.push_back(it);
+      cur.nitems++;
+      cur_bytes += (size_t)take * bytes_per_inst;
+      inst += take;
+    }
+  }
+  close_chunk();
+  for (Chunk& ch : b->chunks) {
+    ch.cta0[0] = b->ctas.size();
+    build_ctas(b->blocks, b->items, ch.item0, ch.nitems, 2, 0, b->ctas);
+    ch.ncta[0] = b->ctas.size() - ch.cta0[0];
+    ch.cta0[1] = b->ctas.size();
+    build_ctas(b->blocks, b->items, ch.item0, ch.nitems, 1, 1, b->ctas);
+    ch.ncta[1] = b->ctas.size() - ch.cta0[1];
+    b->sigma_floats = std::max(b->sigma_floats, ch.sigma_floats);
+    b->rec_count = std::max(b->rec_count, ch.rec_count);
+  }
+
+  // device allocations
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { delete b; return RC_ERR_CUDA; }
+  size_t total = 0;
+  auto dalloc = [&](void** p, size_t bytes) -> bool {
+    bytes = std::max<size_t>(bytes, 256);
+    total += bytes;
+    return cudaMalloc(p, bytes) == cudaSuccess;
+  };
+  bool ok = dalloc((void**)&b->d_blocks, sizeof(BlockDev) * n_blocks) &&
+            dalloc((void**)&b->d_items, sizeof(Item) * b->items.size()) &&
+            dalloc((void**)&b->d_ctas, sizeof(CtaDesc) * b->ctas.size()) && dalloc((void**)&b->d_raw, b->raw_bytes) &&
+            dalloc((void**)&b->d_cls, b->raw_bytes) && dalloc((void**)&b->d_cols0, sizeof(int) * b->cols0_ints) &&
+            dalloc((void**)&b->d_scores, sizeof(float) * b->scores_floats) &&
+            dalloc((void**)&b->d_z, sizeof(unsigned) * b->z_words) && dalloc((void**)&b->d_res, sizeof(float) * b->res_floats) &&
+            dalloc((void**)&b->d_hss, sizeof(HssDev) * b->hss_count) &&
+            dalloc((void**)&b->d_hsscnt, sizeof(int) * b->hsscnt_ints) && dalloc((void**)&b->d_ovf, sizeof(int)) &&
+            dalloc((void**)&b->d_tables, sizeof(SigmaTables)) && dalloc((void**)&b->d_sigma, sizeof(float) * b->sigma_floats) &&
+            dalloc((void**)&b->d_recs, sizeof(RowRec) * b->rec_count);
+  if (!ok) {
+    ctx_fail(ctx, std::string("rc_batch_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    free_batch_device(b);
+    delete b;
+    return RC_ERR_NOMEM;
+  }
+  b->device_bytes = total;
+  b->h_res.assign(b->res_floats, -1.0f);
+  b->h_hss.resize(b->hss_count);
+  b->h_hsscnt.assign(b->hsscnt_ints, 0);
+  *out = b;
+  return RC_OK;
+}
+
+extern "C" void rc_batch_destroy(rc_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  free_batch_device(b);
+  delete b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload
+// ------------------------------------------------------------------------------------------------
+extern "C" int rc_batch_upload(rc_batch* b) {
+  if (!b) return RC_ERR_ARG;
+  rc_ctx* ctx = b->ctx;
+  RC_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  size_t h2d = 0;
+  b->h_scores.resize(b->scores_floats);
+  for (int i = 0; i < b->n_blocks; i++) {
+    const rc_block_desc& d = b->descs[i];
+    const BlockDev& bd = b->blocks[i];
+    const size_t rowbytes = (size_t)d.N * d.cols;
+    RC_CUDA(cudaMemcpyAsync(b->d_raw + bd.raw_off, d.rows, rowbytes, cudaMemcpyHostToDevice, st));
+    h2d += rowbytes;
+    if (d.n_samples > 0) {
+      RC_CUDA(cudaMemcpy2DAsync(b->d_raw + bd.raw_off + bd.inst_stride, bd.inst_stride, d.samples, rowbytes, rowbytes,
+                                d.n_samples, cudaMemcpyHostToDevice, st));
+      h2d += rowbytes * d.n_samples;
+    }
+    memcpy(&b->h_scores[bd.scores_off], d.scores_fwd, sizeof(float) * d.N * 4);
+    memcpy(&b->h_scores[bd.scores_off + (size_t)d.N * 4], d.scores_rev, sizeof(float) * d.N * 4);
+  }
+  RC_CUDA(cudaMemcpyAsync(b->d_scores, b->h_scores.data(), sizeof(float) * b->scores_floats, cudaMemcpyHostToDevice, st));
+  RC_CUDA(cudaMemcpyAsync(b->d_blocks, b->blocks.data(), sizeof(BlockDev) * b->n_blocks, cudaMemcpyHostToDevice, st));
+  if (!b->items.empty())
+    RC_CUDA(cudaMemcpyAsync(b->d_items, b->items.data(), sizeof(Item) * b->items.size(), cudaMemcpyHostToDevice, st));
+  if (!b->ctas.empty())
+    RC_CUDA(cudaMemcpyAsync(b->d_ctas, b->ctas.data(), sizeof(CtaDesc) * b->ctas.size(), cudaMemcpyHostToDevice, st));
+  RC_CUDA(cudaMemcpyAsync(b->d_tables, &b->tables, sizeof(SigmaTables), cudaMemcpyHostToDevice, st));
+  h2d += sizeof(float) * b->scores_floats + sizeof(BlockDev) * b->n_blocks + sizeof(Item) * b->items.size() +
+         sizeof(CtaDesc) * b->ctas.size() + sizeof(SigmaTables);
+  // descriptors may go away after this call returns
+  RC_CUDA(cudaStreamSynchronize(st));
+  b->stats.h2d_bytes = h2d;
+  b->uploaded = true;
+  b->ran = false;
+  b->downloaded = false;
+  return RC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// run
+// ------------------------------------------------------------------------------------------------
+static int ev_begin(rc_batch* b, int stage) {
+  EventPair ep;
+  ep.stage = stage;
+  if (cudaEventCreate(&ep.a) != cudaSuccess || cudaEventCreate(&ep.b) != cudaSuccess) return -1;
+  cudaEventRecord(ep.a, b->ctx->stream);
+  b->events.push_back(ep);
+  return (int)b->events.size() - 1;
+}
+static void ev_end(rc_batch* b, int idx) {
+  if (idx >= 0) cudaEventRecord(b->events[idx].b, b->ctx->stream);
+}
+
+template <int R, bool DENSE>
+static int launch_dp(rc_batch* b, const CtaDesc* d_ctas, size_t ncta, int maxNK, int maxZs) {
+  rc_ctx* ctx = b->ctx;
+  if (ncta == 0) return RC_OK;
+  const size_t smem = DP_WARPS * DpSmem<R>::per_warp(maxNK, maxZs);
+  if (smem > (size_t)ctx->smem_optin) {
+    ctx_fail(ctx, "alignment has too many rows for the shared-memory resident DP state (N-1 = " + std::to_string(maxNK) + ")");
+    return RC_ERR_ARG;
+  }
+  RC_CUDA(cudaFuncSetAttribute(k_dp<R, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dp<R, DENSE><<<(unsigned)ncta, DP_WARPS * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+                                                                      b->d_recs, b->d_dense, b->prm, (int)ctx->band_slots,
+                                                                      maxNK, maxZs);
+  RC_CUDA(cudaGetLastError());
+  b->stats.launches++;
+  b->stats.dp_launches++;
+  return RC_OK;
+}
+
+// Dense (exact fallback) scoring of a list of single-instance items.
+static int run_dense_items(rc_batch* b, const std::vector<Item>& src_items) {
+  rc_ctx* ctx = b->ctx;
+  cudaStream_t st = ctx->stream;
+  // process one item at a time: dense S is P(L) floats per strand
+  for (const Item& src : src_items) {
+    const BlockDev& bd = b->blocks[src.block];
+    Item it = src;
+    size_t sig = 0, dn = 0;
+    for (int s = 0; s < 2; s++)
+      for (int f = 0; f < 3; f++) {
+        it.sigma_off[s][f] = (long long)sig;
+        sig += (size_t)it.ninst * bd.ntiles[f] * bd.NK * TILE;
+        it.rec_off[s][f] = 0;
+        it.dense_off[s][f] = (long long)dn;
+        dn += (size_t)it.ninst * ((size_t)bd.sites[f] * (bd.sites[f] + 1) / 2);
+      }
+    if (sig > b->sigma_floats) {
+      ctx_fail(ctx, "internal: dense item exceeds sigma scratch");
+      return RC_ERR_STATE;
+    }
+    if (dn > b->dense_floats) {
+      if (b->d_dense) cudaFree(b->d_dense);
+      b->d_dense = nullptr;
+      RC_CUDA(cudaMalloc((void**)&b->d_dense, std::max<size_t>(dn * sizeof(float), 256)));
+      b->dense_floats = dn;
+    }
+    std::vector<Item> one{it};
+    std::vector<CtaDesc> ctas;
+    build_ctas(b->blocks, one, 0, 1, 1, -1, ctas);
+    Item* d_item = nullptr;
+    CtaDesc* d_cta = nullptr;
+    RC_CUDA(cudaMalloc((void**)&d_item, sizeof(Item)));
+    RC_CUDA(cudaMalloc((void**)&d_cta, sizeof(CtaDesc) * std::max<size_t>(ctas.size(), 1)));
+    RC_CUDA(cudaMemcpyAsync(d_item, &it, sizeof(Item), cudaMemcpyHostToDevice, st));
+    RC_CUDA(cudaMemcpyAsync(d_cta, ctas.data(), sizeof(CtaDesc) * ctas.size(), cudaMemcpyHostToDevice, st));
+    const long long work = (long long)it.ninst * 2 * (bd.L - 2);
+    dim3 gs(1, (unsigned)std::min<long long>((work + 255) / 256, 4096));
+    k_sigma<<<gs, 256, 0, st>>>(b->d_blocks, d_item, b->d_cls, b->d_cols0, b->d_scores, b->d_tables, b->d_sigma, b->prm);
+    RC_CUDA(cudaGetLastError());
+    // temporarily point the batch's item array at the single item
+    Item* saved = b->d_items;
+    b->d_items = d_item;
+    int rcode = launch_dp<1, true>(b, d_cta, ctas.size(), bd.NK, bd.zstride);
+    b->d_items = saved;
+    if (rcode != RC_OK) { cudaFree(d_item); cudaFree(d_cta); return rcode; }
+    dim3 gh(1, (unsigned)((it.ninst * 6 * 32 + 127) / 128));
+    k_hss_dense<<<gh, 128, 0, st>>>(b->d_blocks, d_item, b->d_dense, b->d_res, b->d_hss, b->d_hsscnt);
+    RC_CUDA(cudaGetLastError());
+    b->stats.launches += 2;
+    RC_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_item);
+    cudaFree(d_cta);
+    b->stats.dense_fallbacks += it.ninst;
+  }
+  return RC_OK;
+}
+
+extern "C" int rc_batch_run(rc_batch* b) {
+  if (!b) return RC_ERR_ARG;
+  rc_ctx* ctx = b->ctx;
+  if (!b->uploaded) {
+    ctx_fail(ctx, "rc_batch_run before rc_batch_upload");
+    return RC_ERR_STATE;
+  }
+  RC_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  for (auto& e : b->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  b->events.clear();
+  b->stats.launches = 0;
+  b->stats.dp_launches = 0;
+  b->stats.dense_fallbacks = 0;
+
+  int maxchunks = 1;
+  for (const BlockDev& bd : b->blocks) maxchunks = std::max(maxchunks, (int)(((size_t)bd.inst_stride >> 4) * bd.n_inst / 256 + 1));
+  int ev = ev_begin(b, 0);
+  {
+    dim3 g((unsigned)b->n_blocks, (unsigned)std::min(maxchunks, 2048));
+    k_pack<<<g, 256, 0, st>>>(b->d_blocks, b->d_raw, b->d_cls, ctx->d_lut);
+    RC_CUDA(cudaGetLastError());
+    k_prep<<<b->n_blocks, 256, 0, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_z);
+    RC_CUDA(cudaGetLastError());
+    b->stats.launches += 2;
+  }
+  ev_end(b, ev);
+  RC_CUDA(cudaMemsetAsync(b->d_ovf, 0, sizeof(int), st));
+  // results of blocks that are never scored (L < 3): no HSS, every sample maximum -1
+  RC_CUDA(cudaMemsetAsync(b->d_hsscnt, 0, sizeof(int) * b->hsscnt_ints, st));
+
+  if (ctx->force_dense) {
+    // test hook: everything through the exact dense path, one instance at a time
+    std::vector<Item> singles;
+    for (const Item& it : b->items)
+      for (int i = 0; i < it.ninst; i++) {
+        Item s = it;
+        s.inst0 = it.inst0 + i;
+        s.ninst = 1;
+        singles.push_back(s);
+      }
+    int rcode = run_dense_items(b, singles);
+    if (rcode != RC_OK) return rcode;
+    b->ran = true;
+    b->downloaded = false;
+    return RC_OK;
+  }
+
+  for (const Chunk& ch : b->chunks) {
+    ev = ev_begin(b, 1);
+    {
+      dim3 g((unsigned)ch.nitems, (unsigned)std::min<long long>((ch.max_sigma_work + 255) / 256, 8192));
+      k_sigma<<<g, 256, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores, b->d_tables,
+                                 b->d_sigma, b->prm);
+      RC_CUDA(cudaGetLastError());
+      b->stats.launches++;
+    }
+    ev_end(b, ev);
+    ev = ev_begin(b, 2);
+    {
+      // CtaDesc.item indexes the batch-wide item array
+      int rcode = launch_dp<2, false>(b, b->d_ctas + ch.cta0[0], ch.ncta[0], ch.maxNK[0], ch.maxZs[0]);
+      if (rcode != RC_OK) return rcode;
+      rcode = launch_dp<1, false>(b, b->d_ctas + ch.cta0[1], ch.ncta[1], ch.maxNK[1], ch.maxZs[1]);
+      if (rcode != RC_OK) return rcode;
+    }
+    ev_end(b, ev);
+    ev = ev_begin(b, 3);
+    {
+      dim3 g((unsigned)ch.nitems, (unsigned)((ch.max_ninst * 6 + 127) / 128));
+      k_hss<<<g, 128, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_recs, b->d_res, b->d_hss, b->d_hsscnt, b->d_ovf);
+      RC_CUDA(cudaGetLastError());
+      b->stats.launches++;
+    }
+    ev_end(b, ev);
+  }
+
+  // band overflow -> exact dense re-scoring of the affected alignments (rare)
+  int ovf = 0;
+  RC_CUDA(cudaMemcpyAsync(&ovf, b->d_ovf, sizeof(int), cudaMemcpyDeviceToHost, st));
+  RC_CUDA(cudaStreamSynchronize(st));
+  if (ovf > 0) {
+    RC_CUDA(cudaMemcpy(b->h_res.data(), b->d_res, sizeof(float) * b->res_floats, cudaMemcpyDeviceToHost));
+    std::vector<Item> singles;
+    for (int i = 0; i < b->n_blocks; i++) {
+      const BlockDev& bd = b->blocks[i];
+      if (bd.L < 3) continue;
+      for (int inst = 0; inst < bd.n_inst; inst++) {
+        bool hit = false;
+        for (int sf = 0; sf < 6; sf++) hit |= b->h_res[bd.res_off + (size_t)inst * 6 + sf] == -2.0f;
+        if (hit) {
+          Item s;
+          memset(&s, 0, sizeof(s));
+          s.block = i;
+          s.inst0 = inst;
+          s.ninst = 1;
+          singles.push_back(s);
+        }
+      }
+    }
+    int rcode = run_dense_items(b, singles);
+    if (rcode != RC_OK) return rcode;
+  }
+  // stage timings
+  b->stats.ms_pack = b->stats.ms_sigma = b->stats.ms_dp = b->stats.ms_hss = 0.0f;
+  for (auto& e : b->events) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+      if (e.stage == 0) b->stats.ms_pack += ms;
+      else if (e.stage == 1) b->stats.ms_sigma += ms;
+      else if (e.stage == 2) b->stats.ms_dp += ms;
+      else b->stats.ms_hss += ms;
+    }
+  }
+  b->ran = true;
+  b->downloaded = false;
+  return RC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// download + result access
+// ------------------------------------------------------------------------------------------------
+extern "C" int rc_batch_download(rc_batch* b) {
+  if (!b) return RC_ERR_ARG;
+  rc_ctx* ctx = b->ctx;
+  if (!b->ran) {
+    ctx_fail(ctx, "rc_batch_download before rc_batch_run");
+    return RC_ERR_STATE;
+  }
+  RC_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  RC_CUDA(cudaMemcpyAsync(b->h_res.data(), b->d_res, sizeof(float) * b->res_floats, cudaMemcpyDeviceToHost, st));
+  RC_CUDA(cudaMemcpyAsync(b->h_hss.data(), b->d_hss, sizeof(HssDev) * b->hss_count, cudaMemcpyDeviceToHost, st));
+  RC_CUDA(cudaMemcpyAsync(b->h_hsscnt.data(), b->d_hsscnt, sizeof(int) * b->hsscnt_ints, cudaMemcpyDeviceToHost, st));
+  RC_CUDA(cudaStreamSynchronize(st));
+  b->stats.d2h_bytes = sizeof(float) * b->res_floats + sizeof(HssDev) * b->hss_count + sizeof(int) * b->hsscnt_ints;
+  b->downloaded = true;
+  return RC_OK;
+}
+
+extern "C" int rc_batch_native_hss(rc_batch* b, int block, rc_hss* out, int max_hss, int* n_hss) {
+  if (!b || block < 0 || block >= b->n_blocks || !n_hss) return RC_ERR_ARG;
+  if (!b->downloaded) {
+    ctx_fail(b->ctx, "rc_batch_native_hss before rc_batch_download");
+    return RC_ERR_STATE;
+  }
+  const BlockDev& bd = b->blocks[block];
+  int n = 0;
+  if (bd.L >= 3) {
+    for (int s = 0; s < 2; s++)      // '+' first, then '-' (src/score.c:1107-1127)
+      for (int f = 0; f < 3; f++) {  // frames in order (src/score.c:880)
+        const int cnt = b->h_hsscnt[bd.hsscnt_off + s * 3 + f];
+        if (cnt < 0) {
+          ctx_fail(b->ctx, "internal: unresolved band overflow");
+          return RC_ERR_STATE;
+        }
+        for (int i = 0; i < cnt; i++) {
+          const HssDev& h = b->h_hss[bd.hss_off[s][f] + i];
+          if (out && n < max_hss) {
+            out[n].strand = s ? '-' : '+';
+            out[n].frame = f;
+            out[n].startSite = h.startSite;
+            out[n].endSite = h.endSite;
+            out[n].score = h.score;
+          }
+          n++;
+        }
+      }
+  }
+  *n_hss = n;
+  return (out == nullptr || n <= max_hss) ? RC_OK : RC_ERR_CAPACITY;
+}
+
+extern "C" int rc_batch_max_scores(rc_batch* b, int block, double* max_scores) {
+  if (!b || block < 0 || block >= b->n_blocks || !max_scores) return RC_ERR_ARG;
+  if (!b->downloaded) {
+    ctx_fail(b->ctx, "rc_batch_max_scores before rc_batch_download");
+    return RC_ERR_STATE;
+  }
+  const BlockDev& bd = b->blocks[block];
+  for (int inst = 1; inst < bd.n_inst; inst++) {
+    float best = -1.0f;  // results[0].score of an empty list (src/score.c:1129-1134, :1044)
+    if (bd.L >= 3)
+      for (int sf = 0; sf < 6; sf++) best = std::max(best, b->h_res[bd.res_off + (size_t)inst * 6 + sf]);
+    max_scores[inst - 1] = (double)best;
+  }
+  return RC_OK;
+}
+
+extern "C" int rc_batch_get_stats(rc_batch* b, rc_batch_stats* stats) {
+  if (!b || !stats) return RC_ERR_ARG;
+  b->stats.device_bytes = b->device_bytes + b->dense_floats * sizeof(float);
+  *stats = b->stats;
+  return RC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one block at a time
+// ------------------------------------------------------------------------------------------------
+extern "C" int rc_score_aln(rc_ctx* ctx, const rc_block_desc* block, const rc_params* params, const int* blosum,
+                            rc_hss* out, int max_hss, int* n_hss) {
+  if (!ctx || !block || !n_hss) return RC_ERR_ARG;
+  rc_block_desc d = *block;
+  d.n_samples = 0;
+  d.samples = nullptr;
+  rc_batch* b = nullptr;
+  int r = rc_batch_create(ctx, &d, 1, params, blosum, &b);
+  if (r != RC_OK) return r;
+  if ((r = rc_batch_upload(b)) == RC_OK && (r = rc_batch_run(b)) == RC_OK && (r = rc_batch_download(b)) == RC_OK)
+    r = rc_batch_native_hss(b, 0, out, max_hss, n_hss);
+  rc_batch_destroy(b);
+  return r;
+}
+
+extern "C" int rc_score_samples(rc_ctx* ctx, const rc_block_desc* block, const rc_params* params, const int* blosum,
+                                double* max_scores) {
+  if (!ctx || !block || !max_scores) return RC_ERR_ARG;
+  rc_batch* b = nullptr;
+  int r = rc_batch_create(ctx, block, 1, params, blosum, &b);
+  if (r != RC_OK) return r;
+  if ((r = rc_batch_upload(b)) == RC_OK && (r = rc_batch_run(b)) == RC_OK && (r = rc_batch_download(b)) == RC_OK)
+    r = rc_batch_max_scores(b, 0, max_scores);
+  rc_batch_destroy(b);
+  return r;
+}

@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.json.gz from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+1. builds oracle/_ref/{RNAcode_ref,RNAcode_det,ref_probe} from /root/reference (oracle/Makefile target ref),
+2. runs ref_probe (deterministic seeds via oracle/ref_wrap.c) on the reference's example alignments and
+   on synthetic MAF written by rnacode_b200.synth (gappy, with N / lower-case / odd symbols, non-default
+   --pars), and stores the JSON dumps gzip-compressed,
+3. runs the deterministic reference CLI (RNAcode_det) on the examples with several option sets and stores
+   its stdout (tests/golden/cli_*.txt.gz) for the drop-in CLI comparison.
+The fixtures pin oracle/rnacode_oracle.c (tests/test_oracle_golden.py) and, on the GPU box, the CUDA path.
+"""
+import gzip
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from rnacode_b200 import synth  # noqa: E402
+
+REF = os.environ.get("RNACODE_REF", "/root/reference")
+ORC = os.path.join(ROOT, "oracle")
+PROBE = os.path.join(ORC, "_ref", "ref_probe")
+DET = os.path.join(ORC, "_ref", "RNAcode_det")
+TMP = os.path.join(ORC, "_ref", "tmp")
+
+
+def probe(path, n, dump, extra=(), seed=1):
+    env = dict(os.environ, RNACODE_SEED=str(seed))
+    out = subprocess.run([PROBE, "-n", str(n), "--dump-samples", str(dump), *extra, path], check=True,
+                         capture_output=True, env=env).stdout
+    return json.loads(out)
+
+
+def save(name, doc):
+    p = os.path.join(HERE, name + ".json.gz")
+    with gzip.GzipFile(p, "wb", mtime=0) as fh:
+        fh.write(json.dumps(doc, separators=(",", ":")).encode())
+    print("wrote", p, os.path.getsize(p) // 1024, "KiB")
+
+
+def decorate(rows, rng):
+    """Sprinkle N, lower-case and IUPAC symbols into a synthetic block (exercises ntMap / 'N' rules)."""
+    rows = rows.copy()
+    N, cols = rows.shape
+    for sym, cnt in ((ord("N"), 6), (ord("R"), 3), (ord("Y"), 2), (ord("X"), 3)):
+        for _ in range(cnt):
+            s, c = rng.integers(0, N), rng.integers(0, cols)
+            if rows[s, c] != synth.GAP:
+                rows[s, c] = sym
+    # one run of three X in a species row aligned to a reference codon, one NNN run in the reference
+    rows[1, 30:33] = ord("X")
+    rows[0, 60:63] = ord("N")
+    return rows
+
+
+def main():
+    subprocess.run(["make", "-C", ORC, "-j8", "ref"], check=True, stdout=subprocess.DEVNULL)
+    os.makedirs(TMP, exist_ok=True)
+    ex = os.path.join(REF, "examples")
+    save("coding_aln", probe(os.path.join(ex, "coding.aln"), 100, 100))
+    save("noncoding_aln", probe(os.path.join(ex, "noncoding.aln"), 50, 50))
+    save("coding_maf", probe(os.path.join(ex, "coding.maf"), 20, 20))
+    save("noncoding_maf", probe(os.path.join(ex, "noncoding.maf"), 20, 20))
+    save("genomic_maf", probe(os.path.join(ex, "genomic.maf"), 3, 3))
+    save("genomic_pre_maf", probe(os.path.join(ex, "genomic-preprocessed.maf"), 8, 8))
+    save("coding_aln_pars", probe(os.path.join(ex, "coding.aln"), 20, 20, extra=("--pars", "-9.5,-3.25,-1.5,-50")))
+
+    rng = np.random.default_rng(7)
+    blocks = [synth.synth_block(11, i, N, cols, gap_rate=gr)
+              for i, (N, cols, gr) in enumerate([(10, 120, 0.0067), (10, 120, 0.03), (5, 200, 0.02), (12, 90, 0.05),
+                                                 (3, 150, 0.01), (10, 333, 0.02), (25, 100, 0.02), (30, 75, 0.03)])]
+    blocks[1] = decorate(blocks[1], rng)
+    blocks[3] = decorate(blocks[3], rng)
+    p = os.path.join(TMP, "synth_gappy.maf")
+    synth.to_maf(blocks, p)
+    save("synth_gappy", probe(p, 12, 12))
+    blocks = [synth.synth_block(12, i, 10, 120, gap_rate=0.0) for i in range(3)]
+    p = os.path.join(TMP, "synth_gapfree.maf")
+    synth.to_maf(blocks, p)
+    save("synth_gapfree", probe(p, 12, 12))
+
+    # reference CLI outputs (deterministic seeds) for the drop-in comparison
+    cli = {}
+    for f, opts in (("coding.aln", []), ("coding.aln", ["--tabular"]), ("coding.aln", ["--gtf"]),
+                    ("coding.maf", ["--gtf"]), ("coding.maf", ["--tabular", "-b"]), ("noncoding.aln", ["--tabular"]),
+                    ("genomic-preprocessed.maf", ["--tabular", "-n", "20"]),
+                    ("genomic-preprocessed.maf", ["--gtf", "-r", "-n", "20"]),
+                    ("genomic-preprocessed.maf", ["--tabular", "-s", "-p", "0.05", "-n", "20"]),
+                    ("coding.aln", ["--tabular", "-c", "-9.5,-3.25,-1.5,-50"])):
+        env = dict(os.environ, RNACODE_SEED="1")
+        out = subprocess.run([DET, *opts, os.path.join(ex, f)], check=True, capture_output=True, env=env).stdout.decode()
+        cli[f + " " + " ".join(opts)] = out
+    save("cli_outputs", cli)
+
+
+if __name__ == "__main__":
+    main()

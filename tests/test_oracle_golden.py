@@ -1,0 +1,66 @@
+"""Pins the CPU oracle (oracle/rnacode_oracle.c) against dumps of the UNMODIFIED reference
+(tests/golden/*.json.gz, produced by oracle/_ref/ref_probe -- see tests/golden/make_golden.py).
+Bit-exact: HSS coordinates and float32 scores, per-sample maxima, background-model scores."""
+import numpy as np
+import pytest
+
+from tests import oracle_py as op
+
+
+@pytest.mark.parametrize("name", op.GOLDEN_SETS)
+def test_tables_match_reference(oracle, name):
+    doc = op.golden(name)
+    assert list(oracle.transcode) == doc["transcode"]
+    assert list(oracle.blosum62) == doc["blosum"]
+
+
+@pytest.mark.parametrize("name", op.GOLDEN_SETS)
+def test_native_hss_bit_exact(oracle, name):
+    doc = op.golden(name)
+    prm = oracle.params(**op.golden_params(doc))
+    scored = 0
+    for blk in doc["blocks"]:
+        if blk.get("skipped"):
+            continue
+        if blk["N"] * blk["L"] ** 2 > 4e8:  # the 10x4806 block of genomic.maf: covered by the GPU suite, too slow here
+            continue
+        rows, sf, sr, _ = op.block_arrays(doc, blk)
+        got = oracle.score_aln(rows, sf, sr, prm)
+        assert got == op.expected_hss(blk), (name, blk["index"])
+        scored += 1
+    assert scored > 0
+
+
+@pytest.mark.parametrize("name", op.GOLDEN_SETS)
+def test_sample_maxima_bit_exact(oracle, name):
+    doc = op.golden(name)
+    prm = oracle.params(**op.golden_params(doc))
+    checked = 0
+    for blk in doc["blocks"]:
+        if blk.get("skipped") or blk["N"] * blk["L"] ** 2 > 4e8:
+            continue
+        rows, sf, sr, smp = op.block_arrays(doc, blk)
+        if smp is None:
+            continue
+        got = oracle.sample_maxima(rows, smp, sf, sr, prm)
+        exp = np.array(blk["maxScores"][:len(smp)])
+        assert np.array_equal(got.astype(np.float32), exp.astype(np.float32)), (name, blk["index"])
+        checked += len(smp)
+    assert checked > 0
+
+
+@pytest.mark.parametrize("name", ["coding_aln", "genomic_pre_maf", "synth_gappy"])
+def test_background_model_bit_exact(oracle, name):
+    """calculateBG / probHKY / countFreqsMono restatement vs models[].scores of the reference."""
+    doc = op.golden(name)
+    for blk in doc["blocks"]:
+        if blk.get("skipped"):
+            continue
+        rows, sf, sr, _ = op.block_arrays(doc, blk)
+        fr = oracle.count_freqs(rows)
+        assert np.array_equal(fr, np.array(blk["freqs_fwd"], dtype=np.float32))
+        for k in range(1, blk["N"]):
+            sc = oracle.calculate_bg(blk["dist"][k], blk["freqs_fwd"], blk["kappa"])
+            assert np.array_equal(sc, sf[k]), (name, blk["index"], k)
+            sc = oracle.calculate_bg(blk["dist"][k], blk["freqs_rev"], blk["kappa"])
+            assert np.array_equal(sc, sr[k]), (name, blk["index"], k)
