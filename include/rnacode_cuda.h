@@ -122,6 +122,10 @@ typedef struct {
 } rc_batch_stats;
 int rc_batch_get_stats(rc_batch *batch, rc_batch_stats *stats);
 
+/* Runs a register-only kernel with the DP fast path's instruction mix (4 FADD : 1 FMNMX3) and returns the
+ * achieved lane-operations per second: the practical FP32/ALU issue ceiling at the device's current clocks. */
+int rc_calibrate_issue(rc_ctx *ctx, double *lane_ops_per_s);
+
 /* Library / build identification, e.g. "libRNAcode_cuda 0.1 sm_100a". */
 const char *rc_version(void);
 

@@ -43,6 +43,7 @@ EXPORTS = [
     "rc_create", "rc_destroy", "rc_last_error", "rc_default_params", "rc_set_stream", "rc_set_option",
     "rc_score_aln", "rc_score_samples", "rc_batch_create", "rc_batch_upload", "rc_batch_run", "rc_batch_download",
     "rc_batch_native_hss", "rc_batch_max_scores", "rc_batch_destroy", "rc_batch_get_stats", "rc_version",
+    "rc_calibrate_issue",
 ]
 
 _lib = None
@@ -78,6 +79,7 @@ def load():
     lib.rc_batch_destroy.restype = None
     lib.rc_batch_get_stats.argtypes = [vp, C.POINTER(rc_batch_stats)]
     lib.rc_version.restype = C.c_char_p
+    lib.rc_calibrate_issue.argtypes = [vp, C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -180,6 +182,11 @@ class Context:
         res = np.zeros(block.n_samples, dtype=np.float64)
         self._check(self.lib.rc_score_samples(self.h, C.byref(d), C.byref(params), bl.ctypes.data, res.ctypes.data))
         return res
+
+    def calibrate_issue(self):
+        v = C.c_double()
+        self._check(self.lib.rc_calibrate_issue(self.h, C.byref(v)))
+        return v.value
 
     def batch(self, blocks, params, blosum):
         return Batch(self, blocks, params, blosum)

@@ -659,4 +659,33 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Issue-rate calibration: the instruction mix of the DP fast path (4 FADD : 1 FMNMX3 per cell) on
+// register-resident chains, no memory traffic.  Gives the practical FP32/ALU issue ceiling of the
+// device at its current clocks; bench.py reports the DP kernel against it.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_calib(float* __restrict__ out, int iters, float sg, float om) {
+  float S0[8], S1[8], S2[8], acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    S0[i] = threadIdx.x * 0.001f + i;
+    S1[i] = S0[i] - 1.0f;
+    S2[i] = S0[i] - 2.0f;
+    acc[i] = 0.0f;
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      S0[i] += sg;
+      S1[i] += om;
+      S2[i] += om;
+      acc[i] += max3f(S0[i], S1[i], S2[i]);
+    }
+  }
+  float r = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 }  // namespace rc

@@ -215,6 +215,33 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
   return RC_OK;
 }
 
+extern "C" int rc_calibrate_issue(rc_ctx* ctx, double* lane_ops_per_s) {
+  if (!ctx || !lane_ops_per_s) return RC_ERR_ARG;
+  RC_CUDA(cudaSetDevice(ctx->device));
+  const int ctas = ctx->sm_count * 8, threads = 256, iters = 8192;
+  float* d_out = nullptr;
+  RC_CUDA(cudaMalloc((void**)&d_out, sizeof(float) * ctas * threads));
+  cudaEvent_t a, b;
+  RC_CUDA(cudaEventCreate(&a));
+  RC_CUDA(cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {  // first repetition warms up
+    RC_CUDA(cudaEventRecord(a, ctx->stream));
+    k_calib<<<ctas, threads, 0, ctx->stream>>>(d_out, iters, 0.25f, -2.0f);
+    RC_CUDA(cudaEventRecord(b, ctx->stream));
+    RC_CUDA(cudaEventSynchronize(b));
+    float ms = 0.0f;
+    RC_CUDA(cudaEventElapsedTime(&ms, a, b));
+    const double ops = (double)ctas * threads * iters * 8.0 * 5.0;  // 8 chains x (4 FADD + 1 FMNMX3)
+    if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d_out);
+  *lane_ops_per_s = best;
+  return RC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // planning
 // ------------------------------------------------------------------------------------------------

@@ -45,7 +45,7 @@ def synth_block(seed, index, N, cols, gap_rate=0.0067):
                 rows[s, st:st + ln] = GAP
         # keep at least 3 reference positions
         if (rows[0] != GAP).sum() < 3:
-            rows[0, :3] = ACGT[:3]
+            rows[0, :min(3, cols)] = ACGT[:min(3, cols)]
     return rows
 
 

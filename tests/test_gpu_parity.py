@@ -1,0 +1,176 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against (1) golden dumps of the
+unmodified reference and (2) the CPU oracle on seeded synthetic inputs.  Bit-exact: HSS strand / frame /
+codon coordinates, float32 scores, per-sample maxima."""
+import numpy as np
+import pytest
+
+from tests import oracle_py as op
+
+pytestmark = pytest.mark.gpu
+
+
+def _capi():
+    from rnacode_b200 import capi
+    return capi
+
+
+def _block(rows, sf, sr, smp=None):
+    return _capi().Block(rows, sf, sr, smp)
+
+
+@pytest.mark.parametrize("name", op.GOLDEN_SETS)
+def test_golden_native_and_samples(rc_ctx, name):
+    capi = _capi()
+    doc = op.golden(name)
+    prm = capi.make_params(**op.golden_params(doc))
+    blocks, blks = [], []
+    for blk in doc["blocks"]:
+        if blk.get("skipped"):
+            continue
+        rows, sf, sr, smp = op.block_arrays(doc, blk)
+        blocks.append(_block(rows, sf, sr, smp))
+        blks.append(blk)
+    bt = rc_ctx.batch(blocks, prm, doc["blosum"])
+    bt.upload()
+    bt.run()
+    bt.download()
+    for i, blk in enumerate(blks):
+        assert bt.native_hss(i) == op.expected_hss(blk), (name, blk["index"], "native HSS")
+        if blocks[i].n_samples:
+            got = bt.max_scores(i).astype(np.float32)
+            exp = np.array(blk["maxScores"][:blocks[i].n_samples], dtype=np.float32)
+            assert np.array_equal(got, exp), (name, blk["index"], "sample maxima")
+    assert bt.stats()["launches"] > 0
+    bt.close()
+
+
+@pytest.mark.parametrize("name", ["coding_aln", "synth_gappy", "genomic_pre_maf"])
+def test_one_block_api_matches_reference(rc_ctx, name):
+    """rc_score_aln / rc_score_samples (the scoreAln-shaped calls)."""
+    capi = _capi()
+    doc = op.golden(name)
+    prm = capi.make_params(**op.golden_params(doc))
+    for blk in doc["blocks"][:4]:
+        if blk.get("skipped"):
+            continue
+        rows, sf, sr, smp = op.block_arrays(doc, blk)
+        b = _block(rows, sf, sr, smp)
+        assert rc_ctx.score_aln(b, prm, doc["blosum"]) == op.expected_hss(blk)
+        if smp is not None:
+            got = rc_ctx.score_samples(b, prm, doc["blosum"]).astype(np.float32)
+            assert np.array_equal(got, np.array(blk["maxScores"][:len(smp)], dtype=np.float32))
+
+
+@pytest.mark.parametrize("mode", ["force_dense", "band1"])
+def test_dense_fallback_is_exact(mode, oracle):
+    """The exact dense-S path (taken on tie-band overflow) gives the same answers as the digest path."""
+    capi = _capi()
+    ctx = capi.Context(0)
+    if mode == "force_dense":
+        ctx.set_option("force_dense", 1)
+    else:
+        ctx.set_option("band_slots", 1)
+    try:
+        for name in ("coding_aln", "synth_gappy"):
+            doc = op.golden(name)
+            prm = capi.make_params(**op.golden_params(doc))
+            for blk in doc["blocks"]:
+                if blk.get("skipped"):
+                    continue
+                rows, sf, sr, smp = op.block_arrays(doc, blk)
+                smp = smp[:6] if smp is not None else None
+                b = _block(rows, sf, sr, smp)
+                bt = ctx.batch([b], prm, doc["blosum"])
+                bt.upload(); bt.run(); bt.download()
+                assert bt.native_hss(0) == op.expected_hss(blk), (mode, name, blk["index"])
+                if smp is not None:
+                    assert np.array_equal(bt.max_scores(0).astype(np.float32),
+                                          np.array(blk["maxScores"][:len(smp)], dtype=np.float32))
+                if mode == "force_dense":
+                    assert bt.stats()["dense_fallbacks"] == 1 + b.n_samples
+                bt.close()
+    finally:
+        ctx.close()
+
+
+SHAPES = [
+    # (N, cols, n_samples, gap_rate)
+    (3, 9, 4, 0.0), (3, 3, 2, 0.0), (4, 5, 2, 0.0), (2, 60, 3, 0.02), (10, 120, 33, 0.0067), (10, 120, 5, 0.0),
+    (6, 47, 7, 0.05), (6, 48, 7, 0.05), (6, 49, 7, 0.05), (10, 97, 3, 0.1), (26, 150, 5, 0.02), (50, 130, 3, 0.02),
+    (100, 96, 2, 0.02), (10, 600, 4, 0.02), (8, 1000, 2, 0.0067),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "N%d_c%d_n%d_g%g" % s)
+def test_synthetic_vs_oracle(rc_ctx, oracle, shape):
+    from rnacode_b200 import synth
+    capi = _capi()
+    N, cols, n, gr = shape
+    prm = capi.make_params()
+    oprm = oracle.params()
+    blocks, data = [], []
+    for idx in range(3):
+        rows = synth.synth_block(21, idx * 1000 + N * 7 + cols, N, cols, gap_rate=gr)
+        sf, sr = synth.synth_scores(21, idx, N)
+        smp = synth.synth_samples(21, idx * 1000 + cols, n, N, cols)
+        blocks.append(_block(rows, sf, sr, smp))
+        data.append((rows, sf, sr, smp))
+    bt = rc_ctx.batch(blocks, prm, oracle.blosum62)
+    bt.upload(); bt.run(); bt.download()
+    for i, (rows, sf, sr, smp) in enumerate(data):
+        assert bt.native_hss(i) == oracle.score_aln(rows, sf, sr, oprm), (shape, i)
+        exp = oracle.sample_maxima(rows, smp, sf, sr, oprm).astype(np.float32)
+        assert np.array_equal(bt.max_scores(i).astype(np.float32), exp), (shape, i)
+    bt.close()
+
+
+def test_mixed_batch_and_chunking(oracle):
+    """Blocks of different shapes in one batch, with a scratch budget so small that instances of one block
+    are split across chunks."""
+    from rnacode_b200 import synth
+    capi = _capi()
+    ctx = capi.Context(0)
+    ctx.set_option("scratch_mb", 1)
+    try:
+        shapes = [(10, 200, 40), (4, 30, 3), (30, 90, 10), (3, 2, 2), (12, 333, 9)]
+        blocks, data = [], []
+        for idx, (N, cols, n) in enumerate(shapes):
+            rows = synth.synth_block(5, idx, N, cols, gap_rate=0.02)
+            sf, sr = synth.synth_scores(5, idx, N)
+            smp = synth.synth_samples(5, idx, n, N, cols)
+            blocks.append(_block(rows, sf, sr, smp))
+            data.append((rows, sf, sr, smp))
+        bt = ctx.batch(blocks, capi.make_params(), oracle.blosum62)
+        bt.upload(); bt.run(); bt.download()
+        for i, (rows, sf, sr, smp) in enumerate(data):
+            if synth.ungapped_len(rows) < 3:
+                assert bt.native_hss(i) == []
+                assert np.all(bt.max_scores(i) == -1.0)
+                continue
+            assert bt.native_hss(i) == oracle.score_aln(rows, sf, sr, oracle.params()), i
+            exp = oracle.sample_maxima(rows, smp, sf, sr, oracle.params()).astype(np.float32)
+            assert np.array_equal(bt.max_scores(i).astype(np.float32), exp), i
+        bt.close()
+    finally:
+        ctx.close()
+
+
+def test_nondefault_parameters(rc_ctx, oracle):
+    from rnacode_b200 import synth
+    capi = _capi()
+    kw = dict(Delta=-7.5, Omega=-3.25, omega=-1.5, stopPenalty_0=-50.0, stopPenalty_k=-6.0)
+    rows = synth.synth_block(9, 1, 8, 150, gap_rate=0.04)
+    sf, sr = synth.synth_scores(9, 1, 8)
+    smp = synth.synth_samples(9, 1, 6, 8, 150)
+    b = _block(rows, sf, sr, smp)
+    assert rc_ctx.score_aln(b, capi.make_params(**kw), oracle.blosum62) == oracle.score_aln(rows, sf, sr, oracle.params(**kw))
+    exp = oracle.sample_maxima(rows, smp, sf, sr, oracle.params(**kw)).astype(np.float32)
+    assert np.array_equal(rc_ctx.score_samples(b, capi.make_params(**kw), oracle.blosum62).astype(np.float32), exp)
+
+
+def test_bad_arguments(rc_ctx, oracle):
+    capi = _capi()
+    rows = np.frombuffer(b"ACGTACGTAC", dtype=np.uint8).reshape(1, 10)
+    b = capi.Block(rows, np.zeros((1, 4)), np.zeros((1, 4)))
+    with pytest.raises(capi.RcError):
+        rc_ctx.score_aln(b, capi.make_params(), oracle.blosum62)
