@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDev* __restrict__ block
 // (a) k_prep: one CTA per block.
 //   cols0[strand][x], x = 1..L : forward 0-based column of the x-th non-gap character of the reference
 //   row when read in that strand's direction (pos2col, src/misc.c:250-269, as a prefix sum).
-//   z word per (strand, frame, tile, species): bit c = z != 0 at step c of the tile, bit 16+c = z == -1
+//   z word, layout 0, per (strand, frame, tile, species): bit c = z != 0 at step c of the tile, bit 16+c = z == -1;
+//   layout 1, per (strand, frame, tile, step): bit 2k = z != 0 for species k, bit 2k+1 = z == -1
 //   (getBlock, src/misc.c:198-244: |gaps_k - gaps_0| mod 3 over the columns of the codon ending at
 //   position x plus the reference-gap columns in front of it; from column 1 for x == 3).
 // ---------------------------------------------------------------------------------------------
@@ -139,30 +140,36 @@ __global__ void __launch_bounds__(256) k_prep(const BlockDev* __restrict__ block
       unsigned* zt = ztiles + bd.z_off[s][f];
       const int work = nt * bd.zstride;
       for (int w = threadIdx.x; w < work; w += blockDim.x) {
-        const int tile = w / bd.zstride, k = w % bd.zstride;
+        const int tile = w / bd.zstride, u = w % bd.zstride;
         unsigned word = 0;
-        if (k < NK) {
+        // layout 0: u = species, loop over the tile's steps; layout 1: u = step, loop over species
+        const int n_inner = bd.layout ? NK : TILE;
+        for (int v = 0; v < n_inner; v++) {
+          const int k = bd.layout ? v : u;
+          const int c = bd.layout ? u : v;
+          const int j = tile * TILE + c;
+          if (k >= NK || j >= sites) continue;
           const unsigned char* rowk = nat + (size_t)(k + 1) * cols;
-          for (int c = 0; c < TILE; c++) {
-            const int j = tile * TILE + c;
-            if (j >= sites) break;
-            const int x = 3 * j + 3 + f;
-            // forward-column range covered by the block; on the reverse strand the range is mirrored,
-            // the gap counts are the same
-            int a, b;
-            if (s == 0) {
-              a = (x > 3) ? c0[x - 3] + 1 : 0;
-              b = c0[x];
-            } else {
-              a = c0[x];
-              b = (x > 3) ? c0[x - 3] - 1 : cols - 1;
-            }
-            int gk = 0;
-            for (int col = a; col <= b; col++) gk += (rowk[col] & CLS_GAP) ? 1 : 0;
-            const int g0 = (b - a + 1) - 3;
-            int diff = gk - g0;
-            diff = diff < 0 ? -diff : diff;
-            const int m = diff % 3;
+          const int x = 3 * j + 3 + f;
+          // forward-column range covered by the block; on the reverse strand the range is mirrored,
+          // the gap counts are the same
+          int a, b;
+          if (s == 0) {
+            a = (x > 3) ? c0[x - 3] + 1 : 0;
+            b = c0[x];
+          } else {
+            a = c0[x];
+            b = (x > 3) ? c0[x - 3] - 1 : cols - 1;
+          }
+          int gk = 0;
+          for (int col = a; col <= b; col++) gk += (rowk[col] & CLS_GAP) ? 1 : 0;
+          const int g0 = (b - a + 1) - 3;
+          int diff = gk - g0;
+          diff = diff < 0 ? -diff : diff;
+          const int m = diff % 3;
+          if (bd.layout) {
+            if (m != 0) word |= (m == 2 ? 3u : 1u) << (2 * k);  // bit 2k: z != 0, bit 2k+1: z == -1
+          } else {
             if (m != 0) word |= 1u << c;
             if (m == 2) word |= 1u << (16 + c);
           }
@@ -220,7 +227,8 @@ __global__ void __launch_bounds__(256)
     const int pepA = s_tab.transcode[qa];
     const int f = xi % 3, j = xi / 3;
     const int tile = j / TILE, c = j % TILE;
-    float* out = sigma + it.sigma_off[s][f] + ((size_t)inst_l * bd.ntiles[f] + tile) * NK * TILE + c;
+    float* out = sigma + it.sigma_off[s][f] + ((size_t)inst_l * bd.ntiles[f] + tile) * bd.sig_tile + (size_t)c * bd.sig_cs;
+    const int ks = bd.sig_ks;
     const float* sc = scores + bd.scores_off + (size_t)s * N * 4;
     for (int k = 0; k < NK; k++) {
       const unsigned char* rowk = base + (size_t)(k + 1) * cols;
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(256)
           v = s_tab.blosum[pepA * 24 + pepB] - sc[(k + 1) * 4 + h];  // observed - expected, float32 (:422-425)
         }
       }
-      out[(size_t)k * TILE] = v;
+      out[(size_t)k * ks] = v;
     }
   }
 }
@@ -519,6 +527,204 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
         rec->jF = (unsigned short)rs[t].jF;
         rec->n = (unsigned short)rs[t].nb;
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (c) k_dp_reg: the DP for alignments with at most REG_MAX_NK scored species (the common case: the
+// reference's examples have 3..9).  Same task decomposition, staging and getHSS digest as k_dp, but the
+// loop nest is step-major: for each end codon the warp walks all species, so the 3*NK*R state floats stay
+// in registers for the whole task and the species sum is a scalar.  sigma tiles are laid out
+// [step][species] (one or more broadcast LDS.128 per step), z is one word per step with 2 bits per
+// species, so a step without any frameshift costs one test.  Steps with a frameshift branch per species
+// (warp-uniform).  Float operations and their order are the reference's, as in k_dp.
+// ---------------------------------------------------------------------------------------------
+template <int NK, int R, bool DIAG>
+struct RegStep {
+  // one end codon j for all species; returns nothing, updates state / row digests
+  static __device__ __forceinline__ void run(float (&S0)[NK][R], float (&S1)[NK][R], float (&S2)[NK][R],
+                                             const float* __restrict__ sgc, unsigned zw, int j, int r0, int sites,
+                                             bool check_end, float Delta, float Omega, float omega, float fNK, float rcpNK,
+                                             RowSt (&rs)[R], RowRec* rec0, int band_slots) {
+    constexpr int NKP = (NK + 3) / 4 * 4;
+    float sv[NKP];
+#pragma unroll
+    for (int q = 0; q < NKP / 4; q++) {
+      const float4 v = reinterpret_cast<const float4*>(sgc)[q];
+      sv[4 * q] = v.x;
+      sv[4 * q + 1] = v.y;
+      sv[4 * q + 2] = v.z;
+      sv[4 * q + 3] = v.w;
+    }
+    if (DIAG) {
+#pragma unroll
+      for (int t = 0; t < R; t++) {
+        if (j == r0 + t) {  // the row starts here from (0,0,0) (src/score.c:500-504)
+#pragma unroll
+          for (int k = 0; k < NK; k++) {
+            S0[k][t] = 0.0f;
+            S1[k][t] = 0.0f;
+            S2[k][t] = 0.0f;
+          }
+        }
+      }
+    }
+    float sum[R];
+    if (zw == 0u) {  // no species has a frameshift at this codon (src/score.c:506-510)
+#pragma unroll
+      for (int k = 0; k < NK; k++) {
+#pragma unroll
+        for (int t = 0; t < R; t++) {
+          S0[k][t] += sv[k];
+          S1[k][t] += omega;
+          S2[k][t] += omega;
+          const float m = max3f(S0[k][t], S1[k][t], S2[k][t]);
+          sum[t] = (k == 0) ? (0.0f + m) : (sum[t] + m);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NK; k++) {
+        const unsigned z2 = (zw >> (2 * k)) & 3u;
+        if (z2 == 0u) {
+#pragma unroll
+          for (int t = 0; t < R; t++) {
+            S0[k][t] += sv[k];
+            S1[k][t] += omega;
+            S2[k][t] += omega;
+          }
+        } else {
+          const bool neg = (z2 & 2u) != 0u;
+#pragma unroll
+          for (int t = 0; t < R; t++) {
+            const float a0 = S0[k][t], a1 = S1[k][t], a2 = S2[k][t];
+            // z = +1 (src/score.c:512-521): (0<-2, 1<-0, 2<-1);  z = -1 (:523-533): (0<-1, 1<-2, 2<-0)
+            const float x0 = neg ? a1 : a2, x1 = neg ? a2 : a0, x2 = neg ? a0 : a1;
+            S0[k][t] = fmaxf(a0 + Delta, x0 + Omega);
+            S1[k][t] = fmaxf(a1 + Delta, x1 + Omega);
+            S2[k][t] = fmaxf(a2 + Delta, x2 + Omega);
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < R; t++) {
+          const float m = max3f(S0[k][t], S1[k][t], S2[k][t]);
+          sum[t] = (k == 0) ? (0.0f + m) : (sum[t] + m);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+      const float m = fmaxf(sum[t], Delta);  // src/score.c:841-843
+      bool live = m > 0.0f;
+      if (DIAG) live = live && (j >= r0 + t);
+      if (check_end) live = live && (j < sites);
+      if (live) {
+        const float q = m * rcpNK;
+        const float e = __fmaf_rn(__fmaf_rn(-fNK, q, m), rcpNK, q);
+        rs[t] = hss_accept(rs[t], e, j, rec0 + t, band_slots);
+      }
+    }
+  }
+};
+
+template <int NK, int R>
+__global__ void __launch_bounds__(DP_WARPS * 32)
+    k_dp_reg(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
+             const float* __restrict__ sigma, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm,
+             int band_slots) {
+  constexpr int NKP = (NK + 3) / 4 * 4;
+  constexpr int SIG_TILE = TILE * NKP;  // floats
+  constexpr int STAGE_BYTES = SIG_TILE * 4 + TILE * 4;
+  __shared__ __align__(128) unsigned char smem[DP_WARPS][2 * STAGE_BYTES + 16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const CtaDesc cd = ctas[blockIdx.x];
+  const Item& it = items[cd.item];
+  const BlockDev& bd = blocks[it.block];
+  const int strand = cd.sf / 3, frame = cd.sf % 3;
+  const int sites = bd.sites[frame], ntiles = bd.ntiles[frame];
+  const int ngroups = (sites + 32 * R - 1) / (32 * R);
+  const int task = cd.task0 + warp;
+  if (task >= it.ninst * ngroups) return;
+  const int inst_l = task / ngroups, g = task % ngroups;
+  const int row_base = g * 32 * R;
+  const int r0 = row_base + lane * R;
+
+  unsigned char* ring = smem[warp];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * STAGE_BYTES);
+  const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * ntiles * SIG_TILE;
+  const unsigned* z_src = ztiles + bd.z_off[strand][frame];
+  const int t0 = row_base / TILE;
+  const int t_last_diag = (row_base + 32 * R - 1) / TILE;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+    for (int s = 0; s < 2 && t0 + s < ntiles; s++) {
+      unsigned char* dst = ring + s * STAGE_BYTES;
+      mbar_expect_tx(&bars[s], STAGE_BYTES);
+      bulk_g2s(dst, sig_src + (size_t)(t0 + s) * SIG_TILE, SIG_TILE * 4, &bars[s]);
+      bulk_g2s(dst + SIG_TILE * 4, z_src + (size_t)(t0 + s) * TILE, TILE * 4, &bars[s]);
+    }
+  }
+  __syncwarp();
+
+  float S0[NK][R], S1[NK][R], S2[NK][R];
+#pragma unroll
+  for (int k = 0; k < NK; k++)
+#pragma unroll
+    for (int t = 0; t < R; t++) S0[k][t] = S1[k][t] = S2[k][t] = 0.0f;
+  RowSt rs[R];
+#pragma unroll
+  for (int t = 0; t < R; t++) {
+    rs[t].lb = -INFINITY;
+    rs[t].M = -INFINITY;
+    rs[t].jF = 0;
+    rs[t].nb = 0;
+  }
+  RowRec* rec0 = recs + it.rec_off[strand][frame] + (size_t)inst_l * sites + r0;
+  const float Delta = prm.Delta, Omega = prm.Omega, omega = prm.omega;
+  const float fNK = bd.fNK, rcpNK = bd.rcpNK;
+
+  for (int tile = t0; tile < ntiles; tile++) {
+    const int s = (tile - t0) & 1;
+    const unsigned parity = ((tile - t0) >> 1) & 1;
+    const float* sg = reinterpret_cast<const float*>(ring + s * STAGE_BYTES);
+    const unsigned* zt = reinterpret_cast<const unsigned*>(ring + s * STAGE_BYTES + SIG_TILE * 4);
+    const int j0 = tile * TILE;
+    mbar_wait(&bars[s], parity);
+    if (tile <= t_last_diag) {
+#pragma unroll 1
+      for (int c = 0; c < TILE; c++)
+        RegStep<NK, R, true>::run(S0, S1, S2, sg + c * NKP, zt[c], j0 + c, r0, sites, true, Delta, Omega, omega, fNK, rcpNK,
+                                  rs, rec0, band_slots);
+    } else if (tile == ntiles - 1) {
+#pragma unroll 1
+      for (int c = 0; c < TILE; c++)
+        RegStep<NK, R, false>::run(S0, S1, S2, sg + c * NKP, zt[c], j0 + c, r0, sites, true, Delta, Omega, omega, fNK,
+                                   rcpNK, rs, rec0, band_slots);
+    } else {
+#pragma unroll 2
+      for (int c = 0; c < TILE; c++)
+        RegStep<NK, R, false>::run(S0, S1, S2, sg + c * NKP, zt[c], j0 + c, r0, sites, false, Delta, Omega, omega, fNK,
+                                   rcpNK, rs, rec0, band_slots);
+    }
+    __syncwarp();
+    if (lane == 0 && tile + 2 < ntiles) {
+      unsigned char* dst = ring + s * STAGE_BYTES;
+      mbar_expect_tx(&bars[s], STAGE_BYTES);
+      bulk_g2s(dst, sig_src + (size_t)(tile + 2) * SIG_TILE, SIG_TILE * 4, &bars[s]);
+      bulk_g2s(dst + SIG_TILE * 4, z_src + (size_t)(tile + 2) * TILE, TILE * 4, &bars[s]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < R; t++) {
+    if (r0 + t < sites) {
+      RowRec* rec = rec0 + t;
+      rec->Emax = rs[t].M;
+      rec->vF = rs[t].lb;
+      rec->jF = (unsigned short)rs[t].jF;
+      rec->n = (unsigned short)rs[t].nb;
     }
   }
 }

@@ -47,10 +47,13 @@ static void ctx_fail(rc_ctx* ctx, const std::string& msg) {
 
 namespace {
 
+// DP launch classes: 0..15 = k_dp_reg<NK = class+1, R = 2>; 16 = k_dp<R = 2> (17 <= NK <= 24); 17 = k_dp<R = 1>
+constexpr int N_CLASSES = REG_MAX_NK + 2;
+
 struct Chunk {
   size_t item0 = 0, nitems = 0;          // range in the batch's item array
-  size_t cta0[2] = {0, 0}, ncta[2] = {0, 0};  // per class (0: R=2, 1: R=1) range in the CTA array
-  int maxNK[2] = {0, 0}, maxZs[2] = {0, 0};
+  size_t cta0[N_CLASSES] = {}, ncta[N_CLASSES] = {};  // per class range in the CTA array
+  int maxNK[N_CLASSES] = {}, maxZs[N_CLASSES] = {};
   size_t sigma_floats = 0, rec_count = 0;
   long long max_sigma_work = 0;  // largest ninst*2*(L-2) of an item, for the k_sigma grid
   int max_ninst = 0;
@@ -63,7 +66,25 @@ struct EventPair {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int class_of(int NK) { return NK <= 24 ? 0 : 1; }
+int class_of(int NK) { return NK <= REG_MAX_NK ? NK - 1 : (NK <= 24 ? REG_MAX_NK : REG_MAX_NK + 1); }
+int class_R(int cl) { return cl == REG_MAX_NK + 1 ? 1 : 2; }
+
+// sigma / z layout of a block (see BlockDev)
+void set_layout(BlockDev& bd, int layout) {
+  bd.layout = layout;
+  if (layout == 1) {
+    const int nkp = (bd.NK + 3) / 4 * 4;
+    bd.sig_tile = TILE * nkp;
+    bd.sig_ks = 1;
+    bd.sig_cs = nkp;
+    bd.zstride = TILE;
+  } else {
+    bd.sig_tile = bd.NK * TILE;
+    bd.sig_ks = TILE;
+    bd.sig_cs = 1;
+    bd.zstride = (int)align_up((size_t)bd.NK, 4);
+  }
+}
 
 }  // namespace
 
@@ -319,7 +340,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     bd.NK = d.N - 1;
     bd.n_inst = 1 + d.n_samples;
     bd.inst_stride = (int)align_up((size_t)d.N * d.cols, 16);
-    bd.zstride = (int)align_up((size_t)bd.NK, 4);
+    set_layout(bd, bd.NK <= REG_MAX_NK ? 1 : 0);
     bd.fNK = (float)bd.NK;
     bd.rcpNK = 1.0f / bd.fNK;
     bd.raw_off = (long long)b->raw_bytes;
@@ -366,7 +387,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     if (bd.L < 3) continue;  // nothing to score (the reference skips such blocks, src/RNAcode.c:147-150)
     size_t sig_per_inst = 0, rec_per_inst = 0;
     for (int f = 0; f < 3; f++) {
-      sig_per_inst += 2 * (size_t)bd.ntiles[f] * bd.NK * TILE;
+      sig_per_inst += 2 * (size_t)bd.ntiles[f] * bd.sig_tile;
       rec_per_inst += 2 * (size_t)bd.sites[f];
     }
     const size_t bytes_per_inst = sig_per_inst * sizeof(float) + rec_per_inst * sizeof(RowRec);
@@ -386,7 +407,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       for (int s = 0; s < 2; s++)
         for (int f = 0; f < 3; f++) {
           it.sigma_off[s][f] = (long long)cur.sigma_floats;
-          cur.sigma_floats += (size_t)take * bd.ntiles[f] * bd.NK * TILE;
+          cur.sigma_floats += (size_t)take * bd.ntiles[f] * bd.sig_tile;
           it.rec_off[s][f] = (long long)cur.rec_count;
           cur.rec_count += (size_t)take * bd.sites[f];
         }
@@ -403,12 +424,11 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
   }
   close_chunk();
   for (Chunk& ch : b->chunks) {
-    ch.cta0[0] = b->ctas.size();
-    build_ctas(b->blocks, b->items, ch.item0, ch.nitems, 2, 0, b->ctas);
-    ch.ncta[0] = b->ctas.size() - ch.cta0[0];
-    ch.cta0[1] = b->ctas.size();
-    build_ctas(b->blocks, b->items, ch.item0, ch.nitems, 1, 1, b->ctas);
-    ch.ncta[1] = b->ctas.size() - ch.cta0[1];
+    for (int cl = 0; cl < N_CLASSES; cl++) {
+      ch.cta0[cl] = b->ctas.size();
+      if (ch.maxNK[cl] > 0) build_ctas(b->blocks, b->items, ch.item0, ch.nitems, class_R(cl), cl, b->ctas);
+      ch.ncta[cl] = b->ctas.size() - ch.cta0[cl];
+    }
     b->sigma_floats = std::max(b->sigma_floats, ch.sigma_floats);
     b->rec_count = std::max(b->rec_count, ch.rec_count);
   }
@@ -529,61 +549,145 @@ static int launch_dp(rc_batch* b, const CtaDesc* d_ctas, size_t ncta, int maxNK,
   return RC_OK;
 }
 
-// Dense (exact fallback) scoring of a list of single-instance items.
+template <int NK>
+static int launch_dp_reg_nk(rc_batch* b, const CtaDesc* d_ctas, size_t ncta) {
+  rc_ctx* ctx = b->ctx;
+  k_dp_reg<NK, 2><<<(unsigned)ncta, DP_WARPS * 32, 0, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+                                                                    b->d_recs, b->prm, (int)ctx->band_slots);
+  RC_CUDA(cudaGetLastError());
+  b->stats.launches++;
+  b->stats.dp_launches++;
+  return RC_OK;
+}
+
+static int launch_dp_reg(rc_batch* b, int NK, const CtaDesc* d_ctas, size_t ncta) {
+  if (ncta == 0) return RC_OK;
+  switch (NK) {
+    case 1: return launch_dp_reg_nk<1>(b, d_ctas, ncta);
+    case 2: return launch_dp_reg_nk<2>(b, d_ctas, ncta);
+    case 3: return launch_dp_reg_nk<3>(b, d_ctas, ncta);
+    case 4: return launch_dp_reg_nk<4>(b, d_ctas, ncta);
+    case 5: return launch_dp_reg_nk<5>(b, d_ctas, ncta);
+    case 6: return launch_dp_reg_nk<6>(b, d_ctas, ncta);
+    case 7: return launch_dp_reg_nk<7>(b, d_ctas, ncta);
+    case 8: return launch_dp_reg_nk<8>(b, d_ctas, ncta);
+    case 9: return launch_dp_reg_nk<9>(b, d_ctas, ncta);
+    case 10: return launch_dp_reg_nk<10>(b, d_ctas, ncta);
+    case 11: return launch_dp_reg_nk<11>(b, d_ctas, ncta);
+    case 12: return launch_dp_reg_nk<12>(b, d_ctas, ncta);
+    case 13: return launch_dp_reg_nk<13>(b, d_ctas, ncta);
+    case 14: return launch_dp_reg_nk<14>(b, d_ctas, ncta);
+    case 15: return launch_dp_reg_nk<15>(b, d_ctas, ncta);
+    case 16: return launch_dp_reg_nk<16>(b, d_ctas, ncta);
+    default: ctx_fail(b->ctx, "internal: k_dp_reg NK out of range"); return RC_ERR_STATE;
+  }
+}
+
+// Dense (exact fallback) scoring of a list of single-instance items.  Always runs k_dp<1, DENSE> on
+// layout-0 sigma / z tiles that are rebuilt for the item in scratch, whatever layout the block uses.
 static int run_dense_items(rc_batch* b, const std::vector<Item>& src_items) {
   rc_ctx* ctx = b->ctx;
   cudaStream_t st = ctx->stream;
-  // process one item at a time: dense S is P(L) floats per strand
+  BlockDev* d_blk = nullptr;
+  Item* d_item = nullptr;
+  CtaDesc* d_cta = nullptr;
+  unsigned* d_zs = nullptr;
+  size_t cta_cap = 0, zs_cap = 0;
+  int rcode = RC_OK;
+  auto cleanup = [&]() { cudaFree(d_blk); cudaFree(d_item); cudaFree(d_cta); cudaFree(d_zs); };
+#define RC_CUDA_D(call)                                                         \
+  do {                                                                          \
+    cudaError_t _e = (call);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      ctx_fail(ctx, std::string(#call) + ": " + cudaGetErrorString(_e));        \
+      cleanup();                                                                \
+      return RC_ERR_CUDA;                                                       \
+    }                                                                           \
+  } while (0)
+  RC_CUDA_D(cudaMalloc((void**)&d_blk, sizeof(BlockDev)));
+  RC_CUDA_D(cudaMalloc((void**)&d_item, sizeof(Item)));
   for (const Item& src : src_items) {
-    const BlockDev& bd = b->blocks[src.block];
+    BlockDev bd = b->blocks[src.block];
+    set_layout(bd, 0);
+    size_t zw = 0;
+    for (int s = 0; s < 2; s++)
+      for (int f = 0; f < 3; f++) {
+        bd.z_off[s][f] = (long long)zw;
+        zw += (size_t)bd.ntiles[f] * bd.zstride;
+      }
     Item it = src;
+    it.block = 0;
     size_t sig = 0, dn = 0;
     for (int s = 0; s < 2; s++)
       for (int f = 0; f < 3; f++) {
         it.sigma_off[s][f] = (long long)sig;
-        sig += (size_t)it.ninst * bd.ntiles[f] * bd.NK * TILE;
+        sig += (size_t)it.ninst * bd.ntiles[f] * bd.sig_tile;
         it.rec_off[s][f] = 0;
         it.dense_off[s][f] = (long long)dn;
         dn += (size_t)it.ninst * ((size_t)bd.sites[f] * (bd.sites[f] + 1) / 2);
       }
-    if (sig > b->sigma_floats) {
-      ctx_fail(ctx, "internal: dense item exceeds sigma scratch");
-      return RC_ERR_STATE;
+    if (sig > b->sigma_floats) {  // layout 0 tiles can be larger than the padded layout-1 ones never; guard anyway
+      cudaFree(b->d_sigma);
+      b->d_sigma = nullptr;
+      RC_CUDA_D(cudaMalloc((void**)&b->d_sigma, sig * sizeof(float)));
+      b->sigma_floats = sig;
     }
     if (dn > b->dense_floats) {
-      if (b->d_dense) cudaFree(b->d_dense);
+      cudaFree(b->d_dense);
       b->d_dense = nullptr;
-      RC_CUDA(cudaMalloc((void**)&b->d_dense, std::max<size_t>(dn * sizeof(float), 256)));
+      b->dense_floats = 0;
+      RC_CUDA_D(cudaMalloc((void**)&b->d_dense, std::max<size_t>(dn * sizeof(float), 256)));
       b->dense_floats = dn;
     }
+    if (zw > zs_cap) {
+      cudaFree(d_zs);
+      d_zs = nullptr;
+      RC_CUDA_D(cudaMalloc((void**)&d_zs, std::max<size_t>(zw * sizeof(unsigned), 256)));
+      zs_cap = zw;
+    }
+    std::vector<BlockDev> one_blk{bd};
     std::vector<Item> one{it};
     std::vector<CtaDesc> ctas;
-    build_ctas(b->blocks, one, 0, 1, 1, -1, ctas);
-    Item* d_item = nullptr;
-    CtaDesc* d_cta = nullptr;
-    RC_CUDA(cudaMalloc((void**)&d_item, sizeof(Item)));
-    RC_CUDA(cudaMalloc((void**)&d_cta, sizeof(CtaDesc) * std::max<size_t>(ctas.size(), 1)));
-    RC_CUDA(cudaMemcpyAsync(d_item, &it, sizeof(Item), cudaMemcpyHostToDevice, st));
-    RC_CUDA(cudaMemcpyAsync(d_cta, ctas.data(), sizeof(CtaDesc) * ctas.size(), cudaMemcpyHostToDevice, st));
+    build_ctas(one_blk, one, 0, 1, 1, -1, ctas);
+    if (ctas.size() > cta_cap) {
+      cudaFree(d_cta);
+      d_cta = nullptr;
+      RC_CUDA_D(cudaMalloc((void**)&d_cta, sizeof(CtaDesc) * ctas.size()));
+      cta_cap = ctas.size();
+    }
+    RC_CUDA_D(cudaMemcpyAsync(d_blk, &bd, sizeof(BlockDev), cudaMemcpyHostToDevice, st));
+    RC_CUDA_D(cudaMemcpyAsync(d_item, &it, sizeof(Item), cudaMemcpyHostToDevice, st));
+    RC_CUDA_D(cudaMemcpyAsync(d_cta, ctas.data(), sizeof(CtaDesc) * ctas.size(), cudaMemcpyHostToDevice, st));
+    k_prep<<<1, 256, 0, st>>>(d_blk, b->d_cls, b->d_cols0, d_zs);
+    RC_CUDA_D(cudaGetLastError());
     const long long work = (long long)it.ninst * 2 * (bd.L - 2);
     dim3 gs(1, (unsigned)std::min<long long>((work + 255) / 256, 4096));
-    k_sigma<<<gs, 256, 0, st>>>(b->d_blocks, d_item, b->d_cls, b->d_cols0, b->d_scores, b->d_tables, b->d_sigma, b->prm);
-    RC_CUDA(cudaGetLastError());
-    // temporarily point the batch's item array at the single item
-    Item* saved = b->d_items;
+    k_sigma<<<gs, 256, 0, st>>>(d_blk, d_item, b->d_cls, b->d_cols0, b->d_scores, b->d_tables, b->d_sigma, b->prm);
+    RC_CUDA_D(cudaGetLastError());
+    // the DP kernel reads blocks / items / z through the batch pointers: point them at the private copies
+    BlockDev* saved_blocks = b->d_blocks;
+    Item* saved_items = b->d_items;
+    unsigned* saved_z = b->d_z;
+    b->d_blocks = d_blk;
     b->d_items = d_item;
-    int rcode = launch_dp<1, true>(b, d_cta, ctas.size(), bd.NK, bd.zstride);
-    b->d_items = saved;
-    if (rcode != RC_OK) { cudaFree(d_item); cudaFree(d_cta); return rcode; }
+    b->d_z = d_zs;
+    rcode = launch_dp<1, true>(b, d_cta, ctas.size(), bd.NK, bd.zstride);
+    b->d_blocks = saved_blocks;
+    b->d_items = saved_items;
+    b->d_z = saved_z;
+    if (rcode != RC_OK) {
+      cleanup();
+      return rcode;
+    }
     dim3 gh(1, (unsigned)((it.ninst * 6 * 32 + 127) / 128));
-    k_hss_dense<<<gh, 128, 0, st>>>(b->d_blocks, d_item, b->d_dense, b->d_res, b->d_hss, b->d_hsscnt);
-    RC_CUDA(cudaGetLastError());
-    b->stats.launches += 2;
-    RC_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_item);
-    cudaFree(d_cta);
+    k_hss_dense<<<gh, 128, 0, st>>>(d_blk, d_item, b->d_dense, b->d_res, b->d_hss, b->d_hsscnt);
+    RC_CUDA_D(cudaGetLastError());
+    b->stats.launches += 3;
+    RC_CUDA_D(cudaStreamSynchronize(st));  // the private descriptors are rewritten for the next item
     b->stats.dense_fallbacks += it.ninst;
   }
+  cleanup();
+#undef RC_CUDA_D
   return RC_OK;
 }
 
@@ -648,10 +752,14 @@ extern "C" int rc_batch_run(rc_batch* b) {
     ev = ev_begin(b, 2);
     {
       // CtaDesc.item indexes the batch-wide item array
-      int rcode = launch_dp<2, false>(b, b->d_ctas + ch.cta0[0], ch.ncta[0], ch.maxNK[0], ch.maxZs[0]);
-      if (rcode != RC_OK) return rcode;
-      rcode = launch_dp<1, false>(b, b->d_ctas + ch.cta0[1], ch.ncta[1], ch.maxNK[1], ch.maxZs[1]);
-      if (rcode != RC_OK) return rcode;
+      for (int cl = 0; cl < N_CLASSES; cl++) {
+        if (ch.ncta[cl] == 0) continue;
+        int rcode;
+        if (cl < REG_MAX_NK) rcode = launch_dp_reg(b, cl + 1, b->d_ctas + ch.cta0[cl], ch.ncta[cl]);
+        else if (cl == REG_MAX_NK) rcode = launch_dp<2, false>(b, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.maxNK[cl], ch.maxZs[cl]);
+        else rcode = launch_dp<1, false>(b, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.maxNK[cl], ch.maxZs[cl]);
+        if (rcode != RC_OK) return rcode;
+      }
     }
     ev_end(b, ev);
     ev = ev_begin(b, 3);
