@@ -194,7 +194,7 @@ struct __align__(16) SigmaTables {
 __global__ void __launch_bounds__(256)
     k_sigma(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned char* __restrict__ cls,
             const int* __restrict__ cols0, const float* __restrict__ scores, const SigmaTables* __restrict__ tables,
-            float* __restrict__ sigma, Params prm) {
+            const unsigned* __restrict__ ztiles, float* __restrict__ sigma, Params prm) {
   __shared__ SigmaTables s_tab;
   __shared__ __align__(8) uint64_t s_bar;
   if (threadIdx.x == 0) {
@@ -253,6 +253,8 @@ __global__ void __launch_bounds__(256)
       }
       out[(size_t)k * ks] = v;
     }
+    if (bd.layout == 1)  // the step's z word rides in the sigma row, right after the NK sigma values
+      out[NK] = __uint_as_float(ztiles[bd.z_off[s][f] + (size_t)tile * bd.zstride + c]);
   }
 }
 
@@ -534,108 +536,163 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
 // ---------------------------------------------------------------------------------------------
 // (c) k_dp_reg: the DP for alignments with at most REG_MAX_NK scored species (the common case: the
 // reference's examples have 3..9).  Same task decomposition, staging and getHSS digest as k_dp, but the
-// loop nest is step-major: for each end codon the warp walks all species, so the 3*NK*R state floats stay
-// in registers for the whole task and the species sum is a scalar.  sigma tiles are laid out
-// [step][species] (one or more broadcast LDS.128 per step), z is one word per step with 2 bits per
-// species, so a step without any frameshift costs one test.  Steps with a frameshift branch per species
-// (warp-uniform).  Float operations and their order are the reference's, as in k_dp.
+// loop nest is step-major: for each end codon the warp walks all species, so the state stays in
+// registers for the whole task and the species sum is a scalar per row.  Each lane owns TWO rows and
+// keeps every state as a float2 (row0, row1): the adds are issued as packed FADD2 (add.rn.f32x2, IEEE
+// round-to-nearest per half, bit-identical to two FADDs), which halves the issue slots of the add
+// chains.  sigma tiles are laid out [step][RS] with RS = roundup(NK+1, 4): NK sigma values followed by
+// the step's z word (2 bits per species), so one row of broadcast LDS.128 feeds a step, and a step
+// without any frameshift costs one test.  Steps with a frameshift branch per species (warp-uniform).
+// The kernel requires Delta <= 0 (then max(sum, Delta) > 0 <=> sum > 0 and the quotient is taken from
+// sum itself); the host routes Delta > 0 to k_dp.
 // ---------------------------------------------------------------------------------------------
-template <int NK, int R, bool DIAG>
-struct RegStep {
-  // one end codon j for all species; returns nothing, updates state / row digests
-  static __device__ __forceinline__ void run(float (&S0)[NK][R], float (&S1)[NK][R], float (&S2)[NK][R],
-                                             const float* __restrict__ sgc, unsigned zw, int j, int r0, int sites,
-                                             bool check_end, float Delta, float Omega, float omega, float fNK, float rcpNK,
-                                             RowSt (&rs)[R], RowRec* rec0, int band_slots) {
-    constexpr int NKP = (NK + 3) / 4 * 4;
-    float sv[NKP];
-#pragma unroll
-    for (int q = 0; q < NKP / 4; q++) {
-      const float4 v = reinterpret_cast<const float4*>(sgc)[q];
-      sv[4 * q] = v.x;
-      sv[4 * q + 1] = v.y;
-      sv[4 * q + 2] = v.z;
-      sv[4 * q + 3] = v.w;
-    }
-    if (DIAG) {
-#pragma unroll
-      for (int t = 0; t < R; t++) {
-        if (j == r0 + t) {  // the row starts here from (0,0,0) (src/score.c:500-504)
-#pragma unroll
-          for (int k = 0; k < NK; k++) {
-            S0[k][t] = 0.0f;
-            S1[k][t] = 0.0f;
-            S2[k][t] = 0.0f;
-          }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2s(float2 a, float b) { return add2(a, make_float2(b, b)); }
+
+// RowRec-resident variant of hss_accept: the fold state lives in the row's record (global memory, touched
+// only on the rare positive entries), so the hot loop carries no per-row registers for it.
+// rec->vF = last accepted value (-inf before the first), rec->Emax = row maximum, rec->jF, rec->n as in RowRec.
+__device__ __noinline__ void hss_accept_rec(RowRec* rec, float e, int j, int slots) {
+  const float lb = rec->vF;
+  const float d = e - lb;
+  if (!(d >= -0.0001f)) return;
+  rec->vF = e;
+  rec->jF = (unsigned short)j;
+  int nb = rec->n & 0xff, ovf = rec->n & 0x8000;
+  float M = rec->Emax;
+  if (e > M) {
+    if (M - e < -0.0001f) nb = 0;
+    M = e;
+    rec->Emax = e;
+  }
+  if (nb > 0 && rec->be[nb - 1] == e) {
+    rec->bj[nb - 1] = (unsigned short)j;
+  } else {
+    if (nb == slots) {
+      int w = 0;
+      for (int m = 0; m < nb; m++) {
+        const float b = rec->be[m];
+        if (!(b - M < -0.0001f)) {
+          rec->be[w] = b;
+          rec->bj[w] = rec->bj[m];
+          w++;
         }
       }
+      nb = w;
     }
-    float sum[R];
-    if (zw == 0u) {  // no species has a frameshift at this codon (src/score.c:506-510)
-#pragma unroll
-      for (int k = 0; k < NK; k++) {
-#pragma unroll
-        for (int t = 0; t < R; t++) {
-          S0[k][t] += sv[k];
-          S1[k][t] += omega;
-          S2[k][t] += omega;
-          const float m = max3f(S0[k][t], S1[k][t], S2[k][t]);
-          sum[t] = (k == 0) ? (0.0f + m) : (sum[t] + m);
-        }
-      }
+    if (nb == slots) {
+      ovf = 0x8000;
     } else {
-#pragma unroll
-      for (int k = 0; k < NK; k++) {
-        const unsigned z2 = (zw >> (2 * k)) & 3u;
-        if (z2 == 0u) {
-#pragma unroll
-          for (int t = 0; t < R; t++) {
-            S0[k][t] += sv[k];
-            S1[k][t] += omega;
-            S2[k][t] += omega;
-          }
-        } else {
-          const bool neg = (z2 & 2u) != 0u;
-#pragma unroll
-          for (int t = 0; t < R; t++) {
-            const float a0 = S0[k][t], a1 = S1[k][t], a2 = S2[k][t];
-            // z = +1 (src/score.c:512-521): (0<-2, 1<-0, 2<-1);  z = -1 (:523-533): (0<-1, 1<-2, 2<-0)
-            const float x0 = neg ? a1 : a2, x1 = neg ? a2 : a0, x2 = neg ? a0 : a1;
-            S0[k][t] = fmaxf(a0 + Delta, x0 + Omega);
-            S1[k][t] = fmaxf(a1 + Delta, x1 + Omega);
-            S2[k][t] = fmaxf(a2 + Delta, x2 + Omega);
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < R; t++) {
-          const float m = max3f(S0[k][t], S1[k][t], S2[k][t]);
-          sum[t] = (k == 0) ? (0.0f + m) : (sum[t] + m);
-        }
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < R; t++) {
-      const float m = fmaxf(sum[t], Delta);  // src/score.c:841-843
-      bool live = m > 0.0f;
-      if (DIAG) live = live && (j >= r0 + t);
-      if (check_end) live = live && (j < sites);
-      if (live) {
-        const float q = m * rcpNK;
-        const float e = __fmaf_rn(__fmaf_rn(-fNK, q, m), rcpNK, q);
-        rs[t] = hss_accept(rs[t], e, j, rec0 + t, band_slots);
-      }
+      rec->be[nb] = e;
+      rec->bj[nb] = (unsigned short)j;
+      nb++;
     }
   }
+  rec->n = (unsigned short)(nb | ovf);
+}
+
+template <int NK>
+struct RegCfg {
+  static constexpr int RS = (NK + 1 + 3) / 4 * 4;  // floats per step row: NK sigma + z word, padded to 16 bytes
+  static constexpr int SIG_TILE = TILE * RS;
+  static constexpr int STAGE_BYTES = SIG_TILE * 4;
 };
 
-template <int NK, int R>
+// loads one step row (sigma values + z word) from shared memory at 32-bit shared address `a`
+template <int NK>
+__device__ __forceinline__ void reg_load_row(unsigned a, float (&sv)[RegCfg<NK>::RS]) {
+#pragma unroll
+  for (int q = 0; q < RegCfg<NK>::RS / 4; q++)
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(sv[4 * q]), "=f"(sv[4 * q + 1]), "=f"(sv[4 * q + 2]), "=f"(sv[4 * q + 3])
+                 : "r"(a + 16 * q));
+}
+
+template <int NK, bool DIAG, bool CHECK_END>
+__device__ __forceinline__ void reg_step(float2 (&S0)[NK], float2 (&S1)[NK], float2 (&S2)[NK],
+                                         const float (&sv)[RegCfg<NK>::RS], int j, int r0, int sites, float Delta,
+                                         float Omega, float omega, float fNK, float rcpNK, RowRec* rec0, int band_slots) {
+  const unsigned zw = __float_as_uint(sv[NK]);
+  if (DIAG) {
+    // a row starts from (0,0,0) at its first end codon (src/score.c:500-504)
+    if (j == r0) {
+#pragma unroll
+      for (int k = 0; k < NK; k++) S0[k].x = S1[k].x = S2[k].x = 0.0f;
+    }
+    if (j == r0 + 1) {
+#pragma unroll
+      for (int k = 0; k < NK; k++) S0[k].y = S1[k].y = S2[k].y = 0.0f;
+    }
+  }
+  float2 sum;
+  if (zw == 0u) {  // no species has a frameshift at this codon (src/score.c:506-510)
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      S0[k] = add2s(S0[k], sv[k]);
+      S1[k] = add2s(S1[k], omega);
+      S2[k] = add2s(S2[k], omega);
+      const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
+      sum = (k == 0) ? m : add2(sum, m);  // species sum in k order (src/score.c:834-838); 0 + m == m
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      const unsigned z2 = (zw >> (2 * k)) & 3u;
+      if (z2 == 0u) {
+        S0[k] = add2s(S0[k], sv[k]);
+        S1[k] = add2s(S1[k], omega);
+        S2[k] = add2s(S2[k], omega);
+      } else {
+        const bool neg = (z2 & 2u) != 0u;
+        const float2 a0 = S0[k], a1 = S1[k], a2 = S2[k];
+        // z = +1 (src/score.c:512-521): (0<-2, 1<-0, 2<-1);  z = -1 (:523-533): (0<-1, 1<-2, 2<-0)
+        const float2 x0 = neg ? a1 : a2, x1 = neg ? a2 : a0, x2 = neg ? a0 : a1;
+        const float2 d0 = add2s(a0, Delta), d1 = add2s(a1, Delta), d2 = add2s(a2, Delta);
+        const float2 o0 = add2s(x0, Omega), o1 = add2s(x1, Omega), o2 = add2s(x2, Omega);
+        S0[k] = make_float2(fmaxf(d0.x, o0.x), fmaxf(d0.y, o0.y));
+        S1[k] = make_float2(fmaxf(d1.x, o1.x), fmaxf(d1.y, o1.y));
+        S2[k] = make_float2(fmaxf(d2.x, o2.x), fmaxf(d2.y, o2.y));
+      }
+      const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
+      sum = (k == 0) ? m : add2(sum, m);
+    }
+  }
+  // getHSS only looks at positive entries (src/score.c:891); with Delta <= 0, max(sum, Delta) > 0 <=> sum > 0
+  if (fmaxf(sum.x, sum.y) > 0.0f) {
+    bool l0 = sum.x > 0.0f, l1 = sum.y > 0.0f;
+    if (DIAG) {
+      l0 = l0 && (j >= r0);
+      l1 = l1 && (j >= r0 + 1);
+    }
+    if (CHECK_END) {
+      l0 = l0 && (j < sites);
+      l1 = l1 && (j < sites);
+    }
+    if (l0) {
+      const float q = sum.x * rcpNK;
+      hss_accept_rec(rec0, __fmaf_rn(__fmaf_rn(-fNK, q, sum.x), rcpNK, q), j, band_slots);
+    }
+    if (l1) {
+      const float q = sum.y * rcpNK;
+      hss_accept_rec(rec0 + 1, __fmaf_rn(__fmaf_rn(-fNK, q, sum.y), rcpNK, q), j, band_slots);
+    }
+  }
+}
+
+template <int NK>
 __global__ void __launch_bounds__(DP_WARPS * 32)
     k_dp_reg(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
-             const float* __restrict__ sigma, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm,
-             int band_slots) {
-  constexpr int NKP = (NK + 3) / 4 * 4;
-  constexpr int SIG_TILE = TILE * NKP;  // floats
-  constexpr int STAGE_BYTES = SIG_TILE * 4 + TILE * 4;
+             const float* __restrict__ sigma, RowRec* __restrict__ recs, Params prm, int band_slots) {
+  constexpr int R = 2;
+  constexpr int RS = RegCfg<NK>::RS;
+  constexpr int SIG_TILE = RegCfg<NK>::SIG_TILE;
+  constexpr int STAGE_BYTES = RegCfg<NK>::STAGE_BYTES;
   __shared__ __align__(128) unsigned char smem[DP_WARPS][2 * STAGE_BYTES + 16];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const CtaDesc cd = ctas[blockIdx.x];
@@ -652,8 +709,8 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
 
   unsigned char* ring = smem[warp];
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * STAGE_BYTES);
+  const unsigned ring_a = smem_u32(ring);
   const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * ntiles * SIG_TILE;
-  const unsigned* z_src = ztiles + bd.z_off[strand][frame];
   const int t0 = row_base / TILE;
   const int t_last_diag = (row_base + 32 * R - 1) / TILE;
   if (lane == 0) {
@@ -661,72 +718,75 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
     mbar_init(&bars[1], 1);
     mbar_fence_init();
     for (int s = 0; s < 2 && t0 + s < ntiles; s++) {
-      unsigned char* dst = ring + s * STAGE_BYTES;
       mbar_expect_tx(&bars[s], STAGE_BYTES);
-      bulk_g2s(dst, sig_src + (size_t)(t0 + s) * SIG_TILE, SIG_TILE * 4, &bars[s]);
-      bulk_g2s(dst + SIG_TILE * 4, z_src + (size_t)(t0 + s) * TILE, TILE * 4, &bars[s]);
+      bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(t0 + s) * SIG_TILE, STAGE_BYTES, &bars[s]);
+    }
+  }
+  // the row records double as the fold state of the getHSS digest: initialise them
+  RowRec* rec0 = recs + it.rec_off[strand][frame] + (size_t)inst_l * sites + r0;
+#pragma unroll
+  for (int t = 0; t < R; t++) {
+    if (r0 + t < sites) {
+      RowRec init;
+      init.Emax = -INFINITY;
+      init.vF = -INFINITY;
+      init.be[0] = init.be[1] = init.be[2] = 0.0f;
+      init.jF = 0;
+      init.n = 0;
+      init.bj[0] = init.bj[1] = init.bj[2] = 0;
+      init.pad = 0;
+      reinterpret_cast<uint4*>(rec0 + t)[0] = reinterpret_cast<const uint4*>(&init)[0];
+      reinterpret_cast<uint4*>(rec0 + t)[1] = reinterpret_cast<const uint4*>(&init)[1];
     }
   }
   __syncwarp();
 
-  float S0[NK][R], S1[NK][R], S2[NK][R];
+  float2 S0[NK], S1[NK], S2[NK];
 #pragma unroll
-  for (int k = 0; k < NK; k++)
-#pragma unroll
-    for (int t = 0; t < R; t++) S0[k][t] = S1[k][t] = S2[k][t] = 0.0f;
-  RowSt rs[R];
-#pragma unroll
-  for (int t = 0; t < R; t++) {
-    rs[t].lb = -INFINITY;
-    rs[t].M = -INFINITY;
-    rs[t].jF = 0;
-    rs[t].nb = 0;
-  }
-  RowRec* rec0 = recs + it.rec_off[strand][frame] + (size_t)inst_l * sites + r0;
+  for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
   const float Delta = prm.Delta, Omega = prm.Omega, omega = prm.omega;
   const float fNK = bd.fNK, rcpNK = bd.rcpNK;
 
   for (int tile = t0; tile < ntiles; tile++) {
     const int s = (tile - t0) & 1;
     const unsigned parity = ((tile - t0) >> 1) & 1;
-    const float* sg = reinterpret_cast<const float*>(ring + s * STAGE_BYTES);
-    const unsigned* zt = reinterpret_cast<const unsigned*>(ring + s * STAGE_BYTES + SIG_TILE * 4);
+    const unsigned a0 = ring_a + s * STAGE_BYTES;
     const int j0 = tile * TILE;
     mbar_wait(&bars[s], parity);
     if (tile <= t_last_diag) {
 #pragma unroll 1
-      for (int c = 0; c < TILE; c++)
-        RegStep<NK, R, true>::run(S0, S1, S2, sg + c * NKP, zt[c], j0 + c, r0, sites, true, Delta, Omega, omega, fNK, rcpNK,
-                                  rs, rec0, band_slots);
+      for (int c = 0; c < TILE; c++) {
+        float sv[RS];
+        reg_load_row<NK>(a0 + c * RS * 4, sv);
+        reg_step<NK, true, true>(S0, S1, S2, sv, j0 + c, r0, sites, Delta, Omega, omega, fNK, rcpNK, rec0, band_slots);
+      }
     } else if (tile == ntiles - 1) {
 #pragma unroll 1
-      for (int c = 0; c < TILE; c++)
-        RegStep<NK, R, false>::run(S0, S1, S2, sg + c * NKP, zt[c], j0 + c, r0, sites, true, Delta, Omega, omega, fNK,
-                                   rcpNK, rs, rec0, band_slots);
+      for (int c = 0; c < TILE; c++) {
+        float sv[RS];
+        reg_load_row<NK>(a0 + c * RS * 4, sv);
+        reg_step<NK, false, true>(S0, S1, S2, sv, j0 + c, r0, sites, Delta, Omega, omega, fNK, rcpNK, rec0, band_slots);
+      }
     } else {
-#pragma unroll 2
-      for (int c = 0; c < TILE; c++)
-        RegStep<NK, R, false>::run(S0, S1, S2, sg + c * NKP, zt[c], j0 + c, r0, sites, false, Delta, Omega, omega, fNK,
-                                   rcpNK, rs, rec0, band_slots);
+      // steady state: two steps per iteration, the next row of sigma is loaded before the current one is used
+      float svA[RS], svB[RS];
+      reg_load_row<NK>(a0, svA);
+#pragma unroll 1
+      for (int c = 0; c < TILE; c += 2) {
+        reg_load_row<NK>(a0 + (c + 1) * RS * 4, svB);
+        reg_step<NK, false, false>(S0, S1, S2, svA, j0 + c, r0, sites, Delta, Omega, omega, fNK, rcpNK, rec0, band_slots);
+        if (c + 2 < TILE) reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
+        reg_step<NK, false, false>(S0, S1, S2, svB, j0 + c + 1, r0, sites, Delta, Omega, omega, fNK, rcpNK, rec0,
+                                   band_slots);
+      }
     }
     __syncwarp();
     if (lane == 0 && tile + 2 < ntiles) {
-      unsigned char* dst = ring + s * STAGE_BYTES;
       mbar_expect_tx(&bars[s], STAGE_BYTES);
-      bulk_g2s(dst, sig_src + (size_t)(tile + 2) * SIG_TILE, SIG_TILE * 4, &bars[s]);
-      bulk_g2s(dst + SIG_TILE * 4, z_src + (size_t)(tile + 2) * TILE, TILE * 4, &bars[s]);
+      bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(tile + 2) * SIG_TILE, STAGE_BYTES, &bars[s]);
     }
   }
-#pragma unroll
-  for (int t = 0; t < R; t++) {
-    if (r0 + t < sites) {
-      RowRec* rec = rec0 + t;
-      rec->Emax = rs[t].M;
-      rec->vF = rs[t].lb;
-      rec->jF = (unsigned short)rs[t].jF;
-      rec->n = (unsigned short)rs[t].nb;
-    }
-  }
+  // finalise: rows without any positive entry keep n == 0; accepted rows already hold Emax / vF / jF / band
 }
 
 // ---------------------------------------------------------------------------------------------

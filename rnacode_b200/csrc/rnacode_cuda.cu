@@ -66,17 +66,20 @@ struct EventPair {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int class_of(int NK) { return NK <= REG_MAX_NK ? NK - 1 : (NK <= 24 ? REG_MAX_NK : REG_MAX_NK + 1); }
+int class_of(const BlockDev& bd) {
+  if (bd.layout == 1) return bd.NK - 1;
+  return bd.NK <= 24 ? REG_MAX_NK : REG_MAX_NK + 1;
+}
 int class_R(int cl) { return cl == REG_MAX_NK + 1 ? 1 : 2; }
 
 // sigma / z layout of a block (see BlockDev)
 void set_layout(BlockDev& bd, int layout) {
   bd.layout = layout;
   if (layout == 1) {
-    const int nkp = (bd.NK + 3) / 4 * 4;
-    bd.sig_tile = TILE * nkp;
+    const int rs = (bd.NK + 1 + 3) / 4 * 4;  // RegCfg<NK>::RS
+    bd.sig_tile = TILE * rs;
     bd.sig_ks = 1;
-    bd.sig_cs = nkp;
+    bd.sig_cs = rs;
     bd.zstride = TILE;
   } else {
     bd.sig_tile = bd.NK * TILE;
@@ -281,7 +284,7 @@ static void build_ctas(const std::vector<BlockDev>& blocks, const std::vector<It
   for (size_t i = i0; i < i0 + n; i++) {
     const Item& it = items[i];
     const BlockDev& bd = blocks[it.block];
-    if (want_class >= 0 && class_of(bd.NK) != want_class) continue;
+    if (want_class >= 0 && class_of(bd) != want_class) continue;
     for (int sf = 0; sf < 6; sf++) {
       const int sites = bd.sites[sf % 3];
       if (sites <= 0) continue;
@@ -340,7 +343,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     bd.NK = d.N - 1;
     bd.n_inst = 1 + d.n_samples;
     bd.inst_stride = (int)align_up((size_t)d.N * d.cols, 16);
-    set_layout(bd, bd.NK <= REG_MAX_NK ? 1 : 0);
+    set_layout(bd, (bd.NK <= REG_MAX_NK && params->Delta <= 0.0f) ? 1 : 0);
     bd.fNK = (float)bd.NK;
     bd.rcpNK = 1.0f / bd.fNK;
     bd.raw_off = (long long)b->raw_bytes;
@@ -411,7 +414,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
           it.rec_off[s][f] = (long long)cur.rec_count;
           cur.rec_count += (size_t)take * bd.sites[f];
         }
-      const int cl = class_of(bd.NK);
+      const int cl = class_of(bd);
       cur.maxNK[cl] = std::max(cur.maxNK[cl], bd.NK);
       cur.maxZs[cl] = std::max(cur.maxZs[cl], bd.zstride);
       cur.max_sigma_work = std::max(cur.max_sigma_work, (long long)take * 2 * (bd.L - 2));
@@ -552,8 +555,8 @@ static int launch_dp(rc_batch* b, const CtaDesc* d_ctas, size_t ncta, int maxNK,
 template <int NK>
 static int launch_dp_reg_nk(rc_batch* b, const CtaDesc* d_ctas, size_t ncta) {
   rc_ctx* ctx = b->ctx;
-  k_dp_reg<NK, 2><<<(unsigned)ncta, DP_WARPS * 32, 0, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
-                                                                    b->d_recs, b->prm, (int)ctx->band_slots);
+  k_dp_reg<NK><<<(unsigned)ncta, DP_WARPS * 32, 0, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_recs,
+                                                                 b->prm, (int)ctx->band_slots);
   RC_CUDA(cudaGetLastError());
   b->stats.launches++;
   b->stats.dp_launches++;
@@ -662,7 +665,7 @@ static int run_dense_items(rc_batch* b, const std::vector<Item>& src_items) {
     RC_CUDA_D(cudaGetLastError());
     const long long work = (long long)it.ninst * 2 * (bd.L - 2);
     dim3 gs(1, (unsigned)std::min<long long>((work + 255) / 256, 4096));
-    k_sigma<<<gs, 256, 0, st>>>(d_blk, d_item, b->d_cls, b->d_cols0, b->d_scores, b->d_tables, b->d_sigma, b->prm);
+    k_sigma<<<gs, 256, 0, st>>>(d_blk, d_item, b->d_cls, b->d_cols0, b->d_scores, b->d_tables, d_zs, b->d_sigma, b->prm);
     RC_CUDA_D(cudaGetLastError());
     // the DP kernel reads blocks / items / z through the batch pointers: point them at the private copies
     BlockDev* saved_blocks = b->d_blocks;
@@ -744,7 +747,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
     {
       dim3 g((unsigned)ch.nitems, (unsigned)std::min<long long>((ch.max_sigma_work + 255) / 256, 8192));
       k_sigma<<<g, 256, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores, b->d_tables,
-                                 b->d_sigma, b->prm);
+                                 b->d_z, b->d_sigma, b->prm);
       RC_CUDA(cudaGetLastError());
       b->stats.launches++;
     }
