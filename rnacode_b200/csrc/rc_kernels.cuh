@@ -253,8 +253,12 @@ __global__ void __launch_bounds__(256)
       }
       out[(size_t)k * ks] = v;
     }
-    if (bd.layout == 1)  // the step's z word rides in the sigma row, right after the NK sigma values
+    if (bd.layout == 1) {  // the step's z word rides in the sigma row, right after the NK sigma values
       out[NK] = __uint_as_float(ztiles[bd.z_off[s][f] + (size_t)tile * bd.zstride + c]);
+      if (j == bd.sites[f] - 1)  // rows of the last tile past the end of the frame: sigma = 0, no frameshift
+        for (int cc = c + 1; cc < TILE; cc++)
+          for (int q = 0; q <= NK; q++) out[(size_t)(cc - c) * bd.sig_cs + q] = 0.0f;
+    }
   }
 }
 
@@ -614,12 +618,25 @@ __device__ __forceinline__ void reg_load_row(unsigned a, float (&sv)[RegCfg<NK>:
                  : "r"(a + 16 * q));
 }
 
-template <int NK, bool DIAG, bool CHECK_END>
-__device__ __forceinline__ void reg_step(float2 (&S0)[NK], float2 (&S1)[NK], float2 (&S2)[NK],
-                                         const float (&sv)[RegCfg<NK>::RS], int j, int r0, int sites, float Delta,
-                                         float Omega, float omega, float fNK, float rcpNK, RowRec* rec0, int band_slots) {
+// frameshift update of one species (src/score.c:512-533)
+__device__ __forceinline__ void reg_shift(bool neg, float Delta, float Omega, float2& a0, float2& a1, float2& a2) {
+  // z = +1 (:512-521): (0<-2, 1<-0, 2<-1);  z = -1 (:523-533): (0<-1, 1<-2, 2<-0)
+  const float2 x0 = neg ? a1 : a2, x1 = neg ? a2 : a0, x2 = neg ? a0 : a1;
+  const float2 d0 = add2s(a0, Delta), d1 = add2s(a1, Delta), d2 = add2s(a2, Delta);
+  const float2 o0 = add2s(x0, Omega), o1 = add2s(x1, Omega), o2 = add2s(x2, Omega);
+  a0 = make_float2(fmaxf(d0.x, o0.x), fmaxf(d0.y, o0.y));
+  a1 = make_float2(fmaxf(d1.x, o1.x), fmaxf(d1.y, o1.y));
+  a2 = make_float2(fmaxf(d2.x, o2.x), fmaxf(d2.y, o2.y));
+}
+
+// One end codon for all species: state update + species sum (no getHSS test).  The kernel holds exactly
+// one copy of this code (instruction-cache footprint matters more than the few uniform branches).
+template <int NK>
+__device__ __forceinline__ float2 reg_update(float2 (&S0)[NK], float2 (&S1)[NK], float2 (&S2)[NK],
+                                             const float (&sv)[RegCfg<NK>::RS], bool diag, int j, int r0, float Delta,
+                                             float Omega, float omega) {
   const unsigned zw = __float_as_uint(sv[NK]);
-  if (DIAG) {
+  if (diag) {
     // a row starts from (0,0,0) at its first end codon (src/score.c:500-504)
     if (j == r0) {
 #pragma unroll
@@ -641,48 +658,80 @@ __device__ __forceinline__ void reg_step(float2 (&S0)[NK], float2 (&S1)[NK], flo
       sum = (k == 0) ? m : add2(sum, m);  // species sum in k order (src/score.c:834-838); 0 + m == m
     }
   } else {
+    // some species has a frameshift here: test groups of three species, branch per species only inside a hit group
 #pragma unroll
-    for (int k = 0; k < NK; k++) {
-      const unsigned z2 = (zw >> (2 * k)) & 3u;
-      if (z2 == 0u) {
-        S0[k] = add2s(S0[k], sv[k]);
-        S1[k] = add2s(S1[k], omega);
-        S2[k] = add2s(S2[k], omega);
+    for (int g = 0; g < NK; g += 3) {
+      constexpr unsigned GM3 = 0x3fu;
+      const unsigned gm = (NK - g >= 3) ? GM3 : ((1u << (2 * (NK - g))) - 1u);
+      if (((zw >> (2 * g)) & gm) == 0u) {
+#pragma unroll
+        for (int k = g; k < g + 3 && k < NK; k++) {
+          S0[k] = add2s(S0[k], sv[k]);
+          S1[k] = add2s(S1[k], omega);
+          S2[k] = add2s(S2[k], omega);
+        }
       } else {
-        const bool neg = (z2 & 2u) != 0u;
-        const float2 a0 = S0[k], a1 = S1[k], a2 = S2[k];
-        // z = +1 (src/score.c:512-521): (0<-2, 1<-0, 2<-1);  z = -1 (:523-533): (0<-1, 1<-2, 2<-0)
-        const float2 x0 = neg ? a1 : a2, x1 = neg ? a2 : a0, x2 = neg ? a0 : a1;
-        const float2 d0 = add2s(a0, Delta), d1 = add2s(a1, Delta), d2 = add2s(a2, Delta);
-        const float2 o0 = add2s(x0, Omega), o1 = add2s(x1, Omega), o2 = add2s(x2, Omega);
-        S0[k] = make_float2(fmaxf(d0.x, o0.x), fmaxf(d0.y, o0.y));
-        S1[k] = make_float2(fmaxf(d1.x, o1.x), fmaxf(d1.y, o1.y));
-        S2[k] = make_float2(fmaxf(d2.x, o2.x), fmaxf(d2.y, o2.y));
+#pragma unroll
+        for (int k = g; k < g + 3 && k < NK; k++) {
+          const unsigned z2 = (zw >> (2 * k)) & 3u;
+          if (z2 == 0u) {
+            S0[k] = add2s(S0[k], sv[k]);
+            S1[k] = add2s(S1[k], omega);
+            S2[k] = add2s(S2[k], omega);
+          } else {
+            reg_shift((z2 & 2u) != 0u, Delta, Omega, S0[k], S1[k], S2[k]);
+          }
+        }
       }
-      const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
-      sum = (k == 0) ? m : add2(sum, m);
+#pragma unroll
+      for (int k = g; k < g + 3 && k < NK; k++) {
+        const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
+        sum = (k == 0) ? m : add2(sum, m);
+      }
     }
   }
-  // getHSS only looks at positive entries (src/score.c:891); with Delta <= 0, max(sum, Delta) > 0 <=> sum > 0
-  if (fmaxf(sum.x, sum.y) > 0.0f) {
-    bool l0 = sum.x > 0.0f, l1 = sum.y > 0.0f;
-    if (DIAG) {
-      l0 = l0 && (j >= r0);
-      l1 = l1 && (j >= r0 + 1);
-    }
-    if (CHECK_END) {
-      l0 = l0 && (j < sites);
-      l1 = l1 && (j < sites);
-    }
-    if (l0) {
-      const float q = sum.x * rcpNK;
-      hss_accept_rec(rec0, __fmaf_rn(__fmaf_rn(-fNK, q, sum.x), rcpNK, q), j, band_slots);
-    }
-    if (l1) {
-      const float q = sum.y * rcpNK;
-      hss_accept_rec(rec0 + 1, __fmaf_rn(__fmaf_rn(-fNK, q, sum.y), rcpNK, q), j, band_slots);
+  return sum;
+}
+
+// Two consecutive frameshift-free end codons in one straight-line block: the species-sum chain of the
+// first overlaps with the state updates of the second.
+template <int NK>
+__device__ __forceinline__ void reg_pair_fast(float2 (&S0)[NK], float2 (&S1)[NK], float2 (&S2)[NK],
+                                              const float (&svA)[RegCfg<NK>::RS], const float (&svB)[RegCfg<NK>::RS],
+                                              float omega, float2& sumA, float2& sumB) {
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    S0[k] = add2s(S0[k], svA[k]);
+    S1[k] = add2s(S1[k], omega);
+    S2[k] = add2s(S2[k], omega);
+    const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
+    sumA = (k == 0) ? m : add2(sumA, m);
+  }
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    S0[k] = add2s(S0[k], svB[k]);
+    S1[k] = add2s(S1[k], omega);
+    S2[k] = add2s(S2[k], omega);
+    const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
+    sumB = (k == 0) ? m : add2(sumB, m);
+  }
+}
+
+// getHSS only looks at positive entries (src/score.c:891); with Delta <= 0, max(sum, Delta) > 0 <=> sum > 0.
+// S[b][i] = sum / (N-1) (src/score.c:841-843) as the correctly rounded quotient (see k_dp).  lb mirrors
+// rec->vF (the fresh fold's last accepted value) in a register so that entries the fold rejects cost no
+// memory access.  Out of line: positive entries are rare and the hot loop must stay small.
+__device__ __noinline__ float reg_check_row(float sum, int j, int rstart, int sites, float fNK, float rcpNK, RowRec* rec,
+                                            int band_slots, float lb) {
+  if (sum > 0.0f && j >= rstart && j < sites) {
+    const float q = sum * rcpNK;
+    const float e = __fmaf_rn(__fmaf_rn(-fNK, q, sum), rcpNK, q);
+    if (e - lb >= -0.0001f) {
+      lb = e;
+      hss_accept_rec(rec, e, j, band_slots);
     }
   }
+  return lb;
 }
 
 template <int NK>
@@ -709,7 +758,8 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
 
   unsigned char* ring = smem[warp];
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * STAGE_BYTES);
-  const unsigned ring_a = smem_u32(ring);
+  unsigned ring_a = smem_u32(ring);
+  asm volatile("" : "+r"(ring_a));  // keep the shared-window address in a register (no per-step re-derivation)
   const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * ntiles * SIG_TILE;
   const int t0 = row_base / TILE;
   const int t_last_diag = (row_base + 32 * R - 1) / TILE;
@@ -744,40 +794,57 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
   float2 S0[NK], S1[NK], S2[NK];
 #pragma unroll
   for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
-  const float Delta = prm.Delta, Omega = prm.Omega, omega = prm.omega;
+  float2 lb = make_float2(-INFINITY, -INFINITY);
+  const float Delta = prm.Delta, Omega = prm.Omega;
+  float omega = prm.omega;
+  asm volatile("" : "+f"(omega));  // a vector register operand for the packed adds instead of a constant reload per step
   const float fNK = bd.fNK, rcpNK = bd.rcpNK;
 
+#pragma unroll 1
   for (int tile = t0; tile < ntiles; tile++) {
     const int s = (tile - t0) & 1;
     const unsigned parity = ((tile - t0) >> 1) & 1;
     const unsigned a0 = ring_a + s * STAGE_BYTES;
     const int j0 = tile * TILE;
+    const bool diag = tile <= t_last_diag;  // rows start inside this tile
     mbar_wait(&bars[s], parity);
-    if (tile <= t_last_diag) {
+    if (diag) {
+      // rows start inside the tile: one step at a time with the start-of-row reset
 #pragma unroll 1
       for (int c = 0; c < TILE; c++) {
         float sv[RS];
         reg_load_row<NK>(a0 + c * RS * 4, sv);
-        reg_step<NK, true, true>(S0, S1, S2, sv, j0 + c, r0, sites, Delta, Omega, omega, fNK, rcpNK, rec0, band_slots);
-      }
-    } else if (tile == ntiles - 1) {
-#pragma unroll 1
-      for (int c = 0; c < TILE; c++) {
-        float sv[RS];
-        reg_load_row<NK>(a0 + c * RS * 4, sv);
-        reg_step<NK, false, true>(S0, S1, S2, sv, j0 + c, r0, sites, Delta, Omega, omega, fNK, rcpNK, rec0, band_slots);
+        const float2 sum = reg_update<NK>(S0, S1, S2, sv, true, j0 + c, r0, Delta, Omega, omega);
+        if (fmaxf(sum.x, sum.y) > 0.0f) {
+          lb.x = reg_check_row(sum.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          lb.y = reg_check_row(sum.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+        }
       }
     } else {
-      // steady state: two steps per iteration, the next row of sigma is loaded before the current one is used
+      // steady state: two end codons per iteration; the rows of the next iteration are requested before the
+      // (serial) tail of this iteration's species sums is tested
       float svA[RS], svB[RS];
       reg_load_row<NK>(a0, svA);
+      reg_load_row<NK>(a0 + RS * 4, svB);
 #pragma unroll 1
       for (int c = 0; c < TILE; c += 2) {
-        reg_load_row<NK>(a0 + (c + 1) * RS * 4, svB);
-        reg_step<NK, false, false>(S0, S1, S2, svA, j0 + c, r0, sites, Delta, Omega, omega, fNK, rcpNK, rec0, band_slots);
-        if (c + 2 < TILE) reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
-        reg_step<NK, false, false>(S0, S1, S2, svB, j0 + c + 1, r0, sites, Delta, Omega, omega, fNK, rcpNK, rec0,
-                                   band_slots);
+        float2 sumA, sumB;
+        if ((__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u) {
+          reg_pair_fast<NK>(S0, S1, S2, svA, svB, omega, sumA, sumB);
+        } else {
+          sumA = reg_update<NK>(S0, S1, S2, svA, false, j0 + c, r0, Delta, Omega, omega);
+          sumB = reg_update<NK>(S0, S1, S2, svB, false, j0 + c + 1, r0, Delta, Omega, omega);
+        }
+        if (c + 2 < TILE) {
+          reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
+          reg_load_row<NK>(a0 + (c + 3) * RS * 4, svB);
+        }
+        if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
+          lb.x = reg_check_row(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          lb.y = reg_check_row(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          lb.x = reg_check_row(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          lb.y = reg_check_row(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+        }
       }
     }
     __syncwarp();
@@ -786,7 +853,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
       bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(tile + 2) * SIG_TILE, STAGE_BYTES, &bars[s]);
     }
   }
-  // finalise: rows without any positive entry keep n == 0; accepted rows already hold Emax / vF / jF / band
+  // rows without any positive entry keep n == 0; accepted rows already hold Emax / vF / jF / band
 }
 
 // ---------------------------------------------------------------------------------------------
