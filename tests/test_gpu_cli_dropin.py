@@ -1,0 +1,39 @@
+"""Drop-in check of the whole program: the reference CLI with scoreAln / getExtremeValuePars replaced by
+libRNAcode_cuda (integration/rnacode_cuda_shim.c, linked as oracle/_ref/RNAcode_cuda_det) must print what the
+unmodified reference prints (tests/golden/cli_outputs.json.gz, produced by oracle/_ref/RNAcode_det with the
+same deterministic seeds): identical HSS, coordinates, scores and p-values in default, --gtf and --tabular
+format, with -b, -r, -s/-p, -c and -n."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from tests import oracle_py as op
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+CLI = os.path.join(REFDIR, "RNAcode_cuda_det")
+EXAMPLES = os.path.join(REFDIR, "examples")
+
+
+def _norm(txt):
+    # the footer of the default format reports CPU seconds
+    return re.sub(r"scored in [0-9.]+ seconds", "scored in X seconds", txt)
+
+
+CASES = sorted(op.golden("cli_outputs").keys())
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cli_output_identical_to_reference(case):
+    if not (os.path.exists(CLI) and os.path.isdir(EXAMPLES)):
+        pytest.skip("oracle/_ref/RNAcode_cuda_det not built (needs /root/reference at build time)")
+    parts = case.split(" ")
+    fname, opts = parts[0], [p for p in parts[1:] if p]
+    env = dict(os.environ, RNACODE_SEED="1")
+    res = subprocess.run([CLI, *opts, os.path.join(EXAMPLES, fname)], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr
+    assert _norm(res.stdout) == _norm(op.golden("cli_outputs")[case])
