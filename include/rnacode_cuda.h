@@ -86,7 +86,8 @@ void rc_default_params(rc_params *p);
 int rc_set_stream(rc_ctx *ctx, void *cuda_stream);
 /* Tunables / test hooks: "force_dense" (0/1: route every alignment through the dense-S fallback),
  * "band_slots" (1..3: tie-band slots per row record before the dense fallback is taken),
- * "scratch_mb" (device scratch budget per chunk). */
+ * "scratch_mb" (device scratch budget per chunk), "no_smp" (0/1: do not use the sample-major kernel for short
+ * blocks). */
 int rc_set_option(rc_ctx *ctx, const char *key, long value);
 
 /* -- one block at a time (same call shape as the reference) ----------------------------------- */

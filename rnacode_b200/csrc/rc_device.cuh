@@ -9,7 +9,8 @@ namespace rc {
 constexpr int TILE = 16;          // codon steps per staged sigma/z tile
 constexpr int REC_SLOTS = 3;      // tie-band slots in a row record
 constexpr int DP_WARPS = 4;       // warps per DP CTA (each warp owns one task)
-constexpr int REG_MAX_NK = 16;    // largest N-1 handled by the register-resident DP kernel
+constexpr int REG_MAX_NK = 16;    // largest N-1 handled by the register-resident DP kernels
+constexpr int SMP_WARPS = 4;      // warps per CTA of the sample-major DP kernel
 
 // class byte of one alignment character (k_pack): what calculateSigma / getBlock / revAln need
 //   bits 0-1  ntMap[c]                 (forward strand code; anything but ACGTU -> 0, src/RNAcode.c:94-98)
@@ -49,7 +50,8 @@ struct BlockDev {
   int inst_stride;          // bytes between consecutive instances in raw/cls (N*cols rounded up to 16)
   int zstride;              // u32 words per z tile: layout 0: NK rounded up to 4 (one word per species);
                             // layout 1: TILE (one word per step, 2 bits per species)
-  int layout;               // 0: sigma tile [k][TILE] (k_dp, any NK); 1: sigma tile [TILE][NKP] (k_dp_reg, NK <= 16)
+  int layout;               // 0: sigma tile [k][TILE] (k_dp, any NK); 1: sigma tile [TILE][RS] (k_dp_reg, NK <= 16);
+                            // 2: sample-major [group of 32 instances][step][RSB/4][lane][4] (k_dp_smp, short blocks)
   int sig_tile;             // floats per sigma tile
   int sig_ks, sig_cs;       // strides (floats) of species / step inside a sigma tile
   int sites[3], ntiles[3];  // codon sites / tiles per frame

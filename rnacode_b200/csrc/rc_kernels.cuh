@@ -208,14 +208,24 @@ __global__ void __launch_bounds__(256)
 
   const Item it = items[blockIdx.x];
   const BlockDev bd = blocks[it.block];
+  if (bd.layout == 2) return;  // sample-major items are served by k_sigma_smp
   const int L = bd.L, N = bd.N, NK = bd.NK, cols = bd.cols;
   const int npos = L - 2;
   const long long total = (long long)it.ninst * 2 * npos;
   for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.y * blockDim.x) {
-    const int xi = (int)(idx % npos);
-    const int rest = (int)(idx / npos);
-    const int s = rest & 1, inst_l = rest >> 1;
+    int xi, s, inst_l;
+    if (bd.layout == 2) {  // sample-major output: consecutive threads = consecutive instances (coalesced stores)
+      inst_l = (int)(idx % it.ninst);
+      const int rest = (int)(idx / it.ninst);
+      s = rest & 1;
+      xi = rest >> 1;
+    } else {
+      xi = (int)(idx % npos);
+      const int rest = (int)(idx / npos);
+      s = rest & 1;
+      inst_l = rest >> 1;
+    }
     const int x = xi + 3;
     const int* c0 = cols0 + bd.cols0_off + (size_t)s * (L + 1);
     const int c1 = c0[x - 2], c2 = c0[x - 1], c3 = c0[x];
@@ -227,8 +237,16 @@ __global__ void __launch_bounds__(256)
     const int pepA = s_tab.transcode[qa];
     const int f = xi % 3, j = xi / 3;
     const int tile = j / TILE, c = j % TILE;
-    float* out = sigma + it.sigma_off[s][f] + ((size_t)inst_l * bd.ntiles[f] + tile) * bd.sig_tile + (size_t)c * bd.sig_cs;
-    const int ks = bd.sig_ks;
+    float* out;
+    int ks = bd.sig_ks;
+    if (bd.layout == 2) {
+      // sample-major: [group of 32 instances][step][species quad][lane][4]
+      const int rsb = (NK + 3) / 4 * 4;
+      out = sigma + it.sigma_off[s][f] + ((size_t)(inst_l >> 5) * bd.sites[f] + j) * rsb * 32 + (inst_l & 31) * 4;
+      ks = 0;  // addressed explicitly below
+    } else {
+      out = sigma + it.sigma_off[s][f] + ((size_t)inst_l * bd.ntiles[f] + tile) * bd.sig_tile + (size_t)c * bd.sig_cs;
+    }
     const float* sc = scores + bd.scores_off + (size_t)s * N * 4;
     for (int k = 0; k < NK; k++) {
       const unsigned char* rowk = base + (size_t)(k + 1) * cols;
@@ -251,7 +269,8 @@ __global__ void __launch_bounds__(256)
           v = s_tab.blosum[pepA * 24 + pepB] - sc[(k + 1) * 4 + h];  // observed - expected, float32 (:422-425)
         }
       }
-      out[(size_t)k * ks] = v;
+      if (bd.layout == 2) out[(k >> 2) * 128 + (k & 3)] = v;
+      else out[(size_t)k * ks] = v;
     }
     if (bd.layout == 1) {  // the step's z word rides in the sigma row, right after the NK sigma values
       out[NK] = __uint_as_float(ztiles[bd.z_off[s][f] + (size_t)tile * bd.zstride + c]);
@@ -259,6 +278,108 @@ __global__ void __launch_bounds__(256)
         for (int cc = c + 1; cc < TILE; cc++)
           for (int q = 0; q <= NK; q++) out[(size_t)(cc - c) * bd.sig_cs + q] = 0.0f;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (b) k_sigma_smp: sigma for the sample-major layout (k_dp_smp).  One CTA per (item, group of 32 instances).
+// The class bytes of the group's reference rows and of four species rows at a time are staged in shared
+// memory (coalesced global reads, padded row pitch => conflict-free byte reads with lane = instance); each
+// thread then produces the four sigma values of one (strand, position, instance) and stores them as one
+// float4, so a warp writes 512 contiguous bytes of the [step][species quad][lane][4] table.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int smp_pitch(int cols) {
+  int w = (cols + 3) / 4;  // words per row; make it odd so that 32 lanes hit 32 different banks
+  if ((w & 1) == 0) w++;
+  return w * 4;
+}
+
+__global__ void __launch_bounds__(256)
+    k_sigma_smp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned char* __restrict__ cls,
+                const int* __restrict__ cols0, const float* __restrict__ scores, const SigmaTables* __restrict__ tables,
+                float* __restrict__ sigma, Params prm) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  __shared__ SigmaTables s_tab;
+  __shared__ __align__(8) uint64_t s_bar;
+  const Item it = items[blockIdx.x];
+  const BlockDev bd = blocks[it.block];
+  const int group = blockIdx.y;
+  if (bd.layout != 2 || group * 32 >= it.ninst) return;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&s_bar, (unsigned)sizeof(SigmaTables));
+    bulk_g2s(&s_tab, tables, (unsigned)sizeof(SigmaTables), &s_bar);
+  }
+  const int L = bd.L, N = bd.N, NK = bd.NK, cols = bd.cols;
+  const int pitch = smp_pitch(cols);
+  unsigned char* s_ref = sm;                 // [32][pitch]
+  unsigned char* s_sp = sm + 32 * pitch;     // [4][32][pitch]
+  const int ninst_g = min(32, it.ninst - group * 32);
+  const unsigned char* gbase = cls + bd.cls_off + (size_t)(it.inst0 + group * 32) * bd.inst_stride;
+  // reference rows of the 32 instances
+  for (int e = threadIdx.x; e < 32 * cols; e += blockDim.x) {
+    const int li = e / cols, c = e % cols;
+    s_ref[li * pitch + c] = (li < ninst_g) ? gbase[(size_t)li * bd.inst_stride + c] : (unsigned char)0;
+  }
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+  const int npos = L - 2;
+  const int rsb = (NK + 3) / 4 * 4;
+  for (int kq = 0; kq < rsb / 4; kq++) {
+    // stage species rows 1+4kq .. 4+4kq
+    for (int e = threadIdx.x; e < 4 * 32 * cols; e += blockDim.x) {
+      const int c = e % cols, li = (e / cols) & 31, kk = e / (cols * 32);
+      const int row = 1 + 4 * kq + kk;
+      s_sp[(kk * 32 + li) * pitch + c] =
+          (li < ninst_g && row < N) ? gbase[(size_t)li * bd.inst_stride + (size_t)row * cols + c] : (unsigned char)0;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2 * npos * 32; e += blockDim.x) {
+      const int lane = e & 31;
+      const int rest = e >> 5;
+      const int s = rest & 1, xi = rest >> 1;
+      const int x = xi + 3;
+      const int* c0 = cols0 + bd.cols0_off + (size_t)s * (L + 1);
+      const int c1 = c0[x - 2], c2 = c0[x - 1], c3 = c0[x];
+      const unsigned char* rr = s_ref + lane * pitch;
+      const unsigned a1 = rr[c1], a2 = rr[c2], a3 = rr[c3];
+      const int sh = s ? 2 : 0;
+      const unsigned qa = (((a1 >> sh) & 3u) << 4) | (((a2 >> sh) & 3u) << 2) | ((a3 >> sh) & 3u);
+      const unsigned nA = (a1 | a2 | a3) & CLS_N;
+      const int pepA = s_tab.transcode[qa];
+      const float* sc = scores + bd.scores_off + (size_t)s * N * 4;
+      float v4[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const int k = 4 * kq + kk;
+        float v = 0.0f;
+        if (k < NK) {
+          const unsigned char* rk = s_sp + (kk * 32 + lane) * pitch;
+          const unsigned b1 = rk[c1], b2 = rk[c2], b3 = rk[c3];
+          const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
+          if (nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X)) {
+            v = 0.0f;
+          } else if (qa == qb) {
+            v = 0.0f;
+          } else {
+            const int pepB = s_tab.transcode[qb];
+            if (pepA < 0) v = prm.stop0;
+            else if (pepB < 0) v = prm.stopk;
+            else {
+              const unsigned d = qa ^ qb;
+              const int h = ((d & 0x30u) != 0) + ((d & 0x0cu) != 0) + ((d & 0x03u) != 0);
+              v = s_tab.blosum[pepA * 24 + pepB] - sc[(k + 1) * 4 + h];
+            }
+          }
+        }
+        v4[kk] = v;
+      }
+      const int f = xi % 3, j = xi / 3;
+      float* out = sigma + it.sigma_off[s][f] + (((size_t)group * bd.sites[f] + j) * (rsb / 4) + kq) * 128 + lane * 4;
+      *reinterpret_cast<float4*>(out) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+    }
+    __syncthreads();
   }
 }
 
@@ -734,6 +855,26 @@ __device__ __noinline__ float reg_check_row(float sum, int j, int rstart, int si
   return lb;
 }
 
+// The fold state of the getHSS digest lives in a per-warp shared-memory copy of the two row records while
+// the rows are being scored (positive entries are frequent at the start of a row, and a global-memory
+// read-modify-write per entry would stall the warp); the records are written to HBM once, at the end of the rows.
+__device__ __forceinline__ void rec_init(RowRec* r) {
+  RowRec init;
+  init.Emax = -INFINITY;
+  init.vF = -INFINITY;
+  init.be[0] = init.be[1] = init.be[2] = 0.0f;
+  init.jF = 0;
+  init.n = 0;
+  init.bj[0] = init.bj[1] = init.bj[2] = 0;
+  init.pad = 0;
+  reinterpret_cast<uint4*>(r)[0] = reinterpret_cast<const uint4*>(&init)[0];
+  reinterpret_cast<uint4*>(r)[1] = reinterpret_cast<const uint4*>(&init)[1];
+}
+__device__ __forceinline__ void rec_copy(RowRec* dst, const RowRec* src) {
+  reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(src)[0];
+  reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(src)[1];
+}
+
 template <int NK>
 __global__ void __launch_bounds__(DP_WARPS * 32)
     k_dp_reg(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
@@ -772,23 +913,11 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
       bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(t0 + s) * SIG_TILE, STAGE_BYTES, &bars[s]);
     }
   }
-  // the row records double as the fold state of the getHSS digest: initialise them
-  RowRec* rec0 = recs + it.rec_off[strand][frame] + (size_t)inst_l * sites + r0;
-#pragma unroll
-  for (int t = 0; t < R; t++) {
-    if (r0 + t < sites) {
-      RowRec init;
-      init.Emax = -INFINITY;
-      init.vF = -INFINITY;
-      init.be[0] = init.be[1] = init.be[2] = 0.0f;
-      init.jF = 0;
-      init.n = 0;
-      init.bj[0] = init.bj[1] = init.bj[2] = 0;
-      init.pad = 0;
-      reinterpret_cast<uint4*>(rec0 + t)[0] = reinterpret_cast<const uint4*>(&init)[0];
-      reinterpret_cast<uint4*>(rec0 + t)[1] = reinterpret_cast<const uint4*>(&init)[1];
-    }
-  }
+  // fold state of the getHSS digest: two records per lane in shared memory, flushed at the end of the task
+  __shared__ __align__(16) RowRec srec[DP_WARPS][R * 32];
+  RowRec* rec0 = &srec[warp][lane * R];
+  rec_init(rec0);
+  rec_init(rec0 + 1);
   __syncwarp();
 
   float2 S0[NK], S1[NK], S2[NK];
@@ -853,7 +982,129 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
       bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(tile + 2) * SIG_TILE, STAGE_BYTES, &bars[s]);
     }
   }
-  // rows without any positive entry keep n == 0; accepted rows already hold Emax / vF / jF / band
+  // rows without any positive entry keep n == 0; accepted rows hold Emax / vF / jF / band
+  RowRec* grec = recs + it.rec_off[strand][frame] + (size_t)inst_l * sites + r0;
+#pragma unroll
+  for (int t = 0; t < R; t++)
+    if (r0 + t < sites) rec_copy(grec + t, rec0 + t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// (c) k_dp_smp: the DP for SHORT blocks with many null alignments (N-1 <= 16, sites*RSB*128 B fits in shared
+// memory).  Lane = one alignment instance (native or null sample), warp = 32 instances of the same block,
+// strand and frame, working on the same pair of start codons: the gap pattern and hence z, the row starts and
+// all control flow are identical across the lanes (samples inherit the native gaps, src/misc.c:127-148), so
+// there is no start-of-row (diagonal) waste at all -- that waste dominates k_dp_reg on blocks of ~40 codons.
+// The CTA's sigma table (all end codons of the frame for its 32 instances, lane-interleaved so that each lane
+// reads its own values with conflict-free LDS.128) is brought in by one TMA bulk copy; the CTA's warps then
+// share it and walk the start-codon pairs (long and short rows paired up for balance).  State handling,
+// packed FADD2 arithmetic, float order and the getHSS digest are those of k_dp_reg.
+// ---------------------------------------------------------------------------------------------
+template <int NK>
+__device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv)[RegCfg<NK>::RS]) {
+  constexpr int RSB = (NK + 3) / 4 * 4;
+#pragma unroll
+  for (int q = 0; q < RSB / 4; q++)
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(sv[4 * q]), "=f"(sv[4 * q + 1]), "=f"(sv[4 * q + 2]), "=f"(sv[4 * q + 3])
+                 : "r"(a + 512 * q));
+  sv[NK] = __uint_as_float(zw);
+}
+
+template <int NK>
+__global__ void __launch_bounds__(SMP_WARPS * 32)
+    k_dp_smp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
+             const float* __restrict__ sigma, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm,
+             int band_slots) {
+  constexpr int RS = RegCfg<NK>::RS;
+  constexpr int RSB = (NK + 3) / 4 * 4;
+  constexpr int ROW_BYTES = RSB * 32 * 4;  // one end codon, 32 lanes
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const CtaDesc cd = ctas[blockIdx.x];
+  const Item& it = items[cd.item];
+  const BlockDev& bd = blocks[it.block];
+  const int strand = cd.sf / 3, frame = cd.sf % 3;
+  const int sites = bd.sites[frame];
+  const int group = cd.task0;  // group of 32 instances inside the item
+  const int inst_l = group * 32 + lane;
+  const bool valid = inst_l < it.ninst;
+
+  const size_t sig_bytes = (size_t)sites * ROW_BYTES;
+  const size_t z_bytes = ((size_t)sites * 4 + 15) / 16 * 16;
+  unsigned* zs = reinterpret_cast<unsigned*>(smem + sig_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sig_bytes + z_bytes);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(bar, (unsigned)(sig_bytes + z_bytes));
+    bulk_g2s(smem, sigma + it.sigma_off[strand][frame] + (size_t)group * sites * RSB * 32, (unsigned)sig_bytes, bar);
+    bulk_g2s(zs, ztiles + bd.z_off[strand][frame], (unsigned)z_bytes, bar);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  unsigned sig_a = smem_u32(smem) + lane * 16;
+  asm volatile("" : "+r"(sig_a));
+  const float Delta = prm.Delta, Omega = prm.Omega;
+  float omega = prm.omega;
+  asm volatile("" : "+f"(omega));
+  const float fNK = bd.fNK, rcpNK = bd.rcpNK;
+  RowRec* rec_inst = recs + it.rec_off[strand][frame] + (size_t)(valid ? inst_l : 0) * sites;
+
+  __shared__ __align__(16) RowRec srec[SMP_WARPS][2 * 32];
+  const int npairs = (sites + 1) / 2;
+  // boustrophedon assignment of start-codon pairs to warps: w, 2W-1-w, 2W+w, 4W-1-w, ... (rows get shorter
+  // with the pair index, so every warp receives a similar total length)
+#pragma unroll 1
+  for (int turn = 0;; turn++) {
+    const int p = (turn & 1) ? (turn + 1) * SMP_WARPS - 1 - warp : turn * SMP_WARPS + warp;
+    if (turn * SMP_WARPS >= npairs) break;
+    if (p >= npairs) continue;
+    const int r0 = 2 * p;
+    RowRec* rec0 = &srec[warp][lane * 2];
+    rec_init(rec0);
+    rec_init(rec0 + 1);
+    float2 S0[NK], S1[NK], S2[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
+    float2 lb = make_float2(-INFINITY, -INFINITY);
+    int j = r0;
+#pragma unroll 1
+    while (j < sites) {
+      float svA[RS];
+      const unsigned zA = zs[j];
+      smp_load_row<NK>(sig_a + j * ROW_BYTES, zA, svA);
+      if (j >= r0 + 2 && j + 1 < sites) {
+        const unsigned zB = zs[j + 1];
+        if ((zA | zB) == 0u) {
+          float svB[RS];
+          smp_load_row<NK>(sig_a + (j + 1) * ROW_BYTES, zB, svB);
+          float2 sumA, sumB;
+          reg_pair_fast<NK>(S0, S1, S2, svA, svB, omega, sumA, sumB);
+          if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
+            lb.x = reg_check_row(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+            lb.y = reg_check_row(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+            lb.x = reg_check_row(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+            lb.y = reg_check_row(sumB.y, j + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          }
+          j += 2;
+          continue;
+        }
+      }
+      const float2 sum = reg_update<NK>(S0, S1, S2, svA, j < r0 + 2, j, r0, Delta, Omega, omega);
+      if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
+        lb.x = reg_check_row(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+        if (r0 + 1 < sites) lb.y = reg_check_row(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+      }
+      j += 1;
+    }
+    if (valid) {
+#pragma unroll
+      for (int t = 0; t < 2; t++)
+        if (r0 + t < sites) rec_copy(rec_inst + r0 + t, rec0 + t);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

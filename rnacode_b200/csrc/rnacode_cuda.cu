@@ -37,24 +37,83 @@ struct rc_ctx {
   long force_dense = 0;
   long band_slots = REC_SLOTS;
   long scratch_mb = 2048;
+  long no_smp = 0;
   int smem_optin = 0;
   int sm_count = 0;
+  // device-memory cache: buffers of destroyed batches are kept and handed to the next batch, so that a
+  // steady stream of rc_batch_create / rc_batch_destroy calls does not pay cudaMalloc / cudaFree every time
+  std::vector<std::pair<void*, size_t>> free_blocks;
+  std::vector<std::pair<void*, size_t>> live_blocks;
+  size_t cached_bytes = 0;
 };
 
 static void ctx_fail(rc_ctx* ctx, const std::string& msg) {
   if (ctx) ctx->err = msg;
 }
 
+static void* ctx_alloc(rc_ctx* ctx, size_t bytes) {
+  bytes = (std::max<size_t>(bytes, 256) + 255) / 256 * 256;
+  // best fit among cached blocks that are not wastefully large
+  int best = -1;
+  for (int i = 0; i < (int)ctx->free_blocks.size(); i++) {
+    const size_t sz = ctx->free_blocks[i].second;
+    if (sz >= bytes && sz <= bytes * 2 + (1u << 20) && (best < 0 || sz < ctx->free_blocks[best].second)) best = i;
+  }
+  void* p = nullptr;
+  if (best >= 0) {
+    p = ctx->free_blocks[best].first;
+    ctx->live_blocks.push_back(ctx->free_blocks[best]);
+    ctx->cached_bytes -= ctx->free_blocks[best].second;
+    ctx->free_blocks.erase(ctx->free_blocks.begin() + best);
+    return p;
+  }
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    // release the cache and retry once
+    cudaGetLastError();
+    for (auto& fb : ctx->free_blocks) cudaFree(fb.first);
+    ctx->free_blocks.clear();
+    ctx->cached_bytes = 0;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  }
+  ctx->live_blocks.push_back({p, bytes});
+  return p;
+}
+
+static void ctx_free(rc_ctx* ctx, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < ctx->live_blocks.size(); i++)
+    if (ctx->live_blocks[i].first == p) {
+      ctx->free_blocks.push_back(ctx->live_blocks[i]);
+      ctx->cached_bytes += ctx->live_blocks[i].second;
+      ctx->live_blocks.erase(ctx->live_blocks.begin() + i);
+      // keep the cache bounded: drop the largest blocks beyond 8 GiB
+      while (ctx->cached_bytes > ((size_t)8 << 30) && !ctx->free_blocks.empty()) {
+        size_t big = 0;
+        for (size_t j = 1; j < ctx->free_blocks.size(); j++)
+          if (ctx->free_blocks[j].second > ctx->free_blocks[big].second) big = j;
+        cudaFree(ctx->free_blocks[big].first);
+        ctx->cached_bytes -= ctx->free_blocks[big].second;
+        ctx->free_blocks.erase(ctx->free_blocks.begin() + big);
+      }
+      return;
+    }
+  cudaFree(p);  // not ours (should not happen)
+}
+
 namespace {
 
-// DP launch classes: 0..15 = k_dp_reg<NK = class+1, R = 2>; 16 = k_dp<R = 2> (17 <= NK <= 24); 17 = k_dp<R = 1>
-constexpr int N_CLASSES = REG_MAX_NK + 2;
+// DP launch classes: 0..15 = k_dp_reg<NK = class+1>; 16 = k_dp<R = 2> (17 <= NK <= 24); 17 = k_dp<R = 1>;
+// 18..33 = k_dp_smp<NK = class-17> (sample-major, short blocks)
+constexpr int N_CLASSES = 2 * REG_MAX_NK + 2;
+constexpr int SMP_CLASS0 = REG_MAX_NK + 2;
+constexpr size_t SMP_SMEM_MAX = 200 * 1024;  // sigma table + z words of one CTA of k_dp_smp
+constexpr int SMP_MIN_INST = 16;             // fewer instances than this: the row-major kernels are the better fit
 
 struct Chunk {
   size_t item0 = 0, nitems = 0;          // range in the batch's item array
   size_t cta0[N_CLASSES] = {}, ncta[N_CLASSES] = {};  // per class range in the CTA array
   int maxNK[N_CLASSES] = {}, maxZs[N_CLASSES] = {};
-  size_t sigma_floats = 0, rec_count = 0;
+  size_t sigma_floats = 0, rec_count = 0, max_smp_smem = 0, max_smp_stage = 0;
   long long max_sigma_work = 0;  // largest ninst*2*(L-2) of an item, for the k_sigma grid
   int max_ninst = 0;
 };
@@ -67,15 +126,35 @@ struct EventPair {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int class_of(const BlockDev& bd) {
+  if (bd.layout == 2) return SMP_CLASS0 + bd.NK - 1;
   if (bd.layout == 1) return bd.NK - 1;
   return bd.NK <= 24 ? REG_MAX_NK : REG_MAX_NK + 1;
 }
 int class_R(int cl) { return cl == REG_MAX_NK + 1 ? 1 : 2; }
 
+size_t smp_smem_bytes(const BlockDev& bd, int f) {
+  const size_t rsb = (size_t)(bd.NK + 3) / 4 * 4;
+  return (size_t)bd.sites[f] * rsb * 32 * 4 + ((size_t)bd.sites[f] * 4 + 15) / 16 * 16 + 16;
+}
+
+// floats of sigma scratch for `ninst` instances of one (strand, frame) of a block
+size_t sigma_floats_sf(const BlockDev& bd, int f, int ninst) {
+  if (bd.layout == 2) {
+    const size_t rsb = (size_t)(bd.NK + 3) / 4 * 4;
+    return (size_t)((ninst + 31) / 32) * bd.sites[f] * rsb * 32;
+  }
+  return (size_t)ninst * bd.ntiles[f] * bd.sig_tile;
+}
+
 // sigma / z layout of a block (see BlockDev)
 void set_layout(BlockDev& bd, int layout) {
   bd.layout = layout;
-  if (layout == 1) {
+  if (layout == 2) {  // z as in layout 1 (one word per step); sigma addressed explicitly (sigma_floats_sf)
+    bd.sig_tile = 0;
+    bd.sig_ks = 0;
+    bd.sig_cs = 0;
+    bd.zstride = TILE;
+  } else if (layout == 1) {
     const int rs = (bd.NK + 1 + 3) / 4 * 4;  // RegCfg<NK>::RS
     bd.sig_tile = TILE * rs;
     bd.sig_ks = 1;
@@ -210,6 +289,8 @@ extern "C" void rc_destroy(rc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->d_lut) cudaFree(ctx->d_lut);
+  for (auto& fb : ctx->free_blocks) cudaFree(fb.first);
+  for (auto& lb : ctx->live_blocks) cudaFree(lb.first);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -229,6 +310,8 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
   else if (k == "band_slots") {
     if (value < 1 || value > REC_SLOTS) { ctx_fail(ctx, "band_slots must be 1..3"); return RC_ERR_ARG; }
     ctx->band_slots = value;
+  } else if (k == "no_smp") {
+    ctx->no_smp = value ? 1 : 0;
   } else if (k == "scratch_mb") {
     if (value < 1) { ctx_fail(ctx, "scratch_mb must be >= 1"); return RC_ERR_ARG; }
     ctx->scratch_mb = value;
@@ -270,10 +353,10 @@ extern "C" int rc_calibrate_issue(rc_ctx* ctx, double* lane_ops_per_s) {
 // planning
 // ------------------------------------------------------------------------------------------------
 static void free_batch_device(rc_batch* b) {
-  cudaFree(b->d_blocks); cudaFree(b->d_items); cudaFree(b->d_ctas); cudaFree(b->d_raw); cudaFree(b->d_cls);
-  cudaFree(b->d_cols0); cudaFree(b->d_scores); cudaFree(b->d_z); cudaFree(b->d_res); cudaFree(b->d_hss);
-  cudaFree(b->d_hsscnt); cudaFree(b->d_ovf); cudaFree(b->d_tables); cudaFree(b->d_sigma); cudaFree(b->d_recs);
-  cudaFree(b->d_dense);
+  rc_ctx* ctx = b->ctx;
+  void* ptrs[] = {b->d_blocks, b->d_items, b->d_ctas, b->d_raw, b->d_cls, b->d_cols0, b->d_scores, b->d_z, b->d_res,
+                  b->d_hss, b->d_hsscnt, b->d_ovf, b->d_tables, b->d_sigma, b->d_recs, b->d_dense};
+  for (void* p : ptrs) ctx_free(ctx, p);
   for (auto& e : b->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   b->events.clear();
 }
@@ -285,6 +368,13 @@ static void build_ctas(const std::vector<BlockDev>& blocks, const std::vector<It
     const Item& it = items[i];
     const BlockDev& bd = blocks[it.block];
     if (want_class >= 0 && class_of(bd) != want_class) continue;
+    if (bd.layout == 2 && want_class >= 0) {
+      for (int sf = 0; sf < 6; sf++) {
+        if (bd.sites[sf % 3] <= 0) continue;
+        for (int g = 0; g < (it.ninst + 31) / 32; g++) out.push_back(CtaDesc{(int)i, sf, g});
+      }
+      continue;
+    }
     for (int sf = 0; sf < 6; sf++) {
       const int sites = bd.sites[sf % 3];
       if (sites <= 0) continue;
@@ -343,7 +433,6 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     bd.NK = d.N - 1;
     bd.n_inst = 1 + d.n_samples;
     bd.inst_stride = (int)align_up((size_t)d.N * d.cols, 16);
-    set_layout(bd, (bd.NK <= REG_MAX_NK && params->Delta <= 0.0f) ? 1 : 0);
     bd.fNK = (float)bd.NK;
     bd.rcpNK = 1.0f / bd.fNK;
     bd.raw_off = (long long)b->raw_bytes;
@@ -360,6 +449,14 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       P += (double)bd.sites[f] * (bd.sites[f] + 1) / 2;
     }
     cells += (double)bd.n_inst * 2.0 * bd.NK * P;
+    {
+      int layout = (bd.NK <= REG_MAX_NK && params->Delta <= 0.0f) ? 1 : 0;
+      if (layout == 1 && !ctx->no_smp && bd.n_inst >= SMP_MIN_INST && bd.sites[0] >= 1 &&
+          smp_smem_bytes(bd, 0) <= std::min<size_t>(SMP_SMEM_MAX, (size_t)ctx->smem_optin) &&
+          (size_t)5 * 32 * (bd.cols + 8) <= SMP_SMEM_MAX)
+        layout = 2;  // short block with many instances: sample-major kernel
+      set_layout(bd, layout);
+    }
     for (int s = 0; s < 2; s++)
       for (int f = 0; f < 3; f++) {
         bd.z_off[s][f] = (long long)b->z_words;
@@ -390,7 +487,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     if (bd.L < 3) continue;  // nothing to score (the reference skips such blocks, src/RNAcode.c:147-150)
     size_t sig_per_inst = 0, rec_per_inst = 0;
     for (int f = 0; f < 3; f++) {
-      sig_per_inst += 2 * (size_t)bd.ntiles[f] * bd.sig_tile;
+      sig_per_inst += 2 * sigma_floats_sf(bd, f, 32) / 32;
       rec_per_inst += 2 * (size_t)bd.sites[f];
     }
     const size_t bytes_per_inst = sig_per_inst * sizeof(float) + rec_per_inst * sizeof(RowRec);
@@ -401,7 +498,12 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
         if (cur.nitems == 0) room = 1;  // a single instance always goes through
         else { close_chunk(); continue; }
       }
-      const int take = (int)std::min<size_t>(room, (size_t)(bd.n_inst - inst));
+      int take = (int)std::min<size_t>(room, (size_t)(bd.n_inst - inst));
+      if (bd.layout == 2 && take < bd.n_inst - inst) {  // instance groups of 32 must not straddle chunks
+        if (take >= 32) take = take / 32 * 32;
+        else if (cur.nitems == 0) take = std::min(32, bd.n_inst - inst);
+        else { close_chunk(); continue; }
+      }
       Item it;
       memset(&it, 0, sizeof(it));
       it.block = i;
@@ -410,12 +512,18 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       for (int s = 0; s < 2; s++)
         for (int f = 0; f < 3; f++) {
           it.sigma_off[s][f] = (long long)cur.sigma_floats;
-          cur.sigma_floats += (size_t)take * bd.ntiles[f] * bd.sig_tile;
+          cur.sigma_floats += sigma_floats_sf(bd, f, take);
           it.rec_off[s][f] = (long long)cur.rec_count;
           cur.rec_count += (size_t)take * bd.sites[f];
         }
       const int cl = class_of(bd);
       cur.maxNK[cl] = std::max(cur.maxNK[cl], bd.NK);
+      if (bd.layout == 2) {
+        cur.max_smp_smem = std::max(cur.max_smp_smem, smp_smem_bytes(bd, 0));
+        int w = (bd.cols + 3) / 4;
+        if ((w & 1) == 0) w++;
+        cur.max_smp_stage = std::max(cur.max_smp_stage, (size_t)5 * 32 * w * 4);  // k_sigma_smp staging (smp_pitch)
+      }
       cur.maxZs[cl] = std::max(cur.maxZs[cl], bd.zstride);
       cur.max_sigma_work = std::max(cur.max_sigma_work, (long long)take * 2 * (bd.L - 2));
       cur.max_ninst = std::max(cur.max_ninst, take);
@@ -442,7 +550,8 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
   auto dalloc = [&](void** p, size_t bytes) -> bool {
     bytes = std::max<size_t>(bytes, 256);
     total += bytes;
-    return cudaMalloc(p, bytes) == cudaSuccess;
+    *p = ctx_alloc(ctx, bytes);
+    return *p != nullptr;
   };
   bool ok = dalloc((void**)&b->d_blocks, sizeof(BlockDev) * n_blocks) &&
             dalloc((void**)&b->d_items, sizeof(Item) * b->items.size()) &&
@@ -586,6 +695,41 @@ static int launch_dp_reg(rc_batch* b, int NK, const CtaDesc* d_ctas, size_t ncta
   }
 }
 
+template <int NK>
+static int launch_dp_smp_nk(rc_batch* b, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
+  rc_ctx* ctx = b->ctx;
+  RC_CUDA(cudaFuncSetAttribute(k_dp_smp<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dp_smp<NK><<<(unsigned)ncta, SMP_WARPS * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+                                                                    b->d_recs, b->prm, (int)ctx->band_slots);
+  RC_CUDA(cudaGetLastError());
+  b->stats.launches++;
+  b->stats.dp_launches++;
+  return RC_OK;
+}
+
+static int launch_dp_smp(rc_batch* b, int NK, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
+  if (ncta == 0) return RC_OK;
+  switch (NK) {
+    case 1: return launch_dp_smp_nk<1>(b, d_ctas, ncta, smem);
+    case 2: return launch_dp_smp_nk<2>(b, d_ctas, ncta, smem);
+    case 3: return launch_dp_smp_nk<3>(b, d_ctas, ncta, smem);
+    case 4: return launch_dp_smp_nk<4>(b, d_ctas, ncta, smem);
+    case 5: return launch_dp_smp_nk<5>(b, d_ctas, ncta, smem);
+    case 6: return launch_dp_smp_nk<6>(b, d_ctas, ncta, smem);
+    case 7: return launch_dp_smp_nk<7>(b, d_ctas, ncta, smem);
+    case 8: return launch_dp_smp_nk<8>(b, d_ctas, ncta, smem);
+    case 9: return launch_dp_smp_nk<9>(b, d_ctas, ncta, smem);
+    case 10: return launch_dp_smp_nk<10>(b, d_ctas, ncta, smem);
+    case 11: return launch_dp_smp_nk<11>(b, d_ctas, ncta, smem);
+    case 12: return launch_dp_smp_nk<12>(b, d_ctas, ncta, smem);
+    case 13: return launch_dp_smp_nk<13>(b, d_ctas, ncta, smem);
+    case 14: return launch_dp_smp_nk<14>(b, d_ctas, ncta, smem);
+    case 15: return launch_dp_smp_nk<15>(b, d_ctas, ncta, smem);
+    case 16: return launch_dp_smp_nk<16>(b, d_ctas, ncta, smem);
+    default: ctx_fail(b->ctx, "internal: k_dp_smp NK out of range"); return RC_ERR_STATE;
+  }
+}
+
 // Dense (exact fallback) scoring of a list of single-instance items.  Always runs k_dp<1, DENSE> on
 // layout-0 sigma / z tiles that are rebuilt for the item in scratch, whatever layout the block uses.
 static int run_dense_items(rc_batch* b, const std::vector<Item>& src_items) {
@@ -624,22 +768,22 @@ static int run_dense_items(rc_batch* b, const std::vector<Item>& src_items) {
     for (int s = 0; s < 2; s++)
       for (int f = 0; f < 3; f++) {
         it.sigma_off[s][f] = (long long)sig;
-        sig += (size_t)it.ninst * bd.ntiles[f] * bd.sig_tile;
+        sig += sigma_floats_sf(bd, f, it.ninst);
         it.rec_off[s][f] = 0;
         it.dense_off[s][f] = (long long)dn;
         dn += (size_t)it.ninst * ((size_t)bd.sites[f] * (bd.sites[f] + 1) / 2);
       }
     if (sig > b->sigma_floats) {  // layout 0 tiles can be larger than the padded layout-1 ones never; guard anyway
-      cudaFree(b->d_sigma);
-      b->d_sigma = nullptr;
-      RC_CUDA_D(cudaMalloc((void**)&b->d_sigma, sig * sizeof(float)));
+      ctx_free(ctx, b->d_sigma);
+      b->d_sigma = (float*)ctx_alloc(ctx, sig * sizeof(float));
+      if (!b->d_sigma) { cleanup(); ctx_fail(ctx, "device allocation failed (sigma scratch)"); return RC_ERR_NOMEM; }
       b->sigma_floats = sig;
     }
     if (dn > b->dense_floats) {
-      cudaFree(b->d_dense);
-      b->d_dense = nullptr;
+      ctx_free(ctx, b->d_dense);
       b->dense_floats = 0;
-      RC_CUDA_D(cudaMalloc((void**)&b->d_dense, std::max<size_t>(dn * sizeof(float), 256)));
+      b->d_dense = (float*)ctx_alloc(ctx, dn * sizeof(float));
+      if (!b->d_dense) { cleanup(); ctx_fail(ctx, "device allocation failed (dense S scratch)"); return RC_ERR_NOMEM; }
       b->dense_floats = dn;
     }
     if (zw > zs_cap) {
@@ -750,6 +894,15 @@ extern "C" int rc_batch_run(rc_batch* b) {
                                  b->d_z, b->d_sigma, b->prm);
       RC_CUDA(cudaGetLastError());
       b->stats.launches++;
+      if (ch.max_smp_smem > 0) {  // some items use the sample-major layout
+        const size_t smem = ch.max_smp_stage;
+        RC_CUDA(cudaFuncSetAttribute(k_sigma_smp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 g2((unsigned)ch.nitems, (unsigned)((ch.max_ninst + 31) / 32));
+        k_sigma_smp<<<g2, 256, smem, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores,
+                                          b->d_tables, b->d_sigma, b->prm);
+        RC_CUDA(cudaGetLastError());
+        b->stats.launches++;
+      }
     }
     ev_end(b, ev);
     ev = ev_begin(b, 2);
@@ -758,7 +911,8 @@ extern "C" int rc_batch_run(rc_batch* b) {
       for (int cl = 0; cl < N_CLASSES; cl++) {
         if (ch.ncta[cl] == 0) continue;
         int rcode;
-        if (cl < REG_MAX_NK) rcode = launch_dp_reg(b, cl + 1, b->d_ctas + ch.cta0[cl], ch.ncta[cl]);
+        if (cl >= SMP_CLASS0) rcode = launch_dp_smp(b, cl - SMP_CLASS0 + 1, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smp_smem);
+        else if (cl < REG_MAX_NK) rcode = launch_dp_reg(b, cl + 1, b->d_ctas + ch.cta0[cl], ch.ncta[cl]);
         else if (cl == REG_MAX_NK) rcode = launch_dp<2, false>(b, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.maxNK[cl], ch.maxZs[cl]);
         else rcode = launch_dp<1, false>(b, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.maxNK[cl], ch.maxZs[cl]);
         if (rcode != RC_OK) return rcode;
