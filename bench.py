@@ -384,7 +384,7 @@ def ours(args):
                          "ops_per_cell": OPS_PER_CELL, "kernel_ms_per_step": dp_ms / args.steps,
                          "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}},
             "dense_fallbacks": int(fallbacks),
-            "native_hss_counts": best_native,
+            "native_hss_total": int(sum(best_native)),
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.workload)

@@ -73,6 +73,24 @@ typedef struct {
   const char *samples;     /* n_samples*N*cols bytes or NULL */
 } rc_block_desc;
 
+/* A phylogenetic tree flattened in the order seq-gen evolves it (EvolveSequences / EvolveNode,
+ * seqgen/evolve.c:400-433): the root first, then the subtree of branch1, of branch2 and, for the unrooted
+ * trees PhyML writes, of branch0.  Input of the on-GPU null-alignment simulation that replaces
+ * simulateTree + tree2aln + sortAln (src/treeSimulate.c:52-97, :254-283, src/misc.c:150-171). */
+typedef struct {
+  int n_nodes;
+  const int *parent; /* [n_nodes]; -1 for the root */
+  const int *row;    /* [n_nodes]; for a tip the alignment row (input order) it fills, -1 for internal nodes */
+  const double *cum; /* [n_nodes][16]: the cumulative transition matrix seq-gen's SetMatrix(matrix, length0) gives
+                        for the branch above the node (seqgen/nucmodels.c:187-196, :318-362); for node 0 the first
+                        four entries are the cumulative root frequencies addFreq[0..3] (seqgen/model.c:116-119) */
+} rc_tree_desc;
+
+enum {
+  RC_RNG_MT19937 = 0, /* bit-exact seq-gen: MT19937 seeded per sample, consumed in seq-gen's order (exact mode) */
+  RC_RNG_PHILOX = 1   /* counter-based Philox4x32-10: same distribution, different stream (GPU-RNG mode) */
+};
+
 typedef struct rc_ctx rc_ctx;
 typedef struct rc_batch rc_batch;
 
@@ -100,10 +118,19 @@ int rc_score_aln(rc_ctx *ctx, const rc_block_desc *block, const rc_params *param
 int rc_score_samples(rc_ctx *ctx, const rc_block_desc *block, const rc_params *params, const int *blosum,
                      double *max_scores);
 
+/* Same, with the null alignments simulated on the GPU (block->samples is ignored, block->n_samples of them are drawn). */
+int rc_score_samples_evolve(rc_ctx *ctx, const rc_block_desc *block, const rc_tree_desc *tree, const unsigned int *seeds,
+                            int rng, const rc_params *params, const int *blosum, double *max_scores);
+/* Debug / test access: the simulated rows of sample i of a block (N*cols characters) after rc_batch_run. */
+int rc_batch_get_sample_rows(rc_batch *batch, int block, int sample, char *rows);
+
 /* -- many blocks at once ------------------------------------------------------------------------ */
 /* The descriptors (and the host memory they point to) must stay valid until rc_batch_upload() returns. */
 int rc_batch_create(rc_ctx *ctx, const rc_block_desc *blocks, int n_blocks, const rc_params *params, const int *blosum,
                     rc_batch **batch);
+/* Draw the block's n_samples null alignments on the GPU instead of taking them from desc.samples (which may
+ * then be NULL).  seeds: one per sample (what SetSeed() would receive, low 32 bits).  Call before rc_batch_upload. */
+int rc_batch_set_evolve(rc_batch *batch, int block, const rc_tree_desc *tree, const unsigned int *seeds, int rng);
 int rc_batch_upload(rc_batch *batch);   /* host -> device copies of rows, samples and score tables */
 int rc_batch_run(rc_batch *batch);      /* all kernels; inputs and outputs stay in HBM */
 int rc_batch_download(rc_batch *batch); /* device -> host copy of HSS records and per-sample maxima; synchronises */

@@ -27,6 +27,7 @@
 #include "score.h"
 #include "treeML.h"
 #include "treeSimulate.h"
+#include "model.h"
 
 extern parameters pars;
 extern bgModel *models, *modelsRev;
@@ -45,6 +46,24 @@ static void json_str(const char *s) {
     putchar(*s);
   }
   putchar('"');
+}
+
+/* pre-order walk in the order EvolveSequences visits the nodes (seqgen/evolve.c:400-433) */
+static void dump_node(TTree *tree, TNode *node, int parent, int *counter, const struct aln *aln[], int N) {
+  int me = (*counter)++, k, row = -1;
+  double cum[16];
+  if (node->tipNo != -1)
+    for (k = 0; k < N; k++)
+      if (strcmp(aln[k]->name, tree->names[node->tipNo]) == 0) row = k;
+  SetMatrix(cum, node->length0 * 1.0); /* MutateSequence -> SetMatrix(matrix[0], len), NoRates (seqgen/evolve.c:291-292) */
+  printf("%s{\"parent\":%d,\"row\":%d,\"len\":%.17g,\"cum\":[", me ? "," : "", parent, row, node->length0);
+  for (k = 0; k < 16; k++) printf("%s%.17g", k ? "," : "", parent < 0 ? 0.0 : cum[k]);
+  printf("]}");
+  if (node->tipNo == -1) {
+    dump_node(tree, node->branch1, me, counter, aln, N);
+    dump_node(tree, node->branch2, me, counter, aln, N);
+    if (parent < 0 && !tree->rooted) dump_node(tree, node->branch0, me, counter, aln, N);
+  }
 }
 
 static void dump_hss(segmentStats *r) {
@@ -236,7 +255,14 @@ int main(int argc, char *argv[]) {
       freeAln((struct aln **)sampledAln);
       freeResults(r);
     }
-    printf("],\"maxScores\":[");
+    { /* everything kernel (d) needs to redraw these samples: flattened tree + cumulative matrices of seq-gen */
+      int counter = 0;
+      printf("],\"evolve\":{\"rooted\":%d,\"addFreq\":[%.17g,%.17g,%.17g,%.17g],\"nodes\":[", tree->rooted, addFreq[0],
+             addFreq[1], addFreq[2], addFreq[3]);
+      if (sampleN > 0) dump_node(tree, tree->root, -1, &counter, (const struct aln **)inputAln, N);
+      printf("]}");
+    }
+    printf(",\"maxScores\":[");
     for (i = 0; i < sampleN; i++) printf("%s%.9g", i ? "," : "", maxScores[i]);
     printf("]");
     fitStatus = sampleN > 0 ? EVDMaxLikelyFit(maxScores, NULL, sampleN, &mu, &lambda) : 0;

@@ -417,6 +417,72 @@ void orc_calculate_bg(float dist, const float freqs[4], float kappa, const int *
   }
 }
 
+/* ---- seq-gen restatement --------------------------------------------------------------------------------- */
+
+void orc_mt_init(orc_mt *g, unsigned long s) { /* seqgen/twister.c:73-86 */
+  g->mt[0] = s & 0xffffffffUL;
+  for (g->mti = 1; g->mti < 624; g->mti++) {
+    g->mt[g->mti] = (1812433253UL * (g->mt[g->mti - 1] ^ (g->mt[g->mti - 1] >> 30)) + g->mti);
+    g->mt[g->mti] &= 0xffffffffUL;
+  }
+}
+
+unsigned long orc_mt_next(orc_mt *g) { /* seqgen/twister.c:118-146 */
+  static const unsigned long mag01[2] = {0x0UL, 0x9908b0dfUL};
+  unsigned long y;
+  if (g->mti >= 624) {
+    int kk;
+    for (kk = 0; kk < 624 - 397; kk++) {
+      y = (g->mt[kk] & 0x80000000UL) | (g->mt[kk + 1] & 0x7fffffffUL);
+      g->mt[kk] = g->mt[kk + 397] ^ (y >> 1) ^ mag01[y & 0x1UL];
+    }
+    for (; kk < 623; kk++) {
+      y = (g->mt[kk] & 0x80000000UL) | (g->mt[kk + 1] & 0x7fffffffUL);
+      g->mt[kk] = g->mt[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 0x1UL];
+    }
+    y = (g->mt[623] & 0x80000000UL) | (g->mt[0] & 0x7fffffffUL);
+    g->mt[623] = g->mt[396] ^ (y >> 1) ^ mag01[y & 0x1UL];
+    g->mti = 0;
+  }
+  y = g->mt[g->mti++];
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680UL;
+  y ^= (y << 15) & 0xefc60000UL;
+  y ^= (y >> 18);
+  return y;
+}
+
+/* SetState, seqgen/evolve.c:167-175.  The reference can return 4 when r exceeds the last cumulative value (the
+ * rows end a few 1e-10 below 1); that state indexes past its tables (undefined behaviour), here it is clamped to 3. */
+static int set_state(orc_mt *g, const double *P) {
+  double r = orc_mt_next(g) * (1.0 / 4294967295.0); /* genrand_real1, seqgen/twister.c:162-166 */
+  int j;
+  for (j = 0; j < 4 && r > P[j]; j++);
+  return j > 3 ? 3 : j;
+}
+
+void orc_evolve(unsigned long seed, int n_nodes, const int *parent, const int *row, const double *cum,
+                const double addFreq[4], int N, int cols, char *out_rows) {
+  static const char nucleotides[] = "ACGT"; /* seqgen/nucmodels.c:47 */
+  orc_mt g;
+  unsigned char *seqs = (unsigned char *)malloc((size_t)n_nodes * cols);
+  (void)N;
+  orc_mt_init(&g, seed); /* SetSeed(randomSeed), src/treeSimulate.c:84-85 */
+  for (int nd = 0; nd < n_nodes; nd++) {
+    unsigned char *me = seqs + (size_t)nd * cols;
+    if (parent[nd] < 0) {
+      for (int i = 0; i < cols; i++) me[i] = (unsigned char)set_state(&g, addFreq); /* RandomSequence */
+    } else {
+      const unsigned char *anc = seqs + (size_t)parent[nd] * cols;
+      const double *M = cum + (size_t)nd * 16;
+      for (int i = 0; i < cols; i++) me[i] = (unsigned char)set_state(&g, M + anc[i] * 4); /* MutateSequence, NoRates */
+    }
+    if (row[nd] >= 0) /* tree2aln + sortAln */
+      for (int i = 0; i < cols; i++) out_rows[(size_t)row[nd] * cols + i] = nucleotides[me[i]];
+  }
+  free(seqs);
+}
+
 double orc_cells(int N, int L) {
   double P = 0;
   for (int b = 1; b <= L; b++) P += (L - b + 1) / 3;

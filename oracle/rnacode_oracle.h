@@ -71,6 +71,23 @@ void orc_count_freqs(const char *rows, int N, int cols, float freqs[4]);
 /* probHKY (src/score.c:204-245) + calculateBG (src/score.c:107-193): expected scores per Hamming distance */
 void orc_calculate_bg(float dist, const float freqs[4], float kappa, const int *blosum, float scores[4], float probs[4]);
 
+/* ---- null-alignment simulation (kernel d): seq-gen's HKY / no-rate-heterogeneity path ---------------------- */
+/* MT19937 as seqgen/twister.c:73-146 (init_genrand, genrand_int32) */
+typedef struct {
+  unsigned long mt[624];
+  int mti;
+} orc_mt;
+void orc_mt_init(orc_mt *g, unsigned long seed);
+unsigned long orc_mt_next(orc_mt *g);
+/* One simulated alignment, as simulateTree + tree2aln + sortAln produce it (src/treeSimulate.c:52-97, :254-283,
+ * src/misc.c:150-171; seqgen/evolve.c:167-199, :291-308, :400-433): nodes in the order EvolveSequences visits them
+ * (root first, then branch1 subtree, branch2 subtree, and branch0 subtree of an unrooted root); every node draws one
+ * genrand_real1 per site, in site order; the root picks its state from the cumulative frequencies, every other node
+ * from the cumulative row (of its branch's transition matrix) of its parent's state.  row[node] >= 0 marks a tip and
+ * names the alignment row it fills.  Output: N*cols characters over ACGT. */
+void orc_evolve(unsigned long seed, int n_nodes, const int *parent, const int *row, const double *cum /* n_nodes*16 */,
+                const double addFreq[4], int N, int cols, char *out_rows);
+
 /* DP cell count for one alignment: 2*(N-1)*P(L) */
 double orc_cells(int N, int L);
 

@@ -32,6 +32,25 @@ class rc_block_desc(C.Structure):
                 ("scores_rev", C.c_void_p), ("n_samples", C.c_int), ("samples", C.c_void_p)]
 
 
+class rc_tree_desc(C.Structure):
+    _fields_ = [("n_nodes", C.c_int), ("parent", C.c_void_p), ("row", C.c_void_p), ("cum", C.c_void_p)]
+
+
+RC_RNG_MT19937, RC_RNG_PHILOX = 0, 1
+
+
+class Tree:
+    """Flattened tree in seq-gen's evolution order (see rc_tree_desc in the header)."""
+
+    def __init__(self, parent, row, cum):
+        self.parent = np.ascontiguousarray(parent, dtype=np.int32)
+        self.row = np.ascontiguousarray(row, dtype=np.int32)
+        self.cum = np.ascontiguousarray(cum, dtype=np.float64).reshape(len(self.parent), 16)
+
+    def desc(self):
+        return rc_tree_desc(len(self.parent), self.parent.ctypes.data, self.row.ctypes.data, self.cum.ctypes.data)
+
+
 class rc_batch_stats(C.Structure):
     _fields_ = [("cells", C.c_double), ("launches", C.c_longlong), ("dense_fallbacks", C.c_longlong),
                 ("ms_pack", C.c_float), ("ms_sigma", C.c_float), ("ms_dp", C.c_float), ("ms_hss", C.c_float),
@@ -43,7 +62,7 @@ EXPORTS = [
     "rc_create", "rc_destroy", "rc_last_error", "rc_default_params", "rc_set_stream", "rc_set_option",
     "rc_score_aln", "rc_score_samples", "rc_batch_create", "rc_batch_upload", "rc_batch_run", "rc_batch_download",
     "rc_batch_native_hss", "rc_batch_max_scores", "rc_batch_destroy", "rc_batch_get_stats", "rc_version",
-    "rc_calibrate_issue",
+    "rc_calibrate_issue", "rc_batch_set_evolve", "rc_score_samples_evolve", "rc_batch_get_sample_rows",
 ]
 
 _lib = None
@@ -54,10 +73,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.LIB):
+    path = os.environ.get("RNACODE_CUDA_LIB", _build.LIB)  # override: A/B-testing of differently built libraries
+    if not os.path.exists(path):
         raise ImportError("libRNAcode_cuda.so is missing (%s): run `python -m rnacode_b200.build` "
-                          "or __graft_entry__.build(); no CPU fallback exists" % _build.LIB)
-    lib = C.CDLL(_build.LIB)
+                          "or __graft_entry__.build(); no CPU fallback exists" % path)
+    lib = C.CDLL(path)
     vp, i = C.c_void_p, C.c_int
     lib.rc_create.argtypes = [C.POINTER(vp), i]
     lib.rc_destroy.argtypes = [vp]
@@ -80,6 +100,10 @@ def load():
     lib.rc_batch_get_stats.argtypes = [vp, C.POINTER(rc_batch_stats)]
     lib.rc_version.restype = C.c_char_p
     lib.rc_calibrate_issue.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.rc_batch_set_evolve.argtypes = [vp, i, C.POINTER(rc_tree_desc), vp, i]
+    lib.rc_score_samples_evolve.argtypes = [vp, C.POINTER(rc_block_desc), C.POINTER(rc_tree_desc), vp, i,
+                                            C.POINTER(rc_params), vp, vp]
+    lib.rc_batch_get_sample_rows.argtypes = [vp, i, i, vp]
     _lib = lib
     return lib
 
@@ -97,7 +121,7 @@ def make_params(Delta=-10.0, Omega=-4.0, omega=-2.0, stopPenalty_0=-9999.0, stop
 class Block:
     """Host-side view of one alignment block (arrays are kept alive by this object)."""
 
-    def __init__(self, rows, scores_fwd, scores_rev, samples=None):
+    def __init__(self, rows, scores_fwd, scores_rev, samples=None, n_samples=None):
         rows = np.ascontiguousarray(rows, dtype=np.uint8)
         assert rows.ndim == 2
         self.N, self.cols = rows.shape
@@ -109,7 +133,7 @@ class Block:
                 samples = np.ascontiguousarray(samples, dtype=np.uint8)
             assert samples.shape[1:] == (self.N, self.cols)
         self.samples = samples
-        self.n_samples = 0 if samples is None else samples.shape[0]
+        self.n_samples = (n_samples or 0) if samples is None else samples.shape[0]
 
     @staticmethod
     def from_strings(rows, scores_fwd, scores_rev, samples=None):
@@ -201,6 +225,18 @@ class Batch:
         self.h = C.c_void_p()
         ctx._check(ctx.lib.rc_batch_create(ctx.h, self._descs, len(self.blocks), C.byref(params), self._blosum.ctypes.data,
                                            C.byref(self.h)))
+
+    def set_evolve(self, i, tree, seeds, rng=RC_RNG_MT19937):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        d = tree.desc()
+        self._keep = getattr(self, "_keep", []) + [tree, seeds]
+        self.ctx._check(self.ctx.lib.rc_batch_set_evolve(self.h, i, C.byref(d), seeds.ctypes.data, rng))
+
+    def sample_rows(self, i, sample):
+        b = self.blocks[i]
+        out = np.zeros((b.N, b.cols), dtype=np.uint8)
+        self.ctx._check(self.ctx.lib.rc_batch_get_sample_rows(self.h, i, sample, out.ctypes.data))
+        return out
 
     def upload(self):
         self.ctx._check(self.ctx.lib.rc_batch_upload(self.h))

@@ -73,6 +73,17 @@ struct Item {
   long long dense_off[2][3];  // float offset (dense fallback only): [inst_local][sites*(sites+1)/2]
 };
 
+// Null-alignment simulation (kernel d) of one block: the tree in seq-gen's evolution order.
+struct EvoDev {
+  int block;
+  int n_nodes, n_internal;
+  int rng;                 // 0: MT19937 exactly as seq-gen consumes it; 1: Philox4x32-10 counter-based
+  long long node_off;      // int offset: [n_nodes][4] = parent, alignment row (-1: internal), slot of its sequence in scratch, 0
+  long long thr_off;       // u32 offset: [n_nodes][4 parent states][4]: a draw u moves past cumulative entry j iff u > thr
+  long long seed_off;      // u32 offset: [n_samples]
+  long long seq_off;       // byte offset into the evolve scratch: [n_samples][n_internal][cols]
+};
+
 struct CtaDesc {
   int item;
   int sf;     // strand*3 + frame

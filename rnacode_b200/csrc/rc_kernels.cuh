@@ -875,8 +875,11 @@ __device__ __forceinline__ void rec_copy(RowRec* dst, const RowRec* src) {
   reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(src)[1];
 }
 
+#ifndef RC_REG_MINB
+#define RC_REG_MINB 4
+#endif
 template <int NK>
-__global__ void __launch_bounds__(DP_WARPS * 32)
+__global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
     k_dp_reg(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
              const float* __restrict__ sigma, RowRec* __restrict__ recs, Params prm, int band_slots) {
   constexpr int R = 2;
@@ -1240,6 +1243,138 @@ __global__ void __launch_bounds__(128)
   if (lane == 0) {
     res[bd.res_off + (size_t)inst * 6 + sf] = best;
     if (inst == 0) hsscnt[bd.hsscnt_off + sf] = nout;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (d) k_evolve: null alignments on the GPU, replacing simulateTree / tree2aln / sortAln on the host
+// (src/treeSimulate.c:52-97, :254-283, src/misc.c:150-171; seq-gen HKY, no rate heterogeneity:
+// seqgen/evolve.c:167-199, :291-308, :400-433).
+//
+// rng 0 (exact): one warp per (block, sample) owns a bit-exact MT19937 (seqgen/twister.c:73-146), seeded with
+// the sample's seed, and consumes it in seq-gen's order: nodes in evolution order, one genrand_real1 per site.
+// The 624-word state lives in shared memory and is regenerated by the 32 lanes in place (each lane reads its
+// three source words before any lane writes; the recurrence only reaches words of earlier batches or old words
+// of later ones).  SetState's `r > P[j]` on doubles (r = u * (1/4294967295.0)) is evaluated as `u > thr[j]`
+// with integer thresholds computed on the host from the caller's cumulative matrices with the very same
+// double expression, so the drawn states are identical.  State 4 (r above the last cumulative entry, undefined
+// behaviour in the reference) is clamped to 3.
+// rng 1: Philox4x32-10 keyed by the sample seed, counter = (node, site): same distribution, any order.
+//
+// Internal-node sequences go to a scratch area (one byte per site), tips are written as "ACGT" characters
+// straight into the raw sample rows (input order), which k_pack then treats like host-provided samples.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned mt_temper(unsigned y) {
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+
+__device__ __forceinline__ void mt_twist(unsigned* mt, int lane) {
+#pragma unroll 1
+  for (int base = 0; base < 624; base += 32) {
+    const int kk = base + lane;
+    unsigned a = 0, b = 0, c = 0;
+    if (kk < 624) {
+      a = mt[kk];
+      b = mt[kk + 1 < 624 ? kk + 1 : 0];
+      c = mt[kk + 397 < 624 ? kk + 397 : kk - 227];
+    }
+    __syncwarp();
+    if (kk < 624) {
+      const unsigned y = (a & 0x80000000u) | (b & 0x7fffffffu);
+      mt[kk] = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void philox_round(unsigned (&c)[4], unsigned k0, unsigned k1) {
+  const unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const unsigned n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0;
+  c[1] = lo1;
+  c[2] = n2;
+  c[3] = lo0;
+}
+__device__ __forceinline__ unsigned philox_draw(unsigned seed, unsigned node, unsigned site) {
+  unsigned c[4] = {site, node, 0x52434F44u, 0u};  // "RCOD"
+  unsigned k0 = seed, k1 = 0x9E3779B9u ^ seed;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c[0];
+}
+
+constexpr int EVO_WARPS = 4;
+
+__global__ void __launch_bounds__(EVO_WARPS * 32)
+    k_evolve(const BlockDev* __restrict__ blocks, const EvoDev* __restrict__ evos, const int* __restrict__ nodes,
+             const unsigned* __restrict__ thr, const unsigned* __restrict__ seeds, unsigned char* __restrict__ seqs,
+             unsigned char* __restrict__ raw) {
+  __shared__ unsigned s_mt[EVO_WARPS][624];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const EvoDev ev = evos[blockIdx.y];
+  const BlockDev& bd = blocks[ev.block];
+  const int sample = blockIdx.x * EVO_WARPS + warp;
+  if (sample >= bd.n_inst - 1) return;
+  const int cols = bd.cols;
+  const unsigned seed = seeds[ev.seed_off + sample];
+  const int* nd = nodes + ev.node_off;
+  const unsigned* th = thr + ev.thr_off;
+  unsigned char* myseq = seqs + ev.seq_off + (size_t)sample * ev.n_internal * cols;
+  unsigned char* myraw = raw + bd.raw_off + (size_t)(1 + sample) * bd.inst_stride;
+  unsigned* mt = s_mt[warp];
+  int pos = 624;  // next unread word of the current 624-word batch
+  if (ev.rng == 0) {
+    // init_genrand (seqgen/twister.c:73-86) is a serial recurrence: every lane runs it redundantly in
+    // registers, lane l keeps the words it owns
+    unsigned x = seed;
+    for (int i = 0; i < 624; i++) {
+      if ((i & 31) == lane) mt[i] = x;
+      x = 1812433253u * (x ^ (x >> 30)) + (unsigned)(i + 1);
+    }
+    __syncwarp();
+  }
+  for (int n = 0; n < ev.n_nodes; n++) {
+    const int parent = nd[4 * n], row = nd[4 * n + 1], slot = nd[4 * n + 2];
+    const unsigned char* pseq = parent >= 0 ? myseq + (size_t)nd[4 * parent + 2] * cols : nullptr;
+    const unsigned* tn = th + (size_t)n * 16;
+    for (int c0 = 0; c0 < cols; c0 += 32) {
+      const int site = c0 + lane;
+      const int cnt = min(32, cols - c0);  // draws consumed by this chunk
+      unsigned u;
+      if (ev.rng == 0) {
+        // lanes 0..cnt-1 take the next cnt outputs of the generator, in order
+        int idx = pos + lane;
+        unsigned v = 0;
+        if (lane < cnt && idx < 624) v = mt[idx];
+        if (pos + cnt > 624) {  // the chunk crosses a batch boundary (warp-uniform)
+          __syncwarp();
+          mt_twist(mt, lane);
+          if (lane < cnt && idx >= 624) v = mt[idx - 624];
+          pos -= 624;
+        }
+        pos += cnt;
+        u = mt_temper(v);
+      } else {
+        u = philox_draw(seed, (unsigned)n, (unsigned)site);
+      }
+      if (site < cols) {
+        const int ps = parent >= 0 ? (int)pseq[site] : 0;  // root: row 0 of its table holds the cumulative frequencies
+        const unsigned* t = tn + ps * 4;
+        const int state = (u > t[0]) + (u > t[1]) + (u > t[2]);
+        if (slot >= 0) myseq[(size_t)slot * cols + site] = (unsigned char)state;
+        if (row >= 0) myraw[(size_t)row * cols + site] = (unsigned char)("ACGT"[state]);
+      }
+    }
+    __syncwarp();  // a child reads its parent's sequence written by other lanes
   }
 }
 

@@ -193,6 +193,17 @@ struct rc_batch {
   int* d_hsscnt = nullptr;
   int* d_ovf = nullptr;
   SigmaTables* d_tables = nullptr;
+  // null-alignment simulation (kernel d)
+  std::vector<EvoDev> evos;
+  std::vector<int> evo_nodes;
+  std::vector<unsigned> evo_thr, evo_seeds;
+  std::vector<int> evo_of_block;  // -1: samples come from the host
+  size_t evo_seq_bytes = 0;
+  EvoDev* d_evos = nullptr;
+  int* d_evo_nodes = nullptr;
+  unsigned *d_evo_thr = nullptr, *d_evo_seeds = nullptr;
+  unsigned char* d_evo_seq = nullptr;
+  int evo_max_samples = 0;
   // device, scratch
   float* d_sigma = nullptr;
   RowRec* d_recs = nullptr;
@@ -355,7 +366,8 @@ extern "C" int rc_calibrate_issue(rc_ctx* ctx, double* lane_ops_per_s) {
 static void free_batch_device(rc_batch* b) {
   rc_ctx* ctx = b->ctx;
   void* ptrs[] = {b->d_blocks, b->d_items, b->d_ctas, b->d_raw, b->d_cls, b->d_cols0, b->d_scores, b->d_z, b->d_res,
-                  b->d_hss, b->d_hsscnt, b->d_ovf, b->d_tables, b->d_sigma, b->d_recs, b->d_dense};
+                  b->d_hss, b->d_hsscnt, b->d_ovf, b->d_tables, b->d_sigma, b->d_recs, b->d_dense,
+                  b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq};
   for (void* p : ptrs) ctx_free(ctx, p);
   for (auto& e : b->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   b->events.clear();
@@ -418,7 +430,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
   for (int i = 0; i < n_blocks; i++) {
     const rc_block_desc& d = descs[i];
     if (d.N < 2 || d.N > 500 || d.cols < 1 || d.cols > 190000 || !d.rows || !d.scores_fwd || !d.scores_rev || d.n_samples < 0 ||
-        (d.n_samples > 0 && !d.samples)) {
+        false) {
       ctx_fail(ctx, "rc_batch_create: invalid block descriptor " + std::to_string(i));
       delete b;
       return RC_ERR_ARG;
@@ -570,6 +582,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     return RC_ERR_NOMEM;
   }
   b->device_bytes = total;
+  b->evo_of_block.assign(n_blocks, -1);
   b->h_res.assign(b->res_floats, -1.0f);
   b->h_hss.resize(b->hss_count);
   b->h_hsscnt.assign(b->hsscnt_ints, 0);
@@ -583,6 +596,99 @@ extern "C" void rc_batch_destroy(rc_batch* b) {
   cudaStreamSynchronize(b->ctx->stream);
   free_batch_device(b);
   delete b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// null-alignment simulation set-up
+// ------------------------------------------------------------------------------------------------
+// SetState (seqgen/evolve.c:167-175) compares r = u * (1.0/4294967295.0) (genrand_real1, seqgen/twister.c:162-166)
+// with a cumulative probability P in double.  u -> r is monotone, so `r > P` <=> `u > T(P)` with
+// T(P) = max{u : (double)u * (1.0/4294967295.0) <= P}, found by bisection with the very same expression.
+static unsigned threshold_of(double P) {
+  const double c = 1.0 / 4294967295.0;
+  volatile double r0 = 0.0 * c;
+  if (!(r0 <= P)) return 0u;  // P < 0 (not a probability): treat like 0
+  unsigned lo = 0u, hi = 0xffffffffu;
+  while (lo < hi) {
+    const unsigned mid = lo + (unsigned)(((unsigned long long)hi - lo + 1) / 2);
+    volatile double r = (double)mid * c;
+    if (r <= P) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+extern "C" int rc_batch_set_evolve(rc_batch* b, int block, const rc_tree_desc* tree, const unsigned int* seeds, int rng) {
+  if (!b) return RC_ERR_ARG;
+  rc_ctx* ctx = b->ctx;
+  if (block < 0 || block >= b->n_blocks || !tree || !seeds || tree->n_nodes < 2 || !tree->parent || !tree->row || !tree->cum ||
+      (rng != RC_RNG_MT19937 && rng != RC_RNG_PHILOX)) {
+    ctx_fail(ctx, "rc_batch_set_evolve: bad argument");
+    return RC_ERR_ARG;
+  }
+  if (b->uploaded) {
+    ctx_fail(ctx, "rc_batch_set_evolve after rc_batch_upload");
+    return RC_ERR_STATE;
+  }
+  if (b->evo_of_block[block] >= 0) {
+    ctx_fail(ctx, "rc_batch_set_evolve: block already has a tree");
+    return RC_ERR_STATE;
+  }
+  const BlockDev& bd = b->blocks[block];
+  const int n_samples = bd.n_inst - 1;
+  std::vector<char> seen(bd.N, 0);
+  EvoDev ev;
+  memset(&ev, 0, sizeof(ev));
+  ev.block = block;
+  ev.n_nodes = tree->n_nodes;
+  ev.rng = rng;
+  ev.node_off = (long long)b->evo_nodes.size();
+  ev.thr_off = (long long)b->evo_thr.size();
+  ev.seed_off = (long long)b->evo_seeds.size();
+  int n_internal = 0;
+  for (int n = 0; n < tree->n_nodes; n++) {
+    const int parent = tree->parent[n], row = tree->row[n];
+    if ((n == 0) != (parent < 0) || parent >= n || row >= bd.N || (row >= 0 && seen[row]) ||
+        (parent >= 0 && tree->row[parent] >= 0)) {
+      ctx_fail(ctx, "rc_batch_set_evolve: nodes must be in evolution order (parents first, root at 0), tips map to distinct rows");
+      return RC_ERR_ARG;
+    }
+    if (row >= 0) seen[row] = 1;
+    b->evo_nodes.push_back(parent);
+    b->evo_nodes.push_back(row);
+    b->evo_nodes.push_back(row >= 0 ? -1 : n_internal++);
+    b->evo_nodes.push_back(0);
+    for (int k = 0; k < 16; k++) b->evo_thr.push_back(threshold_of(tree->cum[(size_t)n * 16 + k]));
+  }
+  for (int r = 0; r < bd.N; r++)
+    if (!seen[r]) {
+      ctx_fail(ctx, "rc_batch_set_evolve: alignment row " + std::to_string(r) + " is not a tip of the tree");
+      return RC_ERR_ARG;
+    }
+  ev.n_internal = n_internal;
+  for (int i = 0; i < n_samples; i++) b->evo_seeds.push_back(seeds[i]);
+  ev.seq_off = (long long)b->evo_seq_bytes;
+  b->evo_seq_bytes += (size_t)n_samples * n_internal * bd.cols;
+  b->evo_max_samples = std::max(b->evo_max_samples, n_samples);
+  b->evo_of_block[block] = (int)b->evos.size();
+  b->evos.push_back(ev);
+  return RC_OK;
+}
+
+extern "C" int rc_batch_get_sample_rows(rc_batch* b, int block, int sample, char* rows) {
+  if (!b || block < 0 || block >= b->n_blocks || !rows) return RC_ERR_ARG;
+  rc_ctx* ctx = b->ctx;
+  const BlockDev& bd = b->blocks[block];
+  if (sample < 0 || sample >= bd.n_inst - 1) return RC_ERR_ARG;
+  if (!b->ran) {
+    ctx_fail(ctx, "rc_batch_get_sample_rows before rc_batch_run");
+    return RC_ERR_STATE;
+  }
+  RC_CUDA(cudaSetDevice(ctx->device));
+  RC_CUDA(cudaStreamSynchronize(ctx->stream));
+  RC_CUDA(cudaMemcpy(rows, b->d_raw + bd.raw_off + (size_t)(1 + sample) * bd.inst_stride, (size_t)bd.N * bd.cols,
+                     cudaMemcpyDeviceToHost));
+  return RC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -601,7 +707,11 @@ extern "C" int rc_batch_upload(rc_batch* b) {
     const size_t rowbytes = (size_t)d.N * d.cols;
     RC_CUDA(cudaMemcpyAsync(b->d_raw + bd.raw_off, d.rows, rowbytes, cudaMemcpyHostToDevice, st));
     h2d += rowbytes;
-    if (d.n_samples > 0) {
+    if (d.n_samples > 0 && b->evo_of_block[i] < 0) {
+      if (!d.samples) {
+        ctx_fail(ctx, "block " + std::to_string(i) + " has n_samples > 0 but neither samples nor rc_batch_set_evolve");
+        return RC_ERR_ARG;
+      }
       RC_CUDA(cudaMemcpy2DAsync(b->d_raw + bd.raw_off + bd.inst_stride, bd.inst_stride, d.samples, rowbytes, rowbytes,
                                 d.n_samples, cudaMemcpyHostToDevice, st));
       h2d += rowbytes * d.n_samples;
@@ -616,6 +726,25 @@ extern "C" int rc_batch_upload(rc_batch* b) {
   if (!b->ctas.empty())
     RC_CUDA(cudaMemcpyAsync(b->d_ctas, b->ctas.data(), sizeof(CtaDesc) * b->ctas.size(), cudaMemcpyHostToDevice, st));
   RC_CUDA(cudaMemcpyAsync(b->d_tables, &b->tables, sizeof(SigmaTables), cudaMemcpyHostToDevice, st));
+  if (!b->evos.empty()) {
+    void* ptrs[] = {b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq};
+    for (void* p : ptrs) ctx_free(ctx, p);
+    b->d_evos = (EvoDev*)ctx_alloc(ctx, sizeof(EvoDev) * b->evos.size());
+    b->d_evo_nodes = (int*)ctx_alloc(ctx, sizeof(int) * b->evo_nodes.size());
+    b->d_evo_thr = (unsigned*)ctx_alloc(ctx, sizeof(unsigned) * b->evo_thr.size());
+    b->d_evo_seeds = (unsigned*)ctx_alloc(ctx, sizeof(unsigned) * b->evo_seeds.size());
+    b->d_evo_seq = (unsigned char*)ctx_alloc(ctx, b->evo_seq_bytes);
+    if (!b->d_evos || !b->d_evo_nodes || !b->d_evo_thr || !b->d_evo_seeds || !b->d_evo_seq) {
+      ctx_fail(ctx, "device allocation failed (evolve tables)");
+      return RC_ERR_NOMEM;
+    }
+    RC_CUDA(cudaMemcpyAsync(b->d_evos, b->evos.data(), sizeof(EvoDev) * b->evos.size(), cudaMemcpyHostToDevice, st));
+    RC_CUDA(cudaMemcpyAsync(b->d_evo_nodes, b->evo_nodes.data(), sizeof(int) * b->evo_nodes.size(), cudaMemcpyHostToDevice, st));
+    RC_CUDA(cudaMemcpyAsync(b->d_evo_thr, b->evo_thr.data(), sizeof(unsigned) * b->evo_thr.size(), cudaMemcpyHostToDevice, st));
+    RC_CUDA(cudaMemcpyAsync(b->d_evo_seeds, b->evo_seeds.data(), sizeof(unsigned) * b->evo_seeds.size(), cudaMemcpyHostToDevice, st));
+    h2d += sizeof(EvoDev) * b->evos.size() + sizeof(int) * b->evo_nodes.size() +
+           sizeof(unsigned) * (b->evo_thr.size() + b->evo_seeds.size());
+  }
   h2d += sizeof(float) * b->scores_floats + sizeof(BlockDev) * b->n_blocks + sizeof(Item) * b->items.size() +
          sizeof(CtaDesc) * b->ctas.size() + sizeof(SigmaTables);
   // descriptors may go away after this call returns
@@ -856,6 +985,13 @@ extern "C" int rc_batch_run(rc_batch* b) {
   int maxchunks = 1;
   for (const BlockDev& bd : b->blocks) maxchunks = std::max(maxchunks, (int)(((size_t)bd.inst_stride >> 4) * bd.n_inst / 256 + 1));
   int ev = ev_begin(b, 0);
+  if (!b->evos.empty()) {
+    dim3 ge((unsigned)((b->evo_max_samples + EVO_WARPS - 1) / EVO_WARPS), (unsigned)b->evos.size());
+    k_evolve<<<ge, EVO_WARPS * 32, 0, st>>>(b->d_blocks, b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds,
+                                            b->d_evo_seq, b->d_raw);
+    RC_CUDA(cudaGetLastError());
+    b->stats.launches++;
+  }
   {
     dim3 g((unsigned)b->n_blocks, (unsigned)std::min(maxchunks, 2048));
     k_pack<<<g, 256, 0, st>>>(b->d_blocks, b->d_raw, b->d_cls, ctx->d_lut);
@@ -1062,6 +1198,22 @@ extern "C" int rc_score_aln(rc_ctx* ctx, const rc_block_desc* block, const rc_pa
   if (r != RC_OK) return r;
   if ((r = rc_batch_upload(b)) == RC_OK && (r = rc_batch_run(b)) == RC_OK && (r = rc_batch_download(b)) == RC_OK)
     r = rc_batch_native_hss(b, 0, out, max_hss, n_hss);
+  rc_batch_destroy(b);
+  return r;
+}
+
+extern "C" int rc_score_samples_evolve(rc_ctx* ctx, const rc_block_desc* block, const rc_tree_desc* tree,
+                                       const unsigned int* seeds, int rng, const rc_params* params, const int* blosum,
+                                       double* max_scores) {
+  if (!ctx || !block || !max_scores) return RC_ERR_ARG;
+  rc_block_desc d = *block;
+  d.samples = nullptr;
+  rc_batch* b = nullptr;
+  int r = rc_batch_create(ctx, &d, 1, params, blosum, &b);
+  if (r != RC_OK) return r;
+  if ((r = rc_batch_set_evolve(b, 0, tree, seeds, rng)) == RC_OK && (r = rc_batch_upload(b)) == RC_OK &&
+      (r = rc_batch_run(b)) == RC_OK && (r = rc_batch_download(b)) == RC_OK)
+    r = rc_batch_max_scores(b, 0, max_scores);
   rc_batch_destroy(b);
   return r;
 }
