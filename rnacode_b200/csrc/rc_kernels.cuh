@@ -248,6 +248,9 @@ __global__ void __launch_bounds__(256)
       out = sigma + it.sigma_off[s][f] + ((size_t)inst_l * bd.ntiles[f] + tile) * bd.sig_tile + (size_t)c * bd.sig_cs;
     }
     const float* sc = scores + bd.scores_off + (size_t)s * N * 4;
+    // layout 1: the step's z word (2 bits per species).  Entries of species with a frameshift at this codon are never
+    // read by the recurrence (src/score.c:512-533 ignores sigma); they are stored as +0
+    const unsigned zword = (bd.layout == 1) ? ztiles[bd.z_off[s][f] + (size_t)tile * bd.zstride + c] : 0u;
     for (int k = 0; k < NK; k++) {
       const unsigned char* rowk = base + (size_t)(k + 1) * cols;
       const unsigned b1 = rowk[c1], b2 = rowk[c2], b3 = rowk[c3];
@@ -269,11 +272,12 @@ __global__ void __launch_bounds__(256)
           v = s_tab.blosum[pepA * 24 + pepB] - sc[(k + 1) * 4 + h];  // observed - expected, float32 (:422-425)
         }
       }
+      if ((zword >> (2 * k)) & 1u) v = 0.0f;
       if (bd.layout == 2) out[(k >> 2) * 128 + (k & 3)] = v;
       else out[(size_t)k * ks] = v;
     }
     if (bd.layout == 1) {  // the step's z word rides in the sigma row, right after the NK sigma values
-      out[NK] = __uint_as_float(ztiles[bd.z_off[s][f] + (size_t)tile * bd.zstride + c]);
+      out[NK] = __uint_as_float(zword);
       if (j == bd.sites[f] - 1)  // rows of the last tile past the end of the frame: sigma = 0, no frameshift
         for (int cc = c + 1; cc < TILE; cc++)
           for (int q = 0; q <= NK; q++) out[(size_t)(cc - c) * bd.sig_cs + q] = 0.0f;
@@ -886,7 +890,8 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
   constexpr int RS = RegCfg<NK>::RS;
   constexpr int SIG_TILE = RegCfg<NK>::SIG_TILE;
   constexpr int STAGE_BYTES = RegCfg<NK>::STAGE_BYTES;
-  __shared__ __align__(128) unsigned char smem[DP_WARPS][2 * STAGE_BYTES + 16];
+  // ring of two stages + the two mbarriers + room for the steady-state loop's read-ahead of two step rows
+  __shared__ __align__(128) unsigned char smem[DP_WARPS][2 * STAGE_BYTES + 16 + 2 * RS * 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const CtaDesc cd = ctas[blockIdx.x];
   const Item& it = items[cd.item];
@@ -953,8 +958,11 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
         }
       }
     } else {
-      // steady state: two end codons per iteration; the rows of the next iteration are requested before the
-      // (serial) tail of this iteration's species sums is tested
+      // steady state: two end codons per iteration.  Pairs without any frameshift run one straight-line block (the
+      // species-sum chain of the first codon overlaps the state updates of the second); other pairs take the two
+      // codons one after the other through reg_update.  The rows of the next iteration are requested right after
+      // the arithmetic (unconditionally, so that the loop carries them without register copies: past the tile
+      // they hit the other stage or the pad, and are discarded).
       float svA[RS], svB[RS];
       reg_load_row<NK>(a0, svA);
       reg_load_row<NK>(a0 + RS * 4, svB);
@@ -967,10 +975,8 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
           sumA = reg_update<NK>(S0, S1, S2, svA, false, j0 + c, r0, Delta, Omega, omega);
           sumB = reg_update<NK>(S0, S1, S2, svB, false, j0 + c + 1, r0, Delta, Omega, omega);
         }
-        if (c + 2 < TILE) {
-          reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
-          reg_load_row<NK>(a0 + (c + 3) * RS * 4, svB);
-        }
+        reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
+        reg_load_row<NK>(a0 + (c + 3) * RS * 4, svB);
         if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
           lb.x = reg_check_row(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
           lb.y = reg_check_row(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
