@@ -49,9 +49,12 @@ struct BlockDev {
   int n_inst;               // 1 (native) + n_samples
   int inst_stride;          // bytes between consecutive instances in raw/cls (N*cols rounded up to 16)
   int zstride;              // u32 words per z tile: layout 0: NK rounded up to 4 (one word per species);
-                            // layout 1: TILE (one word per step, 2 bits per species)
+                            // layout 1: TILE (one word per step, 2 bits per species); layout 3: nchunk*TILE
   int layout;               // 0: sigma tile [k][TILE] (k_dp, any NK); 1: sigma tile [TILE][RS] (k_dp_reg, NK <= 16);
-                            // 2: sample-major [group of 32 instances][step][RSB/4][lane][4] (k_dp_smp, short blocks)
+                            // 2: sample-major [group of 32 instances][step][RSB/4][lane][4] (k_dp_smp, short blocks);
+                            // 3: sigma tile [chunk][TILE][RS] (k_dp_chain: species cut into nchunk chunks of <= nkw)
+  int nchunk, nkw;          // layout 3: chunks and species per chunk (template NK of k_dp_chain); chunk g holds
+  int chunk_base, chunk_rem;  //   chunk_base + (g < chunk_rem) species starting at g*chunk_base + min(g, chunk_rem)
   int sig_tile;             // floats per sigma tile
   int sig_ks, sig_cs;       // strides (floats) of species / step inside a sigma tile
   int sites[3], ntiles[3];  // codon sites / tiles per frame

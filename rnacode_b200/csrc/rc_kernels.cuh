@@ -142,11 +142,17 @@ __global__ void __launch_bounds__(256) k_prep(const BlockDev* __restrict__ block
       for (int w = threadIdx.x; w < work; w += blockDim.x) {
         const int tile = w / bd.zstride, u = w % bd.zstride;
         unsigned word = 0;
-        // layout 0: u = species, loop over the tile's steps; layout 1: u = step, loop over species
-        const int n_inner = bd.layout ? NK : TILE;
+        // layout 0: u = species, loop over the tile's steps; layout 1: u = step, loop over species;
+        // layout 3: u = chunk*TILE + step, loop over the chunk's species
+        int n_inner = bd.layout ? NK : TILE, kfirst = 0;
+        if (bd.layout == 3) {
+          const int gch = u / TILE;
+          kfirst = gch * bd.chunk_base + min(gch, bd.chunk_rem);
+          n_inner = bd.chunk_base + (gch < bd.chunk_rem ? 1 : 0);
+        }
         for (int v = 0; v < n_inner; v++) {
-          const int k = bd.layout ? v : u;
-          const int c = bd.layout ? u : v;
+          const int k = bd.layout == 3 ? kfirst + v : (bd.layout ? v : u);
+          const int c = bd.layout == 3 ? u % TILE : (bd.layout ? u : v);
           const int j = tile * TILE + c;
           if (k >= NK || j >= sites) continue;
           const unsigned char* rowk = nat + (size_t)(k + 1) * cols;
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(256) k_prep(const BlockDev* __restrict__ block
           diff = diff < 0 ? -diff : diff;
           const int m = diff % 3;
           if (bd.layout) {
-            if (m != 0) word |= (m == 2 ? 3u : 1u) << (2 * k);  // bit 2k: z != 0, bit 2k+1: z == -1
+            if (m != 0) word |= (m == 2 ? 3u : 1u) << (2 * v);  // bit 2v: z != 0, bit 2v+1: z == -1 (v = species inside the word)
           } else {
             if (m != 0) word |= 1u << c;
             if (m == 2) word |= 1u << (16 + c);
@@ -250,8 +256,27 @@ __global__ void __launch_bounds__(256)
     const float* sc = scores + bd.scores_off + (size_t)s * N * 4;
     // layout 1: the step's z word (2 bits per species).  Entries of species with a frameshift at this codon are never
     // read by the recurrence (src/score.c:512-533 ignores sigma); they are stored as +0
-    const unsigned zword = (bd.layout == 1) ? ztiles[bd.z_off[s][f] + (size_t)tile * bd.zstride + c] : 0u;
+    unsigned zword = (bd.layout == 1) ? ztiles[bd.z_off[s][f] + (size_t)tile * bd.zstride + c] : 0u;
+    // layout 3 (k_dp_chain): species chunk gch holds csize species from cfirst on; its rows are [chunk][step][rs3]
+    const int rs3 = (bd.nkw + 1 + 3) / 4 * 4;
+    int gch = 0, cfirst = 0, csize = bd.chunk_base + (bd.chunk_rem > 0 ? 1 : 0);
+    float* out3 = nullptr;
+    const unsigned* z3 = nullptr;
+    if (bd.layout == 3) {
+      out3 = sigma + it.sigma_off[s][f] + ((size_t)inst_l * bd.ntiles[f] + tile) * bd.sig_tile + (size_t)c * rs3;
+      z3 = ztiles + bd.z_off[s][f] + (size_t)tile * bd.zstride + c;
+      zword = z3[0];
+    }
     for (int k = 0; k < NK; k++) {
+      if (bd.layout == 3 && k == cfirst + csize) {  // close the chunk: dummy species (if any) and the chunk's z word
+        float* oc = out3 + (size_t)gch * TILE * rs3;
+        for (int q = csize; q < bd.nkw; q++) oc[q] = 0.0f;
+        oc[bd.nkw] = __uint_as_float(zword);
+        gch++;
+        cfirst = k;
+        csize = bd.chunk_base + (gch < bd.chunk_rem ? 1 : 0);
+        zword = z3[(size_t)gch * TILE];
+      }
       const unsigned char* rowk = base + (size_t)(k + 1) * cols;
       const unsigned b1 = rowk[c1], b2 = rowk[c2], b3 = rowk[c3];
       const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
@@ -272,9 +297,23 @@ __global__ void __launch_bounds__(256)
           v = s_tab.blosum[pepA * 24 + pepB] - sc[(k + 1) * 4 + h];  // observed - expected, float32 (:422-425)
         }
       }
-      if ((zword >> (2 * k)) & 1u) v = 0.0f;
+      if (bd.layout == 3) {
+        if ((zword >> (2 * (k - cfirst))) & 1u) v = 0.0f;
+        out3[(size_t)gch * TILE * rs3 + (k - cfirst)] = v;
+        continue;
+      }
+      if (bd.layout == 1 && ((zword >> (2 * k)) & 1u)) v = 0.0f;
       if (bd.layout == 2) out[(k >> 2) * 128 + (k & 3)] = v;
       else out[(size_t)k * ks] = v;
+    }
+    if (bd.layout == 3) {
+      float* oc = out3 + (size_t)gch * TILE * rs3;
+      for (int q = csize; q < bd.nkw; q++) oc[q] = 0.0f;
+      oc[bd.nkw] = __uint_as_float(zword);
+      if (j == bd.sites[f] - 1)  // rows of the last tile past the end of the frame: sigma = 0, no frameshift
+        for (int cc = c + 1; cc < TILE; cc++)
+          for (int g2 = 0; g2 < bd.nchunk; g2++)
+            for (int q = 0; q <= bd.nkw; q++) out3[(size_t)g2 * TILE * rs3 + (size_t)(cc - c) * rs3 + q] = 0.0f;
     }
     if (bd.layout == 1) {  // the step's z word rides in the sigma row, right after the NK sigma values
       out[NK] = __uint_as_float(zword);
@@ -477,7 +516,12 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
   const int strand = cd.sf / 3, frame = cd.sf % 3;
   const int sites = bd.sites[frame], ntiles = bd.ntiles[frame], NK = bd.NK, zstride = bd.zstride;
   const int ngroups = (sites + 32 * R - 1) / (32 * R);
-  const int task = cd.task0 + warp;
+  // A CTA descriptor covers DP_WARPS tasks.  Very wide alignments need so much shared-memory state per task that the
+  // kernel is launched with fewer warps; each warp then takes several of the CTA's tasks, one after the other.
+  const int nwarps = blockDim.x >> 5;
+#pragma unroll 1
+  for (int tsk = warp; tsk < DP_WARPS; tsk += nwarps) {
+  const int task = cd.task0 + tsk;
   if (task >= it.ninst * ngroups) return;  // warps are independent: no CTA-wide barrier below
   const int inst_l = task / ngroups, g = task % ngroups;
   const int row_base = g * 32 * R;
@@ -660,6 +704,8 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
       }
     }
   }
+  __syncwarp();  // every copy into the ring has been waited for: the barriers may be re-initialised for the next task
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -756,10 +802,12 @@ __device__ __forceinline__ void reg_shift(bool neg, float Delta, float Omega, fl
 
 // One end codon for all species: state update + species sum (no getHSS test).  The kernel holds exactly
 // one copy of this code (instruction-cache footprint matters more than the few uniform branches).
-template <int NK>
+// HAS_IN: the species sum continues a partial sum `sin` handed over by the warp that owns the preceding species
+// (k_dp_chain); otherwise it starts with the first species (0 + m == m).
+template <int NK, bool HAS_IN = false>
 __device__ __forceinline__ float2 reg_update(float2 (&S0)[NK], float2 (&S1)[NK], float2 (&S2)[NK],
                                              const float (&sv)[RegCfg<NK>::RS], bool diag, int j, int r0, float Delta,
-                                             float Omega, float omega) {
+                                             float Omega, float omega, float2 sin = make_float2(0.0f, 0.0f)) {
   const unsigned zw = __float_as_uint(sv[NK]);
   if (diag) {
     // a row starts from (0,0,0) at its first end codon (src/score.c:500-504)
@@ -780,7 +828,7 @@ __device__ __forceinline__ float2 reg_update(float2 (&S0)[NK], float2 (&S1)[NK],
       S1[k] = add2s(S1[k], omega);
       S2[k] = add2s(S2[k], omega);
       const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
-      sum = (k == 0) ? m : add2(sum, m);  // species sum in k order (src/score.c:834-838); 0 + m == m
+      sum = (k == 0) ? (HAS_IN ? add2(sin, m) : m) : add2(sum, m);  // species sum in k order (src/score.c:834-838); 0 + m == m
     }
   } else {
     // some species has a frameshift here: test groups of three species, branch per species only inside a hit group
@@ -811,7 +859,7 @@ __device__ __forceinline__ float2 reg_update(float2 (&S0)[NK], float2 (&S1)[NK],
 #pragma unroll
       for (int k = g; k < g + 3 && k < NK; k++) {
         const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
-        sum = (k == 0) ? m : add2(sum, m);
+        sum = (k == 0) ? (HAS_IN ? add2(sin, m) : m) : add2(sum, m);
       }
     }
   }
@@ -820,17 +868,18 @@ __device__ __forceinline__ float2 reg_update(float2 (&S0)[NK], float2 (&S1)[NK],
 
 // Two consecutive frameshift-free end codons in one straight-line block: the species-sum chain of the
 // first overlaps with the state updates of the second.
-template <int NK>
+template <int NK, bool HAS_IN = false>
 __device__ __forceinline__ void reg_pair_fast(float2 (&S0)[NK], float2 (&S1)[NK], float2 (&S2)[NK],
                                               const float (&svA)[RegCfg<NK>::RS], const float (&svB)[RegCfg<NK>::RS],
-                                              float omega, float2& sumA, float2& sumB) {
+                                              float omega, float2& sumA, float2& sumB,
+                                              float2 sinA = make_float2(0.0f, 0.0f), float2 sinB = make_float2(0.0f, 0.0f)) {
 #pragma unroll
   for (int k = 0; k < NK; k++) {
     S0[k] = add2s(S0[k], svA[k]);
     S1[k] = add2s(S1[k], omega);
     S2[k] = add2s(S2[k], omega);
     const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
-    sumA = (k == 0) ? m : add2(sumA, m);
+    sumA = (k == 0) ? (HAS_IN ? add2(sinA, m) : m) : add2(sumA, m);
   }
 #pragma unroll
   for (int k = 0; k < NK; k++) {
@@ -838,7 +887,7 @@ __device__ __forceinline__ void reg_pair_fast(float2 (&S0)[NK], float2 (&S1)[NK]
     S1[k] = add2s(S1[k], omega);
     S2[k] = add2s(S2[k], omega);
     const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
-    sumB = (k == 0) ? m : add2(sumB, m);
+    sumB = (k == 0) ? (HAS_IN ? add2(sinB, m) : m) : add2(sumB, m);
   }
 }
 
@@ -996,6 +1045,187 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
 #pragma unroll
   for (int t = 0; t < R; t++)
     if (r0 + t < sites) rec_copy(grec + t, rec0 + t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// (c) k_dp_chain: the register-resident DP for WIDE alignments (N-1 > 16).  The species are cut into W chunks
+// of at most NK species; the CTA has W warps that all work on the same task (instance, strand, frame, 64 start
+// codons), warp g owning chunk g with its 3*NK float2 states in registers exactly like k_dp_reg.  The species
+// sum of the reference is one k-ordered float chain (src/score.c:834-838), so it is pipelined through the warps:
+// warp g continues the partial sums warp g-1 left in shared memory for every (end codon, row) of a tile
+// (2-stage hand-off buffers, full/empty mbarriers per boundary), adds its own species in order and passes the
+// result on; the last warp owns the getHSS digest.  Warp g therefore runs about one tile behind warp g-1.
+// Chunks that are one species short carry a dummy species (sigma = +0, z = 0, state 0): with omega <= 0 its
+// contribution max3(0, t*omega, t*omega) = +0 leaves the sum unchanged (x + 0 == x).
+// sigma layout 3: [instance][tile][chunk][step][RS] (RS = NK sigma values + the chunk's z word, padded to 16 B).
+// ---------------------------------------------------------------------------------------------
+constexpr int CHAIN_MAX_WARPS = 16;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float2 lds_f2(unsigned a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f2(unsigned a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+
+template <int NK>
+struct ChainCfg {
+  static constexpr int RS = RegCfg<NK>::RS;
+  static constexpr int STAGE_BYTES = RegCfg<NK>::STAGE_BYTES;
+  static constexpr int RING_BYTES = 2 * STAGE_BYTES + 16 + 2 * RS * 4;  // two stages, two mbarriers, read-ahead pad
+  static constexpr int HAND_BYTES = 2 * TILE * 32 * 8;                  // per boundary: [stage][step][lane] float2
+  static __host__ __device__ size_t smem_bytes(int W) {
+    return (size_t)W * RING_BYTES + (size_t)(W - 1) * HAND_BYTES + (size_t)(W - 1) * 32 + 64 * sizeof(RowRec);
+  }
+};
+
+template <int NK>
+__global__ void __launch_bounds__(CHAIN_MAX_WARPS * 32)
+    k_dp_chain(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
+               const float* __restrict__ sigma, RowRec* __restrict__ recs, Params prm, int band_slots) {
+  constexpr int R = 2;
+  constexpr int RS = ChainCfg<NK>::RS;
+  constexpr int SIG_TILE = RegCfg<NK>::SIG_TILE;
+  constexpr int STAGE_BYTES = ChainCfg<NK>::STAGE_BYTES;
+  constexpr int RING_BYTES = ChainCfg<NK>::RING_BYTES;
+  constexpr int HAND_BYTES = ChainCfg<NK>::HAND_BYTES;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int W = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const CtaDesc cd = ctas[blockIdx.x];
+  const Item& it = items[cd.item];
+  const BlockDev& bd = blocks[it.block];
+  const int strand = cd.sf / 3, frame = cd.sf % 3;
+  const int sites = bd.sites[frame], ntiles = bd.ntiles[frame];
+  const int ngroups = (sites + 32 * R - 1) / (32 * R);
+  const int task = cd.task0;  // one task per CTA
+  const int inst_l = task / ngroups, g = task % ngroups;
+  const int row_base = g * 32 * R;
+  const int r0 = row_base + lane * R;
+  const bool first = warp == 0, last = warp == W - 1;
+
+  unsigned char* ring = smem + (size_t)warp * RING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * STAGE_BYTES);
+  unsigned char* hand = smem + (size_t)W * RING_BYTES;
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(hand + (size_t)(W - 1) * HAND_BYTES);  // [boundary][full0, full1, empty0, empty1]
+  RowRec* srec = reinterpret_cast<RowRec*>(hbar + 4 * (W - 1));
+  unsigned ring_a = smem_u32(ring);
+  asm volatile("" : "+r"(ring_a));
+  const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * ntiles * bd.sig_tile + (size_t)warp * SIG_TILE;
+  const size_t tile_stride = (size_t)bd.sig_tile;
+  const int t0 = row_base / TILE;
+  const int t_last_diag = (row_base + 32 * R - 1) / TILE;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    if (!last)
+      for (int q = 0; q < 4; q++) mbar_init(&hbar[4 * warp + q], 1);
+    mbar_fence_init();
+    for (int s = 0; s < 2 && t0 + s < ntiles; s++) {
+      mbar_expect_tx(&bars[s], STAGE_BYTES);
+      bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(t0 + s) * tile_stride, STAGE_BYTES, &bars[s]);
+    }
+  }
+  RowRec* rec0 = &srec[lane * R];
+  if (last) {
+    rec_init(rec0);
+    rec_init(rec0 + 1);
+  }
+  __syncthreads();  // hand-off barriers are initialised before any neighbour touches them
+
+  float2 S0[NK], S1[NK], S2[NK];
+#pragma unroll
+  for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
+  float2 lb = make_float2(-INFINITY, -INFINITY);
+  const float Delta = prm.Delta, Omega = prm.Omega;
+  float omega = prm.omega;
+  asm volatile("" : "+f"(omega));
+  const float fNK = bd.fNK, rcpNK = bd.rcpNK;
+  const unsigned hand_in = smem_u32(hand) + (unsigned)((warp - 1) * HAND_BYTES) + lane * 8;  // valid for warp > 0
+  const unsigned hand_out = smem_u32(hand) + (unsigned)(warp * HAND_BYTES) + lane * 8;       // valid for warp < W-1
+  uint64_t* full_in = &hbar[4 * (warp - 1)];
+  uint64_t* empty_in = full_in + 2;
+  uint64_t* full_out = &hbar[4 * warp];
+  uint64_t* empty_out = full_out + 2;
+
+#pragma unroll 1
+  for (int tile = t0; tile < ntiles; tile++) {
+    const int s = (tile - t0) & 1;
+    const unsigned parity = ((tile - t0) >> 1) & 1;
+    const unsigned a0 = ring_a + s * STAGE_BYTES;
+    const unsigned hin = hand_in + s * (TILE * 256), hout = hand_out + s * (TILE * 256);
+    const int j0 = tile * TILE;
+    const bool diag = tile <= t_last_diag;
+    mbar_wait(&bars[s], parity);
+    if (!first) mbar_wait(&full_in[s], parity);                           // partial sums of this tile have arrived
+    if (!last && tile - t0 >= 2) mbar_wait(&empty_out[s], parity ^ 1u);   // the next warp is done with this stage
+    if (diag) {
+#pragma unroll 1
+      for (int c = 0; c < TILE; c++) {
+        float sv[RS];
+        reg_load_row<NK>(a0 + c * RS * 4, sv);
+        float2 sin = make_float2(0.0f, 0.0f);
+        if (!first) sin = lds_f2(hin + c * 256);
+        const float2 sum = reg_update<NK, true>(S0, S1, S2, sv, true, j0 + c, r0, Delta, Omega, omega, sin);
+        if (!last) {
+          sts_f2(hout + c * 256, sum);
+        } else if (fmaxf(sum.x, sum.y) > 0.0f) {
+          lb.x = reg_check_row(sum.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          lb.y = reg_check_row(sum.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+        }
+      }
+    } else {
+      float svA[RS], svB[RS];
+      reg_load_row<NK>(a0, svA);
+      reg_load_row<NK>(a0 + RS * 4, svB);
+#pragma unroll 1
+      for (int c = 0; c < TILE; c += 2) {
+        float2 sumA, sumB;
+        float2 sinA = make_float2(0.0f, 0.0f), sinB = make_float2(0.0f, 0.0f);
+        if (!first) {
+          sinA = lds_f2(hin + c * 256);
+          sinB = lds_f2(hin + (c + 1) * 256);
+        }
+        if ((__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u) {
+          reg_pair_fast<NK, true>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
+        } else {
+          sumA = reg_update<NK, true>(S0, S1, S2, svA, false, j0 + c, r0, Delta, Omega, omega, sinA);
+          sumB = reg_update<NK, true>(S0, S1, S2, svB, false, j0 + c + 1, r0, Delta, Omega, omega, sinB);
+        }
+        reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
+        reg_load_row<NK>(a0 + (c + 3) * RS * 4, svB);
+        if (!last) {
+          sts_f2(hout + c * 256, sumA);
+          sts_f2(hout + (c + 1) * 256, sumB);
+        } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
+          lb.x = reg_check_row(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          lb.y = reg_check_row(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          lb.x = reg_check_row(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          lb.y = reg_check_row(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (tile + 2 < ntiles) {
+        mbar_expect_tx(&bars[s], STAGE_BYTES);
+        bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(tile + 2) * tile_stride, STAGE_BYTES, &bars[s]);
+      }
+      if (!first) mbar_arrive(&empty_in[s]);
+      if (!last) mbar_arrive(&full_out[s]);
+    }
+  }
+  if (last) {
+    RowRec* grec = recs + it.rec_off[strand][frame] + (size_t)inst_l * sites + r0;
+#pragma unroll
+    for (int t = 0; t < R; t++)
+      if (r0 + t < sites) rec_copy(grec + t, rec0 + t);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -38,6 +38,7 @@ struct rc_ctx {
   long band_slots = REC_SLOTS;
   long scratch_mb = 2048;
   long no_smp = 0;
+  long no_chain = 0;
   int smem_optin = 0;
   int sm_count = 0;
   // device-memory cache: buffers of destroyed batches are kept and handed to the next batch, so that a
@@ -103,9 +104,12 @@ static void ctx_free(rc_ctx* ctx, void* p) {
 namespace {
 
 // DP launch classes: 0..15 = k_dp_reg<NK = class+1>; 16 = k_dp<R = 2> (17 <= NK <= 24); 17 = k_dp<R = 1>;
-// 18..33 = k_dp_smp<NK = class-17> (sample-major, short blocks)
-constexpr int N_CLASSES = 2 * REG_MAX_NK + 2;
+// 18..33 = k_dp_smp<NK = class-17> (sample-major, short blocks);
+// 34.. = k_dp_chain<NKW> with W warps: class = CHAIN_CLASS0 + (W-2)*CHAIN_NKW_SPAN + (NKW - CHAIN_NKW_MIN)
 constexpr int SMP_CLASS0 = REG_MAX_NK + 2;
+constexpr int CHAIN_CLASS0 = 2 * REG_MAX_NK + 2;
+constexpr int CHAIN_NKW_MIN = 8, CHAIN_NKW_MAX = 12, CHAIN_NKW_SPAN = CHAIN_NKW_MAX - CHAIN_NKW_MIN + 1;
+constexpr int N_CLASSES = CHAIN_CLASS0 + (CHAIN_MAX_WARPS - 1) * CHAIN_NKW_SPAN;
 constexpr size_t SMP_SMEM_MAX = 200 * 1024;  // sigma table + z words of one CTA of k_dp_smp
 constexpr int SMP_MIN_INST = 16;             // fewer instances than this: the row-major kernels are the better fit
 
@@ -126,6 +130,7 @@ struct EventPair {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int class_of(const BlockDev& bd) {
+  if (bd.layout == 3) return CHAIN_CLASS0 + (bd.nchunk - 2) * CHAIN_NKW_SPAN + (bd.nkw - CHAIN_NKW_MIN);
   if (bd.layout == 2) return SMP_CLASS0 + bd.NK - 1;
   if (bd.layout == 1) return bd.NK - 1;
   return bd.NK <= 24 ? REG_MAX_NK : REG_MAX_NK + 1;
@@ -149,7 +154,19 @@ size_t sigma_floats_sf(const BlockDev& bd, int f, int ninst) {
 // sigma / z layout of a block (see BlockDev)
 void set_layout(BlockDev& bd, int layout) {
   bd.layout = layout;
-  if (layout == 2) {  // z as in layout 1 (one word per step); sigma addressed explicitly (sigma_floats_sf)
+  bd.nchunk = bd.nkw = bd.chunk_base = bd.chunk_rem = 0;
+  if (layout == 3) {  // species chunks for k_dp_chain
+    const int W = (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX;
+    bd.nchunk = W;
+    bd.chunk_base = bd.NK / W;
+    bd.chunk_rem = bd.NK % W;
+    bd.nkw = bd.chunk_base + (bd.chunk_rem ? 1 : 0);
+    const int rs = (bd.nkw + 1 + 3) / 4 * 4;
+    bd.sig_tile = W * TILE * rs;
+    bd.sig_ks = 1;
+    bd.sig_cs = rs;
+    bd.zstride = W * TILE;
+  } else if (layout == 2) {  // z as in layout 1 (one word per step); sigma addressed explicitly (sigma_floats_sf)
     bd.sig_tile = 0;
     bd.sig_ks = 0;
     bd.sig_cs = 0;
@@ -323,6 +340,8 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->band_slots = value;
   } else if (k == "no_smp") {
     ctx->no_smp = value ? 1 : 0;
+  } else if (k == "no_chain") {
+    ctx->no_chain = value ? 1 : 0;
   } else if (k == "scratch_mb") {
     if (value < 1) { ctx_fail(ctx, "scratch_mb must be >= 1"); return RC_ERR_ARG; }
     ctx->scratch_mb = value;
@@ -392,7 +411,8 @@ static void build_ctas(const std::vector<BlockDev>& blocks, const std::vector<It
       if (sites <= 0) continue;
       const long long ngroups = (sites + 32 * R - 1) / (32 * R);
       const long long ntasks = ngroups * it.ninst;
-      for (long long t = 0; t < ntasks; t += DP_WARPS) out.push_back(CtaDesc{(int)i, sf, (int)t});
+      const int per_cta = (bd.layout == 3 && want_class >= 0) ? 1 : DP_WARPS;  // k_dp_chain: the CTA's warps share one task
+      for (long long t = 0; t < ntasks; t += per_cta) out.push_back(CtaDesc{(int)i, sf, (int)t});
     }
   }
 }
@@ -463,6 +483,9 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     cells += (double)bd.n_inst * 2.0 * bd.NK * P;
     {
       int layout = (bd.NK <= REG_MAX_NK && params->Delta <= 0.0f) ? 1 : 0;
+      if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && !ctx->no_chain &&
+          (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX <= CHAIN_MAX_WARPS)
+        layout = 3;  // wide alignment: species chunks pipelined through the warps of a CTA
       if (layout == 1 && !ctx->no_smp && bd.n_inst >= SMP_MIN_INST && bd.sites[0] >= 1 &&
           smp_smem_bytes(bd, 0) <= std::min<size_t>(SMP_SMEM_MAX, (size_t)ctx->smem_optin) &&
           (size_t)5 * 32 * (bd.cols + 8) <= SMP_SMEM_MAX)
@@ -775,13 +798,15 @@ template <int R, bool DENSE>
 static int launch_dp(rc_batch* b, const CtaDesc* d_ctas, size_t ncta, int maxNK, int maxZs) {
   rc_ctx* ctx = b->ctx;
   if (ncta == 0) return RC_OK;
-  const size_t smem = DP_WARPS * DpSmem<R>::per_warp(maxNK, maxZs);
-  if (smem > (size_t)ctx->smem_optin) {
+  const size_t per_warp = DpSmem<R>::per_warp(maxNK, maxZs);
+  const int nw = (int)std::min<size_t>(DP_WARPS, (size_t)ctx->smem_optin / per_warp);
+  if (nw < 1) {
     ctx_fail(ctx, "alignment has too many rows for the shared-memory resident DP state (N-1 = " + std::to_string(maxNK) + ")");
     return RC_ERR_ARG;
   }
+  const size_t smem = nw * per_warp;
   RC_CUDA(cudaFuncSetAttribute(k_dp<R, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dp<R, DENSE><<<(unsigned)ncta, DP_WARPS * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+  k_dp<R, DENSE><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
                                                                       b->d_recs, b->d_dense, b->prm, (int)ctx->band_slots,
                                                                       maxNK, maxZs);
   RC_CUDA(cudaGetLastError());
@@ -856,6 +881,35 @@ static int launch_dp_smp(rc_batch* b, int NK, const CtaDesc* d_ctas, size_t ncta
     case 15: return launch_dp_smp_nk<15>(b, d_ctas, ncta, smem);
     case 16: return launch_dp_smp_nk<16>(b, d_ctas, ncta, smem);
     default: ctx_fail(b->ctx, "internal: k_dp_smp NK out of range"); return RC_ERR_STATE;
+  }
+}
+
+template <int NKW>
+static int launch_dp_chain_nk(rc_batch* b, int W, const CtaDesc* d_ctas, size_t ncta) {
+  rc_ctx* ctx = b->ctx;
+  const size_t smem = ChainCfg<NKW>::smem_bytes(W);
+  if (smem > (size_t)ctx->smem_optin) {
+    ctx_fail(ctx, "internal: k_dp_chain shared memory exceeds the device limit");
+    return RC_ERR_STATE;
+  }
+  RC_CUDA(cudaFuncSetAttribute(k_dp_chain<NKW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dp_chain<NKW><<<(unsigned)ncta, W * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_recs, b->prm,
+                                                                (int)ctx->band_slots);
+  RC_CUDA(cudaGetLastError());
+  b->stats.launches++;
+  b->stats.dp_launches++;
+  return RC_OK;
+}
+
+static int launch_dp_chain(rc_batch* b, int NKW, int W, const CtaDesc* d_ctas, size_t ncta) {
+  if (ncta == 0) return RC_OK;
+  switch (NKW) {
+    case 8: return launch_dp_chain_nk<8>(b, W, d_ctas, ncta);
+    case 9: return launch_dp_chain_nk<9>(b, W, d_ctas, ncta);
+    case 10: return launch_dp_chain_nk<10>(b, W, d_ctas, ncta);
+    case 11: return launch_dp_chain_nk<11>(b, W, d_ctas, ncta);
+    case 12: return launch_dp_chain_nk<12>(b, W, d_ctas, ncta);
+    default: ctx_fail(b->ctx, "internal: k_dp_chain NKW out of range"); return RC_ERR_STATE;
   }
 }
 
@@ -1047,7 +1101,10 @@ extern "C" int rc_batch_run(rc_batch* b) {
       for (int cl = 0; cl < N_CLASSES; cl++) {
         if (ch.ncta[cl] == 0) continue;
         int rcode;
-        if (cl >= SMP_CLASS0) rcode = launch_dp_smp(b, cl - SMP_CLASS0 + 1, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smp_smem);
+        if (cl >= CHAIN_CLASS0)
+          rcode = launch_dp_chain(b, CHAIN_NKW_MIN + (cl - CHAIN_CLASS0) % CHAIN_NKW_SPAN, 2 + (cl - CHAIN_CLASS0) / CHAIN_NKW_SPAN,
+                                  b->d_ctas + ch.cta0[cl], ch.ncta[cl]);
+        else if (cl >= SMP_CLASS0) rcode = launch_dp_smp(b, cl - SMP_CLASS0 + 1, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smp_smem);
         else if (cl < REG_MAX_NK) rcode = launch_dp_reg(b, cl + 1, b->d_ctas + ch.cta0[cl], ch.ncta[cl]);
         else if (cl == REG_MAX_NK) rcode = launch_dp<2, false>(b, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.maxNK[cl], ch.maxZs[cl]);
         else rcode = launch_dp<1, false>(b, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.maxNK[cl], ch.maxZs[cl]);

@@ -98,6 +98,10 @@ SHAPES = [
     (3, 9, 4, 0.0), (3, 3, 2, 0.0), (4, 5, 2, 0.0), (2, 60, 3, 0.02), (10, 120, 33, 0.0067), (10, 120, 5, 0.0),
     (6, 47, 7, 0.05), (6, 48, 7, 0.05), (6, 49, 7, 0.05), (10, 97, 3, 0.1), (26, 150, 5, 0.02), (50, 130, 3, 0.02),
     (100, 96, 2, 0.02), (10, 600, 4, 0.02), (8, 1000, 2, 0.0067),
+    # wide alignments (k_dp_chain: species chunks pipelined through the warps of a CTA): 2, 3, 4, 9 and 16 chunks,
+    # chunk sizes with and without a dummy species, rows longer than several hand-off stages; 17 chunks -> k_dp
+    (18, 700, 3, 0.02), (25, 520, 2, 0.03), (26, 333, 2, 0.0), (38, 410, 2, 0.03), (100, 260, 1, 0.02),
+    (193, 120, 1, 0.02), (200, 70, 1, 0.02),
 ]
 
 
@@ -151,6 +155,36 @@ def test_mixed_batch_and_chunking(oracle):
             exp = oracle.sample_maxima(rows, smp, sf, sr, oracle.params()).astype(np.float32)
             assert np.array_equal(bt.max_scores(i).astype(np.float32), exp), i
         bt.close()
+    finally:
+        ctx.close()
+
+
+def test_chain_kernel_equals_generic_kernel(oracle):
+    """The chained-warp DP (layout 3) and the generic shared-memory DP (no_chain) agree bit for bit, and wide
+    alignments with omega > 0 (dummy species not neutral) are routed to the generic kernel and still exact."""
+    from rnacode_b200 import synth
+    capi = _capi()
+    rows = synth.synth_block(33, 2, 31, 900, gap_rate=0.03)
+    sf, sr = synth.synth_scores(33, 2, 31)
+    smp = synth.synth_samples(33, 2, 3, 31, 900)
+    res = []
+    for no_chain in (0, 1):
+        ctx = capi.Context(0)
+        ctx.set_option("no_chain", no_chain)
+        try:
+            b = _block(rows, sf, sr, smp)
+            res.append((ctx.score_aln(b, capi.make_params(), oracle.blosum62),
+                        ctx.score_samples(b, capi.make_params(), oracle.blosum62).astype(np.float32)))
+        finally:
+            ctx.close()
+    assert res[0][0] == res[1][0] == oracle.score_aln(rows, sf, sr, oracle.params())
+    assert np.array_equal(res[0][1], res[1][1])
+    kw = dict(Delta=-6.0, Omega=-3.0, omega=0.25, stopPenalty_0=-100.0, stopPenalty_k=-5.0)
+    ctx = capi.Context(0)
+    try:
+        b = _block(rows[:20, :300], sf[:20], sr[:20], smp[:, :20, :300])
+        assert ctx.score_aln(b, capi.make_params(**kw), oracle.blosum62) == oracle.score_aln(rows[:20, :300], sf[:20], sr[:20],
+                                                                                             oracle.params(**kw))
     finally:
         ctx.close()
 
