@@ -14,8 +14,12 @@
  * (oracle/Makefile, target `cli`):   -Wl,--wrap=scoreAln -Wl,--wrap=getExtremeValuePars
  * In a source tree one would instead delete the two functions from src/score.c and compile this file.
  *
- * Exact mode: the null alignments come from the reference's own seq-gen (same RNG stream), are scored on the
- * GPU, and the maxima feed the reference's own EVD fit, so HSS, scores and p-values are identical.
+ * Exact mode: the null alignments are the ones the reference's own seq-gen would draw -- the same MT19937 stream
+ * (one CreateSeed() per sample, as src/treeSimulate.c:84), consumed in seq-gen's order, with the transition
+ * matrices seq-gen's own SetMatrix() computes -- and the maxima feed the reference's own EVD fit, so HSS, scores
+ * and p-values are identical.  By default the simulation itself runs on the GPU (kernel d, rc_score_samples_evolve);
+ * RNACODE_CUDA_EVOLVE=host keeps simulateTree/tree2aln/sortAln on the host, RNACODE_CUDA_EVOLVE=philox switches to
+ * the counter-based GPU generator (same distribution, different stream: GPU-RNG mode).
  */
 #include <math.h>
 #include <stdio.h>
@@ -29,9 +33,16 @@
 #include "score.h"
 #include "treeSimulate.h"
 
+/* seq-gen's model state, for the on-GPU simulation of the null alignments */
+#include "model.h"
+#include "nucmodels.h"
+#include "twister.h"
+
 #include "rnacode_cuda.h"
 
 extern parameters pars;
+extern int numSites, equalTstv, numTaxa;
+extern double tstv;
 extern bgModel *models, *modelsRev;
 extern float ****Sk, ****Sk_native, ****Sk_native_rev;
 
@@ -168,6 +179,56 @@ segmentStats *__wrap_scoreAln(const struct aln *inputAln[], TTree *tree, float k
   return res;
 }
 
+/* The tree flattened in the order EvolveSequences visits its nodes (seqgen/evolve.c:400-433): root, subtree of
+ * branch1, of branch2 and, for the unrooted trees PhyML writes, of branch0.  cum = what MutateSequence would pass to
+ * SetState for the branch above the node (SetMatrix(matrix[0], length0 * 1.0), NoRates, seqgen/evolve.c:291-292). */
+static void flatten_node(TTree *tree, TNode *node, int parent, const struct aln *alignment[], int N, int *n, int *par,
+                         int *row, double *cum) {
+  int me = (*n)++, k;
+  par[me] = parent;
+  row[me] = -1;
+  if (node->tipNo != -1)
+    for (k = 0; k < N; k++)
+      if (strcmp(alignment[k]->name, tree->names[node->tipNo]) == 0) row[me] = k; /* sortAln, src/misc.c:150-171 */
+  if (parent < 0) {
+    for (k = 0; k < 16; k++) cum[k] = 0.0;
+    for (k = 0; k < 4; k++) cum[k] = addFreq[k]; /* RandomSequence draws from the cumulative frequencies */
+  } else {
+    SetMatrix(cum + (size_t)me * 16, node->length0 * 1.0);
+  }
+  if (node->tipNo == -1) {
+    flatten_node(tree, node->branch1, me, alignment, N, n, par, row, cum);
+    flatten_node(tree, node->branch2, me, alignment, N, n, par, row, cum);
+    if (parent < 0 && !tree->rooted) flatten_node(tree, node->branch0, me, alignment, N, n, par, row, cum);
+  }
+}
+
+/* seq-gen's model set-up as simulateTree does it before evolving (src/treeSimulate.c:59-93), without evolving */
+static void setup_seqgen_model(TTree *tree, const float freqs[], float kap, int L) {
+  int i;
+  double fR, fY;
+  isNucModel = 1;
+  numStates = 4;
+  model = 0; /* HKY */
+  equalFreqs = 0;
+  equalTstv = 0;
+  for (i = 0; i < 4; i++) nucFreq[i] = (double)freqs[i];
+  fR = nucFreq[0] + nucFreq[2];
+  fY = nucFreq[1] + nucFreq[3];
+  tstv = (double)kap * (nucFreq[0] * nucFreq[2] + nucFreq[1] * nucFreq[3]) / (fR * fY);
+  numSites = L;
+  numTaxa = tree->numTips;
+  SetModel(model);
+}
+
+/* 0: host seq-gen, 1: GPU MT19937 (exact), 2: GPU Philox */
+static int evolve_mode(void) {
+  const char *e = getenv("RNACODE_CUDA_EVOLVE");
+  if (e && strcmp(e, "host") == 0) return 0;
+  if (e && strcmp(e, "philox") == 0) return 2;
+  return 1;
+}
+
 int __wrap_getExtremeValuePars(TTree *tree, const struct aln *alignment[], int sampleN, float maxNativeScore, float *parMu,
                                float *parLambda) {
   rc_block_desc d;
@@ -180,26 +241,53 @@ int __wrap_getExtremeValuePars(TTree *tree, const struct aln *alignment[], int s
   /* under --stop-early work in small batches so that little is simulated past the stopping point;
    * seeds depend on (block, sample) only, so batching never changes the drawn alignments */
   const int batch = pars.stopEarly ? 32 : sampleN;
+  const int mode = evolve_mode();
   size_t per;
+  rc_tree_desc td;
+  int *tpar = NULL, *trow = NULL, nn = 0;
+  double *tcum = NULL;
+  unsigned int *seeds = NULL;
 
   stopCutoff = (int)(pars.cutoff * pars.sampleN); /* src/score.c:992 */
   fill_desc(alignment, &d, &rows, &sf, &sr, &blosum);
   per = (size_t)d.N * d.cols;
-  samples = (char *)malloc(per * (size_t)(batch > 0 ? batch : 1));
+  samples = (char *)malloc(mode == 0 ? per * (size_t)(batch > 0 ? batch : 1) : 16);
   maxScores = (double *)malloc(sizeof(double) * (sampleN > 0 ? sampleN : 1));
+  if (mode != 0 && sampleN > 0) {
+    const int max_nodes = 2 * tree->numTips + 2;
+    tpar = (int *)malloc(sizeof(int) * max_nodes);
+    trow = (int *)malloc(sizeof(int) * max_nodes);
+    tcum = (double *)malloc(sizeof(double) * 16 * max_nodes);
+    seeds = (unsigned int *)malloc(sizeof(unsigned int) * (batch > 0 ? batch : 1));
+    setup_seqgen_model(tree, models[0].freqs, models[0].kappa, d.cols);
+    flatten_node(tree, tree->root, -1, alignment, d.N, &nn, tpar, trow, tcum);
+    td.n_nodes = nn;
+    td.parent = tpar;
+    td.row = trow;
+    td.cum = tcum;
+  }
 
   for (done = 0; done < sampleN && status == 1;) {
     int nb = sampleN - done < batch ? sampleN - done : batch;
-    for (i = 0; i < nb; i++) { /* src/score.c:1006-1010; the library re-imposes the native gaps itself */
-      simulateTree(tree, models[0].freqs, models[0].kappa, d.cols);
-      tree2aln(tree, sampledAln);
-      sortAln(alignment, sampledAln);
-      for (k = 0; k < d.N; k++) memcpy(samples + per * i + (size_t)k * d.cols, sampledAln[k]->seq, d.cols);
-      freeAln((struct aln **)sampledAln);
-    }
     d.n_samples = nb;
-    d.samples = samples;
-    if (rc_score_samples(ctx(), &d, &p, blosum, maxScores + done) != RC_OK) die("rc_score_samples");
+    if (mode == 0) {
+      for (i = 0; i < nb; i++) { /* src/score.c:1006-1010; the library re-imposes the native gaps itself */
+        simulateTree(tree, models[0].freqs, models[0].kappa, d.cols);
+        tree2aln(tree, sampledAln);
+        sortAln(alignment, sampledAln);
+        for (k = 0; k < d.N; k++) memcpy(samples + per * i + (size_t)k * d.cols, sampledAln[k]->seq, d.cols);
+        freeAln((struct aln **)sampledAln);
+      }
+      d.samples = samples;
+      if (rc_score_samples(ctx(), &d, &p, blosum, maxScores + done) != RC_OK) die("rc_score_samples");
+    } else {
+      /* one CreateSeed() per null alignment, in sample order, exactly where simulateTree would call it */
+      for (i = 0; i < nb; i++) seeds[i] = (unsigned int)(CreateSeed() & 0xffffffffUL);
+      d.samples = NULL;
+      if (rc_score_samples_evolve(ctx(), &d, &td, seeds, mode == 2 ? RC_RNG_PHILOX : RC_RNG_MT19937, &p, blosum,
+                                  maxScores + done) != RC_OK)
+        die("rc_score_samples_evolve");
+    }
     for (i = 0; i < nb; i++) { /* src/score.c:1036-1042, in sample order */
       if ((float)maxScores[done + i] > maxNativeScore) betterThanNative++;
       if (pars.stopEarly && betterThanNative > stopCutoff) {
@@ -219,6 +307,10 @@ int __wrap_getExtremeValuePars(TTree *tree, const struct aln *alignment[], int s
   }
   free(maxScores);
   free(samples);
+  free(tpar);
+  free(trow);
+  free(tcum);
+  free(seeds);
   free(rows);
   free(sf);
   free(sr);

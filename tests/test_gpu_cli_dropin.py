@@ -27,13 +27,18 @@ def _norm(txt):
 CASES = sorted(op.golden("cli_outputs").keys())
 
 
+# default: the null alignments are simulated on the GPU (bit-exact MT19937 in seq-gen's order); "host": by the
+# reference's seq-gen on the host.  Both must reproduce the reference's output byte for byte.
+@pytest.mark.parametrize("evolve", ["gpu", "host"])
 @pytest.mark.parametrize("case", CASES)
-def test_cli_output_identical_to_reference(case):
+def test_cli_output_identical_to_reference(case, evolve):
     if not (os.path.exists(CLI) and os.path.isdir(EXAMPLES)):
         pytest.skip("oracle/_ref/RNAcode_cuda_det not built (needs /root/reference at build time)")
     parts = case.split(" ")
     fname, opts = parts[0], [p for p in parts[1:] if p]
     env = dict(os.environ, RNACODE_SEED="1")
+    if evolve == "host":
+        env["RNACODE_CUDA_EVOLVE"] = "host"
     res = subprocess.run([CLI, *opts, os.path.join(EXAMPLES, fname)], capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0, res.stderr
     assert _norm(res.stdout) == _norm(op.golden("cli_outputs")[case])
