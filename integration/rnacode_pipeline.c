@@ -1,0 +1,440 @@
+/* integration/rnacode_pipeline.c -- RNAcode_b200: the batched host pipeline around libRNAcode_cuda.
+ *
+ * Same command line, same input formats and same output as the reference's RNAcode (src/RNAcode.c:52-233); what
+ * changes is the order of work.  The reference handles one alignment block per iteration of main()'s loop:
+ * parse, PhyML (treeML), models, score, n x (simulate, score), fit, print.  Here blocks are taken in windows:
+ *
+ *   1. parse a window of blocks with the reference's readers (read_maf / read_clustal), same filters and messages;
+ *   2. the per-block host stage for all of them in parallel: treeML, string2tree, getModels (both strands) and
+ *      seq-gen's transition matrices for every branch.  PhyML and seq-gen keep global state and are not re-entrant,
+ *      so the window is split over forked worker processes (one per host core) that send back plain tables;
+ *   3. in the parent, per block: one CreateSeed() per null alignment, in the reference's order;
+ *   4. ONE library batch for the whole window: native alignments and all null alignments of all blocks are
+ *      simulated (kernel d), packed, scored and reduced on the GPU (rc_batch_*);
+ *   5. in input order: sort, EVDMaxLikelyFit, p-values, printResults -- all the reference's own code.
+ *
+ * --stop-early only changes what is reported (p = 99.0 when more than cutoff*n null alignments beat the native
+ * score, src/score.c:1036-1042): the count is monotone in the sample index, so evaluating all n samples gives the
+ * same decision.
+ *
+ * Not supported here: --eps (the colour plots need the reference's dense Sk matrices; use RNAcode_cuda or the
+ * reference for those blocks).
+ *
+ * Link: the reference's objects (RNAcode.c compiled with -Dmain=rnacode_reference_main provides the globals),
+ * libRNAcode_cuda; see oracle/Makefile target `pipeline`.
+ */
+#include <ctype.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/types.h>
+#include <sys/wait.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "RNAcode.h"
+#include "cmdline.h"
+#include "code.h"
+#include "extreme_fit.h"
+#include "misc.h"
+#include "rnaz_utils.h"
+#include "score.h"
+#include "treeML.h"
+#include "treeSimulate.h"
+#include "utils.h"
+
+#include "model.h"
+#include "nucmodels.h"
+#include "twister.h"
+
+#include "rnacode_cuda.h"
+
+#include "rnacode_cuda_host.h"
+
+extern long int hitCounter;
+void freeModels(bgModel *models, int N);
+
+/* deterministic test builds (oracle/ref_wrap.c) derive seeds from (scored block index, sample index) */
+void rc_wrap_set_block(long b) __attribute__((weak));
+
+typedef struct {
+  struct aln **aln; /* NULL-terminated, owned */
+  int N, L, cols;
+  long scored_idx; /* index among the blocks that reach treeML */
+  int ok;
+  /* what the tree worker sends back (host_prepare) */
+  float *sf, *sr;     /* models[k].scores[0..3] / modelsRev[k].scores[0..3], N*4 each */
+  int n_nodes;        /* flattened tree, see rc_tree_desc */
+  int *tpar, *trow;
+  double *tcum;
+  char *rows;
+} blk_t;
+
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static int n_workers(int nblocks) {
+  const char *e = getenv("RNACODE_CUDA_WORKERS");
+  long n = e ? atol(e) : sysconf(_SC_NPROCESSORS_ONLN);
+  if (n < 1) n = 1;
+  if (n > 256) n = 256;
+  if (n > nblocks) n = nblocks;
+  return (int)n;
+}
+
+/* Everything the reference does on the host between parsing and scoring, for one block: PhyML tree and kappa
+ * (treeML, src/RNAcode.c:153), string2tree, the background models of both strands (getModels, :161-165), and seq-gen's
+ * model set-up with one cumulative transition matrix per branch (what simulateTree would hand to MutateSequence). */
+static int host_prepare(blk_t *b) {
+  char *ts = NULL;
+  float kappa = 0.0f;
+  struct aln *rev[MAX_NUM_NAMES];
+  bgModel *mod, *modRev;
+  TTree *tree;
+  int k, j, max_nodes;
+  if (treeML((const struct aln **)b->aln, &ts, &kappa) == 0) return 0;
+  tree = string2tree(ts);
+  free(ts);
+  copyAln(b->aln, rev);
+  revAln(rev);
+  models = mod = getModels(tree, b->aln, kappa);
+  modelsRev = modRev = getModels(tree, rev, kappa);
+  freeAln(rev);
+  b->sf = (float *)malloc(sizeof(float) * 4 * b->N);
+  b->sr = (float *)malloc(sizeof(float) * 4 * b->N);
+  for (k = 0; k < b->N; k++)
+    for (j = 0; j < 4; j++) {
+      b->sf[4 * k + j] = mod[k].scores[j];
+      b->sr[4 * k + j] = modRev[k].scores[j];
+    }
+  max_nodes = 2 * tree->numTips + 2;
+  b->tpar = (int *)malloc(sizeof(int) * max_nodes);
+  b->trow = (int *)malloc(sizeof(int) * max_nodes);
+  b->tcum = (double *)malloc(sizeof(double) * 16 * max_nodes);
+  b->n_nodes = 0;
+  setup_seqgen_model(tree, mod[0].freqs, mod[0].kappa, b->cols);
+  flatten_node(tree, tree->root, -1, (const struct aln **)b->aln, b->N, &b->n_nodes, b->tpar, b->trow, b->tcum);
+  freeSeqgenTree(tree);
+  freeModels(mod, b->N);
+  freeModels(modRev, b->N);
+  return 1;
+}
+
+/* phase 2: host_prepare for blocks w, w+P, ... in child w (PhyML and seq-gen keep global state: processes, not
+ * threads); the results come back through one temporary file per child */
+static void run_host_stage(blk_t *blk, int nb) {
+  int P = n_workers(nb), w, i, *next;
+  FILE **chan;
+  pid_t *pid;
+  if (nb == 0) return;
+  if (P == 1) { /* no need to fork */
+    for (i = 0; i < nb; i++) blk[i].ok = host_prepare(&blk[i]);
+    return;
+  }
+  chan = (FILE **)malloc(sizeof(FILE *) * P);
+  pid = (pid_t *)malloc(sizeof(pid_t) * P);
+  /* blocks differ a lot in cost (PhyML is about N^2 * cols): the workers pull the next block from a shared counter */
+  next = (int *)mmap(NULL, 4096, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+  if (next == MAP_FAILED) nrerror("ERROR: mmap failed.\n");
+  *next = 0;
+  fflush(NULL);
+  for (w = 0; w < P; w++) {
+    chan[w] = tmpfile();
+    if (!chan[w]) nrerror("ERROR: could not create a temporary file for the tree workers.\n");
+    pid[w] = fork();
+    if (pid[w] < 0) nrerror("ERROR: fork failed.\n");
+    if (pid[w] == 0) {
+      while ((i = __sync_fetch_and_add(next, 1)) < nb) {
+        blk_t *b = &blk[i];
+        int ok = host_prepare(b);
+        fwrite(&i, sizeof(int), 1, chan[w]);
+        fwrite(&ok, sizeof(int), 1, chan[w]);
+        if (!ok) continue;
+        fwrite(&b->n_nodes, sizeof(int), 1, chan[w]);
+        fwrite(b->sf, sizeof(float), 4 * b->N, chan[w]);
+        fwrite(b->sr, sizeof(float), 4 * b->N, chan[w]);
+        fwrite(b->tpar, sizeof(int), b->n_nodes, chan[w]);
+        fwrite(b->trow, sizeof(int), b->n_nodes, chan[w]);
+        fwrite(b->tcum, sizeof(double), 16 * (size_t)b->n_nodes, chan[w]);
+      }
+      fflush(chan[w]);
+      _exit(0);
+    }
+  }
+  ctx(); /* bring the CUDA context up while the workers run PhyML (the children never touch CUDA) */
+  for (w = 0; w < P; w++) {
+    int status = 0, idx, ok;
+    waitpid(pid[w], &status, 0);
+    rewind(chan[w]);
+    while (fread(&idx, sizeof(int), 1, chan[w]) == 1) {
+      blk_t *b;
+      int good;
+      if (fread(&ok, sizeof(int), 1, chan[w]) != 1 || idx < 0 || idx >= nb) break;
+      if (!ok) continue;
+      b = &blk[idx];
+      if (fread(&b->n_nodes, sizeof(int), 1, chan[w]) != 1 || b->n_nodes < 2 || b->n_nodes > 2 * MAX_NUM_NAMES + 2) break;
+      b->sf = (float *)malloc(sizeof(float) * 4 * b->N);
+      b->sr = (float *)malloc(sizeof(float) * 4 * b->N);
+      b->tpar = (int *)malloc(sizeof(int) * b->n_nodes);
+      b->trow = (int *)malloc(sizeof(int) * b->n_nodes);
+      b->tcum = (double *)malloc(sizeof(double) * 16 * b->n_nodes);
+      good = fread(b->sf, sizeof(float), 4 * b->N, chan[w]) == (size_t)(4 * b->N) &&
+             fread(b->sr, sizeof(float), 4 * b->N, chan[w]) == (size_t)(4 * b->N) &&
+             fread(b->tpar, sizeof(int), b->n_nodes, chan[w]) == (size_t)b->n_nodes &&
+             fread(b->trow, sizeof(int), b->n_nodes, chan[w]) == (size_t)b->n_nodes &&
+             fread(b->tcum, sizeof(double), 16 * (size_t)b->n_nodes, chan[w]) == 16 * (size_t)b->n_nodes;
+      if (!good) break; /* truncated: the worker died */
+      b->ok = 1;
+    }
+    fclose(chan[w]);
+    /* a worker that died leaves its remaining blocks with ok == 0: they are reported like a failed tree */
+  }
+  munmap(next, 4096);
+  free(chan);
+  free(pid);
+}
+
+static void process_window(blk_t *blk, int nb, int *blosum) {
+  const int n = pars.sampleN;
+  const int mode = evolve_mode();
+  rc_params p = current_params();
+  rc_block_desc *descs;
+  rc_batch *batch = NULL;
+  int *map, nok = 0, i, k, j;
+  double t0 = now_s(), t1, t2, t3, t_models = 0, t_create = 0;
+  const int verbose = getenv("RNACODE_CUDA_VERBOSE") != NULL;
+
+  run_host_stage(blk, nb);
+  t1 = now_s();
+
+  descs = (rc_block_desc *)malloc(sizeof(rc_block_desc) * (nb > 0 ? nb : 1));
+  map = (int *)malloc(sizeof(int) * (nb > 0 ? nb : 1));
+  for (i = 0; i < nb; i++) {
+    blk_t *b = &blk[i];
+    if (!b->ok) continue;
+    b->rows = (char *)malloc((size_t)b->N * b->cols);
+    for (k = 0; k < b->N; k++) memcpy(b->rows + (size_t)k * b->cols, b->aln[k]->seq, b->cols);
+    descs[nok].N = b->N;
+    descs[nok].cols = b->cols;
+    descs[nok].rows = b->rows;
+    descs[nok].scores_fwd = b->sf;
+    descs[nok].scores_rev = b->sr;
+    descs[nok].n_samples = n > 0 ? n : 0;
+    descs[nok].samples = NULL;
+    map[nok++] = i;
+  }
+  t_models = now_s() - t1;
+  if (nok > 0) {
+    t_create = now_s();
+    if (rc_batch_create(ctx(), descs, nok, &p, blosum, &batch) != RC_OK) die("rc_batch_create");
+    t_create = now_s() - t_create;
+    if (n > 0) {
+      unsigned int *seeds = (unsigned int *)malloc(sizeof(unsigned int) * n);
+      for (k = 0; k < nok; k++) {
+        blk_t *b = &blk[map[k]];
+        rc_tree_desc td;
+        td.n_nodes = b->n_nodes;
+        td.parent = b->tpar;
+        td.row = b->trow;
+        td.cum = b->tcum;
+        if (rc_wrap_set_block) rc_wrap_set_block(b->scored_idx);
+        for (j = 0; j < n; j++) seeds[j] = (unsigned int)(CreateSeed() & 0xffffffffUL); /* src/treeSimulate.c:84 */
+        if (rc_batch_set_evolve(batch, k, &td, seeds, mode == 2 ? RC_RNG_PHILOX : RC_RNG_MT19937) != RC_OK)
+          die("rc_batch_set_evolve");
+      }
+      free(seeds);
+    }
+    t2 = now_s();
+    if (rc_batch_upload(batch) != RC_OK) die("rc_batch_upload");
+    if (rc_batch_run(batch) != RC_OK) die("rc_batch_run");
+    if (rc_batch_download(batch) != RC_OK) die("rc_batch_download");
+  } else {
+    t2 = now_s();
+  }
+  t3 = now_s();
+
+  /* phase 5: the reference's reporting, in input order */
+  {
+    double *maxScores = (double *)malloc(sizeof(double) * (n > 0 ? n : 1));
+    int cap = 1024, nh = 0;
+    rc_hss *h = (rc_hss *)malloc(sizeof(rc_hss) * cap);
+    k = 0;
+    for (i = 0; i < nb; i++) {
+      blk_t *b = &blk[i];
+      segmentStats *results;
+      int hssCount, status = 1, better = 0, stopCutoff, rc;
+      float maxScore, parMu = 0, parLambda = 0;
+      double mu, lambda;
+      if (!b->ok) {
+        fprintf(stderr, "\nSkipping alignment. Failed to build ML tree.\n");
+        freeAln(b->aln);
+        free(b->aln);
+        continue;
+      }
+      rc = rc_batch_native_hss(batch, k, h, cap, &nh);
+      if (rc == RC_ERR_CAPACITY) {
+        cap = nh;
+        h = (rc_hss *)realloc(h, sizeof(rc_hss) * cap);
+        rc = rc_batch_native_hss(batch, k, h, cap, &nh);
+      }
+      if (rc != RC_OK) die("rc_batch_native_hss");
+      results = hss_to_segments((const struct aln **)b->aln, h, nh);
+      hssCount = 0;
+      while (results[hssCount++].score > 0.0);
+      qsort(results, hssCount, sizeof(segmentStats), compareScores); /* src/RNAcode.c:176 */
+      maxScore = results[0].score;
+      /* getExtremeValuePars, src/score.c:1034-1062, on the maxima the GPU returned */
+      if (n > 0 && rc_batch_max_scores(batch, k, maxScores) != RC_OK) die("rc_batch_max_scores");
+      stopCutoff = (int)(pars.cutoff * pars.sampleN);
+      for (j = 0; j < n && status == 1; j++) {
+        if ((float)maxScores[j] > maxScore) better++;
+        if (pars.stopEarly && better > stopCutoff) status = -1;
+      }
+      if (status == 1) {
+        if (EVDMaxLikelyFit(maxScores, NULL, n, &mu, &lambda) == 1) {
+          parMu = mu;
+          parLambda = lambda;
+        } else {
+          status = -1;
+        }
+      }
+      for (j = 0; j < hssCount; j++)
+        results[j].pvalue = status == 1 ? 1 - exp((-1) * exp((-1) * parLambda * (results[j].score - parMu))) : 99.0;
+      printResults(pars.outputFile, pars.outputFormat, (const struct aln **)b->aln, results);
+      freeResults(results);
+      free(b->rows);
+      free(b->sf);
+      free(b->sr);
+      free(b->tpar);
+      free(b->trow);
+      free(b->tcum);
+      freeAln(b->aln);
+      free(b->aln);
+      k++;
+    }
+    free(h);
+    free(maxScores);
+  }
+  if (batch) rc_batch_destroy(batch);
+  free(descs);
+  free(map);
+  if (verbose)
+    fprintf(stderr,
+            "[RNAcode_b200] window of %d blocks (%d scored): trees+models (workers) %.3f s, pack rows %.3f s, batch create %.3f s, seeds %.3f s, "
+            "GPU upload+run+download %.3f s, fit+report %.3f s\n",
+            nb, nok, t1 - t0, t_models, t_create, t2 - t1 - t_models - t_create, t3 - t2, now_s() - t3);
+}
+
+int main(int argc, char *argv[]) {
+  int i, j, N, L, alnCounter = 0, nb = 0, win_blocks, blosum[576];
+  long scored = 0;
+  size_t win_bytes = 0, max_bytes;
+  clock_t startTime;
+  double wall0 = now_s();
+  int (*readFunction)(FILE * clust, struct aln * alignedSeqs[]) = NULL;
+  struct aln *inputAln[MAX_NUM_NAMES];
+  blk_t *blk;
+  const char *e;
+
+  /* the reference's defaults, src/RNAcode.c:68-90 */
+  pars.Delta = -10.0;
+  pars.Omega = -4.0;
+  pars.omega = -2.0;
+  pars.stopPenalty_k = -8.0;
+  pars.stopPenalty_0 = -9999.0;
+  pars.inputFile = stdin;
+  pars.outputFile = stdout;
+  pars.debugFile = stdout;
+  pars.bestOnly = 0;
+  pars.bestRegion = 0;
+  pars.stopEarly = 0;
+  pars.postscript = 0;
+  pars.postscript_cutoff = 0.05;
+  strcpy(pars.postscriptDir, "eps");
+  pars.sampleN = 100;
+  pars.blosum = 62;
+  strcpy(pars.limit, "");
+  pars.cutoff = 1.0;
+  pars.outputFormat = 0;
+  strcpy(pars.debugFileName, "");
+  strcpy(pars.inputFileName, "STDIN");
+
+  read_commandline(argc, argv);
+  if (pars.postscript) nrerror("ERROR: --eps is not available in the batched GPU pipeline; use RNAcode_cuda for plots.\n");
+  srand(time(NULL));
+
+  ntMap['A'] = ntMap['a'] = 0;
+  ntMap['C'] = ntMap['c'] = 1;
+  ntMap['G'] = ntMap['g'] = 2;
+  ntMap['T'] = ntMap['t'] = 3;
+  ntMap['U'] = ntMap['u'] = 3;
+
+  switch (checkFormat(pars.inputFile)) {
+    case CLUSTAL: readFunction = &read_clustal; break;
+    case MAF: readFunction = &read_maf; break;
+    default: nrerror("ERROR: Unknown alignment file format. Use Clustal W or MAF format.\n");
+  }
+  {
+    int **mat = getScoringMatrix(); /* what getModels puts into bgModel.matrix (src/score.c:50-75) */
+    for (i = 0; i < 24; i++)
+      for (j = 0; j < 24; j++) blosum[i * 24 + j] = mat[i][j];
+    for (i = 0; i < 24; i++) free(mat[i]);
+    free(mat);
+  }
+  e = getenv("RNACODE_CUDA_WINDOW");
+  win_blocks = e ? atoi(e) : 4096;
+  if (win_blocks < 1) win_blocks = 1;
+  e = getenv("RNACODE_CUDA_WINDOW_MB"); /* bound on the bytes of simulated alignments per window */
+  max_bytes = (size_t)(e ? atol(e) : 4096) << 20;
+  blk = (blk_t *)calloc(win_blocks, sizeof(blk_t));
+  startTime = clock();
+
+  while (readFunction(pars.inputFile, inputAln) != 0) {
+    alnCounter++;
+    for (i = 0; inputAln[i] != NULL; i++)
+      for (j = 0; inputAln[i]->seq[j]; j++) inputAln[i]->seq[j] = toupper(inputAln[i]->seq[j]);
+    if (strcmp(pars.limit, "") != 0) pruneAln(pars.limit, (struct aln **)inputAln);
+    L = getSeqLength(inputAln[0]->seq);
+    for (N = 0; inputAln[N] != NULL; N++);
+    if (N <= 2) { /* src/RNAcode.c:142-145 */
+      fprintf(stderr, "Skipping alignment. There must be at least three sequences in the alignment.\n");
+      continue;
+    }
+    if (L < 3) {
+      fprintf(stderr, "Skipping alignment. Too short.\n");
+      continue;
+    }
+    memset(&blk[nb], 0, sizeof(blk_t));
+    blk[nb].aln = (struct aln **)malloc(sizeof(struct aln *) * (N + 1));
+    memcpy(blk[nb].aln, inputAln, sizeof(struct aln *) * (N + 1));
+    blk[nb].N = N;
+    blk[nb].L = L;
+    blk[nb].cols = (int)strlen(inputAln[0]->seq);
+    blk[nb].scored_idx = scored++;
+    win_bytes += (size_t)N * blk[nb].cols * (size_t)(pars.sampleN + 1) * 2;
+    nb++;
+    if (nb == win_blocks || win_bytes >= max_bytes) {
+      process_window(blk, nb, blosum);
+      nb = 0;
+      win_bytes = 0;
+    }
+  }
+  if (nb > 0) process_window(blk, nb, blosum);
+
+  if (pars.outputFormat == 0) {
+    float runtime = (float)(clock() - startTime) / CLOCKS_PER_SEC;
+    fprintf(pars.outputFile,
+            "\n%i alignment(s) scored in %.2f seconds. Parameters used:\nN=%i, Delta=%.2f, Omega=%.2f, omega=%.2f, stop penalty=%.2f\n\n",
+            alnCounter, runtime, pars.sampleN, pars.Delta, pars.Omega, pars.omega, pars.stopPenalty_k);
+  }
+  if (getenv("RNACODE_CUDA_VERBOSE"))
+    fprintf(stderr, "[RNAcode_b200] %d alignments in %.3f s wall (%.1f blocks/s)\n", alnCounter, now_s() - wall0,
+            alnCounter / (now_s() - wall0));
+  free(blk);
+  exit(EXIT_SUCCESS);
+}

@@ -25,6 +25,7 @@ def _norm(txt):
 
 
 CASES = sorted(op.golden("cli_outputs").keys())
+PIPELINE = os.path.join(REFDIR, "RNAcode_b200_det")
 
 
 # default: the null alignments are simulated on the GPU (bit-exact MT19937 in seq-gen's order); "host": by the
@@ -40,5 +41,22 @@ def test_cli_output_identical_to_reference(case, evolve):
     if evolve == "host":
         env["RNACODE_CUDA_EVOLVE"] = "host"
     res = subprocess.run([CLI, *opts, os.path.join(EXAMPLES, fname)], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr
+    assert _norm(res.stdout) == _norm(op.golden("cli_outputs")[case])
+
+
+@pytest.mark.parametrize("workers", ["1", "5"])
+@pytest.mark.parametrize("case", CASES)
+def test_batched_pipeline_output_identical_to_reference(case, workers):
+    """integration/rnacode_pipeline.c: all blocks of the file in one GPU batch, PhyML in forked workers, null
+    alignments drawn on the GPU -- and still the reference's output, byte for byte."""
+    if not (os.path.exists(PIPELINE) and os.path.isdir(EXAMPLES)):
+        pytest.skip("oracle/_ref/RNAcode_b200_det not built (needs /root/reference at build time)")
+    parts = case.split(" ")
+    fname, opts = parts[0], [p for p in parts[1:] if p]
+    env = dict(os.environ, RNACODE_SEED="1", RNACODE_CUDA_WORKERS=workers)
+    if workers == "5":
+        env["RNACODE_CUDA_WINDOW"] = "4"  # several windows per file
+    res = subprocess.run([PIPELINE, *opts, os.path.join(EXAMPLES, fname)], capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0, res.stderr
     assert _norm(res.stdout) == _norm(op.golden("cli_outputs")[case])
