@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256)
 
   const Item it = items[blockIdx.x];
   const BlockDev bd = blocks[it.block];
-  if (bd.layout == 2) return;  // sample-major items are served by k_sigma_smp
+  if (bd.layout == 2 || bd.layout == 1) return;  // served by k_sigma_smp / k_sigma_rows
   const int L = bd.L, N = bd.N, NK = bd.NK, cols = bd.cols;
   const int npos = L - 2;
   const long long total = (long long)it.ninst * 2 * npos;
@@ -320,6 +320,91 @@ __global__ void __launch_bounds__(256)
       if (j == bd.sites[f] - 1)  // rows of the last tile past the end of the frame: sigma = 0, no frameshift
         for (int cc = c + 1; cc < TILE; cc++)
           for (int q = 0; q <= NK; q++) out[(size_t)(cc - c) * bd.sig_cs + q] = 0.0f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (b) k_sigma_rows: sigma for layout 1 (k_dp_reg).  One thread per (instance, strand, frame, end codon): it
+// produces the whole step row -- NK sigma values, the z word, padding -- and stores it as RS/4 float4, so a warp
+// writes 32 consecutive rows (fully coalesced 128-bit stores; k_sigma's position-major mapping scatters 4-byte
+// stores over the three frames).  Steps past the end of the frame in the last tile get all-zero rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_sigma_rows(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned char* __restrict__ cls,
+                 const int* __restrict__ cols0, const float* __restrict__ scores, const SigmaTables* __restrict__ tables,
+                 const unsigned* __restrict__ ztiles, float* __restrict__ sigma, Params prm) {
+  __shared__ SigmaTables s_tab;
+  __shared__ __align__(8) uint64_t s_bar;
+  const Item it = items[blockIdx.x];
+  const BlockDev bd = blocks[it.block];
+  if (bd.layout != 1) return;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&s_bar, (unsigned)sizeof(SigmaTables));
+    bulk_g2s(&s_tab, tables, (unsigned)sizeof(SigmaTables), &s_bar);
+  }
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+  const int L = bd.L, N = bd.N, NK = bd.NK, cols = bd.cols;
+  const int rs = bd.sig_cs;
+  const int st0 = bd.ntiles[0] * TILE, st1 = bd.ntiles[1] * TILE, st2 = bd.ntiles[2] * TILE;  // padded steps per frame
+  const int per_is = st0 + st1 + st2;
+  const long long total = (long long)it.ninst * 2 * per_is;
+  for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.y * blockDim.x) {
+    int r = (int)(idx % per_is);
+    const int is = (int)(idx / per_is);
+    const int s = is & 1, inst_l = is >> 1;
+    int f = 0;
+    if (r >= st0) { r -= st0; f = 1; }
+    if (f == 1 && r >= st1) { r -= st1; f = 2; }
+    const int j = r;
+    float4* out = reinterpret_cast<float4*>(sigma + it.sigma_off[s][f] + ((size_t)inst_l * bd.ntiles[f]) * bd.sig_tile +
+                                            (size_t)j * rs);
+    if (j >= bd.sites[f]) {  // padding rows of the last tile
+      for (int q = 0; q < rs / 4; q++) out[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      continue;
+    }
+    const int x = 3 * j + 3 + f;
+    const int* c0 = cols0 + bd.cols0_off + (size_t)s * (L + 1);
+    const int c1 = c0[x - 2], c2 = c0[x - 1], c3 = c0[x];
+    const unsigned char* base = cls + bd.cls_off + (size_t)(it.inst0 + inst_l) * bd.inst_stride;
+    const unsigned a1 = base[c1], a2 = base[c2], a3 = base[c3];
+    const int sh = s ? 2 : 0;
+    const unsigned qa = (((a1 >> sh) & 3u) << 4) | (((a2 >> sh) & 3u) << 2) | ((a3 >> sh) & 3u);
+    const unsigned nA = (a1 | a2 | a3) & CLS_N;
+    const int pepA = s_tab.transcode[qa];
+    const float* sc = scores + bd.scores_off + (size_t)s * N * 4;
+    const unsigned zword = ztiles[bd.z_off[s][f] + j];  // zstride == TILE: one word per step
+    for (int q = 0; q < rs / 4; q++) {
+      float v4[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int k = 4 * q + t;
+        float v = 0.0f;
+        if (k < NK) {
+          const unsigned char* rowk = base + (size_t)(k + 1) * cols;
+          const unsigned b1 = rowk[c1], b2 = rowk[c2], b3 = rowk[c3];
+          const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
+          // src/score.c:394-425, see k_sigma; entries with a frameshift are never read by the recurrence: +0
+          if (!(nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X)) && qa != qb && !((zword >> (2 * k)) & 1u)) {
+            const int pepB = s_tab.transcode[qb];
+            if (pepA < 0) v = prm.stop0;
+            else if (pepB < 0) v = prm.stopk;
+            else {
+              const unsigned d = qa ^ qb;
+              const int h = ((d & 0x30u) != 0) + ((d & 0x0cu) != 0) + ((d & 0x03u) != 0);
+              v = s_tab.blosum[pepA * 24 + pepB] - sc[(k + 1) * 4 + h];
+            }
+          }
+        } else if (k == NK) {
+          v = __uint_as_float(zword);
+        }
+        v4[t] = v;
+      }
+      out[q] = make_float4(v4[0], v4[1], v4[2], v4[3]);
     }
   }
 }
@@ -1348,15 +1433,114 @@ __global__ void __launch_bounds__(SMP_WARPS * 32)
 
 // ---------------------------------------------------------------------------------------------
 // (c) k_hss: the sequential scan of getHSS (src/score.c:888-961) over row digests.
-// One thread per (instance, strand, frame).  grid = (x: item, y over ninst*6).
+// One WARP per (instance, strand, frame): the lanes fetch 32 row records at a time (coalesced 1 KB), rows without
+// a positive entry are skipped by ballot, the others are replayed in row order with their fields broadcast by
+// shuffles (every lane runs the same state machine; lane 0 writes).  grid = (x: item, y over ninst*6 warps).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int HSS_WARPS = 4;
+constexpr int HSS_WARP_MIN_SITES = 96;  // shorter frames: one thread per (instance, strand, frame) is the better fit (k_hss_thr)
+
+__global__ void __launch_bounds__(HSS_WARPS * 32)
     k_hss(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const RowRec* __restrict__ recs,
           float* __restrict__ res, HssDev* __restrict__ hss, int* __restrict__ hsscnt, int* __restrict__ ovf_counter) {
   const Item it = items[blockIdx.x];
   const BlockDev& bd = blocks[it.block];
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.y * HSS_WARPS + (threadIdx.x >> 5);
+  if (idx >= it.ninst * 6 || bd.sites[0] < HSS_WARP_MIN_SITES) return;
+  const int inst_l = idx / 6, sf = idx % 6;
+  const int strand = sf / 3, frame = sf % 3;
+  const int sites = bd.sites[frame];
+  const int inst = it.inst0 + inst_l;
+  const uint4* rp = reinterpret_cast<const uint4*>(recs + it.rec_off[strand][frame] + (size_t)inst_l * sites);
+  HssDev* out = hss + bd.hss_off[strand][frame];
+  const unsigned FULL = 0xffffffffu;
+  int nout = 0;
+  float best = -1.0f;
+  bool overflow = false;
+  float cur = 0.0f;
+  int segS = -1, segE = -1;
+  const int nrows = sites - 1;  // the last row only holds the frame's final entry, which never survives (:893-900)
+  for (int i0 = 0; i0 < nrows; i0 += 32) {
+    const int i_mine = i0 + lane;
+    uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = make_uint4(0u, 0u, 0u, 0u);
+    if (i_mine < nrows) {
+      w0 = rp[2 * i_mine];
+      w1 = rp[2 * i_mine + 1];
+    }
+    // RowRec: w0 = {Emax, vF, be0, be1}, w1 = {be2, jF | n << 16, bj0 | bj1 << 16, bj2 | pad << 16}
+    unsigned mask = __ballot_sync(FULL, (w1.y >> 16) != 0u);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int i = i0 + src;
+      const float Emax = __uint_as_float(__shfl_sync(FULL, w0.x, src));
+      const float vF = __uint_as_float(__shfl_sync(FULL, w0.y, src));
+      const unsigned jn = __shfl_sync(FULL, w1.y, src);
+      const int n = (int)(jn >> 16), jF = (int)(jn & 0xffffu);
+      if (n & 0x8000) overflow = true;
+      bool take;
+      if (cur > 0.0f && segE < i) {  // flush (:897-949)
+        if (segE - segS >= 2) {
+          if (inst == 0 && lane == 0) {
+            out[nout].startSite = segS;
+            out[nout].endSite = segE;
+            out[nout].score = cur;
+          }
+          nout++;
+          best = fmaxf(best, cur);
+        }
+        take = true;
+      } else {  // overlap with the current segment (:953-959)
+        take = Emax > cur;
+        if (!take) {
+          const int nb = n & 0xff;
+          const float be0 = __uint_as_float(__shfl_sync(FULL, w0.z, src)), be1 = __uint_as_float(__shfl_sync(FULL, w0.w, src)),
+                      be2 = __uint_as_float(__shfl_sync(FULL, w1.x, src));
+          const unsigned bj01 = __shfl_sync(FULL, w1.z, src), bj2 = __shfl_sync(FULL, w1.w, src);
+          const float be[3] = {be0, be1, be2};
+          const int bj[3] = {(int)(bj01 & 0xffffu), (int)(bj01 >> 16), (int)(bj2 & 0xffffu)};
+#pragma unroll
+          for (int m = 0; m < REC_SLOTS; m++) {
+            const float d = be[m] - cur;
+            if (m < nb && d >= -0.0001f && d <= 0.0001f && (bj[m] - i) >= (segE - segS)) take = true;
+          }
+        }
+      }
+      if (take) {
+        cur = vF;
+        segS = i;
+        segE = jF;
+      }
+    }
+  }
+  if (sites > 0 && segE - segS >= 2) {  // forced flush on the frame's last entry
+    if (inst == 0 && lane == 0) {
+      out[nout].startSite = segS;
+      out[nout].endSite = segE;
+      out[nout].score = cur;
+    }
+    nout++;
+    best = fmaxf(best, cur);
+  }
+  if (lane == 0) {
+    if (overflow) {
+      best = -2.0f;
+      atomicAdd(ovf_counter, 1);
+    }
+    res[bd.res_off + (size_t)inst * 6 + sf] = best;
+    if (inst == 0) hsscnt[bd.hsscnt_off + sf] = overflow ? -1 : nout;
+  }
+}
+
+// Same scan, one thread per (instance, strand, frame): for short frames (many small blocks).
+__global__ void __launch_bounds__(128)
+    k_hss_thr(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const RowRec* __restrict__ recs,
+          float* __restrict__ res, HssDev* __restrict__ hss, int* __restrict__ hsscnt, int* __restrict__ ovf_counter) {
+  const Item it = items[blockIdx.x];
+  const BlockDev& bd = blocks[it.block];
   const int idx = blockIdx.y * blockDim.x + threadIdx.x;
-  if (idx >= it.ninst * 6) return;
+  if (idx >= it.ninst * 6 || bd.sites[0] >= HSS_WARP_MIN_SITES) return;
   const int inst_l = idx / 6, sf = idx % 6;
   const int strand = sf / 3, frame = sf % 3;
   const int sites = bd.sites[frame];

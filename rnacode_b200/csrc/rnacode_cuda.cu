@@ -120,6 +120,8 @@ struct Chunk {
   size_t sigma_floats = 0, rec_count = 0, max_smp_smem = 0, max_smp_stage = 0;
   long long max_sigma_work = 0;  // largest ninst*2*(L-2) of an item, for the k_sigma grid
   int max_ninst = 0;
+  int n_layout[4] = {0, 0, 0, 0};  // items per sigma layout
+  int hss_warp_items = 0;  // items whose frames are long enough for the warp-per-task k_hss
 };
 
 struct EventPair {
@@ -562,6 +564,8 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       cur.maxZs[cl] = std::max(cur.maxZs[cl], bd.zstride);
       cur.max_sigma_work = std::max(cur.max_sigma_work, (long long)take * 2 * (bd.L - 2));
       cur.max_ninst = std::max(cur.max_ninst, take);
+      if (bd.sites[0] >= HSS_WARP_MIN_SITES) cur.hss_warp_items++;
+      cur.n_layout[bd.layout]++;
       b->items.push_back(it);
       cur.nitems++;
       cur_bytes += (size_t)take * bytes_per_inst;
@@ -1080,10 +1084,18 @@ extern "C" int rc_batch_run(rc_batch* b) {
     ev = ev_begin(b, 1);
     {
       dim3 g((unsigned)ch.nitems, (unsigned)std::min<long long>((ch.max_sigma_work + 255) / 256, 8192));
-      k_sigma<<<g, 256, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores, b->d_tables,
-                                 b->d_z, b->d_sigma, b->prm);
-      RC_CUDA(cudaGetLastError());
-      b->stats.launches++;
+      if (ch.n_layout[0] + ch.n_layout[3] > 0) {
+        k_sigma<<<g, 256, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores, b->d_tables,
+                                   b->d_z, b->d_sigma, b->prm);
+        RC_CUDA(cudaGetLastError());
+        b->stats.launches++;
+      }
+      if (ch.n_layout[1] > 0) {
+        k_sigma_rows<<<g, 256, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores, b->d_tables,
+                                        b->d_z, b->d_sigma, b->prm);
+        RC_CUDA(cudaGetLastError());
+        b->stats.launches++;
+      }
       if (ch.max_smp_smem > 0) {  // some items use the sample-major layout
         const size_t smem = ch.max_smp_stage;
         RC_CUDA(cudaFuncSetAttribute(k_sigma_smp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1114,10 +1126,19 @@ extern "C" int rc_batch_run(rc_batch* b) {
     ev_end(b, ev);
     ev = ev_begin(b, 3);
     {
-      dim3 g((unsigned)ch.nitems, (unsigned)((ch.max_ninst * 6 + 127) / 128));
-      k_hss<<<g, 128, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_recs, b->d_res, b->d_hss, b->d_hsscnt, b->d_ovf);
-      RC_CUDA(cudaGetLastError());
-      b->stats.launches++;
+      // long frames: one warp per (instance, strand, frame); short frames: one thread (each kernel skips the other's items)
+      if (ch.hss_warp_items > 0) {
+        dim3 g((unsigned)ch.nitems, (unsigned)((ch.max_ninst * 6 + HSS_WARPS - 1) / HSS_WARPS));
+        k_hss<<<g, HSS_WARPS * 32, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_recs, b->d_res, b->d_hss, b->d_hsscnt, b->d_ovf);
+        RC_CUDA(cudaGetLastError());
+        b->stats.launches++;
+      }
+      if (ch.hss_warp_items < (int)ch.nitems) {
+        dim3 g((unsigned)ch.nitems, (unsigned)((ch.max_ninst * 6 + 127) / 128));
+        k_hss_thr<<<g, 128, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_recs, b->d_res, b->d_hss, b->d_hsscnt, b->d_ovf);
+        RC_CUDA(cudaGetLastError());
+        b->stats.launches++;
+      }
     }
     ev_end(b, ev);
   }
