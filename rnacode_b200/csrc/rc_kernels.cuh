@@ -976,6 +976,74 @@ __device__ __forceinline__ void reg_pair_fast(float2 (&S0)[NK], float2 (&S1)[NK]
   }
 }
 
+// Tiles in which the warp's rows start ("diagonal" tiles).  A row starts from (0,0,0) at its first end codon
+// (src/score.c:500-504).  The states are zero-initialised, and until a row has started every addend that reaches it
+// is replaced by +0 (per-lane selects on sigma, omega, Delta, Omega): 0 + 0 == 0 and max(0, 0) == 0 keep the state
+// exactly (0,0,0) up to the row's first codon, from where the reference's operations apply unchanged.  This lets
+// the diagonal tiles use the same two-codon straight-line blocks as the steady state.  With the lane's rows
+// r0 (even) and r0+1 and a codon pair (j, j+1), j even:  P = (j >= r0): row r0 live at j, both rows live at j+1;
+// Q = (j > r0): row r0+1 live at j.
+template <int NK, bool HAS_IN = false>
+__device__ __forceinline__ void reg_pair_diag(float2 (&S0)[NK], float2 (&S1)[NK], float2 (&S2)[NK],
+                                              const float (&svA)[RegCfg<NK>::RS], const float (&svB)[RegCfg<NK>::RS],
+                                              float omega, bool P, bool Q, float2& sumA, float2& sumB,
+                                              float2 sinA = make_float2(0.0f, 0.0f), float2 sinB = make_float2(0.0f, 0.0f)) {
+  const float2 omA = make_float2(P ? omega : 0.0f, Q ? omega : 0.0f);
+  const float omB = P ? omega : 0.0f;
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    S0[k] = add2(S0[k], make_float2(P ? svA[k] : 0.0f, Q ? svA[k] : 0.0f));
+    S1[k] = add2(S1[k], omA);
+    S2[k] = add2(S2[k], omA);
+    const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
+    sumA = (k == 0) ? (HAS_IN ? add2(sinA, m) : m) : add2(sumA, m);
+  }
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    S0[k] = add2s(S0[k], P ? svB[k] : 0.0f);
+    S1[k] = add2s(S1[k], omB);
+    S2[k] = add2s(S2[k], omB);
+    const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
+    sumB = (k == 0) ? (HAS_IN ? add2(sinB, m) : m) : add2(sumB, m);
+  }
+}
+
+// frameshift update of one species with per-row penalties (src/score.c:512-533)
+__device__ __forceinline__ void reg_shift2(bool neg, float2 Delta, float2 Omega, float2& a0, float2& a1, float2& a2) {
+  const float2 x0 = neg ? a1 : a2, x1 = neg ? a2 : a0, x2 = neg ? a0 : a1;
+  const float2 d0 = add2(a0, Delta), d1 = add2(a1, Delta), d2 = add2(a2, Delta);
+  const float2 o0 = add2(x0, Omega), o1 = add2(x1, Omega), o2 = add2(x2, Omega);
+  a0 = make_float2(fmaxf(d0.x, o0.x), fmaxf(d0.y, o0.y));
+  a1 = make_float2(fmaxf(d1.x, o1.x), fmaxf(d1.y, o1.y));
+  a2 = make_float2(fmaxf(d2.x, o2.x), fmaxf(d2.y, o2.y));
+}
+
+// One end codon of a diagonal tile, any frameshift pattern; mx / my: the lane's two rows are live at this codon.
+template <int NK, bool HAS_IN = false>
+__device__ __forceinline__ float2 reg_update_diag(float2 (&S0)[NK], float2 (&S1)[NK], float2 (&S2)[NK],
+                                                  const float (&sv)[RegCfg<NK>::RS], bool mx, bool my, float Delta,
+                                                  float Omega, float omega, float2 sin = make_float2(0.0f, 0.0f)) {
+  const unsigned zw = __float_as_uint(sv[NK]);
+  const float2 om2 = make_float2(mx ? omega : 0.0f, my ? omega : 0.0f);
+  const float2 D2 = make_float2(mx ? Delta : 0.0f, my ? Delta : 0.0f);
+  const float2 O2 = make_float2(mx ? Omega : 0.0f, my ? Omega : 0.0f);
+  float2 sum;
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    const unsigned z2 = (zw >> (2 * k)) & 3u;
+    if (z2 == 0u) {
+      S0[k] = add2(S0[k], make_float2(mx ? sv[k] : 0.0f, my ? sv[k] : 0.0f));
+      S1[k] = add2(S1[k], om2);
+      S2[k] = add2(S2[k], om2);
+    } else {
+      reg_shift2((z2 & 2u) != 0u, D2, O2, S0[k], S1[k], S2[k]);
+    }
+    const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
+    sum = (k == 0) ? (HAS_IN ? add2(sin, m) : m) : add2(sum, m);
+  }
+  return sum;
+}
+
 // getHSS only looks at positive entries (src/score.c:891); with Delta <= 0, max(sum, Delta) > 0 <=> sum > 0.
 // S[b][i] = sum / (N-1) (src/score.c:841-843) as the correctly rounded quotient (see k_dp).  lb mirrors
 // rec->vF (the fresh fold's last accepted value) in a register so that entries the fold rejects cost no
@@ -1016,22 +1084,30 @@ __device__ __forceinline__ void rec_copy(RowRec* dst, const RowRec* src) {
 #ifndef RC_REG_MINB
 #define RC_REG_MINB 4
 #endif
+#ifndef RC_REG_TILE
+#define RC_REG_TILE 32  // end codons per TMA stage of k_dp_reg (a multiple of TILE; layout 1 rows are contiguous over tiles)
+#endif
+#ifndef RC_REG_DIAG_MASKED
+#define RC_REG_DIAG_MASKED 0
+#endif
 template <int NK>
 __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
     k_dp_reg(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
              const float* __restrict__ sigma, RowRec* __restrict__ recs, Params prm, int band_slots) {
   constexpr int R = 2;
   constexpr int RS = RegCfg<NK>::RS;
-  constexpr int SIG_TILE = RegCfg<NK>::SIG_TILE;
-  constexpr int STAGE_BYTES = RegCfg<NK>::STAGE_BYTES;
-  // ring of two stages + the two mbarriers + room for the steady-state loop's read-ahead of two step rows
+  constexpr int RT = RC_REG_TILE;
+  constexpr int STAGE_BYTES = RT * RS * 4;
+  // ring of two stages + the two mbarriers + room for the loop's read-ahead of two step rows
   __shared__ __align__(128) unsigned char smem[DP_WARPS][2 * STAGE_BYTES + 16 + 2 * RS * 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const CtaDesc cd = ctas[blockIdx.x];
   const Item& it = items[cd.item];
   const BlockDev& bd = blocks[it.block];
   const int strand = cd.sf / 3, frame = cd.sf % 3;
-  const int sites = bd.sites[frame], ntiles = bd.ntiles[frame];
+  const int sites = bd.sites[frame];
+  const int nsteps = bd.ntiles[frame] * TILE;  // padded end codons of the frame: a multiple of RT (rows past `sites` are zero)
+  const int ntiles = nsteps / RT;
   const int ngroups = (sites + 32 * R - 1) / (32 * R);
   const int task = cd.task0 + warp;
   if (task >= it.ninst * ngroups) return;
@@ -1043,16 +1119,16 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * STAGE_BYTES);
   unsigned ring_a = smem_u32(ring);
   asm volatile("" : "+r"(ring_a));  // keep the shared-window address in a register (no per-step re-derivation)
-  const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * ntiles * SIG_TILE;
-  const int t0 = row_base / TILE;
-  const int t_last_diag = (row_base + 32 * R - 1) / TILE;
+  const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * nsteps * RS;
+  const int t0 = row_base / RT;
+  const int t_last_diag = (row_base + 32 * R - 1) / RT;
   if (lane == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_fence_init();
     for (int s = 0; s < 2 && t0 + s < ntiles; s++) {
       mbar_expect_tx(&bars[s], STAGE_BYTES);
-      bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(t0 + s) * SIG_TILE, STAGE_BYTES, &bars[s]);
+      bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(t0 + s) * RT * RS, STAGE_BYTES, &bars[s]);
     }
   }
   // fold state of the getHSS digest: two records per lane in shared memory, flushed at the end of the task
@@ -1076,13 +1152,15 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
     const int s = (tile - t0) & 1;
     const unsigned parity = ((tile - t0) >> 1) & 1;
     const unsigned a0 = ring_a + s * STAGE_BYTES;
-    const int j0 = tile * TILE;
+    const int j0 = tile * RT;
+    constexpr int tsteps = RT;
     const bool diag = tile <= t_last_diag;  // rows start inside this tile
     mbar_wait(&bars[s], parity);
+#if !RC_REG_DIAG_MASKED
     if (diag) {
       // rows start inside the tile: one step at a time with the start-of-row reset
 #pragma unroll 1
-      for (int c = 0; c < TILE; c++) {
+      for (int c = 0; c < tsteps; c++) {
         float sv[RS];
         reg_load_row<NK>(a0 + c * RS * 4, sv);
         const float2 sum = reg_update<NK>(S0, S1, S2, sv, true, j0 + c, r0, Delta, Omega, omega);
@@ -1091,19 +1169,33 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
           lb.y = reg_check_row(sum.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
         }
       }
-    } else {
-      // steady state: two end codons per iteration.  Pairs without any frameshift run one straight-line block (the
-      // species-sum chain of the first codon overlaps the state updates of the second); other pairs take the two
-      // codons one after the other through reg_update.  The rows of the next iteration are requested right after
-      // the arithmetic (unconditionally, so that the loop carries them without register copies: past the tile
-      // they hit the other stage or the pad, and are discarded).
+    } else
+#endif
+    {
+      // Two end codons per iteration.  Pairs without any frameshift run one straight-line block (the species-sum
+      // chain of the first codon overlaps the state updates of the second); other pairs take the two codons one
+      // after the other.  The rows of the next iteration are requested right after the arithmetic (unconditionally,
+      // so that the loop carries them without register copies: past the tile they hit the other stage or the pad,
+      // and are discarded).
       float svA[RS], svB[RS];
       reg_load_row<NK>(a0, svA);
       reg_load_row<NK>(a0 + RS * 4, svB);
 #pragma unroll 1
-      for (int c = 0; c < TILE; c += 2) {
+      for (int c = 0; c < tsteps; c += 2) {
         float2 sumA, sumB;
-        if ((__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u) {
+        const bool clean = (__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u;
+#if RC_REG_DIAG_MASKED
+        if (diag) {  // masked variants, see reg_pair_diag
+          const bool P = j0 + c >= r0, Q = j0 + c > r0;
+          if (clean) {
+            reg_pair_diag<NK>(S0, S1, S2, svA, svB, omega, P, Q, sumA, sumB);
+          } else {
+            sumA = reg_update_diag<NK>(S0, S1, S2, svA, P, Q, Delta, Omega, omega);
+            sumB = reg_update_diag<NK>(S0, S1, S2, svB, P, P, Delta, Omega, omega);
+          }
+        } else
+#endif
+        if (clean) {
           reg_pair_fast<NK>(S0, S1, S2, svA, svB, omega, sumA, sumB);
         } else {
           sumA = reg_update<NK>(S0, S1, S2, svA, false, j0 + c, r0, Delta, Omega, omega);
@@ -1112,17 +1204,17 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
         reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
         reg_load_row<NK>(a0 + (c + 3) * RS * 4, svB);
         if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
-          lb.x = reg_check_row(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-          lb.y = reg_check_row(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
-          lb.x = reg_check_row(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-          lb.y = reg_check_row(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          if (sumA.x > 0.0f) lb.x = reg_check_row(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumA.y > 0.0f) lb.y = reg_check_row(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          if (sumB.x > 0.0f) lb.x = reg_check_row(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumB.y > 0.0f) lb.y = reg_check_row(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
         }
       }
     }
     __syncwarp();
     if (lane == 0 && tile + 2 < ntiles) {
       mbar_expect_tx(&bars[s], STAGE_BYTES);
-      bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(tile + 2) * SIG_TILE, STAGE_BYTES, &bars[s]);
+      bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(tile + 2) * RT * RS, STAGE_BYTES, &bars[s]);
     }
   }
   // rows without any positive entry keep n == 0; accepted rows hold Emax / vF / jF / band
@@ -1249,22 +1341,7 @@ __global__ void __launch_bounds__(CHAIN_MAX_WARPS * 32)
     mbar_wait(&bars[s], parity);
     if (!first) mbar_wait(&full_in[s], parity);                           // partial sums of this tile have arrived
     if (!last && tile - t0 >= 2) mbar_wait(&empty_out[s], parity ^ 1u);   // the next warp is done with this stage
-    if (diag) {
-#pragma unroll 1
-      for (int c = 0; c < TILE; c++) {
-        float sv[RS];
-        reg_load_row<NK>(a0 + c * RS * 4, sv);
-        float2 sin = make_float2(0.0f, 0.0f);
-        if (!first) sin = lds_f2(hin + c * 256);
-        const float2 sum = reg_update<NK, true>(S0, S1, S2, sv, true, j0 + c, r0, Delta, Omega, omega, sin);
-        if (!last) {
-          sts_f2(hout + c * 256, sum);
-        } else if (fmaxf(sum.x, sum.y) > 0.0f) {
-          lb.x = reg_check_row(sum.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-          lb.y = reg_check_row(sum.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
-        }
-      }
-    } else {
+    {
       float svA[RS], svB[RS];
       reg_load_row<NK>(a0, svA);
       reg_load_row<NK>(a0 + RS * 4, svB);
@@ -1276,11 +1353,22 @@ __global__ void __launch_bounds__(CHAIN_MAX_WARPS * 32)
           sinA = lds_f2(hin + c * 256);
           sinB = lds_f2(hin + (c + 1) * 256);
         }
-        if ((__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u) {
-          reg_pair_fast<NK, true>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
+        const bool clean = (__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u;
+        if (!diag) {
+          if (clean) {
+            reg_pair_fast<NK, true>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
+          } else {
+            sumA = reg_update<NK, true>(S0, S1, S2, svA, false, j0 + c, r0, Delta, Omega, omega, sinA);
+            sumB = reg_update<NK, true>(S0, S1, S2, svB, false, j0 + c + 1, r0, Delta, Omega, omega, sinB);
+          }
         } else {
-          sumA = reg_update<NK, true>(S0, S1, S2, svA, false, j0 + c, r0, Delta, Omega, omega, sinA);
-          sumB = reg_update<NK, true>(S0, S1, S2, svB, false, j0 + c + 1, r0, Delta, Omega, omega, sinB);
+          const bool P = j0 + c >= r0, Q = j0 + c > r0;
+          if (clean) {
+            reg_pair_diag<NK, true>(S0, S1, S2, svA, svB, omega, P, Q, sumA, sumB, sinA, sinB);
+          } else {
+            sumA = reg_update_diag<NK, true>(S0, S1, S2, svA, P, Q, Delta, Omega, omega, sinA);
+            sumB = reg_update_diag<NK, true>(S0, S1, S2, svB, P, P, Delta, Omega, omega, sinB);
+          }
         }
         reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
         reg_load_row<NK>(a0 + (c + 3) * RS * 4, svB);
@@ -1288,10 +1376,10 @@ __global__ void __launch_bounds__(CHAIN_MAX_WARPS * 32)
           sts_f2(hout + c * 256, sumA);
           sts_f2(hout + (c + 1) * 256, sumB);
         } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
-          lb.x = reg_check_row(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-          lb.y = reg_check_row(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
-          lb.x = reg_check_row(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-          lb.y = reg_check_row(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          if (sumA.x > 0.0f) lb.x = reg_check_row(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumA.y > 0.0f) lb.y = reg_check_row(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          if (sumB.x > 0.0f) lb.x = reg_check_row(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumB.y > 0.0f) lb.y = reg_check_row(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
         }
       }
     }

@@ -493,6 +493,8 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
           (size_t)5 * 32 * (bd.cols + 8) <= SMP_SMEM_MAX)
         layout = 2;  // short block with many instances: sample-major kernel
       set_layout(bd, layout);
+      if (layout == 1)  // k_dp_reg stages RC_REG_TILE end codons at a time: pad the frame to whole stages
+        for (int f = 0; f < 3; f++) bd.ntiles[f] = (bd.ntiles[f] + RC_REG_TILE / TILE - 1) / (RC_REG_TILE / TILE) * (RC_REG_TILE / TILE);
     }
     for (int s = 0; s < 2; s++)
       for (int f = 0; f < 3; f++) {
@@ -943,6 +945,7 @@ static int run_dense_items(rc_batch* b, const std::vector<Item>& src_items) {
   for (const Item& src : src_items) {
     BlockDev bd = b->blocks[src.block];
     set_layout(bd, 0);
+    for (int f = 0; f < 3; f++) bd.ntiles[f] = (bd.sites[f] + TILE - 1) / TILE;  // without the padding of layout 1
     size_t zw = 0;
     for (int s = 0; s < 2; s++)
       for (int f = 0; f < 3; f++) {
