@@ -53,6 +53,10 @@ segmentStats *__wrap_scoreAln(const struct aln *inputAln[], TTree *tree, float k
   (void)tree;
   (void)kappa;
 
+  if (pars.postscript) { /* the colour plots read the dense Sk matrices (src/postscript.c:303), which the GPU path never builds */
+    fprintf(stderr, "RNAcode: --eps is not available with libRNAcode_cuda (dense score matrices are not materialised)\n");
+    exit(EXIT_FAILURE);
+  }
   fill_desc(inputAln, &d, &rows, &sf, &sr, &blosum);
   h = (rc_hss *)malloc(sizeof(rc_hss) * cap);
   rc = rc_score_aln(ctx(), &d, &p, blosum, h, cap, &n);

@@ -13,9 +13,9 @@
  *      simulated (kernel d), packed, scored and reduced on the GPU (rc_batch_*);
  *   5. in input order: sort, EVDMaxLikelyFit, p-values, printResults -- all the reference's own code.
  *
- * --stop-early only changes what is reported (p = 99.0 when more than cutoff*n null alignments beat the native
- * score, src/score.c:1036-1042): the count is monotone in the sample index, so evaluating all n samples gives the
- * same decision.
+ * --stop-early (p = 99.0 as soon as more than cutoff*n null alignments beat the native score,
+ * src/score.c:1036-1042): the count is monotone in the sample index, so it is evaluated in two rounds -- 32 null
+ * alignments for every block, the remaining n-32 only for the blocks still undecided -- with the same outcome.
  *
  * Not supported here: --eps (the colour plots need the reference's dense Sk matrices; use RNAcode_cuda or the
  * reference for those blocks).
@@ -58,6 +58,7 @@ void freeModels(bgModel *models, int N);
 
 /* deterministic test builds (oracle/ref_wrap.c) derive seeds from (scored block index, sample index) */
 void rc_wrap_set_block(long b) __attribute__((weak));
+void rc_wrap_set_sample(long s) __attribute__((weak));
 
 typedef struct {
   struct aln **aln; /* NULL-terminated, owned */
@@ -70,6 +71,12 @@ typedef struct {
   int *tpar, *trow;
   double *tcum;
   char *rows;
+  /* scoring results */
+  rc_hss *hss;
+  int n_hss, hssCount, status, better;
+  float maxScore;
+  double *maxScores;
+  segmentStats *results;
 } blk_t;
 
 static double now_s(void) {
@@ -199,135 +206,159 @@ static void run_host_stage(blk_t *blk, int nb) {
   free(pid);
 }
 
-static void process_window(blk_t *blk, int nb, int *blosum) {
-  const int n = pars.sampleN;
+/* One library batch: the native alignment and the null alignments [s0, s0 + ns) of the listed blocks.  Fills
+ * blk[].maxScores[s0 .. s0+ns) and, when want_native, blk[].hss / blk[].n_hss. */
+static void gpu_batch(blk_t *blk, const int *list, int nlist, int s0, int ns, const int *blosum, int want_native,
+                      double *t_seeds, double *t_gpu) {
   const int mode = evolve_mode();
   rc_params p = current_params();
-  rc_block_desc *descs;
+  rc_block_desc *descs = (rc_block_desc *)malloc(sizeof(rc_block_desc) * nlist);
   rc_batch *batch = NULL;
-  int *map, nok = 0, i, k, j;
-  double t0 = now_s(), t1, t2, t3, t_models = 0, t_create = 0;
+  unsigned int *seeds = (unsigned int *)malloc(sizeof(unsigned int) * (ns > 0 ? ns : 1));
+  double ta = now_s(), tb;
+  int k, j;
+  for (k = 0; k < nlist; k++) {
+    blk_t *b = &blk[list[k]];
+    descs[k].N = b->N;
+    descs[k].cols = b->cols;
+    descs[k].rows = b->rows;
+    descs[k].scores_fwd = b->sf;
+    descs[k].scores_rev = b->sr;
+    descs[k].n_samples = ns;
+    descs[k].samples = NULL;
+  }
+  if (rc_batch_create(ctx(), descs, nlist, &p, blosum, &batch) != RC_OK) die("rc_batch_create");
+  for (k = 0; k < nlist && ns > 0; k++) {
+    blk_t *b = &blk[list[k]];
+    rc_tree_desc td;
+    td.n_nodes = b->n_nodes;
+    td.parent = b->tpar;
+    td.row = b->trow;
+    td.cum = b->tcum;
+    if (rc_wrap_set_block) rc_wrap_set_block(b->scored_idx);
+    if (rc_wrap_set_sample) rc_wrap_set_sample(s0);
+    for (j = 0; j < ns; j++) seeds[j] = (unsigned int)(CreateSeed() & 0xffffffffUL); /* src/treeSimulate.c:84 */
+    if (rc_batch_set_evolve(batch, k, &td, seeds, mode == 2 ? RC_RNG_PHILOX : RC_RNG_MT19937) != RC_OK)
+      die("rc_batch_set_evolve");
+  }
+  tb = now_s();
+  *t_seeds += tb - ta;
+  if (rc_batch_upload(batch) != RC_OK) die("rc_batch_upload");
+  if (rc_batch_run(batch) != RC_OK) die("rc_batch_run");
+  if (rc_batch_download(batch) != RC_OK) die("rc_batch_download");
+  for (k = 0; k < nlist; k++) {
+    blk_t *b = &blk[list[k]];
+    if (ns > 0 && rc_batch_max_scores(batch, k, b->maxScores + s0) != RC_OK) die("rc_batch_max_scores");
+    if (want_native) {
+      int cap = 256, rc;
+      b->hss = (rc_hss *)malloc(sizeof(rc_hss) * cap);
+      rc = rc_batch_native_hss(batch, k, b->hss, cap, &b->n_hss);
+      if (rc == RC_ERR_CAPACITY) {
+        cap = b->n_hss;
+        b->hss = (rc_hss *)realloc(b->hss, sizeof(rc_hss) * cap);
+        rc = rc_batch_native_hss(batch, k, b->hss, cap, &b->n_hss);
+      }
+      if (rc != RC_OK) die("rc_batch_native_hss");
+    }
+  }
+  rc_batch_destroy(batch);
+  free(descs);
+  free(seeds);
+  *t_gpu += now_s() - tb;
+}
+
+static void process_window(blk_t *blk, int nb, int *blosum) {
+  const int n = pars.sampleN > 0 ? pars.sampleN : 0;
+  /* --stop-early: a first round of few null alignments per block decides most non-coding blocks
+   * (src/score.c:1036-1042: more than cutoff*n of them beat the native score); only the others get the rest */
+  const int n1 = (pars.stopEarly && n > 32) ? 32 : n;
+  const int stopCutoff = (int)(pars.cutoff * pars.sampleN); /* src/score.c:992 */
+  int *list, nok = 0, nlist2 = 0, i, k, j;
+  double t0 = now_s(), t1, t3, t_seeds = 0, t_gpu = 0;
   const int verbose = getenv("RNACODE_CUDA_VERBOSE") != NULL;
 
   run_host_stage(blk, nb);
   t1 = now_s();
 
-  descs = (rc_block_desc *)malloc(sizeof(rc_block_desc) * (nb > 0 ? nb : 1));
-  map = (int *)malloc(sizeof(int) * (nb > 0 ? nb : 1));
+  list = (int *)malloc(sizeof(int) * (nb > 0 ? nb : 1));
   for (i = 0; i < nb; i++) {
     blk_t *b = &blk[i];
     if (!b->ok) continue;
     b->rows = (char *)malloc((size_t)b->N * b->cols);
     for (k = 0; k < b->N; k++) memcpy(b->rows + (size_t)k * b->cols, b->aln[k]->seq, b->cols);
-    descs[nok].N = b->N;
-    descs[nok].cols = b->cols;
-    descs[nok].rows = b->rows;
-    descs[nok].scores_fwd = b->sf;
-    descs[nok].scores_rev = b->sr;
-    descs[nok].n_samples = n > 0 ? n : 0;
-    descs[nok].samples = NULL;
-    map[nok++] = i;
+    b->maxScores = (double *)malloc(sizeof(double) * (n > 0 ? n : 1));
+    list[nok++] = i;
   }
-  t_models = now_s() - t1;
-  if (nok > 0) {
-    t_create = now_s();
-    if (rc_batch_create(ctx(), descs, nok, &p, blosum, &batch) != RC_OK) die("rc_batch_create");
-    t_create = now_s() - t_create;
-    if (n > 0) {
-      unsigned int *seeds = (unsigned int *)malloc(sizeof(unsigned int) * n);
-      for (k = 0; k < nok; k++) {
-        blk_t *b = &blk[map[k]];
-        rc_tree_desc td;
-        td.n_nodes = b->n_nodes;
-        td.parent = b->tpar;
-        td.row = b->trow;
-        td.cum = b->tcum;
-        if (rc_wrap_set_block) rc_wrap_set_block(b->scored_idx);
-        for (j = 0; j < n; j++) seeds[j] = (unsigned int)(CreateSeed() & 0xffffffffUL); /* src/treeSimulate.c:84 */
-        if (rc_batch_set_evolve(batch, k, &td, seeds, mode == 2 ? RC_RNG_PHILOX : RC_RNG_MT19937) != RC_OK)
-          die("rc_batch_set_evolve");
-      }
-      free(seeds);
+  if (nok > 0) gpu_batch(blk, list, nok, 0, n1, blosum, 1, &t_seeds, &t_gpu);
+
+  /* the reference's bookkeeping on the native result: sort, best score (src/RNAcode.c:173-178), then the first round's count */
+  for (k = 0; k < nok; k++) {
+    blk_t *b = &blk[list[k]];
+    b->results = hss_to_segments((const struct aln **)b->aln, b->hss, b->n_hss);
+    free(b->hss);
+    b->hssCount = 0;
+    while (b->results[b->hssCount++].score > 0.0);
+    qsort(b->results, b->hssCount, sizeof(segmentStats), compareScores);
+    b->maxScore = b->results[0].score;
+    b->status = 1;
+    b->better = 0;
+    for (j = 0; j < n1 && b->status == 1; j++) {
+      if ((float)b->maxScores[j] > b->maxScore) b->better++;
+      if (pars.stopEarly && b->better > stopCutoff) b->status = -1;
     }
-    t2 = now_s();
-    if (rc_batch_upload(batch) != RC_OK) die("rc_batch_upload");
-    if (rc_batch_run(batch) != RC_OK) die("rc_batch_run");
-    if (rc_batch_download(batch) != RC_OK) die("rc_batch_download");
-  } else {
-    t2 = now_s();
+    if (b->status == 1 && n1 < n) list[nlist2++] = list[k];
+  }
+  if (nlist2 > 0) {
+    gpu_batch(blk, list, nlist2, n1, n - n1, blosum, 0, &t_seeds, &t_gpu);
+    for (k = 0; k < nlist2; k++) {
+      blk_t *b = &blk[list[k]];
+      for (j = n1; j < n && b->status == 1; j++) {
+        if ((float)b->maxScores[j] > b->maxScore) b->better++;
+        if (pars.stopEarly && b->better > stopCutoff) b->status = -1;
+      }
+    }
   }
   t3 = now_s();
 
-  /* phase 5: the reference's reporting, in input order */
-  {
-    double *maxScores = (double *)malloc(sizeof(double) * (n > 0 ? n : 1));
-    int cap = 1024, nh = 0;
-    rc_hss *h = (rc_hss *)malloc(sizeof(rc_hss) * cap);
-    k = 0;
-    for (i = 0; i < nb; i++) {
-      blk_t *b = &blk[i];
-      segmentStats *results;
-      int hssCount, status = 1, better = 0, stopCutoff, rc;
-      float maxScore, parMu = 0, parLambda = 0;
-      double mu, lambda;
-      if (!b->ok) {
-        fprintf(stderr, "\nSkipping alignment. Failed to build ML tree.\n");
-        freeAln(b->aln);
-        free(b->aln);
-        continue;
-      }
-      rc = rc_batch_native_hss(batch, k, h, cap, &nh);
-      if (rc == RC_ERR_CAPACITY) {
-        cap = nh;
-        h = (rc_hss *)realloc(h, sizeof(rc_hss) * cap);
-        rc = rc_batch_native_hss(batch, k, h, cap, &nh);
-      }
-      if (rc != RC_OK) die("rc_batch_native_hss");
-      results = hss_to_segments((const struct aln **)b->aln, h, nh);
-      hssCount = 0;
-      while (results[hssCount++].score > 0.0);
-      qsort(results, hssCount, sizeof(segmentStats), compareScores); /* src/RNAcode.c:176 */
-      maxScore = results[0].score;
-      /* getExtremeValuePars, src/score.c:1034-1062, on the maxima the GPU returned */
-      if (n > 0 && rc_batch_max_scores(batch, k, maxScores) != RC_OK) die("rc_batch_max_scores");
-      stopCutoff = (int)(pars.cutoff * pars.sampleN);
-      for (j = 0; j < n && status == 1; j++) {
-        if ((float)maxScores[j] > maxScore) better++;
-        if (pars.stopEarly && better > stopCutoff) status = -1;
-      }
-      if (status == 1) {
-        if (EVDMaxLikelyFit(maxScores, NULL, n, &mu, &lambda) == 1) {
-          parMu = mu;
-          parLambda = lambda;
-        } else {
-          status = -1;
-        }
-      }
-      for (j = 0; j < hssCount; j++)
-        results[j].pvalue = status == 1 ? 1 - exp((-1) * exp((-1) * parLambda * (results[j].score - parMu))) : 99.0;
-      printResults(pars.outputFile, pars.outputFormat, (const struct aln **)b->aln, results);
-      freeResults(results);
-      free(b->rows);
-      free(b->sf);
-      free(b->sr);
-      free(b->tpar);
-      free(b->trow);
-      free(b->tcum);
+  /* the reference's fit and reporting, in input order */
+  for (i = 0; i < nb; i++) {
+    blk_t *b = &blk[i];
+    float parMu = 0, parLambda = 0;
+    double mu, lambda;
+    if (!b->ok) {
+      fprintf(stderr, "\nSkipping alignment. Failed to build ML tree.\n");
       freeAln(b->aln);
       free(b->aln);
-      k++;
+      continue;
     }
-    free(h);
-    free(maxScores);
+    if (b->status == 1) { /* src/score.c:1050-1062 */
+      if (EVDMaxLikelyFit(b->maxScores, NULL, n, &mu, &lambda) == 1) {
+        parMu = mu;
+        parLambda = lambda;
+      } else {
+        b->status = -1;
+      }
+    }
+    for (j = 0; j < b->hssCount; j++)
+      b->results[j].pvalue = b->status == 1 ? 1 - exp((-1) * exp((-1) * parLambda * (b->results[j].score - parMu))) : 99.0;
+    printResults(pars.outputFile, pars.outputFormat, (const struct aln **)b->aln, b->results);
+    freeResults(b->results);
+    free(b->maxScores);
+    free(b->rows);
+    free(b->sf);
+    free(b->sr);
+    free(b->tpar);
+    free(b->trow);
+    free(b->tcum);
+    freeAln(b->aln);
+    free(b->aln);
   }
-  if (batch) rc_batch_destroy(batch);
-  free(descs);
-  free(map);
+  free(list);
   if (verbose)
     fprintf(stderr,
-            "[RNAcode_b200] window of %d blocks (%d scored): trees+models (workers) %.3f s, pack rows %.3f s, batch create %.3f s, seeds %.3f s, "
-            "GPU upload+run+download %.3f s, fit+report %.3f s\n",
-            nb, nok, t1 - t0, t_models, t_create, t2 - t1 - t_models - t_create, t3 - t2, now_s() - t3);
+            "[RNAcode_b200] window of %d blocks (%d scored, %d in the second sampling round): trees+models (workers) %.3f s, "
+            "batch set-up+seeds %.3f s, GPU upload+run+download %.3f s, fit+report %.3f s\n",
+            nb, nok, nlist2, t1 - t0, t_seeds, t_gpu, now_s() - t3);
 }
 
 int main(int argc, char *argv[]) {

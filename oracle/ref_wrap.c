@@ -37,6 +37,7 @@ static unsigned long base_seed(void) {
 
 /* the probe may set these explicitly */
 void rc_wrap_set_block(long b) { g_block = b; g_sample = 0; }
+void rc_wrap_set_sample(long s) { g_sample = s; }
 long rc_wrap_block(void) { return g_block; }
 long rc_wrap_sample(void) { return g_sample; }
 

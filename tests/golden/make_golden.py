@@ -93,6 +93,9 @@ def main():
                     ("genomic-preprocessed.maf", ["--tabular", "-n", "20"]),
                     ("genomic-preprocessed.maf", ["--gtf", "-r", "-n", "20"]),
                     ("genomic-preprocessed.maf", ["--tabular", "-s", "-p", "0.05", "-n", "20"]),
+                    # more than 32 samples under --stop-early: the batched pipeline samples in two rounds
+                    ("genomic-preprocessed.maf", ["--tabular", "-s", "-p", "0.05", "-n", "70"]),
+                    ("genomic.maf", ["--gtf", "-s", "-p", "0.1", "-n", "40"]),
                     ("coding.aln", ["--tabular", "-c", "-9.5,-3.25,-1.5,-50"])):
         env = dict(os.environ, RNACODE_SEED="1")
         out = subprocess.run([DET, *opts, os.path.join(ex, f)], check=True, capture_output=True, env=env).stdout.decode()
