@@ -360,6 +360,11 @@ def ours(args):
         dp_per_step_s = (dp_ms / args.steps) * 1e-3   # rank-local k_dp time per step
         achieved = cells * OPS_PER_CELL / dp_per_step_s
         nblocks = len(blocks) * world
+        traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -376,7 +381,9 @@ def ours(args):
                     "blocks_per_s": nblocks / (e2e_ms / e2e_steps * 1e-3)},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "fp32_issue", "kernel": "k_dp", "achieved": achieved / 1e12, "peak": nominal_peak / 1e12,
-                         "unit": "TFLOP/s", "frac": achieved / nominal_peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / nominal_peak,
+                         "traffic": traffic["dram_bytes_per_launch"] if traffic and not args.samples else None,
+                         "traffic_source": traffic["source"] if traffic and not args.samples else None,
                          "peak_source": "nominal %d SMs x 128 lanes x %.0f MHz (no FP32-issue figure in MEASURED_PEAKS.json)" % (
                              sm_count, sm_max),
                          "peak_measured": issue_measured / 1e12,
