@@ -41,6 +41,7 @@ WORKLOADS = {
     "genomic": (GENOMIC_SHAPES, 1000, 2, "synthetic MAF with the 11 block shapes of examples/genomic.maf, -n 1000"),
     "short": ([(10, 120)] * 2000, 100, 1, "synthetic MAF 2000 blocks x 10 species x 120 cols, -n 100 (config 3 shape)"),
     "wide": ([(50, 5000)] * 1, 200, 3, "synthetic MAF 1 block x 50 species x 5000 cols, -n 200 (config 4 shape, reduced n)"),
+    "hundred": ([(100, 1000)] * 4, 250, 4, "synthetic MAF 4 blocks x 100 species x 1000 cols, -n 250 (config 5 row count)"),
 }
 METRIC = "codon_dp_cells_per_s"
 UNIT = "cells/s"
@@ -291,12 +292,14 @@ def ours(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dp_ms, stage_ms, launches, dp_launches = 0.0, {"pack": 0.0, "sigma": 0.0, "dp": 0.0, "hss": 0.0}, 0, 0
+    pack_kernel_ms = 0.0
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
         bt.run()
         st = bt.stats()
         dp_ms += st["ms_dp"]
+        pack_kernel_ms += st["ms_pack_kernel"]
         for k in stage_ms:
             stage_ms[k] += st["ms_" + k]
         launches += st["launches"]
@@ -390,6 +393,14 @@ def ours(args):
                          "frac_of_measured": achieved / issue_measured if issue_measured else None,
                          "ops_per_cell": OPS_PER_CELL, "kernel_ms_per_step": dp_ms / args.steps,
                          "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}},
+            # subsystem (a): k_pack against the measured HBM copy bandwidth; algorithmic bytes = 2 B per character
+            # (16 B read + 16 B written per 16 characters)
+            "roofline_pack": {"bound": "hbm", "kernel": "k_pack", "unit": "GB/s",
+                              "achieved": 2.0 * st["pack_chars"] / (pack_kernel_ms / args.steps * 1e-3) / 1e9 if pack_kernel_ms else None,
+                              "peak": peaks.get("hbm_gbs"),
+                              "frac": (2.0 * st["pack_chars"] / (pack_kernel_ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"])
+                              if pack_kernel_ms and peaks.get("hbm_gbs") else None,
+                              "kernel_ms_per_step": pack_kernel_ms / args.steps},
             "dense_fallbacks": int(fallbacks),
             "native_hss_total": int(sum(best_native)),
         }

@@ -147,6 +147,8 @@ typedef struct {
   long long dp_launches;
   size_t h2d_bytes, d2h_bytes; /* bytes moved by upload / download */
   size_t device_bytes;         /* device memory held by the batch */
+  float ms_pack_kernel;        /* k_pack alone (ms_pack also covers k_evolve and k_prep) */
+  double pack_chars;           /* characters k_pack classifies per run: sum over blocks of instances*N*cols (padded to 16) */
 } rc_batch_stats;
 int rc_batch_get_stats(rc_batch *batch, rc_batch_stats *stats);
 

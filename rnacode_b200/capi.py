@@ -55,7 +55,7 @@ class rc_batch_stats(C.Structure):
     _fields_ = [("cells", C.c_double), ("launches", C.c_longlong), ("dense_fallbacks", C.c_longlong),
                 ("ms_pack", C.c_float), ("ms_sigma", C.c_float), ("ms_dp", C.c_float), ("ms_hss", C.c_float),
                 ("dp_launches", C.c_longlong), ("h2d_bytes", C.c_size_t), ("d2h_bytes", C.c_size_t),
-                ("device_bytes", C.c_size_t)]
+                ("device_bytes", C.c_size_t), ("ms_pack_kernel", C.c_float), ("pack_chars", C.c_double)]
 
 
 EXPORTS = [

@@ -53,6 +53,7 @@ struct BlockDev {
   int layout;               // 0: sigma tile [k][TILE] (k_dp, any NK); 1: sigma tile [TILE][RS] (k_dp_reg, NK <= 16);
                             // 2: sample-major [group of 32 instances][step][RSB/4][lane][4] (k_dp_smp, short blocks);
                             // 3: sigma tile [chunk][TILE][RS] (k_dp_chain: species cut into nchunk chunks of <= nkw)
+  int chain_tasks;          // layout 3: consecutive tasks one CTA of k_dp_chain works through
   int nchunk, nkw;          // layout 3: chunks and species per chunk (template NK of k_dp_chain); chunk g holds
   int chunk_base, chunk_rem;  //   chunk_base + (g < chunk_rem) species starting at g*chunk_base + min(g, chunk_rem)
   int sig_tile;             // floats per sigma tile

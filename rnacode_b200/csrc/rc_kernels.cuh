@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDev* __restrict__ block
 //   (getBlock, src/misc.c:198-244: |gaps_k - gaps_0| mod 3 over the columns of the codon ending at
 //   position x plus the reference-gap columns in front of it; from column 1 for x == 3).
 // ---------------------------------------------------------------------------------------------
+// PHASE 0: both parts in one CTA per block (dense fallback set-up); 1: cols0 only (one CTA per block);
+// 2: z words only, the work of a block spread over gridDim.y CTAs (cols0 comes from a PHASE 1 launch)
+template <int PHASE>
 __global__ void __launch_bounds__(256) k_prep(const BlockDev* __restrict__ blocks, const unsigned char* __restrict__ cls,
                                               int* __restrict__ cols0, unsigned* __restrict__ ztiles) {
   __shared__ int s_cnt[256];
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(256) k_prep(const BlockDev* __restrict__ block
   const int cols = bd.cols, L = bd.L;
   int* c0f = cols0 + bd.cols0_off;
   int* c0r = c0f + (L + 1);
+  if (PHASE != 2) {
   // 1) prefix count of non-gap characters of row 0
   const int per = (cols + 255) / 256;
   const int lo = min(cols, (int)threadIdx.x * per), hi = min(cols, lo + per);
@@ -131,6 +135,8 @@ __global__ void __launch_bounds__(256) k_prep(const BlockDev* __restrict__ block
     }
   if (threadIdx.x == 0) c0f[0] = c0r[0] = -1;
   __syncthreads();  // cols0 written by this CTA is visible to it below (global writes + barrier)
+  }
+  if (PHASE == 1) return;
   // 2) z words
   const int NK = bd.NK;
   for (int s = 0; s < 2; s++) {
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(256) k_prep(const BlockDev* __restrict__ block
       const int sites = bd.sites[f], nt = bd.ntiles[f];
       unsigned* zt = ztiles + bd.z_off[s][f];
       const int work = nt * bd.zstride;
-      for (int w = threadIdx.x; w < work; w += blockDim.x) {
+      for (int w = blockIdx.y * blockDim.x + threadIdx.x; w < work; w += gridDim.y * blockDim.x) {
         const int tile = w / bd.zstride, u = w % bd.zstride;
         unsigned word = 0;
         // layout 0: u = species, loop over the tile's steps; layout 1: u = step, loop over species;
@@ -1230,13 +1236,17 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
 // codons), warp g owning chunk g with its 3*NK float2 states in registers exactly like k_dp_reg.  The species
 // sum of the reference is one k-ordered float chain (src/score.c:834-838), so it is pipelined through the warps:
 // warp g continues the partial sums warp g-1 left in shared memory for every (end codon, row) of a tile
-// (2-stage hand-off buffers, full/empty mbarriers per boundary), adds its own species in order and passes the
+// (RC_CHAIN_STAGES hand-off buffers with full/empty mbarriers per boundary), adds its own species in order and passes the
 // result on; the last warp owns the getHSS digest.  Warp g therefore runs about one tile behind warp g-1.
 // Chunks that are one species short carry a dummy species (sigma = +0, z = 0, state 0): with omega <= 0 its
 // contribution max3(0, t*omega, t*omega) = +0 leaves the sum unchanged (x + 0 == x).
 // sigma layout 3: [instance][tile][chunk][step][RS] (RS = NK sigma values + the chunk's z word, padded to 16 B).
 // ---------------------------------------------------------------------------------------------
 constexpr int CHAIN_MAX_WARPS = 16;
+constexpr int CHAIN_MAX_TASKS = 8;  // upper bound of BlockDev.chain_tasks
+#ifndef RC_CHAIN_STAGES
+#define RC_CHAIN_STAGES 3
+#endif
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -1255,14 +1265,23 @@ struct ChainCfg {
   static constexpr int RS = RegCfg<NK>::RS;
   static constexpr int STAGE_BYTES = RegCfg<NK>::STAGE_BYTES;
   static constexpr int RING_BYTES = 2 * STAGE_BYTES + 16 + 2 * RS * 4;  // two stages, two mbarriers, read-ahead pad
-  static constexpr int HAND_BYTES = 2 * TILE * 32 * 8;                  // per boundary: [stage][step][lane] float2
+  static constexpr int HAND_STAGES = RC_CHAIN_STAGES;                   // hand-off buffers per boundary
+  static constexpr int HAND_BYTES = HAND_STAGES * TILE * 32 * 8;        // per boundary: [stage][step][lane] float2
   static __host__ __device__ size_t smem_bytes(int W) {
-    return (size_t)W * RING_BYTES + (size_t)(W - 1) * HAND_BYTES + (size_t)(W - 1) * 32 + 64 * sizeof(RowRec);
+    return (size_t)W * RING_BYTES + (size_t)(W - 1) * HAND_BYTES + (size_t)(W - 1) * 16 * HAND_STAGES + 64 * sizeof(RowRec);
   }
 };
 
+#ifndef RC_CHAIN_MAXREG
+#define RC_CHAIN_MAXREG 128
+#endif
 template <int NK>
-__global__ void __launch_bounds__(CHAIN_MAX_WARPS * 32)
+__global__ void
+#if RC_CHAIN_MAXREG < 128
+    __maxnreg__(RC_CHAIN_MAXREG)
+#else
+    __launch_bounds__(CHAIN_MAX_WARPS * 32)
+#endif
     k_dp_chain(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
                const float* __restrict__ sigma, RowRec* __restrict__ recs, Params prm, int band_slots) {
   constexpr int R = 2;
@@ -1280,67 +1299,81 @@ __global__ void __launch_bounds__(CHAIN_MAX_WARPS * 32)
   const int strand = cd.sf / 3, frame = cd.sf % 3;
   const int sites = bd.sites[frame], ntiles = bd.ntiles[frame];
   const int ngroups = (sites + 32 * R - 1) / (32 * R);
-  const int task = cd.task0;  // one task per CTA
-  const int inst_l = task / ngroups, g = task % ngroups;
-  const int row_base = g * 32 * R;
-  const int r0 = row_base + lane * R;
+  const int ntasks = it.ninst * ngroups;
   const bool first = warp == 0, last = warp == W - 1;
 
   unsigned char* ring = smem + (size_t)warp * RING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * STAGE_BYTES);
   unsigned char* hand = smem + (size_t)W * RING_BYTES;
-  uint64_t* hbar = reinterpret_cast<uint64_t*>(hand + (size_t)(W - 1) * HAND_BYTES);  // [boundary][full0, full1, empty0, empty1]
-  RowRec* srec = reinterpret_cast<RowRec*>(hbar + 4 * (W - 1));
+  constexpr int HS = ChainCfg<NK>::HAND_STAGES;
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(hand + (size_t)(W - 1) * HAND_BYTES);  // [boundary][full 0..HS-1, empty 0..HS-1]
+  RowRec* srec = reinterpret_cast<RowRec*>(hbar + 2 * HS * (W - 1));
   unsigned ring_a = smem_u32(ring);
   asm volatile("" : "+r"(ring_a));
-  const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * ntiles * bd.sig_tile + (size_t)warp * SIG_TILE;
   const size_t tile_stride = (size_t)bd.sig_tile;
-  const int t0 = row_base / TILE;
-  const int t_last_diag = (row_base + 32 * R - 1) / TILE;
   if (lane == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     if (!last)
-      for (int q = 0; q < 4; q++) mbar_init(&hbar[4 * warp + q], 1);
+      for (int q = 0; q < 2 * HS; q++) mbar_init(&hbar[2 * HS * warp + q], 1);
     mbar_fence_init();
-    for (int s = 0; s < 2 && t0 + s < ntiles; s++) {
-      mbar_expect_tx(&bars[s], STAGE_BYTES);
-      bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(t0 + s) * tile_stride, STAGE_BYTES, &bars[s]);
-    }
   }
   RowRec* rec0 = &srec[lane * R];
-  if (last) {
-    rec_init(rec0);
-    rec_init(rec0 + 1);
-  }
   __syncthreads();  // hand-off barriers are initialised before any neighbour touches them
 
-  float2 S0[NK], S1[NK], S2[NK];
-#pragma unroll
-  for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
-  float2 lb = make_float2(-INFINITY, -INFINITY);
   const float Delta = prm.Delta, Omega = prm.Omega;
   float omega = prm.omega;
   asm volatile("" : "+f"(omega));
   const float fNK = bd.fNK, rcpNK = bd.rcpNK;
   const unsigned hand_in = smem_u32(hand) + (unsigned)((warp - 1) * HAND_BYTES) + lane * 8;  // valid for warp > 0
   const unsigned hand_out = smem_u32(hand) + (unsigned)(warp * HAND_BYTES) + lane * 8;       // valid for warp < W-1
-  uint64_t* full_in = &hbar[4 * (warp - 1)];
-  uint64_t* empty_in = full_in + 2;
-  uint64_t* full_out = &hbar[4 * warp];
-  uint64_t* empty_out = full_out + 2;
+  uint64_t* full_in = &hbar[2 * HS * (warp - 1)];
+  uint64_t* empty_in = full_in + HS;
+  uint64_t* full_out = &hbar[2 * HS * warp];
+  uint64_t* empty_out = full_out + HS;
+  int hs = 0;            // hand-off stage of the current tile, and how often it has been used before
+  unsigned hround = 0;
+  unsigned ring_it = 0;  // tiles this warp has consumed so far (sigma ring stage = ring_it & 1, phase = ring_it >> 1)
+
+  // The CTA works through bd.chain_tasks consecutive tasks.  The warps only meet through the hand-off barriers, so the
+  // first warps start the next task while the last ones finish the current one: the pipeline drains once per CTA,
+  // not once per task (rows of a 1000-column block are only ~20 tiles long, the pipeline is W-1 tiles deep).
+#pragma unroll 1
+  for (int task = cd.task0; task < min(cd.task0 + bd.chain_tasks, ntasks); task++) {
+  const int inst_l = task / ngroups, g = task % ngroups;
+  const int row_base = g * 32 * R;
+  const int r0 = row_base + lane * R;
+  const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * ntiles * bd.sig_tile + (size_t)warp * SIG_TILE;
+  const int t0 = row_base / TILE;
+  const int t_last_diag = (row_base + 32 * R - 1) / TILE;
+  if (lane == 0) {
+    for (int q = 0; q < 2 && t0 + q < ntiles; q++) {
+      const unsigned sq = (ring_it + q) & 1u;
+      mbar_expect_tx(&bars[sq], STAGE_BYTES);
+      bulk_g2s(ring + sq * STAGE_BYTES, sig_src + (size_t)(t0 + q) * tile_stride, STAGE_BYTES, &bars[sq]);
+    }
+  }
+  if (last) {
+    rec_init(rec0);
+    rec_init(rec0 + 1);
+    __syncwarp();
+  }
+  float2 S0[NK], S1[NK], S2[NK];
+#pragma unroll
+  for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
+  float2 lb = make_float2(-INFINITY, -INFINITY);
 
 #pragma unroll 1
-  for (int tile = t0; tile < ntiles; tile++) {
-    const int s = (tile - t0) & 1;
-    const unsigned parity = ((tile - t0) >> 1) & 1;
+  for (int tile = t0; tile < ntiles; tile++, ring_it++) {
+    const unsigned s = ring_it & 1u;
+    const unsigned parity = (ring_it >> 1) & 1u;
     const unsigned a0 = ring_a + s * STAGE_BYTES;
-    const unsigned hin = hand_in + s * (TILE * 256), hout = hand_out + s * (TILE * 256);
+    const unsigned hin = hand_in + hs * (TILE * 256), hout = hand_out + hs * (TILE * 256);
     const int j0 = tile * TILE;
     const bool diag = tile <= t_last_diag;
     mbar_wait(&bars[s], parity);
-    if (!first) mbar_wait(&full_in[s], parity);                           // partial sums of this tile have arrived
-    if (!last && tile - t0 >= 2) mbar_wait(&empty_out[s], parity ^ 1u);   // the next warp is done with this stage
+    if (!first) mbar_wait(&full_in[hs], hround & 1u);                           // partial sums of this tile have arrived
+    if (!last && hround > 0) mbar_wait(&empty_out[hs], (hround & 1u) ^ 1u);     // the next warp is done with this stage
     {
       float svA[RS], svB[RS];
       reg_load_row<NK>(a0, svA);
@@ -1389,8 +1422,12 @@ __global__ void __launch_bounds__(CHAIN_MAX_WARPS * 32)
         mbar_expect_tx(&bars[s], STAGE_BYTES);
         bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(tile + 2) * tile_stride, STAGE_BYTES, &bars[s]);
       }
-      if (!first) mbar_arrive(&empty_in[s]);
-      if (!last) mbar_arrive(&full_out[s]);
+      if (!first) mbar_arrive(&empty_in[hs]);
+      if (!last) mbar_arrive(&full_out[hs]);
+    }
+    if (++hs == HS) {
+      hs = 0;
+      hround++;
     }
   }
   if (last) {
@@ -1398,6 +1435,8 @@ __global__ void __launch_bounds__(CHAIN_MAX_WARPS * 32)
 #pragma unroll
     for (int t = 0; t < R; t++)
       if (r0 + t < sites) rec_copy(grec + t, rec0 + t);
+    __syncwarp();
+  }
   }
 }
 

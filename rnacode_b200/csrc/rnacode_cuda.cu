@@ -126,7 +126,7 @@ struct Chunk {
 
 struct EventPair {
   cudaEvent_t a, b;
-  int stage;  // 0 pack, 1 sigma, 2 dp, 3 hss
+  int stage;  // 0 pack (evolve + pack + prep), 1 sigma, 2 dp, 3 hss, 4 k_pack alone (nested in 0)
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -413,7 +413,7 @@ static void build_ctas(const std::vector<BlockDev>& blocks, const std::vector<It
       if (sites <= 0) continue;
       const long long ngroups = (sites + 32 * R - 1) / (32 * R);
       const long long ntasks = ngroups * it.ninst;
-      const int per_cta = (bd.layout == 3 && want_class >= 0) ? 1 : DP_WARPS;  // k_dp_chain: the CTA's warps share one task
+      const int per_cta = (bd.layout == 3 && want_class >= 0) ? bd.chain_tasks : DP_WARPS;  // k_dp_chain: the CTA's warps share each task
       for (long long t = 0; t < ntasks; t += per_cta) out.push_back(CtaDesc{(int)i, sf, (int)t});
     }
   }
@@ -493,6 +493,13 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
           (size_t)5 * 32 * (bd.cols + 8) <= SMP_SMEM_MAX)
         layout = 2;  // short block with many instances: sample-major kernel
       set_layout(bd, layout);
+      if (layout == 3) {
+        // tasks per CTA: enough tiles per CTA to amortise the W-1 tiles the warp pipeline needs to fill and drain
+        // (a row group of a frame with T tiles has T - 4g tiles: about T/2 on average), but not more: long rows are
+        // better balanced with one task per CTA
+        const double avg_tiles = std::max(1.0, 0.5 * bd.ntiles[0]);
+        bd.chain_tasks = (int)std::min<double>(CHAIN_MAX_TASKS, std::max(1.0, std::ceil(4.0 * (bd.nchunk - 1) / avg_tiles)));
+      }
       if (layout == 1)  // k_dp_reg stages RC_REG_TILE end codons at a time: pad the frame to whole stages
         for (int f = 0; f < 3; f++) bd.ntiles[f] = (bd.ntiles[f] + RC_REG_TILE / TILE - 1) / (RC_REG_TILE / TILE) * (RC_REG_TILE / TILE);
     }
@@ -509,6 +516,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     b->hsscnt_ints += 6;
   }
   b->stats.cells = cells;
+  b->stats.pack_chars = (double)b->raw_bytes;
 
   // chunking: fill items until the scratch budget is reached
   const size_t budget = (size_t)ctx->scratch_mb << 20;
@@ -995,7 +1003,7 @@ static int run_dense_items(rc_batch* b, const std::vector<Item>& src_items) {
     RC_CUDA_D(cudaMemcpyAsync(d_blk, &bd, sizeof(BlockDev), cudaMemcpyHostToDevice, st));
     RC_CUDA_D(cudaMemcpyAsync(d_item, &it, sizeof(Item), cudaMemcpyHostToDevice, st));
     RC_CUDA_D(cudaMemcpyAsync(d_cta, ctas.data(), sizeof(CtaDesc) * ctas.size(), cudaMemcpyHostToDevice, st));
-    k_prep<<<1, 256, 0, st>>>(d_blk, b->d_cls, b->d_cols0, d_zs);
+    k_prep<0><<<1, 256, 0, st>>>(d_blk, b->d_cls, b->d_cols0, d_zs);
     RC_CUDA_D(cudaGetLastError());
     const long long work = (long long)it.ninst * 2 * (bd.L - 2);
     dim3 gs(1, (unsigned)std::min<long long>((work + 255) / 256, 4096));
@@ -1055,11 +1063,19 @@ extern "C" int rc_batch_run(rc_batch* b) {
   }
   {
     dim3 g((unsigned)b->n_blocks, (unsigned)std::min(maxchunks, 2048));
+    const int evk = ev_begin(b, 4);  // k_pack alone (HBM roofline of subsystem (a))
     k_pack<<<g, 256, 0, st>>>(b->d_blocks, b->d_raw, b->d_cls, ctx->d_lut);
     RC_CUDA(cudaGetLastError());
-    k_prep<<<b->n_blocks, 256, 0, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_z);
+    ev_end(b, evk);
+    k_prep<1><<<b->n_blocks, 256, 0, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_z);
     RC_CUDA(cudaGetLastError());
-    b->stats.launches += 2;
+    // z words: a long block would keep a single CTA busy for ~0.2 ms; spread each block over several CTAs
+    size_t maxz = 1;
+    for (const BlockDev& bd : b->blocks) maxz = std::max(maxz, (size_t)bd.ntiles[0] * bd.zstride);
+    dim3 gz((unsigned)b->n_blocks, (unsigned)std::min<size_t>((maxz + 255) / 256, 64));
+    k_prep<2><<<gz, 256, 0, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_z);
+    RC_CUDA(cudaGetLastError());
+    b->stats.launches += 3;
   }
   ev_end(b, ev);
   RC_CUDA(cudaMemsetAsync(b->d_ovf, 0, sizeof(int), st));
@@ -1173,11 +1189,12 @@ extern "C" int rc_batch_run(rc_batch* b) {
     if (rcode != RC_OK) return rcode;
   }
   // stage timings
-  b->stats.ms_pack = b->stats.ms_sigma = b->stats.ms_dp = b->stats.ms_hss = 0.0f;
+  b->stats.ms_pack = b->stats.ms_sigma = b->stats.ms_dp = b->stats.ms_hss = b->stats.ms_pack_kernel = 0.0f;
   for (auto& e : b->events) {
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
-      if (e.stage == 0) b->stats.ms_pack += ms;
+      if (e.stage == 4) b->stats.ms_pack_kernel += ms;
+      else if (e.stage == 0) b->stats.ms_pack += ms;
       else if (e.stage == 1) b->stats.ms_sigma += ms;
       else if (e.stage == 2) b->stats.ms_dp += ms;
       else b->stats.ms_hss += ms;
