@@ -893,6 +893,25 @@ __device__ __forceinline__ void reg_shift(bool neg, float Delta, float Omega, fl
 
 // One end codon for all species: state update + species sum (no getHSS test).  The kernel holds exactly
 // one copy of this code (instruction-cache footprint matters more than the few uniform branches).
+#ifndef RC_FLAG_UNIFIED
+#define RC_FLAG_UNIFIED 0
+#endif
+// Branch-free update of one species that may (f) or may not have a frameshift at this codon; f and neg are
+// warp-uniform.  n_i = max(S_i + p_i, X_i + q): without a frameshift p = (sigma, omega, omega) and q = -inf, so the
+// second term drops out (max(d, -inf) == d); with one p = Delta, q = Omega and X is the state rotated in the
+// direction of the shift (src/score.c:506-533).  Same float operations on the values that matter as the branchy
+// form, no branch: the species of a group with a frameshift cost 24 instead of 6-19 instructions, in a straight line.
+__device__ __forceinline__ void reg_any(bool f, bool neg, float sig, float omega, float Delta, float Omega, float2& a0,
+                                        float2& a1, float2& a2) {
+  const float p0 = f ? Delta : sig, p12 = f ? Delta : omega, q = f ? Omega : -INFINITY;
+  const float2 x0 = neg ? a1 : a2, x1 = neg ? a2 : a0, x2 = neg ? a0 : a1;
+  const float2 d0 = add2s(a0, p0), d1 = add2s(a1, p12), d2 = add2s(a2, p12);
+  const float2 o0 = add2s(x0, q), o1 = add2s(x1, q), o2 = add2s(x2, q);
+  a0 = make_float2(fmaxf(d0.x, o0.x), fmaxf(d0.y, o0.y));
+  a1 = make_float2(fmaxf(d1.x, o1.x), fmaxf(d1.y, o1.y));
+  a2 = make_float2(fmaxf(d2.x, o2.x), fmaxf(d2.y, o2.y));
+}
+
 // HAS_IN: the species sum continues a partial sum `sin` handed over by the warp that owns the preceding species
 // (k_dp_chain); otherwise it starts with the first species (0 + m == m).
 template <int NK, bool HAS_IN = false>
@@ -922,7 +941,17 @@ __device__ __forceinline__ float2 reg_update(float2 (&S0)[NK], float2 (&S1)[NK],
       sum = (k == 0) ? (HAS_IN ? add2(sin, m) : m) : add2(sum, m);  // species sum in k order (src/score.c:834-838); 0 + m == m
     }
   } else {
-    // some species has a frameshift here: test groups of three species, branch per species only inside a hit group
+#if RC_FLAG_UNIFIED == 2
+    // some species has a frameshift here: every species through the branch-free form
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      const unsigned z2 = (zw >> (2 * k)) & 3u;
+      reg_any((z2 & 1u) != 0u, (z2 & 2u) != 0u, sv[k], omega, Delta, Omega, S0[k], S1[k], S2[k]);
+      const float2 m = make_float2(max3f(S0[k].x, S1[k].x, S2[k].x), max3f(S0[k].y, S1[k].y, S2[k].y));
+      sum = (k == 0) ? (HAS_IN ? add2(sin, m) : m) : add2(sum, m);
+    }
+#else
+    // some species has a frameshift here: test groups of three species; a hit group takes the branch-free form
 #pragma unroll
     for (int g = 0; g < NK; g += 3) {
       constexpr unsigned GM3 = 0x3fu;
@@ -938,6 +967,9 @@ __device__ __forceinline__ float2 reg_update(float2 (&S0)[NK], float2 (&S1)[NK],
 #pragma unroll
         for (int k = g; k < g + 3 && k < NK; k++) {
           const unsigned z2 = (zw >> (2 * k)) & 3u;
+#if RC_FLAG_UNIFIED
+          reg_any((z2 & 1u) != 0u, (z2 & 2u) != 0u, sv[k], omega, Delta, Omega, S0[k], S1[k], S2[k]);
+#else
           if (z2 == 0u) {
             S0[k] = add2s(S0[k], sv[k]);
             S1[k] = add2s(S1[k], omega);
@@ -945,6 +977,7 @@ __device__ __forceinline__ float2 reg_update(float2 (&S0)[NK], float2 (&S1)[NK],
           } else {
             reg_shift((z2 & 2u) != 0u, Delta, Omega, S0[k], S1[k], S2[k]);
           }
+#endif
         }
       }
 #pragma unroll
@@ -953,6 +986,7 @@ __device__ __forceinline__ float2 reg_update(float2 (&S0)[NK], float2 (&S1)[NK],
         sum = (k == 0) ? (HAS_IN ? add2(sin, m) : m) : add2(sum, m);
       }
     }
+#endif
   }
   return sum;
 }
