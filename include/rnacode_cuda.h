@@ -156,6 +156,9 @@ int rc_batch_get_stats(rc_batch *batch, rc_batch_stats *stats);
  * achieved lane-operations per second: the practical FP32/ALU issue ceiling at the device's current clocks. */
 int rc_calibrate_issue(rc_ctx *ctx, double *lane_ops_per_s);
 
+/* Number of CUDA devices visible to the process (0 and RC_ERR_CUDA when there is none). */
+int rc_device_count(int *count);
+
 /* Library / build identification, e.g. "libRNAcode_cuda 0.1 sm_100a". */
 const char *rc_version(void);
 

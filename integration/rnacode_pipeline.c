@@ -25,6 +25,7 @@
  */
 #include <ctype.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -77,7 +78,10 @@ typedef struct {
   float maxScore;
   double *maxScores;
   segmentStats *results;
+  unsigned int *seeds;
 } blk_t;
+
+static void init_gpus(void);
 
 static double now_s(void) {
   struct timespec ts;
@@ -173,7 +177,7 @@ static void run_host_stage(blk_t *blk, int nb) {
       _exit(0);
     }
   }
-  ctx(); /* bring the CUDA context up while the workers run PhyML (the children never touch CUDA) */
+  init_gpus(); /* bring the CUDA contexts up while the workers run PhyML (the children never touch CUDA) */
   for (w = 0; w < P; w++) {
     int status = 0, idx, ok;
     waitpid(pid[w], &status, 0);
@@ -206,50 +210,81 @@ static void run_host_stage(blk_t *blk, int nb) {
   free(pid);
 }
 
-/* One library batch: the native alignment and the null alignments [s0, s0 + ns) of the listed blocks.  Fills
- * blk[].maxScores[s0 .. s0+ns) and, when want_native, blk[].hss / blk[].n_hss. */
-static void gpu_batch(blk_t *blk, const int *list, int nlist, int s0, int ns, const int *blosum, int want_native,
-                      double *t_seeds, double *t_gpu) {
-  const int mode = evolve_mode();
+/* ---- GPUs: blocks are independent, so a window is dealt out over the devices by cost; no exchange between them ---- */
+#define MAX_GPUS 16
+static rc_ctx *g_ctxs[MAX_GPUS];
+static int g_ngpus = 0;
+
+static void init_gpus(void) {
+  const char *e = getenv("RNACODE_CUDA_GPUS"), *d = getenv("RNACODE_CUDA_DEVICE");
+  int want = e ? (strcmp(e, "all") == 0 ? -1 : atoi(e)) : 1, have = 0, base = d ? atoi(d) : 0, i;
+  if (g_ngpus) return;
+  if (rc_device_count(&have) != RC_OK || have < 1) {
+    fprintf(stderr, "RNAcode: no usable CUDA device (libRNAcode_cuda has no CPU fallback)\n");
+    exit(EXIT_FAILURE);
+  }
+  if (want < 0 || want > have - base) want = have - base;
+  if (want < 1) want = 1;
+  if (want > MAX_GPUS) want = MAX_GPUS;
+  for (i = 0; i < want; i++)
+    if (rc_create(&g_ctxs[i], base + i) != RC_OK) {
+      fprintf(stderr, "RNAcode: cannot use CUDA device %d\n", base + i);
+      exit(EXIT_FAILURE);
+    }
+  g_ctx = g_ctxs[0];
+  g_ngpus = want;
+}
+
+typedef struct {
+  rc_ctx *c;
+  blk_t *blk;
+  const int *list;
+  int nlist, s0, ns, want_native, mode;
+  const int *blosum;
+} shard_t;
+
+static void shard_die(rc_ctx *c, const char *what) {
+  fprintf(stderr, "RNAcode: %s: %s\n", what, rc_last_error(c));
+  exit(EXIT_FAILURE);
+}
+
+/* one library batch on one device: native alignment + null alignments [s0, s0+ns) of the shard's blocks */
+static void *run_shard(void *arg) {
+  shard_t *sh = (shard_t *)arg;
   rc_params p = current_params();
-  rc_block_desc *descs = (rc_block_desc *)malloc(sizeof(rc_block_desc) * nlist);
+  rc_block_desc *descs;
   rc_batch *batch = NULL;
-  unsigned int *seeds = (unsigned int *)malloc(sizeof(unsigned int) * (ns > 0 ? ns : 1));
-  double ta = now_s(), tb;
-  int k, j;
-  for (k = 0; k < nlist; k++) {
-    blk_t *b = &blk[list[k]];
+  int k;
+  if (sh->nlist == 0) return NULL;
+  descs = (rc_block_desc *)malloc(sizeof(rc_block_desc) * sh->nlist);
+  for (k = 0; k < sh->nlist; k++) {
+    blk_t *b = &sh->blk[sh->list[k]];
     descs[k].N = b->N;
     descs[k].cols = b->cols;
     descs[k].rows = b->rows;
     descs[k].scores_fwd = b->sf;
     descs[k].scores_rev = b->sr;
-    descs[k].n_samples = ns;
+    descs[k].n_samples = sh->ns;
     descs[k].samples = NULL;
   }
-  if (rc_batch_create(ctx(), descs, nlist, &p, blosum, &batch) != RC_OK) die("rc_batch_create");
-  for (k = 0; k < nlist && ns > 0; k++) {
-    blk_t *b = &blk[list[k]];
+  if (rc_batch_create(sh->c, descs, sh->nlist, &p, sh->blosum, &batch) != RC_OK) shard_die(sh->c, "rc_batch_create");
+  for (k = 0; k < sh->nlist && sh->ns > 0; k++) {
+    blk_t *b = &sh->blk[sh->list[k]];
     rc_tree_desc td;
     td.n_nodes = b->n_nodes;
     td.parent = b->tpar;
     td.row = b->trow;
     td.cum = b->tcum;
-    if (rc_wrap_set_block) rc_wrap_set_block(b->scored_idx);
-    if (rc_wrap_set_sample) rc_wrap_set_sample(s0);
-    for (j = 0; j < ns; j++) seeds[j] = (unsigned int)(CreateSeed() & 0xffffffffUL); /* src/treeSimulate.c:84 */
-    if (rc_batch_set_evolve(batch, k, &td, seeds, mode == 2 ? RC_RNG_PHILOX : RC_RNG_MT19937) != RC_OK)
-      die("rc_batch_set_evolve");
+    if (rc_batch_set_evolve(batch, k, &td, b->seeds, sh->mode == 2 ? RC_RNG_PHILOX : RC_RNG_MT19937) != RC_OK)
+      shard_die(sh->c, "rc_batch_set_evolve");
   }
-  tb = now_s();
-  *t_seeds += tb - ta;
-  if (rc_batch_upload(batch) != RC_OK) die("rc_batch_upload");
-  if (rc_batch_run(batch) != RC_OK) die("rc_batch_run");
-  if (rc_batch_download(batch) != RC_OK) die("rc_batch_download");
-  for (k = 0; k < nlist; k++) {
-    blk_t *b = &blk[list[k]];
-    if (ns > 0 && rc_batch_max_scores(batch, k, b->maxScores + s0) != RC_OK) die("rc_batch_max_scores");
-    if (want_native) {
+  if (rc_batch_upload(batch) != RC_OK) shard_die(sh->c, "rc_batch_upload");
+  if (rc_batch_run(batch) != RC_OK) shard_die(sh->c, "rc_batch_run");
+  if (rc_batch_download(batch) != RC_OK) shard_die(sh->c, "rc_batch_download");
+  for (k = 0; k < sh->nlist; k++) {
+    blk_t *b = &sh->blk[sh->list[k]];
+    if (sh->ns > 0 && rc_batch_max_scores(batch, k, b->maxScores + sh->s0) != RC_OK) shard_die(sh->c, "rc_batch_max_scores");
+    if (sh->want_native) {
       int cap = 256, rc;
       b->hss = (rc_hss *)malloc(sizeof(rc_hss) * cap);
       rc = rc_batch_native_hss(batch, k, b->hss, cap, &b->n_hss);
@@ -258,12 +293,65 @@ static void gpu_batch(blk_t *blk, const int *list, int nlist, int s0, int ns, co
         b->hss = (rc_hss *)realloc(b->hss, sizeof(rc_hss) * cap);
         rc = rc_batch_native_hss(batch, k, b->hss, cap, &b->n_hss);
       }
-      if (rc != RC_OK) die("rc_batch_native_hss");
+      if (rc != RC_OK) shard_die(sh->c, "rc_batch_native_hss");
     }
   }
   rc_batch_destroy(batch);
   free(descs);
-  free(seeds);
+  return NULL;
+}
+
+/* The native alignment and the null alignments [s0, s0 + ns) of the listed blocks, on all devices.  Fills
+ * blk[].maxScores[s0 .. s0+ns) and, when want_native, blk[].hss / blk[].n_hss. */
+static void gpu_batch(blk_t *blk, const int *list, int nlist, int s0, int ns, const int *blosum, int want_native,
+                      double *t_seeds, double *t_gpu) {
+  const int mode = evolve_mode();
+  double ta = now_s(), tb;
+  int k, j, d, G;
+  shard_t sh[MAX_GPUS];
+  int *shard_list[MAX_GPUS];
+  double load[MAX_GPUS];
+  pthread_t th[MAX_GPUS];
+  init_gpus();
+  G = g_ngpus < nlist ? g_ngpus : nlist;
+  /* one CreateSeed() per null alignment, block by block in input order (src/treeSimulate.c:84) */
+  for (k = 0; k < nlist; k++) {
+    blk_t *b = &blk[list[k]];
+    b->seeds = (unsigned int *)malloc(sizeof(unsigned int) * (ns > 0 ? ns : 1));
+    if (rc_wrap_set_block) rc_wrap_set_block(b->scored_idx);
+    if (rc_wrap_set_sample) rc_wrap_set_sample(s0);
+    for (j = 0; j < ns; j++) b->seeds[j] = (unsigned int)(CreateSeed() & 0xffffffffUL);
+  }
+  /* deal the blocks out: each to the device with the least work so far, cost ~ (N-1) * L^2 (DP cells per alignment) */
+  for (d = 0; d < G; d++) {
+    shard_list[d] = (int *)malloc(sizeof(int) * nlist);
+    load[d] = 0;
+    memset(&sh[d], 0, sizeof(shard_t));
+    sh[d].c = g_ctxs[d];
+    sh[d].blk = blk;
+    sh[d].list = shard_list[d];
+    sh[d].s0 = s0;
+    sh[d].ns = ns;
+    sh[d].want_native = want_native;
+    sh[d].mode = mode;
+    sh[d].blosum = blosum;
+  }
+  for (k = 0; k < nlist; k++) {
+    blk_t *b = &blk[list[k]];
+    int best = 0;
+    for (d = 1; d < G; d++)
+      if (load[d] < load[best]) best = d;
+    shard_list[best][sh[best].nlist++] = list[k];
+    load[best] += (double)(b->N - 1) * b->L * b->L;
+  }
+  tb = now_s();
+  *t_seeds += tb - ta;
+  for (d = 1; d < G; d++)
+    if (pthread_create(&th[d], NULL, run_shard, &sh[d]) != 0) nrerror("ERROR: pthread_create failed.\n");
+  run_shard(&sh[0]);
+  for (d = 1; d < G; d++) pthread_join(th[d], NULL);
+  for (d = 0; d < G; d++) free(shard_list[d]);
+  for (k = 0; k < nlist; k++) free(blk[list[k]].seeds);
   *t_gpu += now_s() - tb;
 }
 

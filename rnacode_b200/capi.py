@@ -62,7 +62,7 @@ EXPORTS = [
     "rc_create", "rc_destroy", "rc_last_error", "rc_default_params", "rc_set_stream", "rc_set_option",
     "rc_score_aln", "rc_score_samples", "rc_batch_create", "rc_batch_upload", "rc_batch_run", "rc_batch_download",
     "rc_batch_native_hss", "rc_batch_max_scores", "rc_batch_destroy", "rc_batch_get_stats", "rc_version",
-    "rc_calibrate_issue", "rc_batch_set_evolve", "rc_score_samples_evolve", "rc_batch_get_sample_rows",
+    "rc_calibrate_issue", "rc_batch_set_evolve", "rc_score_samples_evolve", "rc_batch_get_sample_rows", "rc_device_count",
 ]
 
 _lib = None

@@ -333,6 +333,18 @@ extern "C" int rc_set_stream(rc_ctx* ctx, void* cuda_stream) {
   return RC_OK;
 }
 
+extern "C" int rc_device_count(int* count) {
+  if (!count) return RC_ERR_ARG;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    *count = 0;
+    return RC_ERR_CUDA;
+  }
+  *count = n;
+  return n > 0 ? RC_OK : RC_ERR_CUDA;
+}
+
 extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
   if (!ctx || !key) return RC_ERR_ARG;
   std::string k(key);

@@ -60,3 +60,20 @@ def test_batched_pipeline_output_identical_to_reference(case, workers):
     res = subprocess.run([PIPELINE, *opts, os.path.join(EXAMPLES, fname)], capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0, res.stderr
     assert _norm(res.stdout) == _norm(op.golden("cli_outputs")[case])
+
+
+@pytest.mark.parametrize("case", ["genomic-preprocessed.maf --tabular -n 20", "genomic.maf --gtf -s -p 0.1 -n 40"])
+def test_batched_pipeline_sharded_over_gpus(case):
+    """RNACODE_CUDA_GPUS: the blocks of a window are dealt out over the devices (no exchange between them); the
+    output does not depend on the number of devices."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    if not (os.path.exists(PIPELINE) and os.path.isdir(EXAMPLES)):
+        pytest.skip("oracle/_ref/RNAcode_b200_det not built (needs /root/reference at build time)")
+    parts = case.split(" ")
+    fname, opts = parts[0], [p for p in parts[1:] if p]
+    env = dict(os.environ, RNACODE_SEED="1", RNACODE_CUDA_GPUS="all")
+    res = subprocess.run([PIPELINE, *opts, os.path.join(EXAMPLES, fname)], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr
+    assert _norm(res.stdout) == _norm(op.golden("cli_outputs")[case])
