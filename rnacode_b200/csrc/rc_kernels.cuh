@@ -589,8 +589,8 @@ struct DpSmem {
   static __host__ __device__ size_t state_bytes(int NK) { return (size_t)NK * 3 * R * 32 * sizeof(float); }
   static __host__ __device__ size_t sig_bytes(int NK) { return (size_t)NK * TILE * sizeof(float); }
   static __host__ __device__ size_t z_bytes(int zstride) { return (size_t)zstride * sizeof(unsigned); }
-  static __host__ __device__ size_t per_warp(int NK, int zstride) {
-    return state_bytes(NK) + 2 * (sig_bytes(NK) + z_bytes(zstride)) + 16;
+  static __host__ __device__ size_t per_warp(int NK, int zstride, int nstages = 2) {
+    return state_bytes(NK) + nstages * (sig_bytes(NK) + z_bytes(zstride)) + 16;
   }
 };
 
@@ -598,7 +598,7 @@ template <int R, bool DENSE>
 __global__ void __launch_bounds__(DP_WARPS * 32)
     k_dp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
          const float* __restrict__ sigma, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs,
-         float* __restrict__ dense, Params prm, int band_slots, int smem_NK, int smem_zstride) {
+         float* __restrict__ dense, Params prm, int band_slots, int smem_NK, int smem_zstride, int nst) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const CtaDesc cd = ctas[blockIdx.x];
@@ -610,6 +610,19 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
   // A CTA descriptor covers DP_WARPS tasks.  Very wide alignments need so much shared-memory state per task that the
   // kernel is launched with fewer warps; each warp then takes several of the CTA's tasks, one after the other.
   const int nwarps = blockDim.x >> 5;
+  // nst: stages of the sigma / z ring (2; 1 when the state of a 500-row alignment leaves no room for a second one)
+  unsigned char* wsm = smem + (size_t)warp * DpSmem<R>::per_warp(smem_NK, smem_zstride, nst);
+  float* st = reinterpret_cast<float*>(wsm);
+  unsigned char* ring = wsm + DpSmem<R>::state_bytes(smem_NK);
+  const size_t stage_bytes = DpSmem<R>::sig_bytes(smem_NK) + DpSmem<R>::z_bytes(smem_zstride);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + nst * stage_bytes);
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  unsigned ring_it = 0;  // tiles this warp has consumed so far, over all its tasks (stage = ring_it % nst, phase = ring_it / nst)
 #pragma unroll 1
   for (int tsk = warp; tsk < DP_WARPS; tsk += nwarps) {
   const int task = cd.task0 + tsk;
@@ -618,12 +631,6 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
   const int row_base = g * 32 * R;
   const int r0 = row_base + lane * R;  // first of this lane's R rows
 
-  unsigned char* wsm = smem + (size_t)warp * DpSmem<R>::per_warp(smem_NK, smem_zstride);
-  float* st = reinterpret_cast<float*>(wsm);
-  unsigned char* ring = wsm + DpSmem<R>::state_bytes(smem_NK);
-  const size_t stage_bytes = DpSmem<R>::sig_bytes(smem_NK) + DpSmem<R>::z_bytes(smem_zstride);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * stage_bytes);
-
   const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * ntiles * NK * TILE;
   const unsigned* z_src = ztiles + bd.z_off[strand][frame];
   const unsigned sig_tx = (unsigned)(NK * TILE * sizeof(float)), z_tx = (unsigned)(zstride * sizeof(unsigned));
@@ -631,14 +638,12 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
   const int t0 = row_base / TILE;
   const int t_last_diag = (row_base + 32 * R - 1) / TILE;
   if (lane == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_fence_init();
-    for (int s = 0; s < 2 && t0 + s < ntiles; s++) {
-      unsigned char* dst = ring + s * stage_bytes;
-      mbar_expect_tx(&bars[s], sig_tx + z_tx);
-      bulk_g2s(dst, sig_src + (size_t)(t0 + s) * NK * TILE, sig_tx, &bars[s]);
-      bulk_g2s(dst + DpSmem<R>::sig_bytes(smem_NK), z_src + (size_t)(t0 + s) * zstride, z_tx, &bars[s]);
+    for (int q = 0; q < nst && t0 + q < ntiles; q++) {
+      const unsigned sq = (ring_it + q) % nst;
+      unsigned char* dst = ring + sq * stage_bytes;
+      mbar_expect_tx(&bars[sq], sig_tx + z_tx);
+      bulk_g2s(dst, sig_src + (size_t)(t0 + q) * NK * TILE, sig_tx, &bars[sq]);
+      bulk_g2s(dst + DpSmem<R>::sig_bytes(smem_NK), z_src + (size_t)(t0 + q) * zstride, z_tx, &bars[sq]);
     }
   }
   for (int i = 0; i < NK * 3 * R; i++) st[i * 32 + lane] = 0.0f;
@@ -667,9 +672,9 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
   const float Delta = prm.Delta, Omega = prm.Omega, omega = prm.omega;
   const float fNK = bd.fNK, rcpNK = bd.rcpNK;
 
-  for (int tile = t0; tile < ntiles; tile++) {
-    const int s = (tile - t0) & 1;
-    const unsigned parity = ((tile - t0) >> 1) & 1;
+  for (int tile = t0; tile < ntiles; tile++, ring_it++) {
+    const int s = (int)(ring_it % nst);
+    const unsigned parity = (ring_it / nst) & 1u;
     const float* sg = reinterpret_cast<const float*>(ring + s * stage_bytes);
     const unsigned* zt = reinterpret_cast<const unsigned*>(ring + s * stage_bytes + DpSmem<R>::sig_bytes(smem_NK));
     const int j0 = tile * TILE;
@@ -749,11 +754,11 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
       }
     }
     __syncwarp();  // every lane has consumed this stage
-    if (lane == 0 && tile + 2 < ntiles) {
+    if (lane == 0 && tile + nst < ntiles) {
       unsigned char* dst = ring + s * stage_bytes;
       mbar_expect_tx(&bars[s], sig_tx + z_tx);
-      bulk_g2s(dst, sig_src + (size_t)(tile + 2) * NK * TILE, sig_tx, &bars[s]);
-      bulk_g2s(dst + DpSmem<R>::sig_bytes(smem_NK), z_src + (size_t)(tile + 2) * zstride, z_tx, &bars[s]);
+      bulk_g2s(dst, sig_src + (size_t)(tile + nst) * NK * TILE, sig_tx, &bars[s]);
+      bulk_g2s(dst + DpSmem<R>::sig_bytes(smem_NK), z_src + (size_t)(tile + nst) * zstride, z_tx, &bars[s]);
     }
 
     // S[b][i] = max(sum, Delta) / (N-1)  (src/score.c:841-843; S[b][i-1], S[b][i-2] are always 0) and the
@@ -795,7 +800,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
       }
     }
   }
-  __syncwarp();  // every copy into the ring has been waited for: the barriers may be re-initialised for the next task
+  __syncwarp();  // every copy into the ring has been waited for: the ring is free for the next task
   }
 }
 

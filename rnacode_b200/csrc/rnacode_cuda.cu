@@ -824,7 +824,12 @@ template <int R, bool DENSE>
 static int launch_dp(rc_batch* b, const CtaDesc* d_ctas, size_t ncta, int maxNK, int maxZs) {
   rc_ctx* ctx = b->ctx;
   if (ncta == 0) return RC_OK;
-  const size_t per_warp = DpSmem<R>::per_warp(maxNK, maxZs);
+  int nst = 2;
+  size_t per_warp = DpSmem<R>::per_warp(maxNK, maxZs, nst);
+  if (per_warp > (size_t)ctx->smem_optin) {  // the reference's maximum of 500 rows only fits with a single-stage ring
+    nst = 1;
+    per_warp = DpSmem<R>::per_warp(maxNK, maxZs, nst);
+  }
   const int nw = (int)std::min<size_t>(DP_WARPS, (size_t)ctx->smem_optin / per_warp);
   if (nw < 1) {
     ctx_fail(ctx, "alignment has too many rows for the shared-memory resident DP state (N-1 = " + std::to_string(maxNK) + ")");
@@ -834,7 +839,7 @@ static int launch_dp(rc_batch* b, const CtaDesc* d_ctas, size_t ncta, int maxNK,
   RC_CUDA(cudaFuncSetAttribute(k_dp<R, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_dp<R, DENSE><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
                                                                       b->d_recs, b->d_dense, b->prm, (int)ctx->band_slots,
-                                                                      maxNK, maxZs);
+                                                                      maxNK, maxZs, nst);
   RC_CUDA(cudaGetLastError());
   b->stats.launches++;
   b->stats.dp_launches++;

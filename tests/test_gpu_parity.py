@@ -102,6 +102,9 @@ SHAPES = [
     # chunk sizes with and without a dummy species, rows longer than several hand-off stages; 17 chunks -> k_dp
     (18, 700, 3, 0.02), (25, 520, 2, 0.03), (26, 333, 2, 0.0), (38, 410, 2, 0.03), (100, 260, 1, 0.02),
     (193, 120, 1, 0.02), (200, 70, 1, 0.02),
+    # beyond 16 chunks the shared-memory DP takes over: fewer warps per CTA, and a single-stage ring at the
+    # reference's maximum of 500 rows (MAX_NUM_NAMES, src/rnaz_utils.h:7)
+    (300, 50, 1, 0.02), (500, 40, 1, 0.02),
 ]
 
 
