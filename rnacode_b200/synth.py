@@ -63,6 +63,22 @@ def synth_samples(seed, index, n, N, cols):
     return out
 
 
+def synth_tree(seed, index, N):
+    """A star tree for the on-GPU simulation (rc_tree_desc arrays: parent, row, cum): root = node 0, one tip per
+    alignment row; branch k mutates a site with the block's rate r_k to a uniform base (Jukes-Cantor-like), root
+    frequencies uniform.  Same null model as synth_samples, drawn on the device instead of the host."""
+    r = rates(seed, index, N)
+    parent = np.array([-1] + [0] * N, dtype=np.int32)
+    row = np.array([-1] + list(range(N)), dtype=np.int32)
+    cum = np.zeros((N + 1, 16), dtype=np.float64)
+    cum[0, :4] = [0.25, 0.5, 0.75, 1.0]
+    for k in range(N):
+        P = np.full((4, 4), r[k] / 4.0)
+        P[np.arange(4), np.arange(4)] += 1.0 - r[k]
+        cum[k + 1] = np.cumsum(P, axis=1).reshape(16)
+    return parent, row, cum
+
+
 def synth_scores(seed, index, N):
     """Plausible expected-score tables (bgModel.scores, src/score.h:35) without running a tree:
     the values calculateBG produces shrink with the reference-species distance; we draw a distance per
