@@ -211,3 +211,38 @@ def test_bad_arguments(rc_ctx, oracle):
     b = capi.Block(rows, np.zeros((1, 4)), np.zeros((1, 4)))
     with pytest.raises(capi.RcError):
         rc_ctx.score_aln(b, capi.make_params(), oracle.blosum62)
+
+
+def test_random_alignments_vs_oracle(rc_ctx, oracle):
+    """Seeded random sweep: shapes, gap rates, stray symbols (N, X, IUPAC, lower case), penalties and sample counts
+    drawn at random; every block must match the oracle bit for bit (native HSS and per-sample maxima)."""
+    from rnacode_b200 import synth
+    capi = _capi()
+    rng = np.random.default_rng(20261017)
+    stray = np.frombuffer(b"NXRYnacgt", dtype=np.uint8)
+    for rep in range(6):
+        kw = dict(Delta=-float(rng.uniform(4, 14)), Omega=-float(rng.uniform(1, 6)), omega=-float(rng.uniform(0.5, 3)),
+                  stopPenalty_0=-float(rng.uniform(50, 9999)), stopPenalty_k=-float(rng.uniform(2, 12)))
+        blocks, data = [], []
+        for idx in range(8):
+            N = int(rng.choice([3, 4, 6, 9, 10, 13, 17, 18, 24, 33, 41]))
+            cols = int(rng.integers(3, 420))
+            n = int(rng.choice([1, 2, 5, 17, 33, 40]))
+            rows = synth.synth_block(1000 + rep, idx, N, cols, gap_rate=float(rng.choice([0.0, 0.005, 0.02, 0.08])))
+            hits = rng.random(rows.shape) < 0.004
+            rows = rows.copy()
+            rows[hits & (rows != synth.GAP)] = stray[rng.integers(0, len(stray), size=int((hits & (rows != synth.GAP)).sum()))]
+            sf, sr = synth.synth_scores(1000 + rep, idx, N)
+            smp = synth.synth_samples(1000 + rep, idx, n, N, cols)
+            blocks.append(_block(rows, sf, sr, smp))
+            data.append((rows, sf, sr, smp))
+        bt = rc_ctx.batch(blocks, capi.make_params(**kw), oracle.blosum62)
+        bt.upload(); bt.run(); bt.download()
+        for i, (rows, sf, sr, smp) in enumerate(data):
+            if synth.ungapped_len(rows) < 3:
+                assert bt.native_hss(i) == []
+                continue
+            assert bt.native_hss(i) == oracle.score_aln(rows, sf, sr, oracle.params(**kw)), (rep, i, rows.shape)
+            exp = oracle.sample_maxima(rows, smp, sf, sr, oracle.params(**kw)).astype(np.float32)
+            assert np.array_equal(bt.max_scores(i).astype(np.float32), exp), (rep, i, rows.shape)
+        bt.close()
