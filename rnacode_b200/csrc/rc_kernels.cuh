@@ -451,10 +451,12 @@ __global__ void __launch_bounds__(256)
   unsigned char* s_sp = sm + 32 * pitch;     // [4][32][pitch]
   const int ninst_g = min(32, it.ninst - group * 32);
   const unsigned char* gbase = cls + bd.cls_off + (size_t)(it.inst0 + group * 32) * bd.inst_stride;
-  // reference rows of the 32 instances
-  for (int e = threadIdx.x; e < 32 * cols; e += blockDim.x) {
-    const int li = e / cols, c = e % cols;
-    s_ref[li * pitch + c] = (li < ninst_g) ? gbase[(size_t)li * bd.inst_stride + c] : (unsigned char)0;
+  // reference rows of the 32 instances: one warp per row, lanes along the columns (no per-byte index arithmetic)
+  const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int li = wid; li < 32; li += nwarps) {
+    const unsigned char* src = gbase + (size_t)li * bd.inst_stride;
+    unsigned char* dst = s_ref + li * pitch;
+    for (int c = ln; c < cols; c += 32) dst[c] = (li < ninst_g) ? src[c] : (unsigned char)0;
   }
   __syncthreads();
   mbar_wait(&s_bar, 0);
@@ -462,11 +464,13 @@ __global__ void __launch_bounds__(256)
   const int rsb = (NK + 3) / 4 * 4;
   for (int kq = 0; kq < rsb / 4; kq++) {
     // stage species rows 1+4kq .. 4+4kq
-    for (int e = threadIdx.x; e < 4 * 32 * cols; e += blockDim.x) {
-      const int c = e % cols, li = (e / cols) & 31, kk = e / (cols * 32);
+    for (int pr = wid; pr < 4 * 32; pr += nwarps) {  // (species of the quad, instance) pairs: one warp per row
+      const int kk = pr >> 5, li = pr & 31;
       const int row = 1 + 4 * kq + kk;
-      s_sp[(kk * 32 + li) * pitch + c] =
-          (li < ninst_g && row < N) ? gbase[(size_t)li * bd.inst_stride + (size_t)row * cols + c] : (unsigned char)0;
+      const bool ok = li < ninst_g && row < N;
+      const unsigned char* src = gbase + (size_t)li * bd.inst_stride + (size_t)row * cols;
+      unsigned char* dst = s_sp + (kk * 32 + li) * pitch;
+      for (int c = ln; c < cols; c += 32) dst[c] = ok ? src[c] : (unsigned char)0;
     }
     __syncthreads();
     for (int e = threadIdx.x; e < 2 * npos * 32; e += blockDim.x) {
