@@ -833,7 +833,7 @@ __device__ __forceinline__ float2 add2s(float2 a, float b) { return add2(a, make
 // RowRec-resident variant of hss_accept: the fold state lives in the row's record (global memory, touched
 // only on the rare positive entries), so the hot loop carries no per-row registers for it.
 // rec->vF = last accepted value (-inf before the first), rec->Emax = row maximum, rec->jF, rec->n as in RowRec.
-__device__ __noinline__ void hss_accept_rec(RowRec* rec, float e, int j, int slots) {
+__device__ __forceinline__ void hss_accept_rec(RowRec* rec, float e, int j, int slots) {
   const float lb = rec->vF;
   const float d = e - lb;
   if (!(d >= -0.0001f)) return;
@@ -1104,7 +1104,49 @@ __device__ __noinline__ float reg_check_row(float sum, int j, int rstart, int si
     const float e = __fmaf_rn(__fmaf_rn(-fNK, q, sum), rcpNK, q);
     if (e - lb >= -0.0001f) {
       lb = e;
-      hss_accept_rec(rec, e, j, band_slots);
+      const float M = rec->Emax;
+      if (M - e < -0.0001f) {
+        // the common case right after a row starts: a new row maximum beyond the old tie band -- the band restarts
+        // with this entry (what hss_accept_rec does for it, without its band bookkeeping)
+        const unsigned short ovf = rec->n & 0x8000;
+        rec->Emax = e;
+        rec->vF = e;
+        rec->be[0] = e;
+        rec->jF = (unsigned short)j;
+        rec->n = (unsigned short)(1 | ovf);
+        rec->bj[0] = (unsigned short)j;
+      } else {
+        hss_accept_rec(rec, e, j, band_slots);
+      }
+    }
+  }
+  return lb;
+}
+
+// Variant with the positive-entry filter and the fresh-fold test inline: only accepted entries leave the loop
+// (four arguments instead of nine).  Used where positive entries are frequent (short rows, k_dp_smp).
+__device__ __noinline__ void hss_accept_call(RowRec* rec, float e, int j, int band_slots) {
+  const float M = rec->Emax;
+  if (M - e < -0.0001f) {
+    const unsigned short ovf = rec->n & 0x8000;
+    rec->Emax = e;
+    rec->vF = e;
+    rec->be[0] = e;
+    rec->jF = (unsigned short)j;
+    rec->n = (unsigned short)(1 | ovf);
+    rec->bj[0] = (unsigned short)j;
+  } else {
+    hss_accept_rec(rec, e, j, band_slots);
+  }
+}
+__device__ __forceinline__ float reg_check_inl(float sum, int j, int rstart, int sites, float fNK, float rcpNK, RowRec* rec,
+                                               int band_slots, float lb) {
+  if (sum > 0.0f && j >= rstart && j < sites) {
+    const float q = sum * rcpNK;
+    const float e = __fmaf_rn(__fmaf_rn(-fNK, q, sum), rcpNK, q);
+    if (e - lb >= -0.0001f) {
+      lb = e;
+      hss_accept_call(rec, e, j, band_slots);
     }
   }
   return lb;
@@ -1577,10 +1619,10 @@ __global__ void __launch_bounds__(SMP_WARPS * 32)
           float2 sumA, sumB;
           reg_pair_fast<NK>(S0, S1, S2, svA, svB, omega, sumA, sumB);
           if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
-            lb.x = reg_check_row(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-            lb.y = reg_check_row(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
-            lb.x = reg_check_row(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-            lb.y = reg_check_row(sumB.y, j + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+            lb.x = reg_check_inl(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+            lb.y = reg_check_inl(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+            lb.x = reg_check_inl(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+            lb.y = reg_check_inl(sumB.y, j + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
           }
           j += 2;
           continue;
@@ -1588,8 +1630,8 @@ __global__ void __launch_bounds__(SMP_WARPS * 32)
       }
       const float2 sum = reg_update<NK>(S0, S1, S2, svA, j < r0 + 2, j, r0, Delta, Omega, omega);
       if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
-        lb.x = reg_check_row(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-        if (r0 + 1 < sites) lb.y = reg_check_row(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+        lb.x = reg_check_inl(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+        if (r0 + 1 < sites) lb.y = reg_check_inl(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
       }
       j += 1;
     }
