@@ -1175,6 +1175,14 @@ __device__ __forceinline__ void rec_copy(RowRec* dst, const RowRec* src) {
 #ifndef RC_REG_MINB
 #define RC_REG_MINB 4
 #endif
+#ifndef RC_REG_CHECK_INL
+#define RC_REG_CHECK_INL 1
+#endif
+#if RC_REG_CHECK_INL
+#define RC_REG_CHECK reg_check_inl
+#else
+#define RC_REG_CHECK reg_check_row
+#endif
 #ifndef RC_REG_TILE
 #define RC_REG_TILE 32  // end codons per TMA stage of k_dp_reg (a multiple of TILE; layout 1 rows are contiguous over tiles)
 #endif
@@ -1256,8 +1264,8 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
         reg_load_row<NK>(a0 + c * RS * 4, sv);
         const float2 sum = reg_update<NK>(S0, S1, S2, sv, true, j0 + c, r0, Delta, Omega, omega);
         if (fmaxf(sum.x, sum.y) > 0.0f) {
-          lb.x = reg_check_row(sum.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-          lb.y = reg_check_row(sum.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          lb.x = RC_REG_CHECK(sum.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          lb.y = RC_REG_CHECK(sum.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
         }
       }
     } else
@@ -1295,10 +1303,10 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
         reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
         reg_load_row<NK>(a0 + (c + 3) * RS * 4, svB);
         if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
-          if (sumA.x > 0.0f) lb.x = reg_check_row(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-          if (sumA.y > 0.0f) lb.y = reg_check_row(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
-          if (sumB.x > 0.0f) lb.x = reg_check_row(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-          if (sumB.y > 0.0f) lb.y = reg_check_row(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          if (sumA.x > 0.0f) lb.x = RC_REG_CHECK(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumA.y > 0.0f) lb.y = RC_REG_CHECK(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          if (sumB.x > 0.0f) lb.x = RC_REG_CHECK(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumB.y > 0.0f) lb.y = RC_REG_CHECK(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
         }
       }
     }
@@ -1494,10 +1502,10 @@ __global__ void
           sts_f2(hout + c * 256, sumA);
           sts_f2(hout + (c + 1) * 256, sumB);
         } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
-          if (sumA.x > 0.0f) lb.x = reg_check_row(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-          if (sumA.y > 0.0f) lb.y = reg_check_row(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
-          if (sumB.x > 0.0f) lb.x = reg_check_row(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-          if (sumB.y > 0.0f) lb.y = reg_check_row(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          if (sumA.x > 0.0f) lb.x = RC_REG_CHECK(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumA.y > 0.0f) lb.y = RC_REG_CHECK(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          if (sumB.x > 0.0f) lb.x = RC_REG_CHECK(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumB.y > 0.0f) lb.y = RC_REG_CHECK(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
         }
       }
     }
