@@ -1187,7 +1187,7 @@ __device__ __forceinline__ void rec_copy(RowRec* dst, const RowRec* src) {
 #define RC_REG_TILE 32  // end codons per TMA stage of k_dp_reg (a multiple of TILE; layout 1 rows are contiguous over tiles)
 #endif
 #ifndef RC_REG_DIAG_MASKED
-#define RC_REG_DIAG_MASKED 0
+#define RC_REG_DIAG_MASKED 1
 #endif
 template <int NK>
 __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
@@ -1255,7 +1255,33 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
     constexpr int tsteps = RT;
     const bool diag = tile <= t_last_diag;  // rows start inside this tile
     mbar_wait(&bars[s], parity);
-#if !RC_REG_DIAG_MASKED
+#if RC_REG_DIAG_MASKED
+    if (diag) {
+      // rows start inside the tile: masked two-codon blocks (reg_pair_diag), in a loop of their own
+      float svA[RS], svB[RS];
+      reg_load_row<NK>(a0, svA);
+      reg_load_row<NK>(a0 + RS * 4, svB);
+#pragma unroll 1
+      for (int c = 0; c < tsteps; c += 2) {
+        float2 sumA, sumB;
+        const bool P = j0 + c >= r0, Q = j0 + c > r0;
+        if ((__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u) {
+          reg_pair_diag<NK>(S0, S1, S2, svA, svB, omega, P, Q, sumA, sumB);
+        } else {
+          sumA = reg_update_diag<NK>(S0, S1, S2, svA, P, Q, Delta, Omega, omega);
+          sumB = reg_update_diag<NK>(S0, S1, S2, svB, P, P, Delta, Omega, omega);
+        }
+        reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
+        reg_load_row<NK>(a0 + (c + 3) * RS * 4, svB);
+        if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
+          if (sumA.x > 0.0f) lb.x = RC_REG_CHECK(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumA.y > 0.0f) lb.y = RC_REG_CHECK(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          if (sumB.x > 0.0f) lb.x = RC_REG_CHECK(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumB.y > 0.0f) lb.y = RC_REG_CHECK(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+        }
+      }
+    } else
+#else
     if (diag) {
       // rows start inside the tile: one step at a time with the start-of-row reset
 #pragma unroll 1
@@ -1283,17 +1309,6 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
       for (int c = 0; c < tsteps; c += 2) {
         float2 sumA, sumB;
         const bool clean = (__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u;
-#if RC_REG_DIAG_MASKED
-        if (diag) {  // masked variants, see reg_pair_diag
-          const bool P = j0 + c >= r0, Q = j0 + c > r0;
-          if (clean) {
-            reg_pair_diag<NK>(S0, S1, S2, svA, svB, omega, P, Q, sumA, sumB);
-          } else {
-            sumA = reg_update_diag<NK>(S0, S1, S2, svA, P, Q, Delta, Omega, omega);
-            sumB = reg_update_diag<NK>(S0, S1, S2, svB, P, P, Delta, Omega, omega);
-          }
-        } else
-#endif
         if (clean) {
           reg_pair_fast<NK>(S0, S1, S2, svA, svB, omega, sumA, sumB);
         } else {
