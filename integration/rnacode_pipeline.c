@@ -235,11 +235,17 @@ static void init_gpus(void) {
   g_ngpus = want;
 }
 
+/* unit of GPU work: the native alignment of a block plus its null alignments [s0, s0 + ns) */
+typedef struct {
+  int blk, s0, ns, want_native;
+  double cost;
+} unit_t;
+
 typedef struct {
   rc_ctx *c;
   blk_t *blk;
-  const int *list;
-  int nlist, s0, ns, want_native, mode;
+  unit_t *units;
+  int nunits, seed0, mode;
   const int *blosum;
 } shard_t;
 
@@ -248,43 +254,46 @@ static void shard_die(rc_ctx *c, const char *what) {
   exit(EXIT_FAILURE);
 }
 
-/* one library batch on one device: native alignment + null alignments [s0, s0+ns) of the shard's blocks */
+/* one library batch on one device */
 static void *run_shard(void *arg) {
   shard_t *sh = (shard_t *)arg;
   rc_params p = current_params();
   rc_block_desc *descs;
   rc_batch *batch = NULL;
   int k;
-  if (sh->nlist == 0) return NULL;
-  descs = (rc_block_desc *)malloc(sizeof(rc_block_desc) * sh->nlist);
-  for (k = 0; k < sh->nlist; k++) {
-    blk_t *b = &sh->blk[sh->list[k]];
+  if (sh->nunits == 0) return NULL;
+  descs = (rc_block_desc *)malloc(sizeof(rc_block_desc) * sh->nunits);
+  for (k = 0; k < sh->nunits; k++) {
+    blk_t *b = &sh->blk[sh->units[k].blk];
     descs[k].N = b->N;
     descs[k].cols = b->cols;
     descs[k].rows = b->rows;
     descs[k].scores_fwd = b->sf;
     descs[k].scores_rev = b->sr;
-    descs[k].n_samples = sh->ns;
+    descs[k].n_samples = sh->units[k].ns;
     descs[k].samples = NULL;
   }
-  if (rc_batch_create(sh->c, descs, sh->nlist, &p, sh->blosum, &batch) != RC_OK) shard_die(sh->c, "rc_batch_create");
-  for (k = 0; k < sh->nlist && sh->ns > 0; k++) {
-    blk_t *b = &sh->blk[sh->list[k]];
+  if (rc_batch_create(sh->c, descs, sh->nunits, &p, sh->blosum, &batch) != RC_OK) shard_die(sh->c, "rc_batch_create");
+  for (k = 0; k < sh->nunits; k++) {
+    const unit_t *u = &sh->units[k];
+    blk_t *b = &sh->blk[u->blk];
     rc_tree_desc td;
+    if (u->ns == 0) continue;
     td.n_nodes = b->n_nodes;
     td.parent = b->tpar;
     td.row = b->trow;
     td.cum = b->tcum;
-    if (rc_batch_set_evolve(batch, k, &td, b->seeds, sh->mode == 2 ? RC_RNG_PHILOX : RC_RNG_MT19937) != RC_OK)
+    if (rc_batch_set_evolve(batch, k, &td, b->seeds + (u->s0 - sh->seed0), sh->mode == 2 ? RC_RNG_PHILOX : RC_RNG_MT19937) != RC_OK)
       shard_die(sh->c, "rc_batch_set_evolve");
   }
   if (rc_batch_upload(batch) != RC_OK) shard_die(sh->c, "rc_batch_upload");
   if (rc_batch_run(batch) != RC_OK) shard_die(sh->c, "rc_batch_run");
   if (rc_batch_download(batch) != RC_OK) shard_die(sh->c, "rc_batch_download");
-  for (k = 0; k < sh->nlist; k++) {
-    blk_t *b = &sh->blk[sh->list[k]];
-    if (sh->ns > 0 && rc_batch_max_scores(batch, k, b->maxScores + sh->s0) != RC_OK) shard_die(sh->c, "rc_batch_max_scores");
-    if (sh->want_native) {
+  for (k = 0; k < sh->nunits; k++) {
+    const unit_t *u = &sh->units[k];
+    blk_t *b = &sh->blk[u->blk];
+    if (u->ns > 0 && rc_batch_max_scores(batch, k, b->maxScores + u->s0) != RC_OK) shard_die(sh->c, "rc_batch_max_scores");
+    if (u->want_native) {
       int cap = 256, rc;
       b->hss = (rc_hss *)malloc(sizeof(rc_hss) * cap);
       rc = rc_batch_native_hss(batch, k, b->hss, cap, &b->n_hss);
@@ -302,18 +311,19 @@ static void *run_shard(void *arg) {
 }
 
 /* The native alignment and the null alignments [s0, s0 + ns) of the listed blocks, on all devices.  Fills
- * blk[].maxScores[s0 .. s0+ns) and, when want_native, blk[].hss / blk[].n_hss. */
+ * blk[].maxScores[s0 .. s0+ns) and, when want_native, blk[].hss / blk[].n_hss.  Blocks are dealt out by cost
+ * (DP cells ~ (N-1) * L^2 per alignment); a block that alone outweighs a device's fair share is cut along its
+ * null alignments, which are independent too (only maxima are gathered). */
 static void gpu_batch(blk_t *blk, const int *list, int nlist, int s0, int ns, const int *blosum, int want_native,
                       double *t_seeds, double *t_gpu) {
   const int mode = evolve_mode();
-  double ta = now_s(), tb;
-  int k, j, d, G;
+  double ta = now_s(), tb, total = 0, load[MAX_GPUS];
+  int k, j, d, G, nunits = 0, pos[MAX_GPUS];
   shard_t sh[MAX_GPUS];
-  int *shard_list[MAX_GPUS];
-  double load[MAX_GPUS];
+  unit_t *units, *sorted;
   pthread_t th[MAX_GPUS];
   init_gpus();
-  G = g_ngpus < nlist ? g_ngpus : nlist;
+  G = g_ngpus;
   /* one CreateSeed() per null alignment, block by block in input order (src/treeSimulate.c:84) */
   for (k = 0; k < nlist; k++) {
     blk_t *b = &blk[list[k]];
@@ -321,36 +331,60 @@ static void gpu_batch(blk_t *blk, const int *list, int nlist, int s0, int ns, co
     if (rc_wrap_set_block) rc_wrap_set_block(b->scored_idx);
     if (rc_wrap_set_sample) rc_wrap_set_sample(s0);
     for (j = 0; j < ns; j++) b->seeds[j] = (unsigned int)(CreateSeed() & 0xffffffffUL);
+    total += (double)(b->N - 1) * b->L * b->L * (ns + 1);
   }
-  /* deal the blocks out: each to the device with the least work so far, cost ~ (N-1) * L^2 (DP cells per alignment) */
+  units = (unit_t *)malloc(sizeof(unit_t) * ((size_t)nlist * G + 1));
+  for (k = 0; k < nlist; k++) {
+    blk_t *b = &blk[list[k]];
+    const double per_aln = (double)(b->N - 1) * b->L * b->L;
+    int parts = 1, p0;
+    if (G > 1 && ns >= 2 * G && per_aln * (ns + 1) > total / (2.0 * G)) parts = G;
+    for (p0 = 0; p0 < parts; p0++) {
+      const int a = (int)((long long)ns * p0 / parts), e = (int)((long long)ns * (p0 + 1) / parts);
+      units[nunits].blk = list[k];
+      units[nunits].s0 = s0 + a;
+      units[nunits].ns = e - a;
+      units[nunits].want_native = want_native && p0 == 0;
+      units[nunits].cost = per_aln * (e - a + 1);
+      nunits++;
+    }
+  }
+  /* heaviest first, each to the device with the least work so far */
+  sorted = (unit_t *)malloc(sizeof(unit_t) * (nunits + 1));
+  memcpy(sorted, units, sizeof(unit_t) * nunits);
+  for (k = 1; k < nunits; k++) { /* insertion sort by descending cost (windows hold at most a few thousand units) */
+    unit_t u = sorted[k];
+    for (j = k - 1; j >= 0 && sorted[j].cost < u.cost; j--) sorted[j + 1] = sorted[j];
+    sorted[j + 1] = u;
+  }
   for (d = 0; d < G; d++) {
-    shard_list[d] = (int *)malloc(sizeof(int) * nlist);
-    load[d] = 0;
     memset(&sh[d], 0, sizeof(shard_t));
     sh[d].c = g_ctxs[d];
     sh[d].blk = blk;
-    sh[d].list = shard_list[d];
-    sh[d].s0 = s0;
-    sh[d].ns = ns;
-    sh[d].want_native = want_native;
+    sh[d].units = (unit_t *)malloc(sizeof(unit_t) * (nunits + 1));
+    sh[d].seed0 = s0;
     sh[d].mode = mode;
     sh[d].blosum = blosum;
+    load[d] = 0;
+    pos[d] = 0;
   }
-  for (k = 0; k < nlist; k++) {
-    blk_t *b = &blk[list[k]];
+  for (k = 0; k < nunits; k++) {
     int best = 0;
     for (d = 1; d < G; d++)
       if (load[d] < load[best]) best = d;
-    shard_list[best][sh[best].nlist++] = list[k];
-    load[best] += (double)(b->N - 1) * b->L * b->L;
+    sh[best].units[sh[best].nunits++] = sorted[k];
+    load[best] += sorted[k].cost;
   }
+  (void)pos;
   tb = now_s();
   *t_seeds += tb - ta;
   for (d = 1; d < G; d++)
     if (pthread_create(&th[d], NULL, run_shard, &sh[d]) != 0) nrerror("ERROR: pthread_create failed.\n");
   run_shard(&sh[0]);
   for (d = 1; d < G; d++) pthread_join(th[d], NULL);
-  for (d = 0; d < G; d++) free(shard_list[d]);
+  for (d = 0; d < G; d++) free(sh[d].units);
+  free(units);
+  free(sorted);
   for (k = 0; k < nlist; k++) free(blk[list[k]].seeds);
   *t_gpu += now_s() - tb;
 }
