@@ -77,3 +77,29 @@ def test_batched_pipeline_sharded_over_gpus(case):
     res = subprocess.run([PIPELINE, *opts, os.path.join(EXAMPLES, fname)], capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0, res.stderr
     assert _norm(res.stdout) == _norm(op.golden("cli_outputs")[case])
+
+
+def test_gpu_rng_mode_pvalues_within_sampling_error():
+    """GPU-RNG mode (RNACODE_CUDA_EVOLVE=philox): the HSS and their scores do not depend on the generator, and the
+    p-values from the Gumbel fit of 2000 Philox-drawn null alignments agree with those of 2000 MT19937-drawn ones
+    within sampling error (the fit's mu / lambda are estimated from the sample)."""
+    import math
+    exe = os.path.join(REFDIR, "RNAcode_cuda_det")
+    if not (os.path.exists(exe) and os.path.isdir(EXAMPLES)):
+        pytest.skip("oracle/_ref/RNAcode_cuda_det not built (needs /root/reference at build time)")
+    outs = {}
+    for mode in ("gpu", "philox"):
+        env = dict(os.environ, RNACODE_SEED="3", RNACODE_CUDA_EVOLVE=mode)
+        res = subprocess.run([exe, "--tabular", "-n", "2000", os.path.join(EXAMPLES, "coding.aln")], capture_output=True,
+                             text=True, env=env, timeout=600)
+        assert res.returncode == 0, res.stderr
+        outs[mode] = [l.split("\t") for l in res.stdout.strip().splitlines()]
+    assert len(outs["gpu"]) == len(outs["philox"]) > 0
+    for a, b in zip(outs["gpu"], outs["philox"]):
+        assert a[:-1] == b[:-1]  # same segment, strand, frame, coordinates, score
+        pa, pb = float(a[-1]), float(b[-1])
+        if min(pa, pb) > 0.5:
+            assert abs(pa - pb) < 0.05
+        else:
+            la, lb = math.log10(max(pa, 1e-300)), math.log10(max(pb, 1e-300))
+            assert abs(la - lb) < 0.3 + 0.06 * abs(la), (pa, pb)
