@@ -273,7 +273,10 @@ static void *run_shard(void *arg) {
     descs[k].n_samples = sh->units[k].ns;
     descs[k].samples = NULL;
   }
+  double tt[6];
+  tt[0] = now_s();
   if (rc_batch_create(sh->c, descs, sh->nunits, &p, sh->blosum, &batch) != RC_OK) shard_die(sh->c, "rc_batch_create");
+  tt[1] = now_s();
   for (k = 0; k < sh->nunits; k++) {
     const unit_t *u = &sh->units[k];
     blk_t *b = &sh->blk[u->blk];
@@ -286,9 +289,16 @@ static void *run_shard(void *arg) {
     if (rc_batch_set_evolve(batch, k, &td, b->seeds + (u->s0 - sh->seed0), sh->mode == 2 ? RC_RNG_PHILOX : RC_RNG_MT19937) != RC_OK)
       shard_die(sh->c, "rc_batch_set_evolve");
   }
+  tt[2] = now_s();
   if (rc_batch_upload(batch) != RC_OK) shard_die(sh->c, "rc_batch_upload");
+  tt[3] = now_s();
   if (rc_batch_run(batch) != RC_OK) shard_die(sh->c, "rc_batch_run");
+  tt[4] = now_s();
   if (rc_batch_download(batch) != RC_OK) shard_die(sh->c, "rc_batch_download");
+  tt[5] = now_s();
+  if (getenv("RNACODE_CUDA_VERBOSE"))
+    fprintf(stderr, "[RNAcode_b200]   device batch of %d units: create %.3f s, trees/thresholds %.3f s, upload %.3f s, run %.3f s, download %.3f s\n",
+            sh->nunits, tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3], tt[5] - tt[4]);
   for (k = 0; k < sh->nunits; k++) {
     const unit_t *u = &sh->units[k];
     blk_t *b = &sh->blk[u->blk];

@@ -657,14 +657,21 @@ static unsigned threshold_of(double P) {
   const double c = 1.0 / 4294967295.0;
   volatile double r0 = 0.0 * c;
   if (!(r0 <= P)) return 0u;  // P < 0 (not a probability): treat like 0
-  unsigned lo = 0u, hi = 0xffffffffu;
-  while (lo < hi) {
-    const unsigned mid = lo + (unsigned)(((unsigned long long)hi - lo + 1) / 2);
-    volatile double r = (double)mid * c;
-    if (r <= P) lo = mid;
-    else hi = mid - 1;
+  // start from the real-number estimate P / c and correct it with the very expression seq-gen evaluates
+  double est = P * 4294967295.0;
+  unsigned long long u = est >= 4294967295.0 ? 0xffffffffull : (est <= 0.0 ? 0ull : (unsigned long long)est);
+  for (;;) {  // largest u with (double)u * c <= P
+    volatile double r = (double)u * c;
+    if (r <= P) break;
+    if (u == 0) return 0u;
+    u--;
   }
-  return lo;
+  while (u < 0xffffffffull) {
+    volatile double r = (double)(u + 1) * c;
+    if (!(r <= P)) break;
+    u++;
+  }
+  return (unsigned)u;
 }
 
 extern "C" int rc_batch_set_evolve(rc_batch* b, int block, const rc_tree_desc* tree, const unsigned int* seeds, int rng) {
