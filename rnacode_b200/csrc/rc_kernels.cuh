@@ -1696,12 +1696,18 @@ __global__ void __launch_bounds__(HSS_WARPS * 32)
   float cur = 0.0f;
   int segS = -1, segE = -1;
   const int nrows = sites - 1;  // the last row only holds the frame's final entry, which never survives (:893-900)
+  uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = make_uint4(0u, 0u, 0u, 0u);  // records of the next 32 rows, fetched ahead
+  if (lane < nrows) {
+    n0 = rp[2 * lane];
+    n1 = rp[2 * lane + 1];
+  }
   for (int i0 = 0; i0 < nrows; i0 += 32) {
-    const int i_mine = i0 + lane;
-    uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = make_uint4(0u, 0u, 0u, 0u);
-    if (i_mine < nrows) {
-      w0 = rp[2 * i_mine];
-      w1 = rp[2 * i_mine + 1];
+    const uint4 w0 = n0, w1 = n1;
+    n0 = make_uint4(0u, 0u, 0u, 0u);
+    n1 = make_uint4(0u, 0u, 0u, 0u);
+    if (i0 + 32 + lane < nrows) {
+      n0 = rp[2 * (i0 + 32 + lane)];
+      n1 = rp[2 * (i0 + 32 + lane) + 1];
     }
     // RowRec: w0 = {Emax, vF, be0, be1}, w1 = {be2, jF | n << 16, bj0 | bj1 << 16, bj2 | pad << 16}
     unsigned mask = __ballot_sync(FULL, (w1.y >> 16) != 0u);
