@@ -42,6 +42,8 @@ WORKLOADS = {
     "short": ([(10, 120)] * 2000, 100, 1, "synthetic MAF 2000 blocks x 10 species x 120 cols, -n 100 (config 3 shape)"),
     "wide": ([(50, 5000)] * 1, 200, 3, "synthetic MAF 1 block x 50 species x 5000 cols, -n 200 (config 4 shape, reduced n)"),
     "hundred": ([(100, 1000)] * 4, 250, 4, "synthetic MAF 4 blocks x 100 species x 1000 cols, -n 250 (config 5 row count)"),
+    "hundred_short": ([(100, 200)] * 200, 100, 5, "synthetic MAF 200 blocks x 100 species x 200 cols, -n 100 (config 5 row count, short blocks)"),
+    "mid_short": ([(30, 200)] * 500, 100, 6, "synthetic MAF 500 blocks x 30 species x 200 cols, -n 100"),
 }
 METRIC = "codon_dp_cells_per_s"
 UNIT = "cells/s"

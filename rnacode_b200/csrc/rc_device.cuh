@@ -10,7 +10,8 @@ constexpr int TILE = 16;          // codon steps per staged sigma/z tile
 constexpr int REC_SLOTS = 3;      // tie-band slots in a row record
 constexpr int DP_WARPS = 4;       // warps per DP CTA (each warp owns one task)
 constexpr int REG_MAX_NK = 16;    // largest N-1 handled by the register-resident DP kernels
-constexpr int SMP_WARPS = 4;      // warps per CTA of the sample-major DP kernel
+constexpr int SMP_WARPS = 4;      // warps per CTA of the sample-major DP kernel (8 when the sigma table limits the CTAs per SM)
+constexpr int SMP_MAX_WARPS = 8;
 
 // class byte of one alignment character (k_pack): what calculateSigma / getBlock / revAln need
 //   bits 0-1  ntMap[c]                 (forward strand code; anything but ACGTU -> 0, src/RNAcode.c:94-98)
@@ -53,6 +54,8 @@ struct BlockDev {
   int layout;               // 0: sigma tile [k][TILE] (k_dp, any NK); 1: sigma tile [TILE][RS] (k_dp_reg, NK <= 16);
                             // 2: sample-major [group of 32 instances][step][RSB/4][lane][4] (k_dp_smp, short blocks);
                             // 3: sigma tile [chunk][TILE][RS] (k_dp_chain: species cut into nchunk chunks of <= nkw)
+                            // 5: sample-major in nchunk species chunks of chunk_base (+1 for the first chunk_rem) QUADS:
+                            //    [chunk][group of 32 instances][step][3 quads][lane][4] (k_dp_smp<., true>, one launch per chunk)
   int chain_tasks;          // layout 3: consecutive tasks one CTA of k_dp_chain works through
   int nchunk, nkw;          // layout 3: chunks and species per chunk (template NK of k_dp_chain); chunk g holds
   int chunk_base, chunk_rem;  //   chunk_base + (g < chunk_rem) species starting at g*chunk_base + min(g, chunk_rem)
@@ -75,6 +78,7 @@ struct Item {
   long long sigma_off[2][3];  // float offset: [inst_local][tile][NK][TILE]
   long long rec_off[2][3];    // RowRec offset: [inst_local][sites]
   long long dense_off[2][3];  // float offset (dense fallback only): [inst_local][sites*(sites+1)/2]
+  long long part_off[2][3];   // float2 offset (layout 5 only): [group][pair][end codon][lane] partial species sums
 };
 
 // Null-alignment simulation (kernel d) of one block: the tree in seq-gen's evolution order.

@@ -156,10 +156,17 @@ __global__ void __launch_bounds__(256) k_prep(const BlockDev* __restrict__ block
           kfirst = gch * bd.chunk_base + min(gch, bd.chunk_rem);
           n_inner = bd.chunk_base + (gch < bd.chunk_rem ? 1 : 0);
         }
+        int j5 = 0;
+        if (bd.layout == 5) {  // [chunk][padded step]: w = chunk * (nt * TILE) + step; chunks are counted in quads of species
+          const int gch = w / (nt * TILE);
+          j5 = w % (nt * TILE);
+          kfirst = 4 * (gch * bd.chunk_base + min(gch, bd.chunk_rem));
+          n_inner = 4 * (bd.chunk_base + (gch < bd.chunk_rem ? 1 : 0));
+        }
         for (int v = 0; v < n_inner; v++) {
-          const int k = bd.layout == 3 ? kfirst + v : (bd.layout ? v : u);
+          const int k = (bd.layout == 3 || bd.layout == 5) ? kfirst + v : (bd.layout ? v : u);
           const int c = bd.layout == 3 ? u % TILE : (bd.layout ? u : v);
-          const int j = tile * TILE + c;
+          const int j = bd.layout == 5 ? j5 : tile * TILE + c;
           if (k >= NK || j >= sites) continue;
           const unsigned char* rowk = nat + (size_t)(k + 1) * cols;
           const int x = 3 * j + 3 + f;
@@ -438,7 +445,7 @@ __global__ void __launch_bounds__(256)
   const Item it = items[blockIdx.x];
   const BlockDev bd = blocks[it.block];
   const int group = blockIdx.y;
-  if (bd.layout != 2 || group * 32 >= it.ninst) return;
+  if ((bd.layout != 2 && bd.layout != 5) || group * 32 >= it.ninst) return;
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
     mbar_fence_init();
@@ -514,7 +521,16 @@ __global__ void __launch_bounds__(256)
         v4[kk] = v;
       }
       const int f = xi % 3, j = xi / 3;
-      float* out = sigma + it.sigma_off[s][f] + (((size_t)group * bd.sites[f] + j) * (rsb / 4) + kq) * 128 + lane * 4;
+      float* out;
+      if (bd.layout == 5) {  // [chunk][group][step][3 quads][lane][4]; quad kq belongs to chunk ch as its quad qq
+        const int big = bd.chunk_rem * (bd.chunk_base + 1);
+        const int ch = kq < big ? kq / (bd.chunk_base + 1) : bd.chunk_rem + (kq - big) / bd.chunk_base;
+        const int qq = kq < big ? kq % (bd.chunk_base + 1) : (kq - big) % bd.chunk_base;
+        const int ngrp = (it.ninst + 31) / 32;
+        out = sigma + it.sigma_off[s][f] + ((((size_t)ch * ngrp + group) * bd.sites[f] + j) * 3 + qq) * 128 + lane * 4;
+      } else {
+        out = sigma + it.sigma_off[s][f] + (((size_t)group * bd.sites[f] + j) * (rsb / 4) + kq) * 128 + lane * 4;
+      }
       *reinterpret_cast<float4*>(out) = make_float4(v4[0], v4[1], v4[2], v4[3]);
     }
     __syncthreads();
@@ -1570,16 +1586,21 @@ __device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv
   sv[NK] = __uint_as_float(zw);
 }
 
-template <int NK>
-__global__ void __launch_bounds__(SMP_WARPS * 32)
+// CHAINED (layout 5, wide alignments in short blocks): the species are cut into chunks of 1-3 quads; chunk g is one
+// launch of this kernel with NK = 4 * (quads of the chunk) and continues, for every (start-codon pair, end codon,
+// instance), the k-ordered partial species sum the launch of chunk g-1 left in global memory (`partial`, float2 per
+// lane = the two rows of the pair).  The last chunk owns the getHSS digest.  Species past the end of the alignment in
+// the last quad are dummies (sigma = +0, z = 0): with omega <= 0 they add max3(0, t*omega, t*omega) = +0.
+template <int NK, bool CHAINED>
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
     k_dp_smp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
              const float* __restrict__ sigma, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm,
-             int band_slots) {
+             int band_slots, int chunk, float2* __restrict__ partial) {
   constexpr int RS = RegCfg<NK>::RS;
   constexpr int RSB = (NK + 3) / 4 * 4;
-  constexpr int ROW_BYTES = RSB * 32 * 4;  // one end codon, 32 lanes
+  constexpr int ROW_BYTES = (CHAINED ? 12 : RSB) * 32 * 4;  // one end codon, 32 lanes (chained: always room for three quads)
   extern __shared__ __align__(128) unsigned char smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;  // 4-8 warps share the CTA's sigma table
   const CtaDesc cd = ctas[blockIdx.x];
   const Item& it = items[cd.item];
   const BlockDev& bd = blocks[it.block];
@@ -1588,17 +1609,22 @@ __global__ void __launch_bounds__(SMP_WARPS * 32)
   const int group = cd.task0;  // group of 32 instances inside the item
   const int inst_l = group * 32 + lane;
   const bool valid = inst_l < it.ninst;
+  const bool first = !CHAINED || chunk == 0, last = !CHAINED || chunk == bd.nchunk - 1;
+  const int ngrp = (it.ninst + 31) / 32;
 
   const size_t sig_bytes = (size_t)sites * ROW_BYTES;
   const size_t z_bytes = ((size_t)sites * 4 + 15) / 16 * 16;
   unsigned* zs = reinterpret_cast<unsigned*>(smem + sig_bytes);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sig_bytes + z_bytes);
+  // fold state of the getHSS digest, two records per lane and warp (only the launch that owns the digest has room for it)
+  RowRec* srec = reinterpret_cast<RowRec*>(smem + sig_bytes + z_bytes + 16);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
     mbar_expect_tx(bar, (unsigned)(sig_bytes + z_bytes));
-    bulk_g2s(smem, sigma + it.sigma_off[strand][frame] + (size_t)group * sites * RSB * 32, (unsigned)sig_bytes, bar);
-    bulk_g2s(zs, ztiles + bd.z_off[strand][frame], (unsigned)z_bytes, bar);
+    const size_t grp_index = CHAINED ? (size_t)chunk * ngrp + group : (size_t)group;
+    bulk_g2s(smem, sigma + it.sigma_off[strand][frame] + grp_index * sites * (ROW_BYTES / 4), (unsigned)sig_bytes, bar);
+    bulk_g2s(zs, ztiles + bd.z_off[strand][frame] + (CHAINED ? (size_t)chunk * bd.ntiles[frame] * TILE : 0), (unsigned)z_bytes, bar);
   }
   __syncthreads();
   mbar_wait(bar, 0);
@@ -1610,20 +1636,28 @@ __global__ void __launch_bounds__(SMP_WARPS * 32)
   asm volatile("" : "+f"(omega));
   const float fNK = bd.fNK, rcpNK = bd.rcpNK;
   RowRec* rec_inst = recs + it.rec_off[strand][frame] + (size_t)(valid ? inst_l : 0) * sites;
-
-  __shared__ __align__(16) RowRec srec[SMP_WARPS][2 * 32];
+  // partial sums of this (item, strand, frame, group): [pair][end codon from the pair's first row on][lane]
   const int npairs = (sites + 1) / 2;
+  float2* part = nullptr;
+  if (CHAINED) {
+    const size_t per_group = ((size_t)npairs * sites - (size_t)npairs * (npairs - 1)) * 32;
+    part = partial + it.part_off[strand][frame] + (size_t)group * per_group + lane;
+  }
+
   // boustrophedon assignment of start-codon pairs to warps: w, 2W-1-w, 2W+w, 4W-1-w, ... (rows get shorter
   // with the pair index, so every warp receives a similar total length)
 #pragma unroll 1
   for (int turn = 0;; turn++) {
-    const int p = (turn & 1) ? (turn + 1) * SMP_WARPS - 1 - warp : turn * SMP_WARPS + warp;
-    if (turn * SMP_WARPS >= npairs) break;
+    const int p = (turn & 1) ? (turn + 1) * nw - 1 - warp : turn * nw + warp;
+    if (turn * nw >= npairs) break;
     if (p >= npairs) continue;
     const int r0 = 2 * p;
-    RowRec* rec0 = &srec[warp][lane * 2];
-    rec_init(rec0);
-    rec_init(rec0 + 1);
+    RowRec* rec0 = srec + (warp * 32 + lane) * 2;
+    if (last) {
+      rec_init(rec0);
+      rec_init(rec0 + 1);
+    }
+    float2* pp = CHAINED ? part + ((size_t)p * sites - (size_t)p * (p - 1) - r0) * 32 : nullptr;  // pp[j * 32] = entry of end codon j
     float2 S0[NK], S1[NK], S2[NK];
 #pragma unroll
     for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
@@ -1639,9 +1673,16 @@ __global__ void __launch_bounds__(SMP_WARPS * 32)
         if ((zA | zB) == 0u) {
           float svB[RS];
           smp_load_row<NK>(sig_a + (j + 1) * ROW_BYTES, zB, svB);
-          float2 sumA, sumB;
-          reg_pair_fast<NK>(S0, S1, S2, svA, svB, omega, sumA, sumB);
-          if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
+          float2 sumA, sumB, sinA = make_float2(0.0f, 0.0f), sinB = make_float2(0.0f, 0.0f);
+          if (CHAINED && !first) {
+            sinA = pp[(size_t)j * 32];
+            sinB = pp[(size_t)(j + 1) * 32];
+          }
+          reg_pair_fast<NK, CHAINED>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
+          if (CHAINED && !last) {
+            pp[(size_t)j * 32] = sumA;
+            pp[(size_t)(j + 1) * 32] = sumB;
+          } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
             lb.x = reg_check_inl(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
             lb.y = reg_check_inl(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
             lb.x = reg_check_inl(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
@@ -1651,14 +1692,18 @@ __global__ void __launch_bounds__(SMP_WARPS * 32)
           continue;
         }
       }
-      const float2 sum = reg_update<NK>(S0, S1, S2, svA, j < r0 + 2, j, r0, Delta, Omega, omega);
-      if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
+      float2 sin = make_float2(0.0f, 0.0f);
+      if (CHAINED && !first) sin = pp[(size_t)j * 32];
+      const float2 sum = reg_update<NK, CHAINED>(S0, S1, S2, svA, j < r0 + 2, j, r0, Delta, Omega, omega, sin);
+      if (CHAINED && !last) {
+        pp[(size_t)j * 32] = sum;
+      } else if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
         lb.x = reg_check_inl(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
         if (r0 + 1 < sites) lb.y = reg_check_inl(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
       }
       j += 1;
     }
-    if (valid) {
+    if (valid && last) {
 #pragma unroll
       for (int t = 0; t < 2; t++)
         if (r0 + t < sites) rec_copy(rec_inst + r0 + t, rec0 + t);

@@ -109,7 +109,10 @@ namespace {
 constexpr int SMP_CLASS0 = REG_MAX_NK + 2;
 constexpr int CHAIN_CLASS0 = 2 * REG_MAX_NK + 2;
 constexpr int CHAIN_NKW_MIN = 8, CHAIN_NKW_MAX = 12, CHAIN_NKW_SPAN = CHAIN_NKW_MAX - CHAIN_NKW_MIN + 1;
-constexpr int N_CLASSES = CHAIN_CLASS0 + (CHAIN_MAX_WARPS - 1) * CHAIN_NKW_SPAN;
+// then k_dp_smp<., true> (layout 5: wide alignments in short blocks), one class per number of species quads Q = ceil(NK/4)
+constexpr int SMPC_CLASS0 = CHAIN_CLASS0 + (CHAIN_MAX_WARPS - 1) * CHAIN_NKW_SPAN;
+constexpr int SMPC_Q_MIN = 5, SMPC_Q_MAX = 125;
+constexpr int N_CLASSES = SMPC_CLASS0 + (SMPC_Q_MAX - SMPC_Q_MIN + 1);
 constexpr size_t SMP_SMEM_MAX = 200 * 1024;  // sigma table + z words of one CTA of k_dp_smp
 constexpr int SMP_MIN_INST = 16;             // fewer instances than this: the row-major kernels are the better fit
 
@@ -117,10 +120,10 @@ struct Chunk {
   size_t item0 = 0, nitems = 0;          // range in the batch's item array
   size_t cta0[N_CLASSES] = {}, ncta[N_CLASSES] = {};  // per class range in the CTA array
   int maxNK[N_CLASSES] = {}, maxZs[N_CLASSES] = {};
-  size_t sigma_floats = 0, rec_count = 0, max_smp_smem = 0, max_smp_stage = 0;
+  size_t sigma_floats = 0, rec_count = 0, part_count = 0, max_smp_smem = 0, max_smp_stage = 0;
   long long max_sigma_work = 0;  // largest ninst*2*(L-2) of an item, for the k_sigma grid
   int max_ninst = 0;
-  int n_layout[4] = {0, 0, 0, 0};  // items per sigma layout
+  int n_layout[6] = {0, 0, 0, 0, 0, 0};  // items per sigma layout
   int hss_warp_items = 0;  // items whose frames are long enough for the warp-per-task k_hss
 };
 
@@ -133,14 +136,21 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int class_of(const BlockDev& bd) {
   if (bd.layout == 3) return CHAIN_CLASS0 + (bd.nchunk - 2) * CHAIN_NKW_SPAN + (bd.nkw - CHAIN_NKW_MIN);
+  if (bd.layout == 5) return SMPC_CLASS0 + ((bd.NK + 3) / 4 - SMPC_Q_MIN);
   if (bd.layout == 2) return SMP_CLASS0 + bd.NK - 1;
   if (bd.layout == 1) return bd.NK - 1;
   return bd.NK <= 24 ? REG_MAX_NK : REG_MAX_NK + 1;
 }
 int class_R(int cl) { return cl == REG_MAX_NK + 1 ? 1 : 2; }
 
-size_t smp_smem_bytes(const BlockDev& bd, int f) {
-  const size_t rsb = (size_t)(bd.NK + 3) / 4 * 4;
+// layout 5: (start-codon pair, end codon) entries of one frame: sum over pairs p of (sites - 2p)
+size_t part_entries(int sites) {
+  const size_t np = (size_t)(sites + 1) / 2;
+  return np * sites - np * (np - 1);
+}
+
+size_t smp_smem_bytes(const BlockDev& bd, int f, int layout) {
+  const size_t rsb = layout == 5 ? 12 : (size_t)(bd.NK + 3) / 4 * 4;
   return (size_t)bd.sites[f] * rsb * 32 * 4 + ((size_t)bd.sites[f] * 4 + 15) / 16 * 16 + 16;
 }
 
@@ -150,6 +160,7 @@ size_t sigma_floats_sf(const BlockDev& bd, int f, int ninst) {
     const size_t rsb = (size_t)(bd.NK + 3) / 4 * 4;
     return (size_t)((ninst + 31) / 32) * bd.sites[f] * rsb * 32;
   }
+  if (bd.layout == 5) return (size_t)bd.nchunk * ((ninst + 31) / 32) * bd.sites[f] * 12 * 32;
   return (size_t)ninst * bd.ntiles[f] * bd.sig_tile;
 }
 
@@ -167,6 +178,15 @@ void set_layout(BlockDev& bd, int layout) {
     bd.sig_tile = W * TILE * rs;
     bd.sig_ks = 1;
     bd.sig_cs = rs;
+    bd.zstride = W * TILE;
+  } else if (layout == 5) {  // species chunks counted in quads: Q quads over W = ceil(Q/3) chunks of 2-3 quads
+    const int Q = (bd.NK + 3) / 4, W = (Q + 2) / 3;
+    bd.nchunk = W;
+    bd.chunk_base = Q / W;
+    bd.chunk_rem = Q % W;
+    bd.sig_tile = 0;
+    bd.sig_ks = 0;
+    bd.sig_cs = 0;
     bd.zstride = W * TILE;
   } else if (layout == 2) {  // z as in layout 1 (one word per step); sigma addressed explicitly (sigma_floats_sf)
     bd.sig_tile = 0;
@@ -226,6 +246,8 @@ struct rc_batch {
   // device, scratch
   float* d_sigma = nullptr;
   RowRec* d_recs = nullptr;
+  float2* d_partial = nullptr;  // layout 5: partial species sums between chunk launches
+  size_t part_count = 0;
   float* d_dense = nullptr;
   size_t dense_floats = 0;
   // sizes
@@ -399,7 +421,7 @@ extern "C" int rc_calibrate_issue(rc_ctx* ctx, double* lane_ops_per_s) {
 static void free_batch_device(rc_batch* b) {
   rc_ctx* ctx = b->ctx;
   void* ptrs[] = {b->d_blocks, b->d_items, b->d_ctas, b->d_raw, b->d_cls, b->d_cols0, b->d_scores, b->d_z, b->d_res,
-                  b->d_hss, b->d_hsscnt, b->d_ovf, b->d_tables, b->d_sigma, b->d_recs, b->d_dense,
+                  b->d_hss, b->d_hsscnt, b->d_ovf, b->d_tables, b->d_sigma, b->d_recs, b->d_dense, b->d_partial,
                   b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq};
   for (void* p : ptrs) ctx_free(ctx, p);
   for (auto& e : b->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -413,7 +435,7 @@ static void build_ctas(const std::vector<BlockDev>& blocks, const std::vector<It
     const Item& it = items[i];
     const BlockDev& bd = blocks[it.block];
     if (want_class >= 0 && class_of(bd) != want_class) continue;
-    if (bd.layout == 2 && want_class >= 0) {
+    if ((bd.layout == 2 || bd.layout == 5) && want_class >= 0) {
       for (int sf = 0; sf < 6; sf++) {
         if (bd.sites[sf % 3] <= 0) continue;
         for (int g = 0; g < (it.ninst + 31) / 32; g++) out.push_back(CtaDesc{(int)i, sf, g});
@@ -497,11 +519,15 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     cells += (double)bd.n_inst * 2.0 * bd.NK * P;
     {
       int layout = (bd.NK <= REG_MAX_NK && params->Delta <= 0.0f) ? 1 : 0;
-      if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && !ctx->no_chain &&
+      if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && !ctx->no_smp && bd.n_inst >= SMP_MIN_INST &&
+          bd.sites[0] >= 1 && smp_smem_bytes(bd, 0, 5) <= std::min<size_t>(SMP_SMEM_MAX, (size_t)ctx->smem_optin) &&
+          (size_t)5 * 32 * (bd.cols + 8) <= SMP_SMEM_MAX)
+        layout = 5;  // wide alignment in a short block with many instances: sample-major, one launch per species chunk
+      else if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && !ctx->no_chain &&
           (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX <= CHAIN_MAX_WARPS)
         layout = 3;  // wide alignment: species chunks pipelined through the warps of a CTA
       if (layout == 1 && !ctx->no_smp && bd.n_inst >= SMP_MIN_INST && bd.sites[0] >= 1 &&
-          smp_smem_bytes(bd, 0) <= std::min<size_t>(SMP_SMEM_MAX, (size_t)ctx->smem_optin) &&
+          smp_smem_bytes(bd, 0, 2) <= std::min<size_t>(SMP_SMEM_MAX, (size_t)ctx->smem_optin) &&
           (size_t)5 * 32 * (bd.cols + 8) <= SMP_SMEM_MAX)
         layout = 2;  // short block with many instances: sample-major kernel
       set_layout(bd, layout);
@@ -549,7 +575,10 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       sig_per_inst += 2 * sigma_floats_sf(bd, f, 32) / 32;
       rec_per_inst += 2 * (size_t)bd.sites[f];
     }
-    const size_t bytes_per_inst = sig_per_inst * sizeof(float) + rec_per_inst * sizeof(RowRec);
+    size_t part_per_inst = 0;  // layout 5: partial species sums handed from one chunk's launch to the next (float2 per lane)
+    if (bd.layout == 5)
+      for (int f = 0; f < 3; f++) part_per_inst += 2 * part_entries(bd.sites[f]);
+    const size_t bytes_per_inst = sig_per_inst * sizeof(float) + rec_per_inst * sizeof(RowRec) + part_per_inst * sizeof(float2);
     int inst = 0;
     while (inst < bd.n_inst) {
       size_t room = budget > cur_bytes ? (budget - cur_bytes) / bytes_per_inst : 0;
@@ -558,7 +587,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
         else { close_chunk(); continue; }
       }
       int take = (int)std::min<size_t>(room, (size_t)(bd.n_inst - inst));
-      if (bd.layout == 2 && take < bd.n_inst - inst) {  // instance groups of 32 must not straddle chunks
+      if ((bd.layout == 2 || bd.layout == 5) && take < bd.n_inst - inst) {  // instance groups of 32 must not straddle chunks
         if (take >= 32) take = take / 32 * 32;
         else if (cur.nitems == 0) take = std::min(32, bd.n_inst - inst);
         else { close_chunk(); continue; }
@@ -574,11 +603,15 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
           cur.sigma_floats += sigma_floats_sf(bd, f, take);
           it.rec_off[s][f] = (long long)cur.rec_count;
           cur.rec_count += (size_t)take * bd.sites[f];
+          if (bd.layout == 5) {
+            it.part_off[s][f] = (long long)cur.part_count;
+            cur.part_count += (size_t)((take + 31) / 32) * part_entries(bd.sites[f]) * 32;
+          }
         }
       const int cl = class_of(bd);
       cur.maxNK[cl] = std::max(cur.maxNK[cl], bd.NK);
-      if (bd.layout == 2) {
-        cur.max_smp_smem = std::max(cur.max_smp_smem, smp_smem_bytes(bd, 0));
+      if (bd.layout == 2 || bd.layout == 5) {
+        cur.max_smp_smem = std::max(cur.max_smp_smem, smp_smem_bytes(bd, 0, bd.layout));
         int w = (bd.cols + 3) / 4;
         if ((w & 1) == 0) w++;
         cur.max_smp_stage = std::max(cur.max_smp_stage, (size_t)5 * 32 * w * 4);  // k_sigma_smp staging (smp_pitch)
@@ -603,6 +636,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     }
     b->sigma_floats = std::max(b->sigma_floats, ch.sigma_floats);
     b->rec_count = std::max(b->rec_count, ch.rec_count);
+    b->part_count = std::max(b->part_count, ch.part_count);
   }
 
   // device allocations
@@ -623,7 +657,8 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
             dalloc((void**)&b->d_hss, sizeof(HssDev) * b->hss_count) &&
             dalloc((void**)&b->d_hsscnt, sizeof(int) * b->hsscnt_ints) && dalloc((void**)&b->d_ovf, sizeof(int)) &&
             dalloc((void**)&b->d_tables, sizeof(SigmaTables)) && dalloc((void**)&b->d_sigma, sizeof(float) * b->sigma_floats) &&
-            dalloc((void**)&b->d_recs, sizeof(RowRec) * b->rec_count);
+            dalloc((void**)&b->d_recs, sizeof(RowRec) * b->rec_count) &&
+            (b->part_count == 0 || dalloc((void**)&b->d_partial, sizeof(float2) * b->part_count));
   if (!ok) {
     ctx_fail(ctx, std::string("rc_batch_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     free_batch_device(b);
@@ -887,12 +922,63 @@ static int launch_dp_reg(rc_batch* b, int NK, const CtaDesc* d_ctas, size_t ncta
   }
 }
 
+// Warps per CTA of k_dp_smp: the CTA's sigma table decides how many CTAs fit an SM; with few of them, more warps
+// share each table (the launch that owns the getHSS digest also needs 2 KB of fold state per warp).
+static int smp_warps(rc_ctx* ctx, size_t smem_table, bool with_fold) {
+  int best = SMP_WARPS, best_warps = 0;
+  for (int nw = SMP_WARPS; nw <= SMP_MAX_WARPS; nw += 2) {
+    const size_t per_cta = smem_table + (with_fold ? (size_t)nw * 64 * sizeof(RowRec) : 0) + 1024;
+    if (per_cta > (size_t)ctx->smem_optin + 1024) break;
+    const int ctas = (int)std::min<size_t>(16 / nw, ((size_t)228 * 1024) / per_cta);  // 128 registers per thread: 16 warps per SM
+    if (ctas * nw > best_warps) {
+      best_warps = ctas * nw;
+      best = nw;
+    }
+  }
+  return best;
+}
+
+// layout 5: one launch per species chunk (1-3 quads each), chunk g continuing the partial sums of chunk g-1
+template <int NK>
+static int launch_dp_smpc_nk(rc_batch* b, int chunk, bool last, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
+  rc_ctx* ctx = b->ctx;
+  const int nw = smp_warps(ctx, smem, last);
+  if (last) smem += (size_t)nw * 64 * sizeof(RowRec);
+  RC_CUDA(cudaFuncSetAttribute(k_dp_smp<NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dp_smp<NK, true><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+                                                                          b->d_recs, b->prm, (int)ctx->band_slots, chunk,
+                                                                          b->d_partial);
+  RC_CUDA(cudaGetLastError());
+  b->stats.launches++;
+  b->stats.dp_launches++;
+  return RC_OK;
+}
+
+static int launch_dp_smpc(rc_batch* b, int Q, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
+  if (ncta == 0) return RC_OK;
+  const int W = (Q + 2) / 3, base = Q / W, rem = Q % W;
+  for (int g = 0; g < W; g++) {
+    const int quads = base + (g < rem ? 1 : 0);
+    int rc;
+    switch (quads) {
+      case 1: rc = launch_dp_smpc_nk<4>(b, g, g == W - 1, d_ctas, ncta, smem); break;
+      case 2: rc = launch_dp_smpc_nk<8>(b, g, g == W - 1, d_ctas, ncta, smem); break;
+      case 3: rc = launch_dp_smpc_nk<12>(b, g, g == W - 1, d_ctas, ncta, smem); break;
+      default: ctx_fail(b->ctx, "internal: k_dp_smp chunk size out of range"); return RC_ERR_STATE;
+    }
+    if (rc != RC_OK) return rc;
+  }
+  return RC_OK;
+}
+
 template <int NK>
 static int launch_dp_smp_nk(rc_batch* b, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
   rc_ctx* ctx = b->ctx;
-  RC_CUDA(cudaFuncSetAttribute(k_dp_smp<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dp_smp<NK><<<(unsigned)ncta, SMP_WARPS * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
-                                                                    b->d_recs, b->prm, (int)ctx->band_slots);
+  const int nw = smp_warps(ctx, smem, true);
+  smem += (size_t)nw * 64 * sizeof(RowRec);
+  RC_CUDA(cudaFuncSetAttribute(k_dp_smp<NK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dp_smp<NK, false><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+                                                                           b->d_recs, b->prm, (int)ctx->band_slots, 0, nullptr);
   RC_CUDA(cudaGetLastError());
   b->stats.launches++;
   b->stats.dp_launches++;
@@ -1156,7 +1242,9 @@ extern "C" int rc_batch_run(rc_batch* b) {
       for (int cl = 0; cl < N_CLASSES; cl++) {
         if (ch.ncta[cl] == 0) continue;
         int rcode;
-        if (cl >= CHAIN_CLASS0)
+        if (cl >= SMPC_CLASS0)
+          rcode = launch_dp_smpc(b, SMPC_Q_MIN + (cl - SMPC_CLASS0), b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smp_smem);
+        else if (cl >= CHAIN_CLASS0)
           rcode = launch_dp_chain(b, CHAIN_NKW_MIN + (cl - CHAIN_CLASS0) % CHAIN_NKW_SPAN, 2 + (cl - CHAIN_CLASS0) / CHAIN_NKW_SPAN,
                                   b->d_ctas + ch.cta0[cl], ch.ncta[cl]);
         else if (cl >= SMP_CLASS0) rcode = launch_dp_smp(b, cl - SMP_CLASS0 + 1, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smp_smem);

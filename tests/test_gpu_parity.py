@@ -105,6 +105,10 @@ SHAPES = [
     # beyond 16 chunks the shared-memory DP takes over: fewer warps per CTA, and a single-stage ring at the
     # reference's maximum of 500 rows (MAX_NUM_NAMES, src/rnaz_utils.h:7)
     (300, 50, 1, 0.02), (500, 40, 1, 0.02),
+    # wide alignments in short blocks with >= 16 instances: sample-major DP, one launch per species chunk of 2-3 quads
+    # (layout 5), partial species sums handed over in global memory: 2, 3, 7, 9 and 25 chunks, with dummy species
+    (18, 200, 17, 0.0), (26, 150, 40, 0.02), (37, 90, 64, 0.05), (50, 130, 33, 0.02), (100, 96, 20, 0.03), (101, 70, 31, 0.02),
+    (300, 45, 15, 0.02),
 ]
 
 
