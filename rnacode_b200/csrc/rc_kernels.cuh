@@ -446,6 +446,7 @@ __global__ void __launch_bounds__(256)
   const BlockDev bd = blocks[it.block];
   const int group = blockIdx.y;
   if ((bd.layout != 2 && bd.layout != 5) || group * 32 >= it.ninst) return;
+  if ((int)blockIdx.z * 4 >= bd.NK) return;  // this CTA's share of the species quads is empty
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
     mbar_fence_init();
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(256)
   mbar_wait(&s_bar, 0);
   const int npos = L - 2;
   const int rsb = (NK + 3) / 4 * 4;
-  for (int kq = 0; kq < rsb / 4; kq++) {
+  for (int kq = blockIdx.z; kq < rsb / 4; kq += gridDim.z) {  // the quads of a wide alignment are spread over gridDim.z CTAs
     // stage species rows 1+4kq .. 4+4kq
     for (int pr = wid; pr < 4 * 32; pr += nwarps) {  // (species of the quad, instance) pairs: one warp per row
       const int kk = pr >> 5, li = pr & 31;

@@ -124,6 +124,7 @@ struct Chunk {
   long long max_sigma_work = 0;  // largest ninst*2*(L-2) of an item, for the k_sigma grid
   int max_ninst = 0;
   int n_layout[6] = {0, 0, 0, 0, 0, 0};  // items per sigma layout
+  int max_smp_quads = 0;  // most species quads of a sample-major item (k_sigma_smp spreads them over gridDim.z)
   int hss_warp_items = 0;  // items whose frames are long enough for the warp-per-task k_hss
 };
 
@@ -612,6 +613,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       cur.maxNK[cl] = std::max(cur.maxNK[cl], bd.NK);
       if (bd.layout == 2 || bd.layout == 5) {
         cur.max_smp_smem = std::max(cur.max_smp_smem, smp_smem_bytes(bd, 0, bd.layout));
+        cur.max_smp_quads = std::max(cur.max_smp_quads, (bd.NK + 3) / 4);
         int w = (bd.cols + 3) / 4;
         if ((w & 1) == 0) w++;
         cur.max_smp_stage = std::max(cur.max_smp_stage, (size_t)5 * 32 * w * 4);  // k_sigma_smp staging (smp_pitch)
@@ -1228,7 +1230,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
       if (ch.max_smp_smem > 0) {  // some items use the sample-major layout
         const size_t smem = ch.max_smp_stage;
         RC_CUDA(cudaFuncSetAttribute(k_sigma_smp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 g2((unsigned)ch.nitems, (unsigned)((ch.max_ninst + 31) / 32));
+        dim3 g2((unsigned)ch.nitems, (unsigned)((ch.max_ninst + 31) / 32), (unsigned)std::min(16, std::max(1, ch.max_smp_quads / 3)));
         k_sigma_smp<<<g2, 256, smem, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores,
                                           b->d_tables, b->d_sigma, b->prm);
         RC_CUDA(cudaGetLastError());
