@@ -12,6 +12,10 @@ constexpr int DP_WARPS = 4;       // warps per DP CTA (each warp owns one task)
 constexpr int REG_MAX_NK = 16;    // largest N-1 handled by the register-resident DP kernels
 constexpr int SMP_WARPS = 4;      // warps per CTA of the sample-major DP kernel (8 when the sigma table limits the CTAs per SM)
 constexpr int SMP_MAX_WARPS = 8;
+#ifndef RC_SMP_SEG
+#define RC_SMP_SEG 16
+#endif
+constexpr int SMP_SEG = RC_SMP_SEG;  // end codons per shared-memory stage of the streaming sample-major DP kernel
 
 // class byte of one alignment character (k_pack): what calculateSigma / getBlock / revAln need
 //   bits 0-1  ntMap[c]                 (forward strand code; anything but ACGTU -> 0, src/RNAcode.c:94-98)
@@ -57,6 +61,7 @@ struct BlockDev {
                             // 5: sample-major in nchunk species chunks of chunk_base (+1 for the first chunk_rem) QUADS:
                             //    [chunk][group of 32 instances][step][3 quads][lane][4] (k_dp_smp<., true>, one launch per chunk)
   int chain_tasks;          // layout 3: consecutive tasks one CTA of k_dp_chain works through
+  int smp_seg;              // layouts 2 / 5: 1 = the frame's sigma table does not fit shared memory, streamed in segments (k_dp_smps)
   int nchunk, nkw;          // layout 3: chunks and species per chunk (template NK of k_dp_chain); chunk g holds
   int chunk_base, chunk_rem;  //   chunk_base + (g < chunk_rem) species starting at g*chunk_base + min(g, chunk_rem)
   int sig_tile;             // floats per sigma tile

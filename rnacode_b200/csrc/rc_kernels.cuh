@@ -1587,7 +1587,7 @@ __device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv
   sv[NK] = __uint_as_float(zw);
 }
 
-// CHAINED (layout 5, wide alignments in short blocks): the species are cut into chunks of 1-3 quads; chunk g is one
+// CHAINED (layout 5, wide alignments): the species are cut into chunks of 1-3 quads; chunk g is one
 // launch of this kernel with NK = 4 * (quads of the chunk) and continues, for every (start-codon pair, end codon,
 // instance), the k-ordered partial species sum the launch of chunk g-1 left in global memory (`partial`, float2 per
 // lane = the two rows of the pair).  The last chunk owns the getHSS digest.  Species past the end of the alignment in
@@ -1705,6 +1705,156 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
       j += 1;
     }
     if (valid && last) {
+#pragma unroll
+      for (int t = 0; t < 2; t++)
+        if (r0 + t < sites) rec_copy(rec_inst + r0 + t, rec0 + t);
+    }
+  }
+}
+
+// k_dp_smps: the same for frames whose sigma table does not fit into shared memory.  The table is streamed through
+// shared memory in segments of SMP_SEG end codons (two stages, TMA bulk
+// copies): the CTA's warps take consecutive start-codon pairs, one pair each (a "batch"), and walk the segments from
+// the batch's first row to the end of the frame together, so every segment is fetched once per batch and the kernel
+// has no limit on the frame length.
+template <int NK, bool CHAINED>
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
+    k_dp_smps(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
+             const float* __restrict__ sigma, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm,
+             int band_slots, int chunk, float2* __restrict__ partial) {
+  constexpr int RS = RegCfg<NK>::RS;
+  constexpr int RSB = (NK + 3) / 4 * 4;
+  constexpr int ROW_BYTES = (CHAINED ? 12 : RSB) * 32 * 4;  // one end codon, 32 lanes (chained: always room for three quads)
+  constexpr int T = SMP_SEG;
+  constexpr int STAGE_BYTES = T * ROW_BYTES;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;  // 4-8 warps share the CTA's sigma stream
+  const CtaDesc cd = ctas[blockIdx.x];
+  const Item& it = items[cd.item];
+  const BlockDev& bd = blocks[it.block];
+  const int strand = cd.sf / 3, frame = cd.sf % 3;
+  const int sites = bd.sites[frame];
+  const int group = cd.task0;  // group of 32 instances inside the item
+  const int inst_l = group * 32 + lane;
+  const bool valid = inst_l < it.ninst;
+  const bool first = !CHAINED || chunk == 0, last = !CHAINED || chunk == bd.nchunk - 1;
+  const int ngrp = (it.ninst + 31) / 32;
+
+  const size_t z_bytes = ((size_t)sites * 4 + 15) / 16 * 16;
+  unsigned* zs = reinterpret_cast<unsigned*>(smem + 2 * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE_BYTES + z_bytes);  // [0], [1]: stages; [2]: z words
+  // fold state of the getHSS digest, two records per lane and warp (only the launch that owns the digest has room for it)
+  RowRec* srec = reinterpret_cast<RowRec*>(smem + 2 * STAGE_BYTES + z_bytes + 32);
+  const size_t grp_index = CHAINED ? (size_t)chunk * ngrp + group : (size_t)group;
+  const float* sig_src = sigma + it.sigma_off[strand][frame] + grp_index * sites * (ROW_BYTES / 4);
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+    mbar_expect_tx(&bars[2], (unsigned)z_bytes);
+    bulk_g2s(zs, ztiles + bd.z_off[strand][frame] + (CHAINED ? (size_t)chunk * bd.ntiles[frame] * TILE : 0), (unsigned)z_bytes, &bars[2]);
+  }
+  __syncthreads();
+  mbar_wait(&bars[2], 0);
+
+  const unsigned stage_a = smem_u32(smem) + lane * 16;
+  const float Delta = prm.Delta, Omega = prm.Omega;
+  float omega = prm.omega;
+  asm volatile("" : "+f"(omega));
+  const float fNK = bd.fNK, rcpNK = bd.rcpNK;
+  RowRec* rec_inst = recs + it.rec_off[strand][frame] + (size_t)(valid ? inst_l : 0) * sites;
+  // partial sums of this (item, strand, frame, group): [pair][end codon from the pair's first row on][lane]
+  const int npairs = (sites + 1) / 2;
+  const int nseg = (sites + T - 1) / T;
+  float2* part = nullptr;
+  if (CHAINED) {
+    const size_t per_group = ((size_t)npairs * sites - (size_t)npairs * (npairs - 1)) * 32;
+    part = partial + it.part_off[strand][frame] + (size_t)group * per_group + lane;
+  }
+  unsigned it_count = 0;  // segments consumed so far by the CTA (stage = it_count & 1, phase = it_count >> 1)
+
+#pragma unroll 1
+  for (int p0 = 0; p0 < npairs; p0 += nw) {
+    const int p = p0 + warp;
+    const bool active = p < npairs;
+    const int r0 = 2 * p;
+    const int seg0 = (2 * p0) / T;  // the batch's first row lies in this segment
+    if (threadIdx.x == 0) {
+      for (int q = 0; q < 2 && seg0 + q < nseg; q++) {
+        const unsigned sq = (it_count + q) & 1u;
+        const unsigned bytes = (unsigned)(min(T, sites - (seg0 + q) * T) * ROW_BYTES);
+        mbar_expect_tx(&bars[sq], bytes);
+        bulk_g2s(smem + sq * STAGE_BYTES, sig_src + (size_t)(seg0 + q) * T * (ROW_BYTES / 4), bytes, &bars[sq]);
+      }
+    }
+    RowRec* rec0 = srec + (warp * 32 + lane) * 2;
+    if (last && active) {
+      rec_init(rec0);
+      rec_init(rec0 + 1);
+    }
+    float2* pp = CHAINED ? part + ((size_t)p * sites - (size_t)p * (p - 1) - r0) * 32 : nullptr;  // pp[j * 32] = entry of end codon j
+    float2 S0[NK], S1[NK], S2[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
+    float2 lb = make_float2(-INFINITY, -INFINITY);
+    int j = r0;
+#pragma unroll 1
+    for (int seg = seg0; seg < nseg; seg++, it_count++) {
+      const unsigned st = it_count & 1u;
+      mbar_wait(&bars[st], (it_count >> 1) & 1u);
+      const int jend = min(sites, (seg + 1) * T);
+      const unsigned row_a = stage_a + st * STAGE_BYTES - (unsigned)(seg * T) * ROW_BYTES;  // row_a + j * ROW_BYTES = row of end codon j
+      if (active) {
+#pragma unroll 1
+        while (j < jend) {
+          float svA[RS];
+          const unsigned zA = zs[j];
+          smp_load_row<NK>(row_a + j * ROW_BYTES, zA, svA);
+          if (j >= r0 + 2 && j + 1 < jend) {
+            const unsigned zB = zs[j + 1];
+            if ((zA | zB) == 0u) {
+              float svB[RS];
+              smp_load_row<NK>(row_a + (j + 1) * ROW_BYTES, zB, svB);
+              float2 sumA, sumB, sinA = make_float2(0.0f, 0.0f), sinB = make_float2(0.0f, 0.0f);
+              if (CHAINED && !first) {
+                sinA = pp[(size_t)j * 32];
+                sinB = pp[(size_t)(j + 1) * 32];
+              }
+              reg_pair_fast<NK, CHAINED>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
+              if (CHAINED && !last) {
+                pp[(size_t)j * 32] = sumA;
+                pp[(size_t)(j + 1) * 32] = sumB;
+              } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
+                lb.x = reg_check_inl(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+                lb.y = reg_check_inl(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+                lb.x = reg_check_inl(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+                lb.y = reg_check_inl(sumB.y, j + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+              }
+              j += 2;
+              continue;
+            }
+          }
+          float2 sin = make_float2(0.0f, 0.0f);
+          if (CHAINED && !first) sin = pp[(size_t)j * 32];
+          const float2 sum = reg_update<NK, CHAINED>(S0, S1, S2, svA, j < r0 + 2, j, r0, Delta, Omega, omega, sin);
+          if (CHAINED && !last) {
+            pp[(size_t)j * 32] = sum;
+          } else if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
+            lb.x = reg_check_inl(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+            if (r0 + 1 < sites) lb.y = reg_check_inl(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          }
+          j += 1;
+        }
+      }
+      __syncthreads();  // every warp is done with this stage
+      if (threadIdx.x == 0 && seg + 2 < nseg) {
+        const unsigned bytes = (unsigned)(min(T, sites - (seg + 2) * T) * ROW_BYTES);
+        mbar_expect_tx(&bars[st], bytes);
+        bulk_g2s(smem + st * STAGE_BYTES, sig_src + (size_t)(seg + 2) * T * (ROW_BYTES / 4), bytes, &bars[st]);
+      }
+    }
+    if (active && valid && last) {
 #pragma unroll
       for (int t = 0; t < 2; t++)
         if (r0 + t < sites) rec_copy(rec_inst + r0 + t, rec0 + t);

@@ -39,6 +39,9 @@ struct rc_ctx {
   long scratch_mb = 2048;
   long no_smp = 0;
   long no_chain = 0;
+  long no_smps = 0;          // never stream the sigma table in segments (k_dp_smps)
+  long smpc_max_sites = 0;    // longest frame (codons) for the STREAMED chunked sample-major route of wide alignments
+                              // (measured slower than k_dp_chain: 50x800 11.3 vs 4.5 ms; kept as an experiment switch)
   int smem_optin = 0;
   int sm_count = 0;
   // device-memory cache: buffers of destroyed batches are kept and handed to the next batch, so that a
@@ -112,7 +115,10 @@ constexpr int CHAIN_NKW_MIN = 8, CHAIN_NKW_MAX = 12, CHAIN_NKW_SPAN = CHAIN_NKW_
 // then k_dp_smp<., true> (layout 5: wide alignments in short blocks), one class per number of species quads Q = ceil(NK/4)
 constexpr int SMPC_CLASS0 = CHAIN_CLASS0 + (CHAIN_MAX_WARPS - 1) * CHAIN_NKW_SPAN;
 constexpr int SMPC_Q_MIN = 5, SMPC_Q_MAX = 125;
-constexpr int N_CLASSES = SMPC_CLASS0 + (SMPC_Q_MAX - SMPC_Q_MIN + 1);
+// and the segmented (streaming) variants k_dp_smps of both sample-major kinds
+constexpr int SMPS_CLASS0 = SMPC_CLASS0 + (SMPC_Q_MAX - SMPC_Q_MIN + 1);
+constexpr int SMPCS_CLASS0 = SMPS_CLASS0 + REG_MAX_NK;
+constexpr int N_CLASSES = SMPCS_CLASS0 + (SMPC_Q_MAX - SMPC_Q_MIN + 1);
 constexpr size_t SMP_SMEM_MAX = 200 * 1024;  // sigma table + z words of one CTA of k_dp_smp
 constexpr int SMP_MIN_INST = 16;             // fewer instances than this: the row-major kernels are the better fit
 
@@ -120,7 +126,7 @@ struct Chunk {
   size_t item0 = 0, nitems = 0;          // range in the batch's item array
   size_t cta0[N_CLASSES] = {}, ncta[N_CLASSES] = {};  // per class range in the CTA array
   int maxNK[N_CLASSES] = {}, maxZs[N_CLASSES] = {};
-  size_t sigma_floats = 0, rec_count = 0, part_count = 0, max_smp_smem = 0, max_smp_stage = 0;
+  size_t sigma_floats = 0, rec_count = 0, part_count = 0, max_smp_smem = 0, max_smps_smem = 0, max_smp_stage = 0;
   long long max_sigma_work = 0;  // largest ninst*2*(L-2) of an item, for the k_sigma grid
   int max_ninst = 0;
   int n_layout[6] = {0, 0, 0, 0, 0, 0};  // items per sigma layout
@@ -137,8 +143,8 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int class_of(const BlockDev& bd) {
   if (bd.layout == 3) return CHAIN_CLASS0 + (bd.nchunk - 2) * CHAIN_NKW_SPAN + (bd.nkw - CHAIN_NKW_MIN);
-  if (bd.layout == 5) return SMPC_CLASS0 + ((bd.NK + 3) / 4 - SMPC_Q_MIN);
-  if (bd.layout == 2) return SMP_CLASS0 + bd.NK - 1;
+  if (bd.layout == 5) return (bd.smp_seg ? SMPCS_CLASS0 : SMPC_CLASS0) + ((bd.NK + 3) / 4 - SMPC_Q_MIN);
+  if (bd.layout == 2) return bd.smp_seg ? SMPS_CLASS0 + bd.NK - 1 : SMP_CLASS0 + bd.NK - 1;
   if (bd.layout == 1) return bd.NK - 1;
   return bd.NK <= 24 ? REG_MAX_NK : REG_MAX_NK + 1;
 }
@@ -150,9 +156,13 @@ size_t part_entries(int sites) {
   return np * sites - np * (np - 1);
 }
 
-size_t smp_smem_bytes(const BlockDev& bd, int f, int layout) {
+// dynamic shared memory of a sample-major DP CTA without the fold state: the frame's sigma table (k_dp_smp) or two
+// stages of SMP_SEG end codons (k_dp_smps), plus the frame's z words and the barriers
+size_t smp_smem_bytes(const BlockDev& bd, int f, int layout, int seg) {
   const size_t rsb = layout == 5 ? 12 : (size_t)(bd.NK + 3) / 4 * 4;
-  return (size_t)bd.sites[f] * rsb * 32 * 4 + ((size_t)bd.sites[f] * 4 + 15) / 16 * 16 + 16;
+  const size_t zb = ((size_t)bd.sites[f] * 4 + 15) / 16 * 16;
+  if (seg) return 2 * (size_t)SMP_SEG * rsb * 32 * 4 + zb + 32;
+  return (size_t)bd.sites[f] * rsb * 32 * 4 + zb + 16;
 }
 
 // floats of sigma scratch for `ninst` instances of one (strand, frame) of a block
@@ -326,6 +336,9 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   ctx->stream = ctx->own_stream;
   cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  // experiment switches (same meaning as rc_set_option): RNACODE_CUDA_NO_SMPS, RNACODE_CUDA_SMPC_MAX_SITES
+  if (const char* e = getenv("RNACODE_CUDA_NO_SMPS")) ctx->no_smps = atol(e) ? 1 : 0;
+  if (const char* e = getenv("RNACODE_CUDA_SMPC_MAX_SITES")) ctx->smpc_max_sites = atol(e);
   unsigned char lut[256];
   build_lut(lut);
   if (cudaMalloc(&ctx->d_lut, 256) != cudaSuccess ||
@@ -379,6 +392,10 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->no_smp = value ? 1 : 0;
   } else if (k == "no_chain") {
     ctx->no_chain = value ? 1 : 0;
+  } else if (k == "no_smps") {
+    ctx->no_smps = value ? 1 : 0;
+  } else if (k == "smpc_max_sites") {
+    ctx->smpc_max_sites = value;
   } else if (k == "scratch_mb") {
     if (value < 1) { ctx_fail(ctx, "scratch_mb must be >= 1"); return RC_ERR_ARG; }
     ctx->scratch_mb = value;
@@ -520,18 +537,23 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     cells += (double)bd.n_inst * 2.0 * bd.NK * P;
     {
       int layout = (bd.NK <= REG_MAX_NK && params->Delta <= 0.0f) ? 1 : 0;
-      if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && !ctx->no_smp && bd.n_inst >= SMP_MIN_INST &&
-          bd.sites[0] >= 1 && smp_smem_bytes(bd, 0, 5) <= std::min<size_t>(SMP_SMEM_MAX, (size_t)ctx->smem_optin) &&
-          (size_t)5 * 32 * (bd.cols + 8) <= SMP_SMEM_MAX)
-        layout = 5;  // wide alignment in a short block with many instances: sample-major, one launch per species chunk
-      else if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && !ctx->no_chain &&
-          (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX <= CHAIN_MAX_WARPS)
+      // sample-major kernels: enough instances to fill the lanes, class-byte staging of k_sigma_smp fits
+      const bool smp_ok = !ctx->no_smp && bd.n_inst >= SMP_MIN_INST && bd.sites[0] >= 1 && (size_t)5 * 32 * (bd.cols + 8) <= SMP_SMEM_MAX;
+      const size_t smem_cap = std::min<size_t>(SMP_SMEM_MAX, (size_t)ctx->smem_optin);
+      int seg = 0;
+      if (layout == 1 && smp_ok) {
+        if (smp_smem_bytes(bd, 0, 2, 0) <= smem_cap) layout = 2;  // short block: the frame's sigma table is resident
+        else if (!ctx->no_smps) { layout = 2; seg = 1; }          // longer: streamed in segments
+      }
+      if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && smp_ok &&
+          (smp_smem_bytes(bd, 0, 5, 0) <= smem_cap || (!ctx->no_smps && bd.sites[0] <= ctx->smpc_max_sites))) {
+        layout = 5;  // wide alignment with many instances: sample-major, one launch per species chunk
+        seg = smp_smem_bytes(bd, 0, 5, 0) <= smem_cap ? 0 : 1;
+      } else if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && !ctx->no_chain &&
+                 (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX <= CHAIN_MAX_WARPS)
         layout = 3;  // wide alignment: species chunks pipelined through the warps of a CTA
-      if (layout == 1 && !ctx->no_smp && bd.n_inst >= SMP_MIN_INST && bd.sites[0] >= 1 &&
-          smp_smem_bytes(bd, 0, 2) <= std::min<size_t>(SMP_SMEM_MAX, (size_t)ctx->smem_optin) &&
-          (size_t)5 * 32 * (bd.cols + 8) <= SMP_SMEM_MAX)
-        layout = 2;  // short block with many instances: sample-major kernel
       set_layout(bd, layout);
+      bd.smp_seg = seg;
       if (layout == 3) {
         // tasks per CTA: enough tiles per CTA to amortise the W-1 tiles the warp pipeline needs to fill and drain
         // (a row group of a frame with T tiles has T - 4g tiles: about T/2 on average), but not more: long rows are
@@ -612,7 +634,8 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       const int cl = class_of(bd);
       cur.maxNK[cl] = std::max(cur.maxNK[cl], bd.NK);
       if (bd.layout == 2 || bd.layout == 5) {
-        cur.max_smp_smem = std::max(cur.max_smp_smem, smp_smem_bytes(bd, 0, bd.layout));
+        if (!bd.smp_seg) cur.max_smp_smem = std::max(cur.max_smp_smem, smp_smem_bytes(bd, 0, bd.layout, 0));
+        if (bd.smp_seg) cur.max_smps_smem = std::max(cur.max_smps_smem, smp_smem_bytes(bd, 0, bd.layout, 1));
         cur.max_smp_quads = std::max(cur.max_smp_quads, (bd.NK + 3) / 4);
         int w = (bd.cols + 3) / 4;
         if ((w & 1) == 0) w++;
@@ -942,30 +965,37 @@ static int smp_warps(rc_ctx* ctx, size_t smem_table, bool with_fold) {
 
 // layout 5: one launch per species chunk (1-3 quads each), chunk g continuing the partial sums of chunk g-1
 template <int NK>
-static int launch_dp_smpc_nk(rc_batch* b, int chunk, bool last, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
+static int launch_dp_smpc_nk(rc_batch* b, int chunk, bool last, bool seg, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
   rc_ctx* ctx = b->ctx;
   const int nw = smp_warps(ctx, smem, last);
   if (last) smem += (size_t)nw * 64 * sizeof(RowRec);
-  RC_CUDA(cudaFuncSetAttribute(k_dp_smp<NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dp_smp<NK, true><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
-                                                                          b->d_recs, b->prm, (int)ctx->band_slots, chunk,
-                                                                          b->d_partial);
+  if (seg) {
+    RC_CUDA(cudaFuncSetAttribute(k_dp_smps<NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dp_smps<NK, true><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+                                                                             b->d_recs, b->prm, (int)ctx->band_slots, chunk,
+                                                                             b->d_partial);
+  } else {
+    RC_CUDA(cudaFuncSetAttribute(k_dp_smp<NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dp_smp<NK, true><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+                                                                            b->d_recs, b->prm, (int)ctx->band_slots, chunk,
+                                                                            b->d_partial);
+  }
   RC_CUDA(cudaGetLastError());
   b->stats.launches++;
   b->stats.dp_launches++;
   return RC_OK;
 }
 
-static int launch_dp_smpc(rc_batch* b, int Q, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
+static int launch_dp_smpc(rc_batch* b, int Q, bool seg, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
   if (ncta == 0) return RC_OK;
   const int W = (Q + 2) / 3, base = Q / W, rem = Q % W;
   for (int g = 0; g < W; g++) {
     const int quads = base + (g < rem ? 1 : 0);
     int rc;
     switch (quads) {
-      case 1: rc = launch_dp_smpc_nk<4>(b, g, g == W - 1, d_ctas, ncta, smem); break;
-      case 2: rc = launch_dp_smpc_nk<8>(b, g, g == W - 1, d_ctas, ncta, smem); break;
-      case 3: rc = launch_dp_smpc_nk<12>(b, g, g == W - 1, d_ctas, ncta, smem); break;
+      case 1: rc = launch_dp_smpc_nk<4>(b, g, g == W - 1, seg, d_ctas, ncta, smem); break;
+      case 2: rc = launch_dp_smpc_nk<8>(b, g, g == W - 1, seg, d_ctas, ncta, smem); break;
+      case 3: rc = launch_dp_smpc_nk<12>(b, g, g == W - 1, seg, d_ctas, ncta, smem); break;
       default: ctx_fail(b->ctx, "internal: k_dp_smp chunk size out of range"); return RC_ERR_STATE;
     }
     if (rc != RC_OK) return rc;
@@ -974,38 +1004,44 @@ static int launch_dp_smpc(rc_batch* b, int Q, const CtaDesc* d_ctas, size_t ncta
 }
 
 template <int NK>
-static int launch_dp_smp_nk(rc_batch* b, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
+static int launch_dp_smp_nk(rc_batch* b, bool seg, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
   rc_ctx* ctx = b->ctx;
   const int nw = smp_warps(ctx, smem, true);
   smem += (size_t)nw * 64 * sizeof(RowRec);
-  RC_CUDA(cudaFuncSetAttribute(k_dp_smp<NK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dp_smp<NK, false><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+  if (seg) {
+    RC_CUDA(cudaFuncSetAttribute(k_dp_smps<NK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dp_smps<NK, false><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+                                                                              b->d_recs, b->prm, (int)ctx->band_slots, 0, nullptr);
+  } else {
+    RC_CUDA(cudaFuncSetAttribute(k_dp_smp<NK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dp_smp<NK, false><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
                                                                            b->d_recs, b->prm, (int)ctx->band_slots, 0, nullptr);
+  }
   RC_CUDA(cudaGetLastError());
   b->stats.launches++;
   b->stats.dp_launches++;
   return RC_OK;
 }
 
-static int launch_dp_smp(rc_batch* b, int NK, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
+static int launch_dp_smp(rc_batch* b, int NK, bool seg, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
   if (ncta == 0) return RC_OK;
   switch (NK) {
-    case 1: return launch_dp_smp_nk<1>(b, d_ctas, ncta, smem);
-    case 2: return launch_dp_smp_nk<2>(b, d_ctas, ncta, smem);
-    case 3: return launch_dp_smp_nk<3>(b, d_ctas, ncta, smem);
-    case 4: return launch_dp_smp_nk<4>(b, d_ctas, ncta, smem);
-    case 5: return launch_dp_smp_nk<5>(b, d_ctas, ncta, smem);
-    case 6: return launch_dp_smp_nk<6>(b, d_ctas, ncta, smem);
-    case 7: return launch_dp_smp_nk<7>(b, d_ctas, ncta, smem);
-    case 8: return launch_dp_smp_nk<8>(b, d_ctas, ncta, smem);
-    case 9: return launch_dp_smp_nk<9>(b, d_ctas, ncta, smem);
-    case 10: return launch_dp_smp_nk<10>(b, d_ctas, ncta, smem);
-    case 11: return launch_dp_smp_nk<11>(b, d_ctas, ncta, smem);
-    case 12: return launch_dp_smp_nk<12>(b, d_ctas, ncta, smem);
-    case 13: return launch_dp_smp_nk<13>(b, d_ctas, ncta, smem);
-    case 14: return launch_dp_smp_nk<14>(b, d_ctas, ncta, smem);
-    case 15: return launch_dp_smp_nk<15>(b, d_ctas, ncta, smem);
-    case 16: return launch_dp_smp_nk<16>(b, d_ctas, ncta, smem);
+    case 1: return launch_dp_smp_nk<1>(b, seg, d_ctas, ncta, smem);
+    case 2: return launch_dp_smp_nk<2>(b, seg, d_ctas, ncta, smem);
+    case 3: return launch_dp_smp_nk<3>(b, seg, d_ctas, ncta, smem);
+    case 4: return launch_dp_smp_nk<4>(b, seg, d_ctas, ncta, smem);
+    case 5: return launch_dp_smp_nk<5>(b, seg, d_ctas, ncta, smem);
+    case 6: return launch_dp_smp_nk<6>(b, seg, d_ctas, ncta, smem);
+    case 7: return launch_dp_smp_nk<7>(b, seg, d_ctas, ncta, smem);
+    case 8: return launch_dp_smp_nk<8>(b, seg, d_ctas, ncta, smem);
+    case 9: return launch_dp_smp_nk<9>(b, seg, d_ctas, ncta, smem);
+    case 10: return launch_dp_smp_nk<10>(b, seg, d_ctas, ncta, smem);
+    case 11: return launch_dp_smp_nk<11>(b, seg, d_ctas, ncta, smem);
+    case 12: return launch_dp_smp_nk<12>(b, seg, d_ctas, ncta, smem);
+    case 13: return launch_dp_smp_nk<13>(b, seg, d_ctas, ncta, smem);
+    case 14: return launch_dp_smp_nk<14>(b, seg, d_ctas, ncta, smem);
+    case 15: return launch_dp_smp_nk<15>(b, seg, d_ctas, ncta, smem);
+    case 16: return launch_dp_smp_nk<16>(b, seg, d_ctas, ncta, smem);
     default: ctx_fail(b->ctx, "internal: k_dp_smp NK out of range"); return RC_ERR_STATE;
   }
 }
@@ -1227,7 +1263,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
         RC_CUDA(cudaGetLastError());
         b->stats.launches++;
       }
-      if (ch.max_smp_smem > 0) {  // some items use the sample-major layout
+      if (ch.max_smp_smem > 0 || ch.max_smps_smem > 0) {  // some items use the sample-major layout
         const size_t smem = ch.max_smp_stage;
         RC_CUDA(cudaFuncSetAttribute(k_sigma_smp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 g2((unsigned)ch.nitems, (unsigned)((ch.max_ninst + 31) / 32), (unsigned)std::min(16, std::max(1, ch.max_smp_quads / 3)));
@@ -1244,12 +1280,16 @@ extern "C" int rc_batch_run(rc_batch* b) {
       for (int cl = 0; cl < N_CLASSES; cl++) {
         if (ch.ncta[cl] == 0) continue;
         int rcode;
-        if (cl >= SMPC_CLASS0)
-          rcode = launch_dp_smpc(b, SMPC_Q_MIN + (cl - SMPC_CLASS0), b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smp_smem);
+        if (cl >= SMPCS_CLASS0)
+          rcode = launch_dp_smpc(b, SMPC_Q_MIN + (cl - SMPCS_CLASS0), true, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smps_smem);
+        else if (cl >= SMPS_CLASS0)
+          rcode = launch_dp_smp(b, cl - SMPS_CLASS0 + 1, true, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smps_smem);
+        else if (cl >= SMPC_CLASS0)
+          rcode = launch_dp_smpc(b, SMPC_Q_MIN + (cl - SMPC_CLASS0), false, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smp_smem);
         else if (cl >= CHAIN_CLASS0)
           rcode = launch_dp_chain(b, CHAIN_NKW_MIN + (cl - CHAIN_CLASS0) % CHAIN_NKW_SPAN, 2 + (cl - CHAIN_CLASS0) / CHAIN_NKW_SPAN,
                                   b->d_ctas + ch.cta0[cl], ch.ncta[cl]);
-        else if (cl >= SMP_CLASS0) rcode = launch_dp_smp(b, cl - SMP_CLASS0 + 1, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smp_smem);
+        else if (cl >= SMP_CLASS0) rcode = launch_dp_smp(b, cl - SMP_CLASS0 + 1, false, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smp_smem);
         else if (cl < REG_MAX_NK) rcode = launch_dp_reg(b, cl + 1, b->d_ctas + ch.cta0[cl], ch.ncta[cl]);
         else if (cl == REG_MAX_NK) rcode = launch_dp<2, false>(b, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.maxNK[cl], ch.maxZs[cl]);
         else rcode = launch_dp<1, false>(b, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.maxNK[cl], ch.maxZs[cl]);

@@ -109,6 +109,8 @@ SHAPES = [
     # (layout 5), partial species sums handed over in global memory: 2, 3, 7, 9 and 25 chunks, with dummy species
     (18, 200, 17, 0.0), (26, 150, 40, 0.02), (37, 90, 64, 0.05), (50, 130, 33, 0.02), (100, 96, 20, 0.03), (101, 70, 31, 0.02),
     (300, 45, 15, 0.02),
+    # the same with frames too long for a resident sigma table: streamed in segments (k_dp_smps), plain and chunked
+    (10, 600, 16, 0.02), (8, 1000, 15, 0.0067), (5, 1201, 31, 0.01), (26, 520, 15, 0.03), (18, 700, 17, 0.02), (50, 450, 16, 0.02),
 ]
 
 
