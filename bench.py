@@ -45,6 +45,8 @@ WORKLOADS = {
     "hundred_short": ([(100, 200)] * 200, 100, 5, "synthetic MAF 200 blocks x 100 species x 200 cols, -n 100 (config 5 row count, short blocks)"),
     "mid_short": ([(30, 200)] * 500, 100, 6, "synthetic MAF 500 blocks x 30 species x 200 cols, -n 100"),
     "mid": ([(10, 800)] * 16, 1000, 7, "synthetic MAF 16 blocks x 10 species x 800 cols, -n 1000"),
+    "mid12": ([(10, 1200)] * 8, 1000, 9, "synthetic MAF 8 blocks x 10 species x 1200 cols, -n 1000"),
+    "mid5": ([(10, 500)] * 32, 1000, 10, "synthetic MAF 32 blocks x 10 species x 500 cols, -n 1000"),
     "mid_wide": ([(50, 800)] * 4, 250, 8, "synthetic MAF 4 blocks x 50 species x 800 cols, -n 250"),
 }
 METRIC = "codon_dp_cells_per_s"
