@@ -423,115 +423,147 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------
-// (b) k_sigma_smp: sigma for the sample-major layout (k_dp_smp).  One CTA per (item, group of 32 instances).
-// The class bytes of the group's reference rows and of four species rows at a time are staged in shared
-// memory (coalesced global reads, padded row pitch => conflict-free byte reads with lane = instance); each
-// thread then produces the four sigma values of one (strand, position, instance) and stores them as one
-// float4, so a warp writes 512 contiguous bytes of the [step][species quad][lane][4] table.
+// (b) k_sigma_smp: sigma for the sample-major layouts (k_dp_smp / k_dp_smps).  One CTA per (item, group of 32
+// instances, strand, chunk of SIG_PCH reference positions, share of the species quads).  sigma only ever reads the
+// alignment at the reference's non-gap columns, so the CTA stages COMPACTED class bytes -- for its position chunk,
+// column t of the staged row is the alignment column of reference position x_lo + t (cols0, gathered once into
+// shared memory) -- of the group's reference rows and of four species rows at a time: the codon ending at
+// position x then sits at three consecutive staged columns, the staging buffer has a fixed size whatever the
+// block length, and long blocks give many CTAs.  Padded row pitch => conflict-free byte reads with lane = instance;
+// each thread produces the four sigma values of one (position, instance) and stores them as one float4, so a warp
+// writes 512 contiguous bytes of the [step][species quad][lane][4] table.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int smp_pitch(int cols) {
-  int w = (cols + 3) / 4;  // words per row; make it odd so that 32 lanes hit 32 different banks
-  if ((w & 1) == 0) w++;
-  return w * 4;
-}
+constexpr int SIG_PCH = 252;              // reference positions per CTA (staged columns: SIG_PCH + 2)
+constexpr int SIG_PITCH = 260;            // bytes per staged row: 65 words, odd => 32 lanes hit 32 banks
 
 __global__ void __launch_bounds__(256)
     k_sigma_smp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned char* __restrict__ cls,
                 const int* __restrict__ cols0, const float* __restrict__ scores, const SigmaTables* __restrict__ tables,
-                float* __restrict__ sigma, Params prm) {
-  extern __shared__ __align__(16) unsigned char sm[];
+                float* __restrict__ sigma, Params prm, int nqz) {
   __shared__ SigmaTables s_tab;
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_col[2][SIG_PITCH];
+  __shared__ __align__(16) unsigned char s_ref[32 * SIG_PITCH];
+  __shared__ __align__(16) unsigned char s_sp[4 * 32 * SIG_PITCH];
   const Item it = items[blockIdx.x];
   const BlockDev bd = blocks[it.block];
   const int group = blockIdx.y;
   if ((bd.layout != 2 && bd.layout != 5) || group * 32 >= it.ninst) return;
-  if ((int)blockIdx.z * 4 >= bd.NK) return;  // this CTA's share of the species quads is empty
+  // blockIdx.z = ((position chunk * 2) + strand) * nqz + quad share
+  const int qz = blockIdx.z % nqz, s_cta = (blockIdx.z / nqz) & 1, pc = blockIdx.z / (2 * nqz);
+  const int L = bd.L, N = bd.N, NK = bd.NK, cols = bd.cols;
+  const int npos = L - 2;
+  // Short blocks (whole rows fit the staging buffer): the rows are staged once, uncompacted, and the CTA of strand 0
+  // serves both strands from them.  Longer blocks: compacted staging, one CTA per strand and position chunk.
+  const bool small = cols <= SIG_PITCH;
+  const int xi_lo = small ? 0 : pc * SIG_PCH;
+  if (qz * 4 >= NK || xi_lo >= npos || (small && (s_cta == 1 || pc > 0))) return;  // nothing to do for this CTA
+  const int xi_n = small ? npos : min(SIG_PCH, npos - xi_lo);  // positions of this CTA
+  const int n_staged = small ? cols : xi_n + 2;                // staged columns per row
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
     mbar_fence_init();
     mbar_expect_tx(&s_bar, (unsigned)sizeof(SigmaTables));
     bulk_g2s(&s_tab, tables, (unsigned)sizeof(SigmaTables), &s_bar);
   }
-  const int L = bd.L, N = bd.N, NK = bd.NK, cols = bd.cols;
-  const int pitch = smp_pitch(cols);
-  unsigned char* s_ref = sm;                 // [32][pitch]
-  unsigned char* s_sp = sm + 32 * pitch;     // [4][32][pitch]
+  // s_col[s][t]: alignment column of reference position xi_lo + 1 + t on strand s (positions x-2 .. x of xi are xi+1 .. xi+3)
+  for (int t = threadIdx.x; t < xi_n + 2; t += blockDim.x) {
+    if (small) {
+      s_col[0][t] = cols0[bd.cols0_off + 1 + t];
+      s_col[1][t] = cols0[bd.cols0_off + (L + 1) + 1 + t];
+    } else {
+      s_col[s_cta][t] = cols0[bd.cols0_off + (size_t)s_cta * (L + 1) + xi_lo + 1 + t];
+    }
+  }
+  __syncthreads();
   const int ninst_g = min(32, it.ninst - group * 32);
   const unsigned char* gbase = cls + bd.cls_off + (size_t)(it.inst0 + group * 32) * bd.inst_stride;
-  // reference rows of the 32 instances: one warp per row, lanes along the columns (no per-byte index arithmetic)
   const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // reference rows of the 32 instances: one warp per row, lanes along the staged columns
   for (int li = wid; li < 32; li += nwarps) {
     const unsigned char* src = gbase + (size_t)li * bd.inst_stride;
-    unsigned char* dst = s_ref + li * pitch;
-    for (int c = ln; c < cols; c += 32) dst[c] = (li < ninst_g) ? src[c] : (unsigned char)0;
+    unsigned char* dst = s_ref + li * SIG_PITCH;
+    for (int t = ln; t < n_staged; t += 32) dst[t] = (li < ninst_g) ? src[small ? t : s_col[s_cta][t]] : (unsigned char)0;
   }
   __syncthreads();
   mbar_wait(&s_bar, 0);
-  const int npos = L - 2;
   const int rsb = (NK + 3) / 4 * 4;
-  for (int kq = blockIdx.z; kq < rsb / 4; kq += gridDim.z) {  // the quads of a wide alignment are spread over gridDim.z CTAs
+  for (int kq = qz; kq < rsb / 4; kq += nqz) {  // the quads of a wide alignment are spread over nqz CTAs
     // stage species rows 1+4kq .. 4+4kq
     for (int pr = wid; pr < 4 * 32; pr += nwarps) {  // (species of the quad, instance) pairs: one warp per row
       const int kk = pr >> 5, li = pr & 31;
       const int row = 1 + 4 * kq + kk;
       const bool ok = li < ninst_g && row < N;
       const unsigned char* src = gbase + (size_t)li * bd.inst_stride + (size_t)row * cols;
-      unsigned char* dst = s_sp + (kk * 32 + li) * pitch;
-      for (int c = ln; c < cols; c += 32) dst[c] = ok ? src[c] : (unsigned char)0;
+      unsigned char* dst = s_sp + (kk * 32 + li) * SIG_PITCH;
+      for (int t = ln; t < n_staged; t += 32) dst[t] = ok ? src[small ? t : s_col[s_cta][t]] : (unsigned char)0;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < 2 * npos * 32; e += blockDim.x) {
+    // output address of quad kq: layout 2 is [group][step][quad][lane][4]; layout 5 is [chunk][group][step][3 quads][lane][4]
+    // with quad kq = quad qq of chunk ch
+    size_t rowmul, step_stride, qoff;  // out = base + rowmul * sites[f] + j * step_stride + qoff + lane * 4
+    if (bd.layout == 5) {
+      const int big = bd.chunk_rem * (bd.chunk_base + 1);
+      const int ch = kq < big ? kq / (bd.chunk_base + 1) : bd.chunk_rem + (kq - big) / bd.chunk_base;
+      const int qq = kq < big ? kq % (bd.chunk_base + 1) : (kq - big) % bd.chunk_base;
+      const int ngrp = (it.ninst + 31) / 32;
+      rowmul = ((size_t)ch * ngrp + group) * 3 * 128;
+      step_stride = 3 * 128;
+      qoff = (size_t)qq * 128;
+    } else {
+      rowmul = (size_t)group * (rsb / 4) * 128;
+      step_stride = (size_t)(rsb / 4) * 128;
+      qoff = (size_t)kq * 128;
+    }
+    const int n_out = (small ? 2 : 1) * xi_n * 32;
+    for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
       const int lane = e & 31;
-      const int rest = e >> 5;
-      const int s = rest & 1, xi = rest >> 1;
-      const int x = xi + 3;
-      const int* c0 = cols0 + bd.cols0_off + (size_t)s * (L + 1);
-      const int c1 = c0[x - 2], c2 = c0[x - 1], c3 = c0[x];
-      const unsigned char* rr = s_ref + lane * pitch;
-      const unsigned a1 = rr[c1], a2 = rr[c2], a3 = rr[c3];
+      int s, tl, i1, i2, i3;  // strand, position inside the CTA's range, staged columns of the codon
+      if (small) {
+        s = (e >> 5) & 1;
+        tl = e >> 6;
+        i1 = s_col[s][tl];
+        i2 = s_col[s][tl + 1];
+        i3 = s_col[s][tl + 2];
+      } else {
+        s = s_cta;
+        tl = e >> 5;
+        i1 = tl;
+        i2 = tl + 1;
+        i3 = tl + 2;
+      }
+      const int xi = xi_lo + tl;
       const int sh = s ? 2 : 0;
+      const float* sc = scores + bd.scores_off + (size_t)s * N * 4;
+      const unsigned char* rr = s_ref + lane * SIG_PITCH;
+      const unsigned a1 = rr[i1], a2 = rr[i2], a3 = rr[i3];
       const unsigned qa = (((a1 >> sh) & 3u) << 4) | (((a2 >> sh) & 3u) << 2) | ((a3 >> sh) & 3u);
       const unsigned nA = (a1 | a2 | a3) & CLS_N;
       const int pepA = s_tab.transcode[qa];
-      const float* sc = scores + bd.scores_off + (size_t)s * N * 4;
       float v4[4];
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {
         const int k = 4 * kq + kk;
         float v = 0.0f;
         if (k < NK) {
-          const unsigned char* rk = s_sp + (kk * 32 + lane) * pitch;
-          const unsigned b1 = rk[c1], b2 = rk[c2], b3 = rk[c3];
+          const unsigned char* rk = s_sp + (kk * 32 + lane) * SIG_PITCH;
+          const unsigned b1 = rk[i1], b2 = rk[i2], b3 = rk[i3];
           const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
-          if (nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X)) {
-            v = 0.0f;
-          } else if (qa == qb) {
-            v = 0.0f;
-          } else {
+          if (!(nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X)) && qa != qb) {  // src/score.c:394-409
             const int pepB = s_tab.transcode[qb];
-            if (pepA < 0) v = prm.stop0;
-            else if (pepB < 0) v = prm.stopk;
+            if (pepA < 0) v = prm.stop0;         // :414-416
+            else if (pepB < 0) v = prm.stopk;    // :418-420
             else {
               const unsigned d = qa ^ qb;
               const int h = ((d & 0x30u) != 0) + ((d & 0x0cu) != 0) + ((d & 0x03u) != 0);
-              v = s_tab.blosum[pepA * 24 + pepB] - sc[(k + 1) * 4 + h];
+              v = s_tab.blosum[pepA * 24 + pepB] - sc[(k + 1) * 4 + h];  // :422-425
             }
           }
         }
         v4[kk] = v;
       }
       const int f = xi % 3, j = xi / 3;
-      float* out;
-      if (bd.layout == 5) {  // [chunk][group][step][3 quads][lane][4]; quad kq belongs to chunk ch as its quad qq
-        const int big = bd.chunk_rem * (bd.chunk_base + 1);
-        const int ch = kq < big ? kq / (bd.chunk_base + 1) : bd.chunk_rem + (kq - big) / bd.chunk_base;
-        const int qq = kq < big ? kq % (bd.chunk_base + 1) : (kq - big) % bd.chunk_base;
-        const int ngrp = (it.ninst + 31) / 32;
-        out = sigma + it.sigma_off[s][f] + ((((size_t)ch * ngrp + group) * bd.sites[f] + j) * 3 + qq) * 128 + lane * 4;
-      } else {
-        out = sigma + it.sigma_off[s][f] + (((size_t)group * bd.sites[f] + j) * (rsb / 4) + kq) * 128 + lane * 4;
-      }
+      float* out = sigma + it.sigma_off[s][f] + rowmul * bd.sites[f] + (size_t)j * step_stride + qoff + lane * 4;
       *reinterpret_cast<float4*>(out) = make_float4(v4[0], v4[1], v4[2], v4[3]);
     }
     __syncthreads();

@@ -40,6 +40,7 @@ struct rc_ctx {
   long no_smp = 0;
   long no_chain = 0;
   long no_smps = 0;          // never stream the sigma table in segments (k_dp_smps)
+  long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
   long smpc_max_sites = 0;    // longest frame (codons) for the STREAMED chunked sample-major route of wide alignments
                               // (measured slower than k_dp_chain: 50x800 11.3 vs 4.5 ms; kept as an experiment switch)
   int smem_optin = 0;
@@ -126,11 +127,12 @@ struct Chunk {
   size_t item0 = 0, nitems = 0;          // range in the batch's item array
   size_t cta0[N_CLASSES] = {}, ncta[N_CLASSES] = {};  // per class range in the CTA array
   int maxNK[N_CLASSES] = {}, maxZs[N_CLASSES] = {};
-  size_t sigma_floats = 0, rec_count = 0, part_count = 0, max_smp_smem = 0, max_smps_smem = 0, max_smp_stage = 0;
+  size_t sigma_floats = 0, rec_count = 0, part_count = 0, max_smp_smem = 0, max_smps_smem = 0;
   long long max_sigma_work = 0;  // largest ninst*2*(L-2) of an item, for the k_sigma grid
   int max_ninst = 0;
   int n_layout[6] = {0, 0, 0, 0, 0, 0};  // items per sigma layout
   int max_smp_quads = 0;  // most species quads of a sample-major item (k_sigma_smp spreads them over gridDim.z)
+  int max_smp_npos = 0;   // most reference positions of a sample-major item (k_sigma_smp: chunks of SIG_PCH positions)
   int hss_warp_items = 0;  // items whose frames are long enough for the warp-per-task k_hss
 };
 
@@ -339,6 +341,7 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   // experiment switches (same meaning as rc_set_option): RNACODE_CUDA_NO_SMPS, RNACODE_CUDA_SMPC_MAX_SITES
   if (const char* e = getenv("RNACODE_CUDA_NO_SMPS")) ctx->no_smps = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_SMPC_MAX_SITES")) ctx->smpc_max_sites = atol(e);
+  if (const char* e = getenv("RNACODE_CUDA_SMPS_MAX_SITES")) ctx->smps_max_sites = atol(e);
   unsigned char lut[256];
   build_lut(lut);
   if (cudaMalloc(&ctx->d_lut, 256) != cudaSuccess ||
@@ -394,6 +397,8 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->no_chain = value ? 1 : 0;
   } else if (k == "no_smps") {
     ctx->no_smps = value ? 1 : 0;
+  } else if (k == "smps_max_sites") {
+    ctx->smps_max_sites = value;
   } else if (k == "smpc_max_sites") {
     ctx->smpc_max_sites = value;
   } else if (k == "scratch_mb") {
@@ -538,12 +543,12 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     {
       int layout = (bd.NK <= REG_MAX_NK && params->Delta <= 0.0f) ? 1 : 0;
       // sample-major kernels: enough instances to fill the lanes, class-byte staging of k_sigma_smp fits
-      const bool smp_ok = !ctx->no_smp && bd.n_inst >= SMP_MIN_INST && bd.sites[0] >= 1 && (size_t)5 * 32 * (bd.cols + 8) <= SMP_SMEM_MAX;
+      const bool smp_ok = !ctx->no_smp && bd.n_inst >= SMP_MIN_INST && bd.sites[0] >= 1;
       const size_t smem_cap = std::min<size_t>(SMP_SMEM_MAX, (size_t)ctx->smem_optin);
       int seg = 0;
       if (layout == 1 && smp_ok) {
         if (smp_smem_bytes(bd, 0, 2, 0) <= smem_cap) layout = 2;  // short block: the frame's sigma table is resident
-        else if (!ctx->no_smps) { layout = 2; seg = 1; }          // longer: streamed in segments
+        else if (!ctx->no_smps && bd.sites[0] <= ctx->smps_max_sites) { layout = 2; seg = 1; }  // longer: streamed in segments
       }
       if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && smp_ok &&
           (smp_smem_bytes(bd, 0, 5, 0) <= smem_cap || (!ctx->no_smps && bd.sites[0] <= ctx->smpc_max_sites))) {
@@ -637,9 +642,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
         if (!bd.smp_seg) cur.max_smp_smem = std::max(cur.max_smp_smem, smp_smem_bytes(bd, 0, bd.layout, 0));
         if (bd.smp_seg) cur.max_smps_smem = std::max(cur.max_smps_smem, smp_smem_bytes(bd, 0, bd.layout, 1));
         cur.max_smp_quads = std::max(cur.max_smp_quads, (bd.NK + 3) / 4);
-        int w = (bd.cols + 3) / 4;
-        if ((w & 1) == 0) w++;
-        cur.max_smp_stage = std::max(cur.max_smp_stage, (size_t)5 * 32 * w * 4);  // k_sigma_smp staging (smp_pitch)
+        cur.max_smp_npos = std::max(cur.max_smp_npos, bd.L - 2);
       }
       cur.maxZs[cl] = std::max(cur.maxZs[cl], bd.zstride);
       cur.max_sigma_work = std::max(cur.max_sigma_work, (long long)take * 2 * (bd.L - 2));
@@ -1263,12 +1266,12 @@ extern "C" int rc_batch_run(rc_batch* b) {
         RC_CUDA(cudaGetLastError());
         b->stats.launches++;
       }
-      if (ch.max_smp_smem > 0 || ch.max_smps_smem > 0) {  // some items use the sample-major layout
-        const size_t smem = ch.max_smp_stage;
-        RC_CUDA(cudaFuncSetAttribute(k_sigma_smp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 g2((unsigned)ch.nitems, (unsigned)((ch.max_ninst + 31) / 32), (unsigned)std::min(16, std::max(1, ch.max_smp_quads / 3)));
-        k_sigma_smp<<<g2, 256, smem, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores,
-                                          b->d_tables, b->d_sigma, b->prm);
+      if (ch.max_smp_smem > 0 || ch.max_smps_smem > 0) {  // some items use the sample-major layouts
+        const int nqz = std::min(16, std::max(1, ch.max_smp_quads / 3));
+        const int npc = (ch.max_smp_npos + SIG_PCH - 1) / SIG_PCH;
+        dim3 g2((unsigned)ch.nitems, (unsigned)((ch.max_ninst + 31) / 32), (unsigned)(npc * 2 * nqz));
+        k_sigma_smp<<<g2, 256, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores, b->d_tables,
+                                        b->d_sigma, b->prm, nqz);
         RC_CUDA(cudaGetLastError());
         b->stats.launches++;
       }
