@@ -47,6 +47,7 @@ WORKLOADS = {
     "mid": ([(10, 800)] * 16, 1000, 7, "synthetic MAF 16 blocks x 10 species x 800 cols, -n 1000"),
     "mid12": ([(10, 1200)] * 8, 1000, 9, "synthetic MAF 8 blocks x 10 species x 1200 cols, -n 1000"),
     "mid5": ([(10, 500)] * 32, 1000, 10, "synthetic MAF 32 blocks x 10 species x 500 cols, -n 1000"),
+    "mid24": ([(10, 2400)] * 4, 1000, 11, "synthetic MAF 4 blocks x 10 species x 2400 cols, -n 1000"),
     "mid_wide": ([(50, 800)] * 4, 250, 8, "synthetic MAF 4 blocks x 50 species x 800 cols, -n 250"),
 }
 METRIC = "codon_dp_cells_per_s"
