@@ -1399,7 +1399,8 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
 // contribution max3(0, t*omega, t*omega) = +0 leaves the sum unchanged (x + 0 == x).
 // sigma layout 3: [instance][tile][chunk][step][RS] (RS = NK sigma values + the chunk's z word, padded to 16 B).
 // ---------------------------------------------------------------------------------------------
-constexpr int CHAIN_MAX_WARPS = 16;
+constexpr int CHAIN_MAX_WARPS = 16;   // warps of one k_dp_chain CTA (launch bound)
+constexpr int CHAIN_PASS_WARPS = 5;   // chunks per pass when an alignment has more (see k_dp_chain)
 constexpr int CHAIN_MAX_TASKS = 8;  // upper bound of BlockDev.chain_tasks
 #ifndef RC_CHAIN_STAGES
 #define RC_CHAIN_STAGES 3
@@ -1432,7 +1433,7 @@ struct ChainCfg {
 #ifndef RC_CHAIN_MAXREG
 #define RC_CHAIN_MAXREG 128
 #endif
-template <int NK>
+template <int NK, bool MULTI>
 __global__ void
 #if RC_CHAIN_MAXREG < 128
     __maxnreg__(RC_CHAIN_MAXREG)
@@ -1440,7 +1441,8 @@ __global__ void
     __launch_bounds__(CHAIN_MAX_WARPS * 32)
 #endif
     k_dp_chain(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
-               const float* __restrict__ sigma, RowRec* __restrict__ recs, Params prm, int band_slots) {
+               const float* __restrict__ sigma, RowRec* __restrict__ recs, Params prm, int band_slots, int c_lo,
+               float2* __restrict__ partial) {
   constexpr int R = 2;
   constexpr int RS = ChainCfg<NK>::RS;
   constexpr int SIG_TILE = RegCfg<NK>::SIG_TILE;
@@ -1457,7 +1459,13 @@ __global__ void
   const int sites = bd.sites[frame], ntiles = bd.ntiles[frame];
   const int ngroups = (sites + 32 * R - 1) / (32 * R);
   const int ntasks = it.ninst * ngroups;
-  const bool first = warp == 0, last = warp == W - 1;
+  const bool first = warp == 0, last = warp == W - 1;  // ends of this CTA's warp pipeline
+  // Very wide alignments run in several PASSES (launches) of at most 5 chunks each, so that three or four CTAs stay
+  // resident per SM: the warps of a launch own the chunks c_lo .. c_lo + W - 1, the first warp of a later pass continues
+  // the partial sums the previous pass left in global memory, the last warp of an earlier pass leaves them there.
+  const int chunk = c_lo + warp;
+  const bool gfirst = !MULTI || chunk == 0, glast = !MULTI || chunk == bd.nchunk - 1;  // ends of the whole species chain
+  // (MULTI = false: single-pass launch, first == gfirst and last == glast, the global hand-over code compiles away)
 
   unsigned char* ring = smem + (size_t)warp * RING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * STAGE_BYTES);
@@ -1500,9 +1508,16 @@ __global__ void
   const int inst_l = task / ngroups, g = task % ngroups;
   const int row_base = g * 32 * R;
   const int r0 = row_base + lane * R;
-  const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * ntiles * bd.sig_tile + (size_t)warp * SIG_TILE;
+  const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * ntiles * bd.sig_tile + (size_t)chunk * SIG_TILE;
   const int t0 = row_base / TILE;
   const int t_last_diag = (row_base + 32 * R - 1) / TILE;
+  // partial sums between passes: [instance][row group][tile from the group's first][end codon][lane] float2
+  float2* gp = nullptr;
+  if (MULTI && ((first && !gfirst) || (last && !glast))) {
+    const size_t per_inst = (size_t)ngroups * ntiles - 2 * (size_t)ngroups * (ngroups - 1);  // tiles
+    gp = partial + it.part_off[strand][frame] +
+         ((size_t)inst_l * per_inst + (size_t)g * ntiles - 2 * (size_t)g * (g - 1) - t0) * (TILE * 32) + lane;  // + tile * TILE * 32
+  }
   if (lane == 0) {
     for (int q = 0; q < 2 && t0 + q < ntiles; q++) {
       const unsigned sq = (ring_it + q) & 1u;
@@ -1510,7 +1525,7 @@ __global__ void
       bulk_g2s(ring + sq * STAGE_BYTES, sig_src + (size_t)(t0 + q) * tile_stride, STAGE_BYTES, &bars[sq]);
     }
   }
-  if (last) {
+  if (last && glast) {
     rec_init(rec0);
     rec_init(rec0 + 1);
     __syncwarp();
@@ -1542,6 +1557,9 @@ __global__ void
         if (!first) {
           sinA = lds_f2(hin + c * 256);
           sinB = lds_f2(hin + (c + 1) * 256);
+        } else if (MULTI && !gfirst) {
+          sinA = gp[((size_t)tile * TILE + c) * 32];
+          sinB = gp[((size_t)tile * TILE + c + 1) * 32];
         }
         const bool clean = (__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u;
         if (!diag) {
@@ -1565,6 +1583,9 @@ __global__ void
         if (!last) {
           sts_f2(hout + c * 256, sumA);
           sts_f2(hout + (c + 1) * 256, sumB);
+        } else if (MULTI && !glast) {
+          gp[((size_t)tile * TILE + c) * 32] = sumA;
+          gp[((size_t)tile * TILE + c + 1) * 32] = sumB;
         } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
           if (sumA.x > 0.0f) lb.x = RC_REG_CHECK(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
           if (sumA.y > 0.0f) lb.y = RC_REG_CHECK(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
@@ -1587,7 +1608,7 @@ __global__ void
       hround++;
     }
   }
-  if (last) {
+  if (last && glast) {
     RowRec* grec = recs + it.rec_off[strand][frame] + (size_t)inst_l * sites + r0;
 #pragma unroll
     for (int t = 0; t < R; t++)

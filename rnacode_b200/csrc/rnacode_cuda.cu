@@ -114,7 +114,8 @@ constexpr int SMP_CLASS0 = REG_MAX_NK + 2;
 constexpr int CHAIN_CLASS0 = 2 * REG_MAX_NK + 2;
 constexpr int CHAIN_NKW_MIN = 8, CHAIN_NKW_MAX = 12, CHAIN_NKW_SPAN = CHAIN_NKW_MAX - CHAIN_NKW_MIN + 1;
 // then k_dp_smp<., true> (layout 5: wide alignments in short blocks), one class per number of species quads Q = ceil(NK/4)
-constexpr int SMPC_CLASS0 = CHAIN_CLASS0 + (CHAIN_MAX_WARPS - 1) * CHAIN_NKW_SPAN;
+constexpr int CHAIN_MAX_CHUNKS = 42;  // 499 scored species / 12; more than CHAIN_PASS_WARPS chunks run in several passes
+constexpr int SMPC_CLASS0 = CHAIN_CLASS0 + (CHAIN_MAX_CHUNKS - 1) * CHAIN_NKW_SPAN;
 constexpr int SMPC_Q_MIN = 5, SMPC_Q_MAX = 125;
 // and the segmented (streaming) variants k_dp_smps of both sample-major kinds
 constexpr int SMPS_CLASS0 = SMPC_CLASS0 + (SMPC_Q_MAX - SMPC_Q_MIN + 1);
@@ -151,6 +152,17 @@ int class_of(const BlockDev& bd) {
   return bd.NK <= 24 ? REG_MAX_NK : REG_MAX_NK + 1;
 }
 int class_R(int cl) { return cl == REG_MAX_NK + 1 ? 1 : 2; }
+
+// k_dp_chain: alignments with more than CHAIN_PASS_WARPS species chunks run in several launches ("passes") of nearly
+// equal width; this is the width of the widest pass
+int chain_passes(int W) { return (W + CHAIN_PASS_WARPS - 1) / CHAIN_PASS_WARPS; }
+int chain_pass_width(int W) { return (W + chain_passes(W) - 1) / chain_passes(W); }
+// float2 entries per instance of the partial sums handed from one pass to the next (layout 3): one per (row group, tile from
+// the group's first tile on, end codon, lane)
+size_t chain_part_entries(int sites, int ntiles) {
+  const size_t ng = (size_t)(sites + 63) / 64;
+  return (ng * ntiles - 2 * ng * (ng - 1)) * TILE * 32;
+}
 
 // layout 5: (start-codon pair, end codon) entries of one frame: sum over pairs p of (sites - 2p)
 size_t part_entries(int sites) {
@@ -555,7 +567,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
         layout = 5;  // wide alignment with many instances: sample-major, one launch per species chunk
         seg = smp_smem_bytes(bd, 0, 5, 0) <= smem_cap ? 0 : 1;
       } else if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && !ctx->no_chain &&
-                 (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX <= CHAIN_MAX_WARPS)
+                 (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX <= CHAIN_MAX_CHUNKS)
         layout = 3;  // wide alignment: species chunks pipelined through the warps of a CTA
       set_layout(bd, layout);
       bd.smp_seg = seg;
@@ -564,7 +576,8 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
         // (a row group of a frame with T tiles has T - 4g tiles: about T/2 on average), but not more: long rows are
         // better balanced with one task per CTA
         const double avg_tiles = std::max(1.0, 0.5 * bd.ntiles[0]);
-        bd.chain_tasks = (int)std::min<double>(CHAIN_MAX_TASKS, std::max(1.0, std::ceil(4.0 * (bd.nchunk - 1) / avg_tiles)));
+        const int wp = chain_pass_width(bd.nchunk);  // warps per CTA = depth of the pipeline
+        bd.chain_tasks = (int)std::min<double>(CHAIN_MAX_TASKS, std::max(1.0, std::ceil(4.0 * (wp - 1) / avg_tiles)));
       }
       if (layout == 1)  // k_dp_reg stages RC_REG_TILE end codons at a time: pad the frame to whole stages
         for (int f = 0; f < 3; f++) bd.ntiles[f] = (bd.ntiles[f] + RC_REG_TILE / TILE - 1) / (RC_REG_TILE / TILE) * (RC_REG_TILE / TILE);
@@ -606,6 +619,8 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     size_t part_per_inst = 0;  // layout 5: partial species sums handed from one chunk's launch to the next (float2 per lane)
     if (bd.layout == 5)
       for (int f = 0; f < 3; f++) part_per_inst += 2 * part_entries(bd.sites[f]);
+    if (bd.layout == 3 && chain_passes(bd.nchunk) > 1)
+      for (int f = 0; f < 3; f++) part_per_inst += 2 * chain_part_entries(bd.sites[f], bd.ntiles[f]);
     const size_t bytes_per_inst = sig_per_inst * sizeof(float) + rec_per_inst * sizeof(RowRec) + part_per_inst * sizeof(float2);
     int inst = 0;
     while (inst < bd.n_inst) {
@@ -634,6 +649,10 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
           if (bd.layout == 5) {
             it.part_off[s][f] = (long long)cur.part_count;
             cur.part_count += (size_t)((take + 31) / 32) * part_entries(bd.sites[f]) * 32;
+          }
+          if (bd.layout == 3 && chain_passes(bd.nchunk) > 1) {
+            it.part_off[s][f] = (long long)cur.part_count;
+            cur.part_count += (size_t)take * chain_part_entries(bd.sites[f], bd.ntiles[f]);
           }
         }
       const int cl = class_of(bd);
@@ -1052,17 +1071,30 @@ static int launch_dp_smp(rc_batch* b, int NK, bool seg, const CtaDesc* d_ctas, s
 template <int NKW>
 static int launch_dp_chain_nk(rc_batch* b, int W, const CtaDesc* d_ctas, size_t ncta) {
   rc_ctx* ctx = b->ctx;
-  const size_t smem = ChainCfg<NKW>::smem_bytes(W);
-  if (smem > (size_t)ctx->smem_optin) {
-    ctx_fail(ctx, "internal: k_dp_chain shared memory exceeds the device limit");
-    return RC_ERR_STATE;
+  // W chunks in chain_passes(W) launches of nearly equal width; each continues the partial sums of the one before
+  const int np = chain_passes(W), base = W / np, rem = W % np;
+  int c_lo = 0;
+  for (int pass = 0; pass < np; pass++) {
+    const int wp = base + (pass < rem ? 1 : 0);
+    const size_t smem = ChainCfg<NKW>::smem_bytes(wp);
+    if (smem > (size_t)ctx->smem_optin) {
+      ctx_fail(ctx, "internal: k_dp_chain shared memory exceeds the device limit");
+      return RC_ERR_STATE;
+    }
+    if (np == 1) {
+      RC_CUDA(cudaFuncSetAttribute(k_dp_chain<NKW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_dp_chain<NKW, false><<<(unsigned)ncta, wp * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_recs,
+                                                                            b->prm, (int)ctx->band_slots, 0, nullptr);
+    } else {
+      RC_CUDA(cudaFuncSetAttribute(k_dp_chain<NKW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_dp_chain<NKW, true><<<(unsigned)ncta, wp * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_recs,
+                                                                           b->prm, (int)ctx->band_slots, c_lo, b->d_partial);
+    }
+    RC_CUDA(cudaGetLastError());
+    b->stats.launches++;
+    b->stats.dp_launches++;
+    c_lo += wp;
   }
-  RC_CUDA(cudaFuncSetAttribute(k_dp_chain<NKW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dp_chain<NKW><<<(unsigned)ncta, W * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_recs, b->prm,
-                                                                (int)ctx->band_slots);
-  RC_CUDA(cudaGetLastError());
-  b->stats.launches++;
-  b->stats.dp_launches++;
   return RC_OK;
 }
 
