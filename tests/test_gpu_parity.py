@@ -145,7 +145,10 @@ def test_mixed_batch_and_chunking(oracle):
     ctx = capi.Context(0)
     ctx.set_option("scratch_mb", 1)
     try:
-        shapes = [(10, 200, 40), (4, 30, 3), (30, 90, 10), (3, 2, 2), (12, 333, 9)]
+        shapes = [(10, 200, 40), (4, 30, 3), (30, 90, 10), (3, 2, 2), (12, 333, 9),
+                  # sample-major layouts whose instance groups of 32 are split over several items / chunks:
+                  # chunked wide (layout 5), streamed (k_dp_smps), chain in passes
+                  (30, 90, 70), (10, 600, 40), (80, 300, 3)]
         blocks, data = [], []
         for idx, (N, cols, n) in enumerate(shapes):
             rows = synth.synth_block(5, idx, N, cols, gap_rate=0.02)
