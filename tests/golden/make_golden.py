@@ -60,6 +60,20 @@ def decorate(rows, rng):
     return rows
 
 
+def mixed_blocks():
+    """36 synthetic blocks of mixed shape (3-33 rows, 30-900 columns, with and without gaps): at -n 30 they exercise every
+    DP route of the library (sample-major resident / streamed / chunked, row-major registers / chain) end to end."""
+    rng = np.random.default_rng(424242)
+    shapes = []
+    for _ in range(36):
+        N = int(rng.choice([3, 4, 5, 8, 10, 12, 17, 20, 26, 33]))
+        cols = int(rng.choice([30, 45, 60, 90, 120, 200, 330, 450, 600, 900]))
+        if N >= 20 and cols > 450:
+            cols = 450
+        shapes.append((N, cols))
+    return [synth.synth_block(77, i, N, cols, gap_rate=float(rng.choice([0.0, 0.0067, 0.02]))) for i, (N, cols) in enumerate(shapes)]
+
+
 def main():
     subprocess.run(["make", "-C", ORC, "-j8", "ref"], check=True, stdout=subprocess.DEVNULL)
     os.makedirs(TMP, exist_ok=True)
@@ -100,6 +114,12 @@ def main():
         env = dict(os.environ, RNACODE_SEED="1")
         out = subprocess.run([DET, *opts, os.path.join(ex, f)], check=True, capture_output=True, env=env).stdout.decode()
         cli[f + " " + " ".join(opts)] = out
+    # synthetic MAF of mixed shapes through the unmodified reference (the tests rebuild the same file with mixed_blocks())
+    p = os.path.join(TMP, "synth_mixed.maf")
+    synth.to_maf(mixed_blocks(), p)
+    env = dict(os.environ, RNACODE_SEED="1")
+    cli["synthetic:mixed --tabular -n 30"] = subprocess.run([DET, "--tabular", "-n", "30", p], check=True, capture_output=True,
+                                                            env=env).stdout.decode()
     save("cli_outputs", cli)
 
 

@@ -19,6 +19,20 @@ CLI = os.path.join(REFDIR, "RNAcode_cuda_det")
 EXAMPLES = os.path.join(REFDIR, "examples")
 
 
+def _input(fname, tmp_path):
+    """Path of a golden case's input: an example of the reference, or the synthetic MAF of mixed shapes (rebuilt here with
+    the generator that produced the golden, tests/golden/make_golden.py:mixed_blocks)."""
+    if fname == "synthetic:mixed":
+        import sys
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import make_golden
+        from rnacode_b200 import synth
+        p = os.path.join(str(tmp_path), "synth_mixed.maf")
+        synth.to_maf(make_golden.mixed_blocks(), p)
+        return p
+    return os.path.join(EXAMPLES, fname)
+
+
 def _norm(txt):
     # the footer of the default format reports CPU seconds
     return re.sub(r"scored in [0-9.]+ seconds", "scored in X seconds", txt)
@@ -32,7 +46,7 @@ PIPELINE = os.path.join(REFDIR, "RNAcode_b200_det")
 # reference's seq-gen on the host.  Both must reproduce the reference's output byte for byte.
 @pytest.mark.parametrize("evolve", ["gpu", "host"])
 @pytest.mark.parametrize("case", CASES)
-def test_cli_output_identical_to_reference(case, evolve):
+def test_cli_output_identical_to_reference(case, evolve, tmp_path):
     if not (os.path.exists(CLI) and os.path.isdir(EXAMPLES)):
         pytest.skip("oracle/_ref/RNAcode_cuda_det not built (needs /root/reference at build time)")
     parts = case.split(" ")
@@ -40,14 +54,14 @@ def test_cli_output_identical_to_reference(case, evolve):
     env = dict(os.environ, RNACODE_SEED="1")
     if evolve == "host":
         env["RNACODE_CUDA_EVOLVE"] = "host"
-    res = subprocess.run([CLI, *opts, os.path.join(EXAMPLES, fname)], capture_output=True, text=True, env=env, timeout=600)
+    res = subprocess.run([CLI, *opts, _input(fname, tmp_path)], capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0, res.stderr
     assert _norm(res.stdout) == _norm(op.golden("cli_outputs")[case])
 
 
 @pytest.mark.parametrize("workers", ["1", "5"])
 @pytest.mark.parametrize("case", CASES)
-def test_batched_pipeline_output_identical_to_reference(case, workers):
+def test_batched_pipeline_output_identical_to_reference(case, workers, tmp_path):
     """integration/rnacode_pipeline.c: all blocks of the file in one GPU batch, PhyML in forked workers, null
     alignments drawn on the GPU -- and still the reference's output, byte for byte."""
     if not (os.path.exists(PIPELINE) and os.path.isdir(EXAMPLES)):
@@ -57,7 +71,7 @@ def test_batched_pipeline_output_identical_to_reference(case, workers):
     env = dict(os.environ, RNACODE_SEED="1", RNACODE_CUDA_WORKERS=workers)
     if workers == "5":
         env["RNACODE_CUDA_WINDOW"] = "4"  # several windows per file
-    res = subprocess.run([PIPELINE, *opts, os.path.join(EXAMPLES, fname)], capture_output=True, text=True, env=env, timeout=600)
+    res = subprocess.run([PIPELINE, *opts, _input(fname, tmp_path)], capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0, res.stderr
     assert _norm(res.stdout) == _norm(op.golden("cli_outputs")[case])
 
