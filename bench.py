@@ -48,6 +48,9 @@ WORKLOADS = {
     "mid12": ([(10, 1200)] * 8, 1000, 9, "synthetic MAF 8 blocks x 10 species x 1200 cols, -n 1000"),
     "mid5": ([(10, 500)] * 32, 1000, 10, "synthetic MAF 32 blocks x 10 species x 500 cols, -n 1000"),
     "mid24": ([(10, 2400)] * 4, 1000, 11, "synthetic MAF 4 blocks x 10 species x 2400 cols, -n 1000"),
+    "n17": ([(17, 3000)] * 2, 500, 12, "synthetic MAF 2 blocks x 17 species x 3000 cols, -n 500"),
+    "n14": ([(14, 3000)] * 2, 500, 13, "synthetic MAF 2 blocks x 14 species x 3000 cols, -n 500"),
+    "n17s": ([(17, 150)] * 500, 100, 14, "synthetic MAF 500 blocks x 17 species x 150 cols, -n 100"),
     "mid_wide": ([(50, 800)] * 4, 250, 8, "synthetic MAF 4 blocks x 50 species x 800 cols, -n 250"),
 }
 METRIC = "codon_dp_cells_per_s"

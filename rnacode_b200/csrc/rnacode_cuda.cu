@@ -39,6 +39,7 @@ struct rc_ctx {
   long scratch_mb = 2048;
   long no_smp = 0;
   long no_chain = 0;
+  long reg_max_nk = 12;  // row-major alignments with more scored species take k_dp_chain (k_dp_reg<13..16> spills: 17x3000 14.7 vs 11.1 ms)
   long no_smps = 0;          // never stream the sigma table in segments (k_dp_smps)
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
   long smpc_max_sites = 0;    // longest frame (codons) for the STREAMED chunked sample-major route of wide alignments
@@ -112,11 +113,11 @@ namespace {
 // 34.. = k_dp_chain<NKW> with W warps: class = CHAIN_CLASS0 + (W-2)*CHAIN_NKW_SPAN + (NKW - CHAIN_NKW_MIN)
 constexpr int SMP_CLASS0 = REG_MAX_NK + 2;
 constexpr int CHAIN_CLASS0 = 2 * REG_MAX_NK + 2;
-constexpr int CHAIN_NKW_MIN = 8, CHAIN_NKW_MAX = 12, CHAIN_NKW_SPAN = CHAIN_NKW_MAX - CHAIN_NKW_MIN + 1;
+constexpr int CHAIN_NKW_MIN = 5, CHAIN_NKW_MAX = 12, CHAIN_NKW_SPAN = CHAIN_NKW_MAX - CHAIN_NKW_MIN + 1;
 // then k_dp_smp<., true> (layout 5: wide alignments in short blocks), one class per number of species quads Q = ceil(NK/4)
 constexpr int CHAIN_MAX_CHUNKS = 42;  // 499 scored species / 12; more than CHAIN_PASS_WARPS chunks run in several passes
 constexpr int SMPC_CLASS0 = CHAIN_CLASS0 + (CHAIN_MAX_CHUNKS - 1) * CHAIN_NKW_SPAN;
-constexpr int SMPC_Q_MIN = 5, SMPC_Q_MAX = 125;
+constexpr int SMPC_Q_MIN = 4, SMPC_Q_MAX = 125;
 // and the segmented (streaming) variants k_dp_smps of both sample-major kinds
 constexpr int SMPS_CLASS0 = SMPC_CLASS0 + (SMPC_Q_MAX - SMPC_Q_MIN + 1);
 constexpr int SMPCS_CLASS0 = SMPS_CLASS0 + REG_MAX_NK;
@@ -354,6 +355,7 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   if (const char* e = getenv("RNACODE_CUDA_NO_SMPS")) ctx->no_smps = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_SMPC_MAX_SITES")) ctx->smpc_max_sites = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_SMPS_MAX_SITES")) ctx->smps_max_sites = atol(e);
+  if (const char* e = getenv("RNACODE_CUDA_REG_MAX_NK")) ctx->reg_max_nk = std::max(12L, std::min<long>(REG_MAX_NK, atol(e)));
   unsigned char lut[256];
   build_lut(lut);
   if (cudaMalloc(&ctx->d_lut, 256) != cudaSuccess ||
@@ -409,6 +411,9 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->no_chain = value ? 1 : 0;
   } else if (k == "no_smps") {
     ctx->no_smps = value ? 1 : 0;
+  } else if (k == "reg_max_nk") {
+    if (value < 12 || value > REG_MAX_NK) { ctx_fail(ctx, "reg_max_nk must be 12..16"); return RC_ERR_ARG; }
+    ctx->reg_max_nk = value;
   } else if (k == "smps_max_sites") {
     ctx->smps_max_sites = value;
   } else if (k == "smpc_max_sites") {
@@ -553,22 +558,30 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     }
     cells += (double)bd.n_inst * 2.0 * bd.NK * P;
     {
-      int layout = (bd.NK <= REG_MAX_NK && params->Delta <= 0.0f) ? 1 : 0;
-      // sample-major kernels: enough instances to fill the lanes, class-byte staging of k_sigma_smp fits
-      const bool smp_ok = !ctx->no_smp && bd.n_inst >= SMP_MIN_INST && bd.sites[0] >= 1;
+      // Which DP kernel.  Delta > 0 needs the general max(sum, Delta) (k_dp); the chunked kernels may carry
+      // a dummy species, which is only neutral for omega <= 0.
+      const int reg_max = (int)std::min<long>(REG_MAX_NK, ctx->reg_max_nk);  // widest alignment for the row-major register kernel
+      const bool wide_ok = params->Delta <= 0.0f && params->omega <= 0.0f;
+      const bool smp_ok = !ctx->no_smp && bd.n_inst >= SMP_MIN_INST && bd.sites[0] >= 1;  // enough instances to fill the lanes
       const size_t smem_cap = std::min<size_t>(SMP_SMEM_MAX, (size_t)ctx->smem_optin);
-      int seg = 0;
-      if (layout == 1 && smp_ok) {
-        if (smp_smem_bytes(bd, 0, 2, 0) <= smem_cap) layout = 2;  // short block: the frame's sigma table is resident
-        else if (!ctx->no_smps && bd.sites[0] <= ctx->smps_max_sites) { layout = 2; seg = 1; }  // longer: streamed in segments
-      }
-      if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && smp_ok &&
-          (smp_smem_bytes(bd, 0, 5, 0) <= smem_cap || (!ctx->no_smps && bd.sites[0] <= ctx->smpc_max_sites))) {
-        layout = 5;  // wide alignment with many instances: sample-major, one launch per species chunk
+      int layout = 0, seg = 0;
+      if (params->Delta <= 0.0f && bd.NK <= REG_MAX_NK && smp_ok && smp_smem_bytes(bd, 0, 2, 0) <= smem_cap) {
+        layout = 2;  // short block, many instances: sample-major with the frame's sigma table resident
+      } else if (params->Delta <= 0.0f && bd.NK <= REG_MAX_NK && smp_ok && !ctx->no_smps && bd.sites[0] <= ctx->smps_max_sites) {
+        layout = 2;  // mid-length block: sample-major, sigma table streamed in segments
+        seg = 1;
+      } else if (params->Delta <= 0.0f && (bd.NK <= reg_max || (bd.NK <= REG_MAX_NK && !wide_ok))) {
+        layout = 1;  // row-major, one warp holds all species in registers
+      } else if (wide_ok && bd.NK > REG_MAX_NK && smp_ok &&
+                 (smp_smem_bytes(bd, 0, 5, 0) <= smem_cap || (!ctx->no_smps && bd.sites[0] <= ctx->smpc_max_sites))) {
+        layout = 5;  // wide alignment, short block, many instances: sample-major, one launch per species chunk
         seg = smp_smem_bytes(bd, 0, 5, 0) <= smem_cap ? 0 : 1;
-      } else if (bd.NK > REG_MAX_NK && params->Delta <= 0.0f && params->omega <= 0.0f && !ctx->no_chain &&
-                 (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX <= CHAIN_MAX_CHUNKS)
+      } else if (wide_ok && !ctx->no_chain && (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX <= CHAIN_MAX_CHUNKS &&
+                 (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX >= 2) {
         layout = 3;  // wide alignment: species chunks pipelined through the warps of a CTA
+      } else if (params->Delta <= 0.0f && bd.NK <= REG_MAX_NK) {
+        layout = 1;
+      }
       set_layout(bd, layout);
       bd.smp_seg = seg;
       if (layout == 3) {
@@ -1101,6 +1114,9 @@ static int launch_dp_chain_nk(rc_batch* b, int W, const CtaDesc* d_ctas, size_t 
 static int launch_dp_chain(rc_batch* b, int NKW, int W, const CtaDesc* d_ctas, size_t ncta) {
   if (ncta == 0) return RC_OK;
   switch (NKW) {
+    case 5: return launch_dp_chain_nk<5>(b, W, d_ctas, ncta);
+    case 6: return launch_dp_chain_nk<6>(b, W, d_ctas, ncta);
+    case 7: return launch_dp_chain_nk<7>(b, W, d_ctas, ncta);
     case 8: return launch_dp_chain_nk<8>(b, W, d_ctas, ncta);
     case 9: return launch_dp_chain_nk<9>(b, W, d_ctas, ncta);
     case 10: return launch_dp_chain_nk<10>(b, W, d_ctas, ncta);
