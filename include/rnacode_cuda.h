@@ -5,6 +5,7 @@
  *
  *   segmentStats* scoreAln(const struct aln *alignment[], TTree*, float kappa, int backtrack)
  *       src/score.h:116, src/score.c:1067-1147, called from src/RNAcode.c:171      -> rc_score_aln()
+ *       (its side effect Sk_native / Sk_native_rev, read by backtrack() for --eps    -> rc_pair_rows())
  *   the scoring half of  int getExtremeValuePars(...)  i.e. the n calls of scoreAln() on the null
  *   alignments and the max over their HSS,
  *       src/score.h:103-104, src/score.c:1004-1044, called from src/RNAcode.c:180  -> rc_score_samples()
@@ -113,6 +114,16 @@ int rc_set_option(rc_ctx *ctx, const char *key, long value);
  * frame order and in order of discovery, like src/score.c:1107-1127.  *n_hss is always the full count. */
 int rc_score_aln(rc_ctx *ctx, const rc_block_desc *block, const rc_params *params, const int *blosum, rc_hss *out,
                  int max_hss, int *n_hss);
+/* Rows of the pairwise matrices of the native alignment, for backtrack() (src/score.h:111, src/score.c:558-797; called from
+ * colorAln, src/postscript.c:303-305, when --eps plots are drawn).  The reference keeps dense copies Sk_native /
+ * Sk_native_rev (3*N*(L+1)^2 floats each, copySk src/score.c:1084-1100) although backtrack(b, i, ...) only reads row b:
+ * this call computes the requested rows on the GPU instead.  strand: 0 = '+', 1 = '-' (the alignment is reversed and
+ * complemented as revAln does, and scores_rev is used).  b[r]: 1-based start position in that strand's coordinates.
+ * out: n_rows * N * 3 * (L+1) floats, out[((r*N + k)*3 + state)*(L+1) + i] = Sk[k][state][b[r]][i] for
+ * i = b-1 (0, src/score.c:500-504), b+2, b+5, ...; every other entry (and all of k = 0) is 0. */
+int rc_pair_rows(rc_ctx *ctx, const rc_block_desc *block, const rc_params *params, const int *blosum, int strand, int n_rows,
+                 const int *b, float *out);
+
 /* maxScores[i] of src/score.c:1044 for every null alignment i: best HSS score over both strands or
  * -1.0 when the sample has none. */
 int rc_score_samples(rc_ctx *ctx, const rc_block_desc *block, const rc_params *params, const int *blosum,

@@ -162,4 +162,72 @@ static segmentStats *hss_to_segments(const struct aln *inputAln[], const rc_hss 
   return res;
 }
 
+/* ---- --eps: backtrack() on rows computed by the GPU ------------------------------------------------------------
+ * colorAln (src/postscript.c:303-305) calls backtrack(b, i, Sk_native or Sk_native_rev, currAln) for up to three
+ * regions per plotted hit; backtrack (src/score.c:558-797) reads SSk[k][state][b][.] of that single row b only.  Linked
+ * with -Wl,--wrap=backtrack: the row comes from rc_pair_rows(), is hung into an otherwise empty SSk skeleton and the
+ * reference's own backtrack() walks it.  `alignment` is already in the strand's orientation (:255-259); which of the
+ * two global matrices was passed tells the strand, i.e. whose background model scores apply.
+ * The batched pipeline has no global models at print time and points these at the block being printed: */
+static const float *g_bt_scores_fwd = NULL, *g_bt_scores_rev = NULL;
+static const int *g_bt_blosum = NULL;
+
+backtrackData *__real_backtrack(int opt_b, int opt_i, float ****SSk, const struct aln *alignment[]);
+
+backtrackData *__wrap_backtrack(int opt_b, int opt_i, float ****SSk, const struct aln *alignment[]) {
+  const int rev = (SSk == Sk_native_rev);
+  rc_block_desc d;
+  rc_params p = current_params();
+  int N, k, x, i, j, cols, L, nrows, *blosum;
+  float *sc, *row, ****tmp;
+  char *rows;
+  backtrackData *out;
+
+  for (N = 0; alignment[N] != NULL; N++);
+  cols = (int)strlen(alignment[0]->seq);
+  L = getSeqLength(alignment[0]->seq);
+  rows = (char *)malloc((size_t)N * cols);
+  sc = (float *)malloc(sizeof(float) * 4 * N);
+  blosum = (int *)malloc(sizeof(int) * 576);
+  for (k = 0; k < N; k++) {
+    memcpy(rows + (size_t)k * cols, alignment[k]->seq, cols);
+    for (i = 0; i < 4; i++)
+      sc[4 * k + i] = g_bt_scores_fwd ? (rev ? g_bt_scores_rev : g_bt_scores_fwd)[4 * k + i]
+                                      : (rev ? modelsRev : models)[k].scores[i];
+  }
+  for (i = 0; i < 24; i++)
+    for (j = 0; j < 24; j++) blosum[i * 24 + j] = g_bt_blosum ? g_bt_blosum[i * 24 + j] : models[0].matrix[i][j];
+  d.N = N;
+  d.cols = cols;
+  d.rows = rows;
+  d.scores_fwd = sc; /* the rows are scored as given (strand 0 of what colorAln passes) with that strand's models */
+  d.scores_rev = sc;
+  d.n_samples = 0;
+  d.samples = NULL;
+
+  row = (float *)calloc((size_t)N * 3 * (L + 1) + 8, sizeof(float));
+  if (opt_b >= 1 && opt_b <= L && rc_pair_rows(ctx(), &d, &p, blosum, 0, 1, &opt_b, row) != RC_OK) die("rc_pair_rows");
+
+  nrows = (opt_b > L ? opt_b : L) + 1;
+  tmp = (float ****)malloc(sizeof(float ***) * (N + 1));
+  for (k = 0; k < N; k++) {
+    tmp[k] = (float ***)malloc(sizeof(float **) * 3);
+    for (x = 0; x < 3; x++) {
+      tmp[k][x] = (float **)calloc(nrows, sizeof(float *));
+      if (opt_b >= 0) tmp[k][x][opt_b] = row + ((size_t)k * 3 + x) * (L + 1);
+    }
+  }
+  out = __real_backtrack(opt_b, opt_i, tmp, alignment);
+  for (k = 0; k < N; k++) {
+    for (x = 0; x < 3; x++) free(tmp[k][x]);
+    free(tmp[k]);
+  }
+  free(tmp);
+  free(row);
+  free(rows);
+  free(sc);
+  free(blosum);
+  return out;
+}
+
 #endif

@@ -11,7 +11,8 @@
  * (EVDMaxLikelyFit), the p-value formula and printResults are the reference's own objects.
  *
  * It is linked with GNU ld's --wrap so that the UNMODIFIED reference objects can be reused as they are
- * (oracle/Makefile, target `cli`):   -Wl,--wrap=scoreAln -Wl,--wrap=getExtremeValuePars
+ * (oracle/Makefile, target `cli`):   -Wl,--wrap=scoreAln -Wl,--wrap=getExtremeValuePars -Wl,--wrap=backtrack
+ * (backtrack: --eps only; the Sk_native row it walks is computed on demand, see rnacode_cuda_host.h)
  * In a source tree one would instead delete the two functions from src/score.c and compile this file.
  *
  * Exact mode: the null alignments are the ones the reference's own seq-gen would draw -- the same MT19937 stream
@@ -53,10 +54,6 @@ segmentStats *__wrap_scoreAln(const struct aln *inputAln[], TTree *tree, float k
   (void)tree;
   (void)kappa;
 
-  if (pars.postscript) { /* the colour plots read the dense Sk matrices (src/postscript.c:303), which the GPU path never builds */
-    fprintf(stderr, "RNAcode: --eps is not available with libRNAcode_cuda (dense score matrices are not materialised)\n");
-    exit(EXIT_FAILURE);
-  }
   fill_desc(inputAln, &d, &rows, &sf, &sr, &blosum);
   h = (rc_hss *)malloc(sizeof(rc_hss) * cap);
   rc = rc_score_aln(ctx(), &d, &p, blosum, h, cap, &n);

@@ -17,8 +17,8 @@
  * src/score.c:1036-1042): the count is monotone in the sample index, so it is evaluated in two rounds -- 32 null
  * alignments for every block, the remaining n-32 only for the blocks still undecided -- with the same outcome.
  *
- * Not supported here: --eps (the colour plots need the reference's dense Sk matrices; use RNAcode_cuda or the
- * reference for those blocks).
+ * --eps: colorAln / backtrack (src/postscript.c, src/score.c:558-797) are the reference's own; the rows of Sk_native they
+ * walk are computed on the GPU when asked for (rc_pair_rows, see __wrap_backtrack in rnacode_cuda_host.h).
  *
  * Link: the reference's objects (RNAcode.c compiled with -Dmain=rnacode_reference_main provides the globals),
  * libRNAcode_cuda; see oracle/Makefile target `pipeline`.
@@ -399,6 +399,8 @@ static void gpu_batch(blk_t *blk, const int *list, int nlist, int s0, int ns, co
   *t_gpu += now_s() - tb;
 }
 
+static float ***g_sk_fwd_tag[1], ***g_sk_rev_tag[1]; /* stand-ins for Sk_native / Sk_native_rev: colorAln only passes them on */
+
 static void process_window(blk_t *blk, int nb, int *blosum) {
   const int n = pars.sampleN > 0 ? pars.sampleN : 0;
   /* --stop-early: a first round of few null alignments per block decides most non-coding blocks
@@ -473,6 +475,9 @@ static void process_window(blk_t *blk, int nb, int *blosum) {
     }
     for (j = 0; j < b->hssCount; j++)
       b->results[j].pvalue = b->status == 1 ? 1 - exp((-1) * exp((-1) * parLambda * (b->results[j].score - parMu))) : 99.0;
+    g_bt_scores_fwd = b->sf; /* --eps: backtrack() rows of this block come from rc_pair_rows (rnacode_cuda_host.h) */
+    g_bt_scores_rev = b->sr;
+    g_bt_blosum = blosum;
     printResults(pars.outputFile, pars.outputFormat, (const struct aln **)b->aln, b->results);
     freeResults(b->results);
     free(b->maxScores);
@@ -528,8 +533,9 @@ int main(int argc, char *argv[]) {
   strcpy(pars.inputFileName, "STDIN");
 
   read_commandline(argc, argv);
-  if (pars.postscript) nrerror("ERROR: --eps is not available in the batched GPU pipeline; use RNAcode_cuda for plots.\n");
   srand(time(NULL));
+  Sk_native = g_sk_fwd_tag; /* told apart by __wrap_backtrack, never dereferenced */
+  Sk_native_rev = g_sk_rev_tag;
 
   ntMap['A'] = ntMap['a'] = 0;
   ntMap['C'] = ntMap['c'] = 1;

@@ -80,7 +80,7 @@ static void dump_hss(segmentStats *r) {
 }
 
 int main(int argc, char *argv[]) {
-  int sampleN = 100, dumpSamples = 0, maxBlocks = 1 << 30;
+  int sampleN = 100, dumpSamples = 0, maxBlocks = 1 << 30, skRows = 0;
   const char *file = NULL;
   int a, i, j, k, N, L, cols, blockIdx = 0, first = 1;
   struct aln *inputAln[MAX_NUM_NAMES];
@@ -111,6 +111,7 @@ int main(int argc, char *argv[]) {
     if (!strcmp(argv[a], "-n") && a + 1 < argc) sampleN = atoi(argv[++a]);
     else if (!strcmp(argv[a], "--dump-samples") && a + 1 < argc) dumpSamples = atoi(argv[++a]);
     else if (!strcmp(argv[a], "--max-blocks") && a + 1 < argc) maxBlocks = atoi(argv[++a]);
+    else if (!strcmp(argv[a], "--sk-rows") && a + 1 < argc) skRows = atoi(argv[++a]);
     else if (!strcmp(argv[a], "--blosum") && a + 1 < argc) pars.blosum = atoi(argv[++a]);
     else if (!strcmp(argv[a], "--pars") && a + 1 < argc) {
       /* same quirk as src/RNAcode.c:318: the 4th number lands in stopPenalty_0 */
@@ -216,9 +217,33 @@ int main(int argc, char *argv[]) {
     Sk = NULL;
     Sk_native = NULL;
     Sk_native_rev = NULL;
-    results = scoreAln((const struct aln **)inputAln, tree, kappa, 0);
+    results = scoreAln((const struct aln **)inputAln, tree, kappa, skRows > 0 && L <= 700);
     printf(",\"native_hss\":");
     dump_hss(results);
+    if (skRows > 0 && L <= 700) { /* rows of Sk_native / Sk_native_rev as backtrack() reads them (src/score.c:558-797) */
+      int r, x, s, firstRow = 1;
+      printf(",\"sk_rows\":[");
+      for (s = 0; s < 2; s++) {
+        float ****M = s ? Sk_native_rev : Sk_native;
+        for (r = 0; r < skRows; r++) {
+          int b = r < 3 ? r + 1 : 1 + (int)((long)(r - 2) * (L - 3) / (skRows - 2));
+          if (b > L - 2) b = L - 2;
+          printf("%s{\"strand\":%d,\"b\":%d,\"v\":[", firstRow ? "" : ",", s, b);
+          firstRow = 0;
+          for (k = 1; k < N; k++)
+            for (x = 0; x < 3; x++) {
+              printf("%s[", (k > 1 || x > 0) ? "," : "");
+              for (i = b - 1; i <= L; i += 3) printf("%s%.9g", i > b - 1 ? "," : "", M[k][x][b][i]);
+              printf("]");
+            }
+          printf("]}");
+        }
+      }
+      printf("]");
+      freeSk(Sk_native, (const struct aln **)inputAln);
+      freeSk(Sk_native_rev, (const struct aln **)inputAln);
+      Sk_native = Sk_native_rev = NULL;
+    }
 
     hssCount = 0;
     while (results[hssCount++].score > 0.0);

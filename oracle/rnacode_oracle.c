@@ -287,6 +287,39 @@ int orc_score_strand(const char *rows, int N, int cols, const float *scores, con
   return count;
 }
 
+void orc_pair_row(const char *rows, int N, int cols, const float *scores, const int *blosum, const orc_params *p, int b,
+                  float *out) {
+  int L = orc_seq_length(rows, cols);
+  float *sigma = (float *)calloc((size_t)N * (L + 1), sizeof(float));
+  int *z = (int *)calloc((size_t)N * (L + 1), sizeof(int));
+  orc_sigma_z(rows, N, cols, scores, blosum, p, sigma, z);
+  memset(out, 0, sizeof(float) * (size_t)N * 3 * (L + 1));
+  const float Delta = p->Delta, Omega = p->Omega, omega = p->omega;
+  for (int k = 1; k < N; k++) {
+    float *r0 = out + ((size_t)k * 3 + 0) * (L + 1), *r1 = r0 + (L + 1), *r2 = r1 + (L + 1);
+    for (int i = b + 2; i < L + 1; i += 3) {
+      int zz = z[(size_t)k * (L + 1) + i];
+      if (i - 3 < b) r0[i - 3] = r1[i - 3] = r2[i - 3] = 0.0f; /* src/score.c:500-504 */
+      float s0 = r0[i - 3], s1 = r1[i - 3], s2 = r2[i - 3];
+      if (zz == 0) { /* :506-510 */
+        r0[i] = s0 + sigma[(size_t)k * (L + 1) + i];
+        r1[i] = s1 + omega;
+        r2[i] = s2 + omega;
+      } else if (zz == +1) { /* :512-521 */
+        r0[i] = ORC_MAX(s0 + Delta, s2 + Omega);
+        r1[i] = ORC_MAX(s0 + Omega, s1 + Delta);
+        r2[i] = ORC_MAX(s1 + Omega, s2 + Delta);
+      } else { /* :523-533 */
+        r0[i] = ORC_MAX(s0 + Delta, s1 + Omega);
+        r1[i] = ORC_MAX(s1 + Delta, s2 + Omega);
+        r2[i] = ORC_MAX(s2 + Delta, s0 + Omega);
+      }
+    }
+  }
+  free(sigma);
+  free(z);
+}
+
 int orc_score_aln(const char *rows, int N, int cols, const float *scores_fwd, const float *scores_rev,
                   const int *blosum, const orc_params *p, orc_hss *out, int max_out) {
   int n = orc_score_strand(rows, N, cols, scores_fwd, blosum, p, '+', out, max_out, NULL);

@@ -49,6 +49,12 @@ void orc_rev_aln(const char *rows, int N, int cols, char *out);
 void orc_sigma_z(const char *rows, int N, int cols, const float *scores /* N*4 */, const int *blosum /* 24*24 */,
                  const orc_params *p, float *sigma, int *z);
 
+/* Row b (1-based start position) of the pairwise matrices Sk[k][state][b][i], src/score.c:496-535, the only part of
+ * Sk that backtrack() (src/score.c:558-797) reads for the --eps plots.  out: N*3*(L+1) floats, out[(k*3+x)*(L+1)+i];
+ * entries outside i = b-1, b+2, b+5, ... (and all of k = 0) are left 0. */
+void orc_pair_row(const char *rows, int N, int cols, const float *scores, const int *blosum, const orc_params *p, int b,
+                  float *out);
+
 /* One full strand: getPairwiseScoreMatrix (src/score.c:441-556) + getMultipleScoreMatrix (:811-848) +
  * getHSS (:864-974) without materialising Sk / S.  If S_dense != NULL it receives S[b][i] at
  * S_dense[b*(L+1)+i] (only for small L, used to cross-check against the reference's matrix).

@@ -63,6 +63,7 @@ EXPORTS = [
     "rc_score_aln", "rc_score_samples", "rc_batch_create", "rc_batch_upload", "rc_batch_run", "rc_batch_download",
     "rc_batch_native_hss", "rc_batch_max_scores", "rc_batch_destroy", "rc_batch_get_stats", "rc_version",
     "rc_calibrate_issue", "rc_batch_set_evolve", "rc_score_samples_evolve", "rc_batch_get_sample_rows", "rc_device_count",
+    "rc_pair_rows",
 ]
 
 _lib = None
@@ -90,6 +91,7 @@ def load():
     lib.rc_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     lib.rc_score_aln.argtypes = [vp, C.POINTER(rc_block_desc), C.POINTER(rc_params), vp, C.POINTER(rc_hss), i, C.POINTER(i)]
     lib.rc_score_samples.argtypes = [vp, C.POINTER(rc_block_desc), C.POINTER(rc_params), vp, vp]
+    lib.rc_pair_rows.argtypes = [vp, C.POINTER(rc_block_desc), C.POINTER(rc_params), vp, i, i, vp, vp]
     lib.rc_batch_create.argtypes = [vp, C.POINTER(rc_block_desc), i, C.POINTER(rc_params), vp, C.POINTER(vp)]
     for f in ("rc_batch_upload", "rc_batch_run", "rc_batch_download"):
         getattr(lib, f).argtypes = [vp]
@@ -199,6 +201,17 @@ class Context:
             self._check(rc)
             return [(chr(out[i].strand), out[i].frame, out[i].startSite, out[i].endSite, np.float32(out[i].score))
                     for i in range(n.value)]
+
+    def pair_rows(self, block, params, blosum, strand, b_list):
+        """rc_pair_rows: Sk[k][state][b][0..L] of the native alignment for every b in b_list: array [len(b_list)][N][3][L+1]."""
+        d = block.desc()
+        bl = _blosum_arr(blosum)
+        bs = np.ascontiguousarray(b_list, dtype=np.int32)
+        L = int((np.asarray(block.rows)[0] != ord("-")).sum())
+        out = np.full((len(bs), d.N, 3, L + 1), np.nan, dtype=np.float32)
+        self._check(self.lib.rc_pair_rows(self.h, C.byref(d), C.byref(params), bl.ctypes.data, strand, len(bs), bs.ctypes.data,
+                                          out.ctypes.data))
+        return out
 
     def score_samples(self, block, params, blosum):
         d = block.desc()

@@ -2289,6 +2289,93 @@ __global__ void __launch_bounds__(EVO_WARPS * 32)
 }
 
 // ---------------------------------------------------------------------------------------------
+// (f4) k_pair_rows: rows b of the pairwise matrices Sk[k][state][b][i] (src/score.c:496-535) of one strand of the native
+// alignment -- the only part of Sk that backtrack() (src/score.c:558-797) reads when the --eps plots are drawn
+// (src/postscript.c:303).  One thread per (requested row, species) walks the end codons i = b+2, b+5, ...; z and sigma are
+// formed on the fly as in k_prep / k_sigma.  cls: class bytes of the N rows in the strand's own orientation (nucleotide code
+// in bits 0-1); c0[x] = column of the x-th non-gap character of row 0.  out: [row][N][3][L+1], zero-filled by the host.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    k_pair_rows(const unsigned char* __restrict__ cls, const int* __restrict__ c0, const float* __restrict__ scores,
+                const SigmaTables* __restrict__ tables, const int* __restrict__ b_list, int n_rows, int N, int cols, int L,
+                Params prm, float* __restrict__ out) {
+  __shared__ SigmaTables s_tab;
+  __shared__ __align__(8) uint64_t s_bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&s_bar, (unsigned)sizeof(SigmaTables));
+    bulk_g2s(&s_tab, tables, (unsigned)sizeof(SigmaTables), &s_bar);
+  }
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = idx / (N - 1), k = idx % (N - 1) + 1;
+  if (r >= n_rows) return;
+  const int b = b_list[r];
+  const unsigned char* row0 = cls;
+  const unsigned char* rowk = cls + (size_t)k * cols;
+  float* o0 = out + ((size_t)r * N + k) * 3 * (L + 1);
+  float* o1 = o0 + (L + 1);
+  float* o2 = o1 + (L + 1);
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;  // :500-504
+  for (int x = b + 2; x <= L; x += 3) {
+    const int c1 = c0[x - 2], c2 = c0[x - 1], c3 = c0[x];
+    const int a = (x > 3) ? c0[x - 3] + 1 : 0;  // getBlock, src/misc.c:198-207
+    int gk = 0;
+    for (int col = a; col <= c3; col++) gk += (rowk[col] & CLS_GAP) ? 1 : 0;
+    int diff = gk - ((c3 - a + 1) - 3);
+    diff = diff < 0 ? -diff : diff;
+    const int m = diff % 3;  // 1: z = +1, 2: z = -1 (src/misc.c:230-244)
+    float n0, n1, n2;
+    if (m == 0) {
+      const unsigned a1 = row0[c1], a2 = row0[c2], a3 = row0[c3];
+      const unsigned b1 = rowk[c1], b2 = rowk[c2], b3 = rowk[c3];
+      const unsigned qa = ((a1 & 3u) << 4) | ((a2 & 3u) << 2) | (a3 & 3u);
+      const unsigned qb = ((b1 & 3u) << 4) | ((b2 & 3u) << 2) | (b3 & 3u);
+      float v;
+      if (((a1 | a2 | a3 | b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X)) {
+        v = 0.0f;  // src/score.c:394-404
+      } else if (qa == qb) {
+        v = 0.0f;  // :409
+      } else {
+        const int pepA = s_tab.transcode[qa], pepB = s_tab.transcode[qb];
+        if (pepA < 0)
+          v = prm.stop0;  // :414-416
+        else if (pepB < 0)
+          v = prm.stopk;  // :418-420
+        else {
+          const unsigned d = qa ^ qb;
+          const int h = ((d & 0x30u) != 0) + ((d & 0x0cu) != 0) + ((d & 0x03u) != 0);
+          v = s_tab.blosum[pepA * 24 + pepB] - scores[k * 4 + h];  // :422-425
+        }
+      }
+      n0 = s0 + v;  // :506-510
+      n1 = s1 + prm.omega;
+      n2 = s2 + prm.omega;
+    } else if (m == 1) {  // :512-521
+      const float d0 = s0 + prm.Delta, d1 = s1 + prm.Delta, d2 = s2 + prm.Delta;
+      const float w0 = s0 + prm.Omega, w1 = s1 + prm.Omega, w2 = s2 + prm.Omega;
+      n0 = d0 > w2 ? d0 : w2;
+      n1 = w0 > d1 ? w0 : d1;
+      n2 = w1 > d2 ? w1 : d2;
+    } else {  // :523-533
+      const float d0 = s0 + prm.Delta, d1 = s1 + prm.Delta, d2 = s2 + prm.Delta;
+      const float w0 = s0 + prm.Omega, w1 = s1 + prm.Omega, w2 = s2 + prm.Omega;
+      n0 = d0 > w1 ? d0 : w1;
+      n1 = d1 > w2 ? d1 : w2;
+      n2 = d2 > w0 ? d2 : w0;
+    }
+    s0 = n0;
+    s1 = n1;
+    s2 = n2;
+    o0[x] = n0;
+    o1[x] = n1;
+    o2[x] = n2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Issue-rate calibration: the instruction mix of the DP fast path (4 FADD : 1 FMNMX3 per cell) on
 // register-resident chains, no memory traffic.  Gives the practical FP32/ALU issue ceiling of the
 // device at its current clocks; bench.py reports the DP kernel against it.

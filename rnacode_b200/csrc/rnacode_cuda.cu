@@ -493,6 +493,20 @@ static void build_ctas(const std::vector<BlockDev>& blocks, const std::vector<It
   }
 }
 
+// BLOSUM as float + the standard genetic code in the reference's encoding (src/code.c:26-35): A,C,G,T = 0..3, amino acids in
+// BLOSUM order ARNDCQEGHILKMFPSTWYV, stop = -1
+static void fill_tables(SigmaTables& t, const int* blosum) {
+  for (int i = 0; i < 576; i++) t.blosum[i] = (float)blosum[i];
+  static const char* tcag_aa = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+  static const char* aa_order = "ARNDCQEGHILKMFPSTWYV";
+  static const int tcag_to_acgt[4] = {3, 1, 0, 2};
+  for (int i = 0; i < 64; i++) {
+    int b1 = tcag_to_acgt[i / 16], b2 = tcag_to_acgt[(i / 4) % 4], b3 = tcag_to_acgt[i % 4];
+    char aa = tcag_aa[i];
+    t.transcode[b1 * 16 + b2 * 4 + b3] = (aa == '*') ? -1 : (signed char)(strchr(aa_order, aa) - aa_order);
+  }
+}
+
 extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_blocks, const rc_params* params,
                                const int* blosum, rc_batch** out) {
   if (!ctx || !out) return RC_ERR_ARG;
@@ -507,19 +521,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
   b->n_blocks = n_blocks;
   b->descs.assign(descs, descs + n_blocks);
   b->prm = Params{params->Delta, params->Omega, params->omega, params->stopPenalty_0, params->stopPenalty_k};
-  for (int i = 0; i < 576; i++) b->tables.blosum[i] = (float)blosum[i];
-  {
-    // standard genetic code in the reference's encoding (src/code.c:26-35): A,C,G,T = 0..3, amino acids in
-    // BLOSUM order ARNDCQEGHILKMFPSTWYV, stop = -1
-    static const char* tcag_aa = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
-    static const char* aa_order = "ARNDCQEGHILKMFPSTWYV";
-    static const int tcag_to_acgt[4] = {3, 1, 0, 2};
-    for (int i = 0; i < 64; i++) {
-      int b1 = tcag_to_acgt[i / 16], b2 = tcag_to_acgt[(i / 4) % 4], b3 = tcag_to_acgt[i % 4];
-      char aa = tcag_aa[i];
-      b->tables.transcode[b1 * 16 + b2 * 4 + b3] = (aa == '*') ? -1 : (signed char)(strchr(aa_order, aa) - aa_order);
-    }
-  }
+  fill_tables(b->tables, blosum);
 
   b->blocks.resize(n_blocks);
   double cells = 0;
@@ -1504,6 +1506,78 @@ extern "C" int rc_score_aln(rc_ctx* ctx, const rc_block_desc* block, const rc_pa
   rc_batch_destroy(b);
   return r;
 }
+
+// (f4) rows of the pairwise matrices for backtrack(), see k_pair_rows
+#define RC_CUDA_D(call)                                                         \
+  do {                                                                          \
+    cudaError_t _e = (call);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      ctx_fail(ctx, std::string(#call) + ": " + cudaGetErrorString(_e));        \
+      cleanup();                                                                \
+      return RC_ERR_CUDA;                                                       \
+    }                                                                           \
+  } while (0)
+extern "C" int rc_pair_rows(rc_ctx* ctx, const rc_block_desc* block, const rc_params* params, const int* blosum, int strand,
+                            int n_rows, const int* b, float* out) {
+  if (!ctx) return RC_ERR_ARG;
+  if (!block || !params || !blosum || !b || !out || n_rows < 1 || strand < 0 || strand > 1 || block->N < 2 || block->N > 500 ||
+      block->cols < 1 || !block->rows || !block->scores_fwd || !block->scores_rev) {
+    ctx_fail(ctx, "rc_pair_rows: invalid argument");
+    return RC_ERR_ARG;
+  }
+  const int N = block->N, cols = block->cols;
+  unsigned char lut[256];
+  build_lut(lut);
+  // class bytes in the strand's own orientation (revAln: reversed and complemented), nucleotide code in bits 0-1
+  std::vector<unsigned char> cls((size_t)N * cols);
+  for (int k = 0; k < N; k++)
+    for (int c = 0; c < cols; c++) {
+      const unsigned char v = lut[(unsigned char)block->rows[(size_t)k * cols + (strand ? cols - 1 - c : c)]];
+      cls[(size_t)k * cols + c] = strand ? (unsigned char)((v & ~3u) | ((v >> 2) & 3u)) : v;
+    }
+  std::vector<int> c0(1, -1);
+  for (int c = 0; c < cols; c++)
+    if (!(cls[c] & CLS_GAP)) c0.push_back(c);
+  const int L = (int)c0.size() - 1;
+  for (int r = 0; r < n_rows; r++)
+    if (b[r] < 1 || b[r] > L) {
+      ctx_fail(ctx, "rc_pair_rows: start position outside 1..L");
+      return RC_ERR_ARG;
+    }
+  SigmaTables tab{};
+  fill_tables(tab, blosum);
+  const Params prm{params->Delta, params->Omega, params->omega, params->stopPenalty_0, params->stopPenalty_k};
+  const size_t out_floats = (size_t)n_rows * N * 3 * (L + 1);
+  unsigned char* d_cls = nullptr;
+  int *d_c0 = nullptr, *d_b = nullptr;
+  float *d_sc = nullptr, *d_out = nullptr;
+  SigmaTables* d_tab = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_cls); cudaFree(d_c0); cudaFree(d_b); cudaFree(d_sc); cudaFree(d_out); cudaFree(d_tab);
+  };
+  cudaStream_t st = ctx->stream;
+  RC_CUDA_D(cudaSetDevice(ctx->device));
+  RC_CUDA_D(cudaMalloc((void**)&d_cls, cls.size()));
+  RC_CUDA_D(cudaMalloc((void**)&d_c0, sizeof(int) * c0.size()));
+  RC_CUDA_D(cudaMalloc((void**)&d_b, sizeof(int) * n_rows));
+  RC_CUDA_D(cudaMalloc((void**)&d_sc, sizeof(float) * 4 * N));
+  RC_CUDA_D(cudaMalloc((void**)&d_out, sizeof(float) * out_floats));
+  RC_CUDA_D(cudaMalloc((void**)&d_tab, sizeof(SigmaTables)));
+  RC_CUDA_D(cudaMemcpyAsync(d_cls, cls.data(), cls.size(), cudaMemcpyHostToDevice, st));
+  RC_CUDA_D(cudaMemcpyAsync(d_c0, c0.data(), sizeof(int) * c0.size(), cudaMemcpyHostToDevice, st));
+  RC_CUDA_D(cudaMemcpyAsync(d_b, b, sizeof(int) * n_rows, cudaMemcpyHostToDevice, st));
+  RC_CUDA_D(cudaMemcpyAsync(d_sc, strand ? block->scores_rev : block->scores_fwd, sizeof(float) * 4 * N, cudaMemcpyHostToDevice, st));
+  RC_CUDA_D(cudaMemcpyAsync(d_tab, &tab, sizeof(SigmaTables), cudaMemcpyHostToDevice, st));
+  RC_CUDA_D(cudaMemsetAsync(d_out, 0, sizeof(float) * out_floats, st));
+  const int threads = n_rows * (N - 1);
+  k_pair_rows<<<(threads + 127) / 128, 128, 0, st>>>(d_cls, d_c0, d_sc, d_tab, d_b, n_rows, N, cols, L, prm, d_out);
+  RC_CUDA_D(cudaGetLastError());
+  RC_CUDA_D(cudaMemcpyAsync(out, d_out, sizeof(float) * out_floats, cudaMemcpyDeviceToHost, st));
+  RC_CUDA_D(cudaStreamSynchronize(st));
+  cleanup();
+  return RC_OK;
+}
+#undef RC_CUDA_D
 
 extern "C" int rc_score_samples_evolve(rc_ctx* ctx, const rc_block_desc* block, const rc_tree_desc* tree,
                                        const unsigned int* seeds, int rng, const rc_params* params, const int* blosum,

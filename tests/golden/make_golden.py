@@ -74,6 +74,26 @@ def mixed_blocks():
     return [synth.synth_block(77, i, N, cols, gap_rate=float(rng.choice([0.0, 0.0067, 0.02]))) for i, (N, cols) in enumerate(shapes)]
 
 
+EPS_CASES = (("coding.aln", ["--tabular"]), ("coding.maf", ["--gtf"]),
+             ("genomic-preprocessed.maf", ["--tabular", "-n", "20", "--eps-cutoff", "0.9"]))
+
+
+def eps_golden(ex):
+    """--eps plots of the unmodified reference (deterministic seeds): stdout and the SHA-256 of every hss-<n>.eps."""
+    import hashlib
+    import shutil
+    doc = {}
+    for f, opts in EPS_CASES:
+        d = os.path.join(TMP, "eps_ref")
+        shutil.rmtree(d, ignore_errors=True)
+        env = dict(os.environ, RNACODE_SEED="1")
+        out = subprocess.run([DET, "--eps", "--eps-dir", d, *opts, os.path.join(ex, f)], check=True, capture_output=True,
+                             env=env).stdout.decode()
+        files = {n: hashlib.sha256(open(os.path.join(d, n), "rb").read()).hexdigest() for n in sorted(os.listdir(d))}
+        doc[f + " " + " ".join(opts)] = {"stdout": out, "files": files}
+    return doc
+
+
 def main():
     subprocess.run(["make", "-C", ORC, "-j8", "ref"], check=True, stdout=subprocess.DEVNULL)
     os.makedirs(TMP, exist_ok=True)
@@ -100,6 +120,11 @@ def main():
     synth.to_maf(blocks, p)
     save("synth_gapfree", probe(p, 12, 12))
 
+    # rows of the reference's pairwise matrices Sk_native / Sk_native_rev (what backtrack() walks for --eps)
+    sk = {"coding_aln": probe(os.path.join(ex, "coding.aln"), 1, 0, extra=("--sk-rows", "8")),
+          "synth_gappy": probe(os.path.join(TMP, "synth_gappy.maf"), 1, 0, extra=("--sk-rows", "6"))}
+    save("sk_rows", sk)
+
     # reference CLI outputs (deterministic seeds) for the drop-in comparison
     cli = {}
     for f, opts in (("coding.aln", []), ("coding.aln", ["--tabular"]), ("coding.aln", ["--gtf"]),
@@ -121,6 +146,7 @@ def main():
     cli["synthetic:mixed --tabular -n 30"] = subprocess.run([DET, "--tabular", "-n", "30", p], check=True, capture_output=True,
                                                             env=env).stdout.decode()
     save("cli_outputs", cli)
+    save("eps_outputs", eps_golden(ex))
 
 
 if __name__ == "__main__":

@@ -32,6 +32,8 @@ class Oracle:
         lib.orc_score_strand.argtypes = [vp, i, i, vp, vp, C.POINTER(orc_params), i, C.POINTER(orc_hss), i, vp]
         lib.orc_sample_max.argtypes = [vp, vp, i, i, vp, vp, vp, C.POINTER(orc_params)]
         lib.orc_sample_max.restype = C.c_double
+        lib.orc_pair_row.argtypes = [vp, i, i, vp, vp, C.POINTER(orc_params), i, vp]
+        lib.orc_rev_aln.argtypes = [vp, i, i, vp]
         lib.orc_calculate_bg.argtypes = [C.c_float, vp, C.c_float, vp, vp, vp]
         lib.orc_count_freqs.argtypes = [vp, i, i, vp]
         lib.orc_cells.argtypes = [i, i]
@@ -72,6 +74,23 @@ class Oracle:
 
     def sample_maxima(self, rows, samples, scores_fwd, scores_rev, params, blosum=None):
         return np.array([self.sample_max(rows, s, scores_fwd, scores_rev, params, blosum) for s in samples])
+
+    def rev_aln(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.uint8)
+        out = np.empty_like(rows)
+        self.lib.orc_rev_aln(rows.ctypes.data, rows.shape[0], rows.shape[1], out.ctypes.data)
+        return out
+
+    def pair_row(self, rows, scores, params, b, blosum=None):
+        """Sk[k][state][b][0..L] of one strand (rows already in that strand's orientation): array [N][3][L+1]."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint8)
+        N, cols = rows.shape
+        L = self.lib.orc_seq_length(rows.ctypes.data, cols)
+        sc = np.ascontiguousarray(scores, dtype=np.float32)
+        bl = np.ascontiguousarray(self.blosum62 if blosum is None else blosum, dtype=np.int32)
+        out = np.zeros((N, 3, L + 1), dtype=np.float32)
+        self.lib.orc_pair_row(rows.ctypes.data, N, cols, sc.ctypes.data, bl.ctypes.data, C.byref(params), b, out.ctypes.data)
+        return out
 
     def calculate_bg(self, dist, freqs, kappa, blosum=None):
         fr = np.ascontiguousarray(freqs, dtype=np.float32)

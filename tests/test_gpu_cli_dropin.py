@@ -117,3 +117,29 @@ def test_gpu_rng_mode_pvalues_within_sampling_error():
         else:
             la, lb = math.log10(max(pa, 1e-300)), math.log10(max(pb, 1e-300))
             assert abs(la - lb) < 0.3 + 0.06 * abs(la), (pa, pb)
+
+
+EPS_CASES = sorted(op.golden("eps_outputs").keys())
+
+
+@pytest.mark.parametrize("binary", ["RNAcode_cuda_det", "RNAcode_b200_det"])
+@pytest.mark.parametrize("case", EPS_CASES)
+def test_eps_plots_identical_to_reference(case, binary, tmp_path):
+    """--eps: the reference's colorAln / backtrack walk rows of Sk_native that rc_pair_rows computes on the GPU
+    (__wrap_backtrack, integration/rnacode_cuda_host.h).  Every hss-<n>.eps must be byte-identical to the file the
+    unmodified reference writes (SHA-256 in tests/golden/eps_outputs.json.gz), and so must stdout."""
+    import hashlib
+    exe = os.path.join(REFDIR, binary)
+    if not (os.path.exists(exe) and os.path.isdir(EXAMPLES)):
+        pytest.skip("oracle/_ref/%s not built (needs /root/reference at build time)" % binary)
+    gold = op.golden("eps_outputs")[case]
+    parts = case.split(" ")
+    fname, opts = parts[0], [p for p in parts[1:] if p]
+    d = os.path.join(str(tmp_path), "eps")
+    env = dict(os.environ, RNACODE_SEED="1")
+    res = subprocess.run([exe, "--eps", "--eps-dir", d, *opts, os.path.join(EXAMPLES, fname)], capture_output=True, text=True,
+                         env=env, timeout=600)
+    assert res.returncode == 0, res.stderr
+    assert _norm(res.stdout) == _norm(gold["stdout"])
+    files = {n: hashlib.sha256(open(os.path.join(d, n), "rb").read()).hexdigest() for n in sorted(os.listdir(d))}
+    assert files == gold["files"]

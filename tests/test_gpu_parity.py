@@ -259,3 +259,39 @@ def test_random_alignments_vs_oracle(rc_ctx, oracle):
             exp = oracle.sample_maxima(rows, smp, sf, sr, oracle.params(**kw)).astype(np.float32)
             assert np.array_equal(bt.max_scores(i).astype(np.float32), exp), (rep, i, rows.shape)
         bt.close()
+
+
+@pytest.mark.parametrize("shape", [(8, 137, 0.02), (10, 600, 0.03), (3, 30, 0.0), (40, 210, 0.05), (2, 3, 0.0), (500, 40, 0.02)],
+                         ids=lambda s: "N%d_c%d_g%g" % s)
+def test_pair_rows_vs_oracle(rc_ctx, oracle, shape):
+    """rc_pair_rows (the Sk_native rows backtrack() walks for --eps) against orc_pair_row, which is pinned to the
+    reference's own matrices in tests/test_oracle_golden.py: both strands, first / inner / last rows, bit-exact."""
+    from rnacode_b200 import synth
+    capi = _capi()
+    N, cols, gr = shape
+    rows = synth.synth_block(33, N + cols, N, cols, gap_rate=gr)
+    sf, sr = synth.synth_scores(33, 1, N)
+    L = int((np.asarray(rows)[0] != ord("-")).sum())
+    bs = sorted({1, 2, 3, max(1, L // 2), max(1, L - 3), max(1, L - 2), L})
+    blk = _block(rows, sf, sr, None)
+    for params in (dict(), dict(Delta=-9.5, Omega=-3.25, omega=-1.5, stopPenalty_0=-50.0)):
+        prm = capi.make_params(**params)
+        oprm = oracle.params(**params)
+        rev = oracle.rev_aln(rows)
+        for strand in (0, 1):
+            got = rc_ctx.pair_rows(blk, prm, oracle.blosum62, strand, bs)
+            assert got.shape == (len(bs), N, 3, L + 1)
+            for r, b in enumerate(bs):
+                exp = oracle.pair_row(rev if strand else rows, sr if strand else sf, oprm, b)
+                assert np.array_equal(got[r].view(np.uint32), exp.view(np.uint32)), (shape, strand, b)
+
+
+def test_pair_rows_rejects_bad_start(rc_ctx, oracle):
+    from rnacode_b200 import synth
+    capi = _capi()
+    rows = synth.synth_block(33, 5, 4, 30, gap_rate=0.0)
+    sf, sr = synth.synth_scores(33, 1, 4)
+    blk = _block(rows, sf, sr, None)
+    for b in (0, 31, -2):
+        with pytest.raises(RuntimeError):
+            rc_ctx.pair_rows(blk, capi.make_params(), oracle.blosum62, 0, [b])

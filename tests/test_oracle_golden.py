@@ -64,3 +64,28 @@ def test_background_model_bit_exact(oracle, name):
             assert np.array_equal(sc, sf[k]), (name, blk["index"], k)
             sc = oracle.calculate_bg(blk["dist"][k], blk["freqs_rev"], blk["kappa"])
             assert np.array_equal(sc, sr[k]), (name, blk["index"], k)
+
+
+@pytest.mark.parametrize("name", ["coding_aln", "synth_gappy"])
+def test_pair_rows_bit_exact(oracle, name):
+    """orc_pair_row against rows of the reference's Sk_native / Sk_native_rev (oracle/ref_probe.c --sk-rows), the
+    matrices backtrack() walks for the --eps plots (src/score.c:558-797)."""
+    doc = op.golden("sk_rows")[name]
+    prm = oracle.params(**op.golden_params(doc))
+    checked = 0
+    for blk in doc["blocks"]:
+        if not blk.get("sk_rows"):
+            continue
+        rows, sf, sr, _ = op.block_arrays(doc, blk)
+        rev = oracle.rev_aln(rows)
+        N, L = blk["N"], blk["L"]
+        for rec in blk["sk_rows"]:
+            b = rec["b"]
+            got = oracle.pair_row(rev if rec["strand"] else rows, sr if rec["strand"] else sf, prm, b)
+            exp = rec["v"]
+            for k in range(1, N):
+                for x in range(3):
+                    e = np.array(exp[(k - 1) * 3 + x], dtype=np.float32)
+                    assert np.array_equal(got[k, x, b - 1:L + 1:3], e), (blk["index"], rec["strand"], b, k, x)
+                    checked += len(e)
+    assert checked > 1000
