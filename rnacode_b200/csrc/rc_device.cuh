@@ -67,7 +67,9 @@ struct BlockDev {
   int sig_tile;             // floats per sigma tile
   int sig_ks, sig_cs;       // strides (floats) of species / step inside a sigma tile
   int sites[3], ntiles[3];  // codon sites / tiles per frame
-  long long raw_off, cls_off;   // byte offsets
+  long long raw_off, cls_off;   // byte offsets.  cls: [instance][inst_stride].  raw: sample i (instance 1+i) at raw_off + i*N*cols,
+                                // exactly as the caller holds them (one contiguous copy per block)
+  long long nat_off;            // byte offset in raw of the native rows (all natives of a batch are contiguous: one copy)
   long long cols0_off;          // int offset: [2][L+1], forward column (0-based) of position x (1-based) per strand
   long long scores_off;         // float offset: [2][N][4]
   long long z_off[2][3];        // u32 offset: [tile][zstride]

@@ -67,12 +67,27 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDev* __restrict__ block
   const BlockDev bd = blocks[blockIdx.x];
   const int chunks_per_inst = bd.inst_stride >> 4;
   const long long total = (long long)chunks_per_inst * bd.n_inst;
-  const uint4* raw4 = reinterpret_cast<const uint4*>(raw + bd.raw_off);
+  const size_t rowbytes = (size_t)bd.N * bd.cols;
+  const uint4* nat4 = reinterpret_cast<const uint4*>(raw + bd.nat_off);
   uint4* cls4 = reinterpret_cast<uint4*>(cls + bd.cls_off);
   for (long long ch = (long long)blockIdx.y * blockDim.x + threadIdx.x; ch < total; ch += (long long)gridDim.y * blockDim.x) {
-    const int within = (int)(ch % chunks_per_inst);
-    uint4 v = raw4[ch];
-    uint4 g = raw4[within];  // native bytes: where the native alignment has '-', the sample gets '-' (src/misc.c:141-145)
+    const int within = (int)(ch % chunks_per_inst), inst = (int)(ch / chunks_per_inst);
+    const uint4 g = nat4[within];  // native bytes: where the native alignment has '-', the sample gets '-' (src/misc.c:141-145)
+    uint4 v = g;
+    if (inst > 0) {
+      // samples sit back to back (stride N*cols, as on the host): a 16-byte window is in general unaligned
+      const unsigned char* src = raw + bd.raw_off + (size_t)(inst - 1) * rowbytes + (size_t)within * 16;
+      const unsigned mis = (unsigned)(reinterpret_cast<size_t>(src) & 15);
+      if (mis == 0) {
+        v = *reinterpret_cast<const uint4*>(src);
+      } else {
+        const unsigned* w = reinterpret_cast<const unsigned*>(src - (mis & 3));
+        const unsigned sh = (mis & 3) * 8;
+        const unsigned w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];  // the buffer ends with 64 bytes of slack
+        v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                       __funnelshift_r(w3, w4, sh));
+      }
+    }
     unsigned vin[4] = {v.x, v.y, v.z, v.w}, gin[4] = {g.x, g.y, g.z, g.w}, out[4];
 #pragma unroll
     for (int w = 0; w < 4; w++) {
@@ -208,6 +223,15 @@ __global__ void __launch_bounds__(256) k_prep(const BlockDev* __restrict__ block
 struct __align__(16) SigmaTables {
   float blosum[576];
   signed char transcode[64];
+};
+
+// calculateSigma (src/score.c:406-425) as two look-ups for k_sigma_smp: t[codonA*64 + codonB] = e, where e & 0x3ff indexes
+// val[] -- the BLOSUM entry of the two peptides as float, or one of the constants 0 (identical codons), stopPenalty_0,
+// stopPenalty_k -- and e >> 10 is the Hamming distance h whose expected score is subtracted (0 for the constants).
+constexpr int PT_ZERO = 576, PT_STOP0 = 577, PT_STOPK = 578;
+struct __align__(16) PairTables {
+  unsigned short t[4096];
+  float val[580];
 };
 
 __global__ void __launch_bounds__(256)
@@ -438,13 +462,14 @@ constexpr int SIG_PITCH = 260;            // bytes per staged row: 65 words, odd
 
 __global__ void __launch_bounds__(256)
     k_sigma_smp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned char* __restrict__ cls,
-                const int* __restrict__ cols0, const float* __restrict__ scores, const SigmaTables* __restrict__ tables,
-                float* __restrict__ sigma, Params prm, int nqz) {
-  __shared__ SigmaTables s_tab;
+                const int* __restrict__ cols0, const float* __restrict__ scores, const PairTables* __restrict__ tables,
+                float* __restrict__ sigma, int nqz) {
+  __shared__ PairTables s_tab;
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_col[2][SIG_PITCH];
+  __shared__ float s_sc[2][4][4];  // expected scores of the quad's species: [strand][species][h], h = 0 -> 0
   __shared__ __align__(16) unsigned char s_ref[32 * SIG_PITCH];
-  __shared__ __align__(16) unsigned char s_sp[4 * 32 * SIG_PITCH];
+  extern __shared__ __align__(16) unsigned char s_sp[];  // [4 * 32 * SIG_PITCH] (dynamic: static shared memory ends at 48 KB)
   const Item it = items[blockIdx.x];
   const BlockDev bd = blocks[it.block];
   const int group = blockIdx.y;
@@ -463,8 +488,8 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
     mbar_fence_init();
-    mbar_expect_tx(&s_bar, (unsigned)sizeof(SigmaTables));
-    bulk_g2s(&s_tab, tables, (unsigned)sizeof(SigmaTables), &s_bar);
+    mbar_expect_tx(&s_bar, (unsigned)sizeof(PairTables));
+    bulk_g2s(&s_tab, tables, (unsigned)sizeof(PairTables), &s_bar);
   }
   // s_col[s][t]: alignment column of reference position xi_lo + 1 + t on strand s (positions x-2 .. x of xi are xi+1 .. xi+3)
   for (int t = threadIdx.x; t < xi_n + 2; t += blockDim.x) {
@@ -497,6 +522,10 @@ __global__ void __launch_bounds__(256)
       const unsigned char* src = gbase + (size_t)li * bd.inst_stride + (size_t)row * cols;
       unsigned char* dst = s_sp + (kk * 32 + li) * SIG_PITCH;
       for (int t = ln; t < n_staged; t += 32) dst[t] = ok ? src[small ? t : s_col[s_cta][t]] : (unsigned char)0;
+    }
+    if (threadIdx.x < 32) {  // [strand][species of the quad][h]
+      const int ss = threadIdx.x >> 4, kk = (threadIdx.x >> 2) & 3, h = threadIdx.x & 3, row = 1 + 4 * kq + kk;
+      s_sc[ss][kk][h] = (h > 0 && row < N) ? scores[bd.scores_off + ((size_t)ss * N + row) * 4 + h] : 0.0f;
     }
     __syncthreads();
     // output address of quad kq: layout 2 is [group][step][quad][lane][4]; layout 5 is [chunk][group][step][3 quads][lane][4]
@@ -534,33 +563,22 @@ __global__ void __launch_bounds__(256)
       }
       const int xi = xi_lo + tl;
       const int sh = s ? 2 : 0;
-      const float* sc = scores + bd.scores_off + (size_t)s * N * 4;
+      const float* sc = &s_sc[s][0][0];
       const unsigned char* rr = s_ref + lane * SIG_PITCH;
       const unsigned a1 = rr[i1], a2 = rr[i2], a3 = rr[i3];
       const unsigned qa = (((a1 >> sh) & 3u) << 4) | (((a2 >> sh) & 3u) << 2) | ((a3 >> sh) & 3u);
       const unsigned nA = (a1 | a2 | a3) & CLS_N;
-      const int pepA = s_tab.transcode[qa];
+      const unsigned short* trow = s_tab.t + (qa << 6);
       float v4[4];
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {
-        const int k = 4 * kq + kk;
-        float v = 0.0f;
-        if (k < NK) {
-          const unsigned char* rk = s_sp + (kk * 32 + lane) * SIG_PITCH;
-          const unsigned b1 = rk[i1], b2 = rk[i2], b3 = rk[i3];
-          const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
-          if (!(nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X)) && qa != qb) {  // src/score.c:394-409
-            const int pepB = s_tab.transcode[qb];
-            if (pepA < 0) v = prm.stop0;         // :414-416
-            else if (pepB < 0) v = prm.stopk;    // :418-420
-            else {
-              const unsigned d = qa ^ qb;
-              const int h = ((d & 0x30u) != 0) + ((d & 0x0cu) != 0) + ((d & 0x03u) != 0);
-              v = s_tab.blosum[pepA * 24 + pepB] - sc[(k + 1) * 4 + h];  // :422-425
-            }
-          }
-        }
-        v4[kk] = v;
+        const unsigned char* rk = s_sp + (kk * 32 + lane) * SIG_PITCH;
+        const unsigned b1 = rk[i1], b2 = rk[i2], b3 = rk[i3];
+        const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
+        const unsigned e = trow[qb];
+        const float v = s_tab.val[e & 0x3ffu] - sc[kk * 4 + (e >> 10)];  // observed - expected (:422-425), or constant - 0
+        const unsigned zero = nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X);  // src/score.c:394-404
+        v4[kk] = (zero || 4 * kq + kk >= NK) ? 0.0f : v;
       }
       const int f = xi % 3, j = xi / 3;
       float* out = sigma + it.sigma_off[s][f] + rowmul * bd.sites[f] + (size_t)j * step_stride + qoff + lane * 4;
@@ -2239,7 +2257,7 @@ __global__ void __launch_bounds__(EVO_WARPS * 32)
   const int* nd = nodes + ev.node_off;
   const unsigned* th = thr + ev.thr_off;
   unsigned char* myseq = seqs + ev.seq_off + (size_t)sample * ev.n_internal * cols;
-  unsigned char* myraw = raw + bd.raw_off + (size_t)(1 + sample) * bd.inst_stride;
+  unsigned char* myraw = raw + bd.raw_off + (size_t)sample * bd.N * cols;
   unsigned* mt = s_mt[warp];
   int pos = 624;  // next unread word of the current 624-word batch
   if (ev.rng == 0) {

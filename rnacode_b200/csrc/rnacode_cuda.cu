@@ -245,6 +245,7 @@ struct rc_batch {
   std::vector<Chunk> chunks;
   Params prm{};
   SigmaTables tables{};
+  PairTables ptab{};
   // device, persistent
   BlockDev* d_blocks = nullptr;
   Item* d_items = nullptr;
@@ -258,6 +259,7 @@ struct rc_batch {
   int* d_hsscnt = nullptr;
   int* d_ovf = nullptr;
   SigmaTables* d_tables = nullptr;
+  PairTables* d_ptab = nullptr;
   // null-alignment simulation (kernel d)
   std::vector<EvoDev> evos;
   std::vector<int> evo_nodes;
@@ -277,13 +279,14 @@ struct rc_batch {
   float* d_dense = nullptr;
   size_t dense_floats = 0;
   // sizes
-  size_t raw_bytes = 0, cols0_ints = 0, scores_floats = 0, z_words = 0, res_floats = 0, hss_count = 0, hsscnt_ints = 0;
+  size_t raw_bytes = 0, cls_bytes = 0, nat_bytes = 0, cols0_ints = 0, scores_floats = 0, z_words = 0, res_floats = 0, hss_count = 0, hsscnt_ints = 0;
   size_t sigma_floats = 0, rec_count = 0;
   // host results
   std::vector<float> h_res;
   std::vector<HssDev> h_hss;
   std::vector<int> h_hsscnt;
   std::vector<float> h_scores;
+  std::vector<unsigned char> h_nat;  // the native rows of all blocks, staged for one copy
   bool uploaded = false, ran = false, downloaded = false;
   rc_batch_stats stats{};
   std::vector<EventPair> events;
@@ -461,7 +464,7 @@ extern "C" int rc_calibrate_issue(rc_ctx* ctx, double* lane_ops_per_s) {
 static void free_batch_device(rc_batch* b) {
   rc_ctx* ctx = b->ctx;
   void* ptrs[] = {b->d_blocks, b->d_items, b->d_ctas, b->d_raw, b->d_cls, b->d_cols0, b->d_scores, b->d_z, b->d_res,
-                  b->d_hss, b->d_hsscnt, b->d_ovf, b->d_tables, b->d_sigma, b->d_recs, b->d_dense, b->d_partial,
+                  b->d_hss, b->d_hsscnt, b->d_ovf, b->d_tables, b->d_ptab, b->d_sigma, b->d_recs, b->d_dense, b->d_partial,
                   b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq};
   for (void* p : ptrs) ctx_free(ctx, p);
   for (auto& e : b->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -507,6 +510,26 @@ static void fill_tables(SigmaTables& t, const int* blosum) {
   }
 }
 
+// calculateSigma's case analysis per (reference codon, species codon), see PairTables
+static void fill_pair_tables(PairTables& pt, const SigmaTables& t, const Params& prm) {
+  for (int i = 0; i < 576; i++) pt.val[i] = t.blosum[i];
+  pt.val[PT_ZERO] = 0.0f;
+  pt.val[PT_STOP0] = prm.stop0;
+  pt.val[PT_STOPK] = prm.stopk;
+  pt.val[579] = 0.0f;
+  for (int qa = 0; qa < 64; qa++)
+    for (int qb = 0; qb < 64; qb++) {
+      const int pepA = t.transcode[qa], pepB = t.transcode[qb];
+      const int d = qa ^ qb, h = ((d & 0x30) != 0) + ((d & 0x0c) != 0) + ((d & 0x03) != 0);
+      unsigned e;
+      if (h == 0) e = PT_ZERO;          // src/score.c:409, tested before the stop codons
+      else if (pepA < 0) e = PT_STOP0;  // :414-416
+      else if (pepB < 0) e = PT_STOPK;  // :418-420
+      else e = (unsigned)(pepA * 24 + pepB) | ((unsigned)h << 10);
+      pt.t[qa * 64 + qb] = (unsigned short)e;
+    }
+}
+
 extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_blocks, const rc_params* params,
                                const int* blosum, rc_batch** out) {
   if (!ctx || !out) return RC_ERR_ARG;
@@ -522,6 +545,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
   b->descs.assign(descs, descs + n_blocks);
   b->prm = Params{params->Delta, params->Omega, params->omega, params->stopPenalty_0, params->stopPenalty_k};
   fill_tables(b->tables, blosum);
+  fill_pair_tables(b->ptab, b->tables, b->prm);
 
   b->blocks.resize(n_blocks);
   double cells = 0;
@@ -545,9 +569,12 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     bd.inst_stride = (int)align_up((size_t)d.N * d.cols, 16);
     bd.fNK = (float)bd.NK;
     bd.rcpNK = 1.0f / bd.fNK;
-    bd.raw_off = (long long)b->raw_bytes;
-    bd.cls_off = bd.raw_off;
-    b->raw_bytes += (size_t)bd.inst_stride * bd.n_inst;
+    bd.cls_off = (long long)b->cls_bytes;
+    b->cls_bytes += (size_t)bd.inst_stride * bd.n_inst;
+    bd.raw_off = (long long)b->raw_bytes;  // the samples, stride N*cols; the natives follow all samples (nat_off, below)
+    b->raw_bytes += align_up((size_t)d.N * d.cols * d.n_samples, 16);
+    bd.nat_off = (long long)b->nat_bytes;
+    b->nat_bytes += (size_t)bd.inst_stride;
     bd.cols0_off = (long long)b->cols0_ints;
     b->cols0_ints += 2 * (size_t)(L + 1);
     bd.scores_off = (long long)b->scores_floats;
@@ -610,7 +637,8 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     b->hsscnt_ints += 6;
   }
   b->stats.cells = cells;
-  b->stats.pack_chars = (double)b->raw_bytes;
+  for (BlockDev& bd : b->blocks) bd.nat_off += (long long)b->raw_bytes;  // the natives follow the samples in d_raw
+  b->stats.pack_chars = (double)b->cls_bytes;
 
   // chunking: fill items until the scratch budget is reached
   const size_t budget = (size_t)ctx->scratch_mb << 20;
@@ -712,13 +740,13 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
   };
   bool ok = dalloc((void**)&b->d_blocks, sizeof(BlockDev) * n_blocks) &&
             dalloc((void**)&b->d_items, sizeof(Item) * b->items.size()) &&
-            dalloc((void**)&b->d_ctas, sizeof(CtaDesc) * b->ctas.size()) && dalloc((void**)&b->d_raw, b->raw_bytes) &&
-            dalloc((void**)&b->d_cls, b->raw_bytes) && dalloc((void**)&b->d_cols0, sizeof(int) * b->cols0_ints) &&
+            dalloc((void**)&b->d_ctas, sizeof(CtaDesc) * b->ctas.size()) &&
+            dalloc((void**)&b->d_raw, b->raw_bytes + b->nat_bytes + 64) && dalloc((void**)&b->d_cls, b->cls_bytes) && dalloc((void**)&b->d_cols0, sizeof(int) * b->cols0_ints) &&
             dalloc((void**)&b->d_scores, sizeof(float) * b->scores_floats) &&
             dalloc((void**)&b->d_z, sizeof(unsigned) * b->z_words) && dalloc((void**)&b->d_res, sizeof(float) * b->res_floats) &&
             dalloc((void**)&b->d_hss, sizeof(HssDev) * b->hss_count) &&
             dalloc((void**)&b->d_hsscnt, sizeof(int) * b->hsscnt_ints) && dalloc((void**)&b->d_ovf, sizeof(int)) &&
-            dalloc((void**)&b->d_tables, sizeof(SigmaTables)) && dalloc((void**)&b->d_sigma, sizeof(float) * b->sigma_floats) &&
+            dalloc((void**)&b->d_tables, sizeof(SigmaTables)) && dalloc((void**)&b->d_ptab, sizeof(PairTables)) && dalloc((void**)&b->d_sigma, sizeof(float) * b->sigma_floats) &&
             dalloc((void**)&b->d_recs, sizeof(RowRec) * b->rec_count) &&
             (b->part_count == 0 || dalloc((void**)&b->d_partial, sizeof(float2) * b->part_count));
   if (!ok) {
@@ -839,7 +867,7 @@ extern "C" int rc_batch_get_sample_rows(rc_batch* b, int block, int sample, char
   }
   RC_CUDA(cudaSetDevice(ctx->device));
   RC_CUDA(cudaStreamSynchronize(ctx->stream));
-  RC_CUDA(cudaMemcpy(rows, b->d_raw + bd.raw_off + (size_t)(1 + sample) * bd.inst_stride, (size_t)bd.N * bd.cols,
+  RC_CUDA(cudaMemcpy(rows, b->d_raw + bd.raw_off + (size_t)sample * bd.N * bd.cols, (size_t)bd.N * bd.cols,
                      cudaMemcpyDeviceToHost));
   return RC_OK;
 }
@@ -854,24 +882,25 @@ extern "C" int rc_batch_upload(rc_batch* b) {
   cudaStream_t st = ctx->stream;
   size_t h2d = 0;
   b->h_scores.resize(b->scores_floats);
+  b->h_nat.assign(b->nat_bytes, 0);
   for (int i = 0; i < b->n_blocks; i++) {
     const rc_block_desc& d = b->descs[i];
     const BlockDev& bd = b->blocks[i];
     const size_t rowbytes = (size_t)d.N * d.cols;
-    RC_CUDA(cudaMemcpyAsync(b->d_raw + bd.raw_off, d.rows, rowbytes, cudaMemcpyHostToDevice, st));
+    memcpy(&b->h_nat[bd.nat_off - (long long)b->raw_bytes], d.rows, rowbytes);
     h2d += rowbytes;
     if (d.n_samples > 0 && b->evo_of_block[i] < 0) {
       if (!d.samples) {
         ctx_fail(ctx, "block " + std::to_string(i) + " has n_samples > 0 but neither samples nor rc_batch_set_evolve");
         return RC_ERR_ARG;
       }
-      RC_CUDA(cudaMemcpy2DAsync(b->d_raw + bd.raw_off + bd.inst_stride, bd.inst_stride, d.samples, rowbytes, rowbytes,
-                                d.n_samples, cudaMemcpyHostToDevice, st));
+      RC_CUDA(cudaMemcpyAsync(b->d_raw + bd.raw_off, d.samples, rowbytes * d.n_samples, cudaMemcpyHostToDevice, st));
       h2d += rowbytes * d.n_samples;
     }
     memcpy(&b->h_scores[bd.scores_off], d.scores_fwd, sizeof(float) * d.N * 4);
     memcpy(&b->h_scores[bd.scores_off + (size_t)d.N * 4], d.scores_rev, sizeof(float) * d.N * 4);
   }
+  RC_CUDA(cudaMemcpyAsync(b->d_raw + b->raw_bytes, b->h_nat.data(), b->nat_bytes, cudaMemcpyHostToDevice, st));
   RC_CUDA(cudaMemcpyAsync(b->d_scores, b->h_scores.data(), sizeof(float) * b->scores_floats, cudaMemcpyHostToDevice, st));
   RC_CUDA(cudaMemcpyAsync(b->d_blocks, b->blocks.data(), sizeof(BlockDev) * b->n_blocks, cudaMemcpyHostToDevice, st));
   if (!b->items.empty())
@@ -879,6 +908,7 @@ extern "C" int rc_batch_upload(rc_batch* b) {
   if (!b->ctas.empty())
     RC_CUDA(cudaMemcpyAsync(b->d_ctas, b->ctas.data(), sizeof(CtaDesc) * b->ctas.size(), cudaMemcpyHostToDevice, st));
   RC_CUDA(cudaMemcpyAsync(b->d_tables, &b->tables, sizeof(SigmaTables), cudaMemcpyHostToDevice, st));
+  RC_CUDA(cudaMemcpyAsync(b->d_ptab, &b->ptab, sizeof(PairTables), cudaMemcpyHostToDevice, st));
   if (!b->evos.empty()) {
     void* ptrs[] = {b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq};
     for (void* p : ptrs) ctx_free(ctx, p);
@@ -1320,8 +1350,10 @@ extern "C" int rc_batch_run(rc_batch* b) {
         const int nqz = std::min(16, std::max(1, ch.max_smp_quads / 3));
         const int npc = (ch.max_smp_npos + SIG_PCH - 1) / SIG_PCH;
         dim3 g2((unsigned)ch.nitems, (unsigned)((ch.max_ninst + 31) / 32), (unsigned)(npc * 2 * nqz));
-        k_sigma_smp<<<g2, 256, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores, b->d_tables,
-                                        b->d_sigma, b->prm, nqz);
+        constexpr int SIGMA_SMP_DYN_SMEM = 4 * 32 * SIG_PITCH;  // species staging; static + dynamic exceed 48 KB
+        RC_CUDA(cudaFuncSetAttribute(k_sigma_smp, cudaFuncAttributeMaxDynamicSharedMemorySize, SIGMA_SMP_DYN_SMEM));
+        k_sigma_smp<<<g2, 256, SIGMA_SMP_DYN_SMEM, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores,
+                                                         b->d_ptab, b->d_sigma, nqz);
         RC_CUDA(cudaGetLastError());
         b->stats.launches++;
       }

@@ -1,0 +1,32 @@
+"""Wall-clock of each C-ABI call of one batch (host + device, synchronised) for a bench workload:
+python tools/time_batch_host.py short"""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import bench
+from rnacode_b200 import capi, synth
+
+w = sys.argv[1] if len(sys.argv) > 1 else "short"
+blocks_np, n, seed, desc = bench.build_workload(w, 0)
+blocks = []
+for rows, sf, sr, idx in blocks_np:
+    N, cols = rows.shape
+    t_ = torch.from_numpy(synth.synth_samples(seed, idx, n, N, cols)).pin_memory()
+    r_ = torch.from_numpy(rows.copy()).pin_memory()
+    keep = globals().setdefault("keep", [])
+    keep += [t_, r_]
+    blocks.append(capi.Block(r_.numpy(), sf, sr, t_.numpy()))
+ctx = capi.Context(0)
+prm = capi.make_params()
+blosum = np.array(bench.BLOSUM62, dtype=np.int32)
+for rep in range(4):
+    t = [time.perf_counter()]
+    b = ctx.batch(blocks, prm, blosum); t.append(time.perf_counter())
+    b.upload(); torch.cuda.synchronize(); t.append(time.perf_counter())
+    b.run(); torch.cuda.synchronize(); t.append(time.perf_counter())
+    b.download(); t.append(time.perf_counter())
+    _ = [b.max_scores(i) for i in range(len(blocks))]; t.append(time.perf_counter())
+    b.close(); t.append(time.perf_counter())
+    names = ["create", "upload", "run", "download", "max_scores", "close"]
+    print(desc[:40], " ".join("%s %.2f" % (nm, (t[i + 1] - t[i]) * 1e3) for i, nm in enumerate(names)), "ms  total %.2f" % ((t[-1] - t[0]) * 1e3))
