@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(256)
   const int npos = L - 2;
   // Short blocks (whole rows fit the staging buffer): the rows are staged once, uncompacted, and the CTA of strand 0
   // serves both strands from them.  Longer blocks: compacted staging, one CTA per strand and position chunk.
-  const bool small = cols <= SIG_PITCH;
+  const bool small = cols <= SIG_PITCH - 4;  // room for the word-copy shift below
   const int xi_lo = small ? 0 : pc * SIG_PCH;
   if (qz * 4 >= NK || xi_lo >= npos || (small && (s_cta == 1 || pc > 0))) return;  // nothing to do for this CTA
   const int xi_n = small ? npos : min(SIG_PCH, npos - xi_lo);  // positions of this CTA
@@ -505,10 +505,17 @@ __global__ void __launch_bounds__(256)
   const unsigned char* gbase = cls + bd.cls_off + (size_t)(it.inst0 + group * 32) * bd.inst_stride;
   const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   // reference rows of the 32 instances: one warp per row, lanes along the staged columns
+  // (short blocks: the row is copied as aligned 32-bit words; rows start 16-byte aligned here, species rows -- below -- at
+  // any byte, so a staged row is shifted by its source's misalignment and column t sits at dst[shift + t])
   for (int li = wid; li < 32; li += nwarps) {
     const unsigned char* src = gbase + (size_t)li * bd.inst_stride;
     unsigned char* dst = s_ref + li * SIG_PITCH;
-    for (int t = ln; t < n_staged; t += 32) dst[t] = (li < ninst_g) ? src[small ? t : s_col[s_cta][t]] : (unsigned char)0;
+    if (small) {
+      for (int w = ln; w < (cols + 3) / 4; w += 32)
+        reinterpret_cast<unsigned*>(dst)[w] = (li < ninst_g) ? reinterpret_cast<const unsigned*>(src)[w] : 0u;
+    } else {
+      for (int t = ln; t < n_staged; t += 32) dst[t] = (li < ninst_g) ? src[s_col[s_cta][t]] : (unsigned char)0;
+    }
   }
   __syncthreads();
   mbar_wait(&s_bar, 0);
@@ -521,7 +528,13 @@ __global__ void __launch_bounds__(256)
       const bool ok = li < ninst_g && row < N;
       const unsigned char* src = gbase + (size_t)li * bd.inst_stride + (size_t)row * cols;
       unsigned char* dst = s_sp + (kk * 32 + li) * SIG_PITCH;
-      for (int t = ln; t < n_staged; t += 32) dst[t] = ok ? src[small ? t : s_col[s_cta][t]] : (unsigned char)0;
+      if (small) {
+        const unsigned shift = (unsigned)((size_t)row * cols) & 3u;  // = src & 3: instances start 16-byte aligned
+        const unsigned* src4 = reinterpret_cast<const unsigned*>(src - shift);
+        for (int w = ln; w < (int)(shift + cols + 3) / 4; w += 32) reinterpret_cast<unsigned*>(dst)[w] = ok ? src4[w] : 0u;
+      } else {
+        for (int t = ln; t < n_staged; t += 32) dst[t] = ok ? src[s_col[s_cta][t]] : (unsigned char)0;
+      }
     }
     if (threadIdx.x < 32) {  // [strand][species of the quad][h]
       const int ss = threadIdx.x >> 4, kk = (threadIdx.x >> 2) & 3, h = threadIdx.x & 3, row = 1 + 4 * kq + kk;
@@ -572,7 +585,7 @@ __global__ void __launch_bounds__(256)
       float v4[4];
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {
-        const unsigned char* rk = s_sp + (kk * 32 + lane) * SIG_PITCH;
+        const unsigned char* rk = s_sp + (kk * 32 + lane) * SIG_PITCH + (small ? ((unsigned)((1 + 4 * kq + kk) * cols) & 3u) : 0u);
         const unsigned b1 = rk[i1], b2 = rk[i2], b3 = rk[i3];
         const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
         const unsigned e = trow[qb];
@@ -1219,6 +1232,51 @@ __device__ __forceinline__ float reg_check_inl(float sum, int j, int rstart, int
   return lb;
 }
 
+// Sample-major kernels: 64 rows of 32 different alignments share a warp, so at almost every end codon SOME row has an
+// accepted entry and a record update per entry (divergent, ~40 instructions, shared-memory read-modify-write) was half
+// of k_dp_smp's time on 40-codon frames.  The common event -- a new row maximum beyond the tie band, after which the
+// whole fold state is "one band entry (M, jF)" -- is therefore kept in registers (RowFold); the record is only
+// materialised (fold_flush) when an entry falls inside the band or below the maximum, and once at the end of the row.
+struct RowFold {
+  float M;  // row maximum (= rec->Emax)
+  int jF;   // >= 0: the state is the single entry (M, jF), last accepted value = M, and the record is stale; < 0: see the record
+};
+__device__ __forceinline__ void fold_init(RowFold& f) {
+  f.M = -INFINITY;
+  f.jF = -1;
+}
+__device__ __forceinline__ void fold_flush(RowRec* rec, float M, int jF) {
+  const unsigned short ovf = rec->n & 0x8000;
+  rec->Emax = M;
+  rec->vF = M;
+  rec->be[0] = M;
+  rec->jF = (unsigned short)jF;
+  rec->n = (unsigned short)(1 | ovf);
+  rec->bj[0] = (unsigned short)jF;
+}
+__device__ __noinline__ void fold_slow(RowRec* rec, float e, int j, int band_slots, float M, int jF) {
+  if (jF >= 0) fold_flush(rec, M, jF);
+  hss_accept_rec(rec, e, j, band_slots);
+}
+__device__ __forceinline__ void fold_entry(float sum, int j, int rstart, int sites, float fNK, float rcpNK, RowRec* rec,
+                                           int band_slots, RowFold& f) {
+  if (sum > 0.0f && j >= rstart && j < sites) {
+    const float q = sum * rcpNK;
+    const float e = __fmaf_rn(__fmaf_rn(-fNK, q, sum), rcpNK, q);
+    if (f.M - e < -0.0001f) {  // new maximum beyond the band (implies acceptance: last accepted value <= M)
+      f.M = e;
+      f.jF = j;
+    } else {
+      const float lb = f.jF >= 0 ? f.M : rec->vF;
+      if (e - lb >= -0.0001f) {
+        fold_slow(rec, e, j, band_slots, f.M, f.jF);
+        f.M = fmaxf(f.M, e);
+        f.jF = -1;
+      }
+    }
+  }
+}
+
 // The fold state of the getHSS digest lives in a per-warp shared-memory copy of the two row records while
 // the rows are being scored (positive entries are frequent at the start of a row, and a global-memory
 // read-modify-write per entry would stall the warp); the records are written to HBM once, at the end of the rows.
@@ -1663,6 +1721,9 @@ __device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv
 // instance), the k-ordered partial species sum the launch of chunk g-1 left in global memory (`partial`, float2 per
 // lane = the two rows of the pair).  The last chunk owns the getHSS digest.  Species past the end of the alignment in
 // the last quad are dummies (sigma = +0, z = 0): with omega <= 0 they add max3(0, t*omega, t*omega) = +0.
+#ifndef RC_SMP_DIAG_PAIR
+#define RC_SMP_DIAG_PAIR 0  // measured: no gain on 40-codon frames (4.54 vs 4.56 ms), 10-20 registers more
+#endif
 template <int NK, bool CHAINED>
 __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
     k_dp_smp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
@@ -1733,14 +1794,16 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
     float2 S0[NK], S1[NK], S2[NK];
 #pragma unroll
     for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
-    float2 lb = make_float2(-INFINITY, -INFINITY);
+    RowFold fx, fy;
+    fold_init(fx);
+    fold_init(fy);
     int j = r0;
 #pragma unroll 1
     while (j < sites) {
       float svA[RS];
       const unsigned zA = zs[j];
       smp_load_row<NK>(sig_a + j * ROW_BYTES, zA, svA);
-      if (j >= r0 + 2 && j + 1 < sites) {
+      if ((j >= r0 + 2 || (RC_SMP_DIAG_PAIR && j == r0)) && j + 1 < sites) {
         const unsigned zB = zs[j + 1];
         if ((zA | zB) == 0u) {
           float svB[RS];
@@ -1750,15 +1813,17 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
             sinA = pp[(size_t)j * 32];
             sinB = pp[(size_t)(j + 1) * 32];
           }
-          reg_pair_fast<NK, CHAINED>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
+          // the pair's first two end codons: row r0 starts at j, row r0+1 at j+1 (masked straight-line block, see reg_pair_diag)
+          if (RC_SMP_DIAG_PAIR && j == r0) reg_pair_diag<NK, CHAINED>(S0, S1, S2, svA, svB, omega, true, false, sumA, sumB, sinA, sinB);
+          else reg_pair_fast<NK, CHAINED>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
           if (CHAINED && !last) {
             pp[(size_t)j * 32] = sumA;
             pp[(size_t)(j + 1) * 32] = sumB;
           } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
-            lb.x = reg_check_inl(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-            lb.y = reg_check_inl(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
-            lb.x = reg_check_inl(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-            lb.y = reg_check_inl(sumB.y, j + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+            fold_entry(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
+            fold_entry(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
+            fold_entry(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
+            fold_entry(sumB.y, j + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
           }
           j += 2;
           continue;
@@ -1770,15 +1835,19 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
       if (CHAINED && !last) {
         pp[(size_t)j * 32] = sum;
       } else if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
-        lb.x = reg_check_inl(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-        if (r0 + 1 < sites) lb.y = reg_check_inl(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+        fold_entry(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
+        if (r0 + 1 < sites) fold_entry(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
       }
       j += 1;
     }
     if (valid && last) {
 #pragma unroll
       for (int t = 0; t < 2; t++)
-        if (r0 + t < sites) rec_copy(rec_inst + r0 + t, rec0 + t);
+        if (r0 + t < sites) {
+          const RowFold& f = t ? fy : fx;
+          if (f.jF >= 0) fold_flush(rec0 + t, f.M, f.jF);
+          rec_copy(rec_inst + r0 + t, rec0 + t);
+        }
     }
   }
 }
@@ -1868,7 +1937,9 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
     float2 S0[NK], S1[NK], S2[NK];
 #pragma unroll
     for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
-    float2 lb = make_float2(-INFINITY, -INFINITY);
+    RowFold fx, fy;
+    fold_init(fx);
+    fold_init(fy);
     int j = r0;
 #pragma unroll 1
     for (int seg = seg0; seg < nseg; seg++, it_count++) {
@@ -1897,10 +1968,10 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
                 pp[(size_t)j * 32] = sumA;
                 pp[(size_t)(j + 1) * 32] = sumB;
               } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
-                lb.x = reg_check_inl(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-                lb.y = reg_check_inl(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
-                lb.x = reg_check_inl(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-                lb.y = reg_check_inl(sumB.y, j + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+                fold_entry(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
+                fold_entry(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
+                fold_entry(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
+                fold_entry(sumB.y, j + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
               }
               j += 2;
               continue;
@@ -1912,8 +1983,8 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
           if (CHAINED && !last) {
             pp[(size_t)j * 32] = sum;
           } else if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
-            lb.x = reg_check_inl(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
-            if (r0 + 1 < sites) lb.y = reg_check_inl(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+            fold_entry(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
+            if (r0 + 1 < sites) fold_entry(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
           }
           j += 1;
         }
@@ -1928,7 +1999,11 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
     if (active && valid && last) {
 #pragma unroll
       for (int t = 0; t < 2; t++)
-        if (r0 + t < sites) rec_copy(rec_inst + r0 + t, rec0 + t);
+        if (r0 + t < sites) {
+          const RowFold& f = t ? fy : fx;
+          if (f.jF >= 0) fold_flush(rec0 + t, f.M, f.jF);
+          rec_copy(rec_inst + r0 + t, rec0 + t);
+        }
     }
   }
 }
