@@ -468,6 +468,8 @@ __global__ void __launch_bounds__(256)
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_col[2][SIG_PITCH];
   __shared__ float s_sc[2][4][4];  // expected scores of the quad's species: [strand][species][h], h = 0 -> 0
+  __shared__ long long s_base[2][3];  // float offset of the quad's output per (strand, frame): indexing Item / BlockDev arrays
+                                      // by a run-time frame inside the loop would put them into local memory
   __shared__ __align__(16) unsigned char s_ref[32 * SIG_PITCH];
   extern __shared__ __align__(16) unsigned char s_sp[];  // [4 * 32 * SIG_PITCH] (dynamic: static shared memory ends at 48 KB)
   const Item it = items[blockIdx.x];
@@ -536,11 +538,6 @@ __global__ void __launch_bounds__(256)
         for (int t = ln; t < n_staged; t += 32) dst[t] = ok ? src[s_col[s_cta][t]] : (unsigned char)0;
       }
     }
-    if (threadIdx.x < 32) {  // [strand][species of the quad][h]
-      const int ss = threadIdx.x >> 4, kk = (threadIdx.x >> 2) & 3, h = threadIdx.x & 3, row = 1 + 4 * kq + kk;
-      s_sc[ss][kk][h] = (h > 0 && row < N) ? scores[bd.scores_off + ((size_t)ss * N + row) * 4 + h] : 0.0f;
-    }
-    __syncthreads();
     // output address of quad kq: layout 2 is [group][step][quad][lane][4]; layout 5 is [chunk][group][step][3 quads][lane][4]
     // with quad kq = quad qq of chunk ch
     size_t rowmul, step_stride, qoff;  // out = base + rowmul * sites[f] + j * step_stride + qoff + lane * 4
@@ -557,19 +554,27 @@ __global__ void __launch_bounds__(256)
       step_stride = (size_t)(rsb / 4) * 128;
       qoff = (size_t)kq * 128;
     }
-    const int n_out = (small ? 2 : 1) * xi_n * 32;
-    for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
-      const int lane = e & 31;
+    if (threadIdx.x < 32) {  // [strand][species of the quad][h]
+      const int ss = threadIdx.x >> 4, kk = (threadIdx.x >> 2) & 3, h = threadIdx.x & 3, row = 1 + 4 * kq + kk;
+      s_sc[ss][kk][h] = (h > 0 && row < N) ? scores[bd.scores_off + ((size_t)ss * N + row) * 4 + h] : 0.0f;
+    } else if (threadIdx.x < 38) {
+      const int ss = (threadIdx.x - 32) / 3, f = (threadIdx.x - 32) % 3;
+      s_base[ss][f] = (long long)(it.sigma_off[ss][f] + rowmul * bd.sites[f] + qoff);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;  // = e & 31 below: the CTA has whole warps
+    const int n_units = (small ? 2 : 1) * xi_n;
+    for (int u = threadIdx.x >> 5; u < n_units; u += blockDim.x >> 5) {
       int s, tl, i1, i2, i3;  // strand, position inside the CTA's range, staged columns of the codon
       if (small) {
-        s = (e >> 5) & 1;
-        tl = e >> 6;
+        s = u & 1;
+        tl = u >> 1;
         i1 = s_col[s][tl];
         i2 = s_col[s][tl + 1];
         i3 = s_col[s][tl + 2];
       } else {
         s = s_cta;
-        tl = e >> 5;
+        tl = u;
         i1 = tl;
         i2 = tl + 1;
         i3 = tl + 2;
@@ -593,8 +598,8 @@ __global__ void __launch_bounds__(256)
         const unsigned zero = nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X);  // src/score.c:394-404
         v4[kk] = (zero || 4 * kq + kk >= NK) ? 0.0f : v;
       }
-      const int f = xi % 3, j = xi / 3;
-      float* out = sigma + it.sigma_off[s][f] + rowmul * bd.sites[f] + (size_t)j * step_stride + qoff + lane * 4;
+      const int j = xi / 3, f = xi - 3 * j;
+      float* out = sigma + s_base[s][f] + (size_t)j * step_stride + lane * 4;
       *reinterpret_cast<float4*>(out) = make_float4(v4[0], v4[1], v4[2], v4[3]);
     }
     __syncthreads();
