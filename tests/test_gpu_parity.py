@@ -295,3 +295,40 @@ def test_pair_rows_rejects_bad_start(rc_ctx, oracle):
     for b in (0, 31, -2):
         with pytest.raises(RuntimeError):
             rc_ctx.pair_rows(blk, capi.make_params(), oracle.blosum62, 0, [b])
+
+
+def test_full_size_kernel_routes_agree(oracle):
+    """BASELINE config 2 at full size (the 11 block shapes of examples/genomic.maf incl. 10 x 4806, -n 1000; the oracle would
+    need hours): every block is scored by three different kernel routes -- the default (k_dp_reg for long frames, k_dp_smp /
+    k_dp_smps for short and mid ones), everything row-major (no_smp), and everything streamed sample-major (k_dp_smps) --
+    whose sigma layouts, task shapes and getHSS folds differ, with the null alignments drawn on the GPU from the same
+    seeds.  All native HSS and all 11 x 1000 sample maxima must agree bit for bit."""
+    import bench
+    from rnacode_b200 import synth
+    capi = _capi()
+    blocks_np, n, seed, _ = bench.build_workload("genomic", 0)
+    assert n == 1000 and max(r.shape[1] for r, _, _, _ in blocks_np) == 4806
+    blocks = [capi.Block(rows, sf, sr, None, n_samples=n) for rows, sf, sr, _ in blocks_np]
+    trees = [capi.Tree(*synth.synth_tree(seed, idx, rows.shape[0])) for rows, _, _, idx in blocks_np]
+    seeds = [np.arange(1, n + 1, dtype=np.uint32) + 104729 * i for i in range(len(blocks))]
+    results = []
+    for opts in ({}, {"no_smp": 1}, {"smps_max_sites": 100000, "scratch_mb": 4096}):
+        ctx = capi.Context(0)
+        try:
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            bt = ctx.batch(blocks, capi.make_params(), oracle.blosum62)
+            for i in range(len(blocks)):
+                bt.set_evolve(i, trees[i], seeds[i], capi.RC_RNG_MT19937)
+            bt.upload(); bt.run(); bt.download()
+            results.append(([bt.native_hss(i) for i in range(len(blocks))],
+                            [bt.max_scores(i).copy() for i in range(len(blocks))], bt.stats()["dense_fallbacks"]))
+            bt.close()
+        finally:
+            ctx.close()
+    ref_hss, ref_max, _ = results[0]
+    assert sum(len(h) for h in ref_hss) > 0 and all((m >= -1.0).all() for m in ref_max)
+    for hss, mx, _ in results[1:]:
+        assert hss == ref_hss
+        for a, b in zip(mx, ref_max):
+            assert np.array_equal(a, b)
