@@ -52,6 +52,7 @@ struct Params {
 struct BlockDev {
   int N, cols, L, NK;       // NK = N-1 scored species
   int n_inst;               // 1 (native) + n_samples
+  int hss_warp;             // getHSS scan: 1 = one warp per (instance, strand, frame) (k_hss), 0 = one thread (k_hss_thr)
   int inst_stride;          // bytes between consecutive instances in raw/cls (N*cols rounded up to 16)
   int zstride;              // u32 words per z tile: layout 0: NK rounded up to 4 (one word per species);
                             // layout 1: TILE (one word per step, 2 bits per species); layout 3: nchunk*TILE

@@ -2021,6 +2021,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
 // ---------------------------------------------------------------------------------------------
 constexpr int HSS_WARPS = 4;
 constexpr int HSS_WARP_MIN_SITES = 96;  // shorter frames: one thread per (instance, strand, frame) is the better fit (k_hss_thr)
+constexpr int HSS_THR_MAX_SITES = 640;  // ... and frames up to this length when the block has thousands of scans (see hss_thr_tasks)
 
 __global__ void __launch_bounds__(HSS_WARPS * 32)
     k_hss(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const RowRec* __restrict__ recs,
@@ -2029,7 +2030,7 @@ __global__ void __launch_bounds__(HSS_WARPS * 32)
   const BlockDev& bd = blocks[it.block];
   const int lane = threadIdx.x & 31;
   const int idx = blockIdx.y * HSS_WARPS + (threadIdx.x >> 5);
-  if (idx >= it.ninst * 6 || bd.sites[0] < HSS_WARP_MIN_SITES) return;
+  if (idx >= it.ninst * 6 || !bd.hss_warp) return;
   const int inst_l = idx / 6, sf = idx % 6;
   const int strand = sf / 3, frame = sf % 3;
   const int sites = bd.sites[frame];
@@ -2128,7 +2129,7 @@ __global__ void __launch_bounds__(128)
   const Item it = items[blockIdx.x];
   const BlockDev& bd = blocks[it.block];
   const int idx = blockIdx.y * blockDim.x + threadIdx.x;
-  if (idx >= it.ninst * 6 || bd.sites[0] >= HSS_WARP_MIN_SITES) return;
+  if (idx >= it.ninst * 6 || bd.hss_warp) return;
   const int inst_l = idx / 6, sf = idx % 6;
   const int strand = sf / 3, frame = sf % 3;
   const int sites = bd.sites[frame];

@@ -39,6 +39,8 @@ struct rc_ctx {
   long scratch_mb = 2048;
   long no_smp = 0;
   long no_chain = 0;
+  long hss_thr_tasks = 3000;  // blocks with at least this many (instance, strand, frame) scans use one thread per scan for frames of up to
+                              // HSS_THR_MAX_SITES codons (0: never).  10x500 n=1000: 0.89 -> 0.39 ms; 10x1200: 0.54 -> 0.37; 10x4806: 0.45 -> 1.24 (kept on warps)
   long reg_max_nk = 12;  // row-major alignments with more scored species take k_dp_chain (k_dp_reg<13..16> spills: 17x3000 14.7 vs 11.1 ms)
   long no_smps = 0;          // never stream the sigma table in segments (k_dp_smps)
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
@@ -358,6 +360,7 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   if (const char* e = getenv("RNACODE_CUDA_NO_SMPS")) ctx->no_smps = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_SMPC_MAX_SITES")) ctx->smpc_max_sites = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_SMPS_MAX_SITES")) ctx->smps_max_sites = atol(e);
+  if (const char* e = getenv("RNACODE_CUDA_HSS_THR_TASKS")) ctx->hss_thr_tasks = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_REG_MAX_NK")) ctx->reg_max_nk = std::max(12L, std::min<long>(REG_MAX_NK, atol(e)));
   unsigned char lut[256];
   build_lut(lut);
@@ -414,6 +417,8 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->no_chain = value ? 1 : 0;
   } else if (k == "no_smps") {
     ctx->no_smps = value ? 1 : 0;
+  } else if (k == "hss_thr_tasks") {
+    ctx->hss_thr_tasks = value;
   } else if (k == "reg_max_nk") {
     if (value < 12 || value > REG_MAX_NK) { ctx_fail(ctx, "reg_max_nk must be 12..16"); return RC_ERR_ARG; }
     ctx->reg_max_nk = value;
@@ -586,6 +591,10 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       P += (double)bd.sites[f] * (bd.sites[f] + 1) / 2;
     }
     cells += (double)bd.n_inst * 2.0 * bd.NK * P;
+    // getHSS scan: long frames get a warp each (coalesced record fetch, skip by ballot) unless the block has so many scans
+    // that one thread each already fills the GPU
+    bd.hss_warp = bd.sites[0] >= HSS_WARP_MIN_SITES &&
+                  !(ctx->hss_thr_tasks > 0 && (long)bd.n_inst * 6 >= ctx->hss_thr_tasks && bd.sites[0] <= HSS_THR_MAX_SITES);
     {
       // Which DP kernel.  Delta > 0 needs the general max(sum, Delta) (k_dp); the chunked kernels may carry
       // a dummy species, which is only neutral for omega <= 0.
@@ -709,7 +718,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       cur.maxZs[cl] = std::max(cur.maxZs[cl], bd.zstride);
       cur.max_sigma_work = std::max(cur.max_sigma_work, (long long)take * 2 * (bd.L - 2));
       cur.max_ninst = std::max(cur.max_ninst, take);
-      if (bd.sites[0] >= HSS_WARP_MIN_SITES) cur.hss_warp_items++;
+      if (bd.hss_warp) cur.hss_warp_items++;
       cur.n_layout[bd.layout]++;
       b->items.push_back(it);
       cur.nitems++;
