@@ -493,28 +493,43 @@ __global__ void __launch_bounds__(256)
     mbar_expect_tx(&s_bar, (unsigned)sizeof(PairTables));
     bulk_g2s(&s_tab, tables, (unsigned)sizeof(PairTables), &s_bar);
   }
-  // s_col[s][t]: alignment column of reference position xi_lo + 1 + t on strand s (positions x-2 .. x of xi are xi+1 .. xi+3)
+  // Window of alignment columns that holds the CTA's positions.  If it fits the staging buffer (always for short blocks;
+  // for a position chunk of a longer block unless the reference row has > ~250 gap columns inside it) the rows' bytes
+  // wlo..whi are staged as they are, with aligned 32-bit copies, and a codon is read at its three columns; otherwise the
+  // columns are gathered byte by byte into a compacted row (codon = three consecutive staged bytes).
+  int wlo = 0, whi = cols - 1;
+  if (!small) {
+    const int ca = cols0[bd.cols0_off + (size_t)s_cta * (L + 1) + xi_lo + 1];
+    const int cb = cols0[bd.cols0_off + (size_t)s_cta * (L + 1) + xi_lo + xi_n + 2];
+    wlo = min(ca, cb);
+    whi = max(ca, cb);
+  }
+  const int wn = whi - wlo + 1;
+  const bool windowed = wn <= SIG_PITCH - 4;  // room for the word-copy shift
+  // s_col[s][t]: (windowed: window-relative) alignment column of reference position xi_lo + 1 + t on strand s
+  // (positions x-2 .. x of xi are xi+1 .. xi+3)
   for (int t = threadIdx.x; t < xi_n + 2; t += blockDim.x) {
     if (small) {
       s_col[0][t] = cols0[bd.cols0_off + 1 + t];
       s_col[1][t] = cols0[bd.cols0_off + (L + 1) + 1 + t];
     } else {
-      s_col[s_cta][t] = cols0[bd.cols0_off + (size_t)s_cta * (L + 1) + xi_lo + 1 + t];
+      s_col[s_cta][t] = cols0[bd.cols0_off + (size_t)s_cta * (L + 1) + xi_lo + 1 + t] - (windowed ? wlo : 0);
     }
   }
   __syncthreads();
   const int ninst_g = min(32, it.ninst - group * 32);
   const unsigned char* gbase = cls + bd.cls_off + (size_t)(it.inst0 + group * 32) * bd.inst_stride;
   const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  // reference rows of the 32 instances: one warp per row, lanes along the staged columns
-  // (short blocks: the row is copied as aligned 32-bit words; rows start 16-byte aligned here, species rows -- below -- at
-  // any byte, so a staged row is shifted by its source's misalignment and column t sits at dst[shift + t])
+  // reference rows of the 32 instances: one warp per row, lanes along the staged columns.  Windowed: instances start
+  // 16-byte aligned, rows and windows at any byte, so a staged row is shifted by its source's misalignment and window
+  // column t sits at dst[shift + t].
+  const unsigned shift_ref = (unsigned)wlo & 3u;
   for (int li = wid; li < 32; li += nwarps) {
     const unsigned char* src = gbase + (size_t)li * bd.inst_stride;
     unsigned char* dst = s_ref + li * SIG_PITCH;
-    if (small) {
-      for (int w = ln; w < (cols + 3) / 4; w += 32)
-        reinterpret_cast<unsigned*>(dst)[w] = (li < ninst_g) ? reinterpret_cast<const unsigned*>(src)[w] : 0u;
+    if (windowed) {
+      const unsigned* src4 = reinterpret_cast<const unsigned*>(src + wlo - shift_ref);
+      for (int w = ln; w < (int)(shift_ref + wn + 3) / 4; w += 32) reinterpret_cast<unsigned*>(dst)[w] = (li < ninst_g) ? src4[w] : 0u;
     } else {
       for (int t = ln; t < n_staged; t += 32) dst[t] = (li < ninst_g) ? src[s_col[s_cta][t]] : (unsigned char)0;
     }
@@ -530,10 +545,10 @@ __global__ void __launch_bounds__(256)
       const bool ok = li < ninst_g && row < N;
       const unsigned char* src = gbase + (size_t)li * bd.inst_stride + (size_t)row * cols;
       unsigned char* dst = s_sp + (kk * 32 + li) * SIG_PITCH;
-      if (small) {
-        const unsigned shift = (unsigned)((size_t)row * cols) & 3u;  // = src & 3: instances start 16-byte aligned
-        const unsigned* src4 = reinterpret_cast<const unsigned*>(src - shift);
-        for (int w = ln; w < (int)(shift + cols + 3) / 4; w += 32) reinterpret_cast<unsigned*>(dst)[w] = ok ? src4[w] : 0u;
+      if (windowed) {
+        const unsigned shift = (unsigned)((size_t)row * cols + wlo) & 3u;  // = (src + wlo) & 3
+        const unsigned* src4 = reinterpret_cast<const unsigned*>(src + wlo - shift);
+        for (int w = ln; w < (int)(shift + wn + 3) / 4; w += 32) reinterpret_cast<unsigned*>(dst)[w] = ok ? src4[w] : 0u;
       } else {
         for (int t = ln; t < n_staged; t += 32) dst[t] = ok ? src[s_col[s_cta][t]] : (unsigned char)0;
       }
@@ -569,12 +584,15 @@ __global__ void __launch_bounds__(256)
       if (small) {
         s = u & 1;
         tl = u >> 1;
+      } else {
+        s = s_cta;
+        tl = u;
+      }
+      if (windowed) {
         i1 = s_col[s][tl];
         i2 = s_col[s][tl + 1];
         i3 = s_col[s][tl + 2];
       } else {
-        s = s_cta;
-        tl = u;
         i1 = tl;
         i2 = tl + 1;
         i3 = tl + 2;
@@ -582,7 +600,7 @@ __global__ void __launch_bounds__(256)
       const int xi = xi_lo + tl;
       const int sh = s ? 2 : 0;
       const float* sc = &s_sc[s][0][0];
-      const unsigned char* rr = s_ref + lane * SIG_PITCH;
+      const unsigned char* rr = s_ref + lane * SIG_PITCH + (windowed ? shift_ref : 0u);
       const unsigned a1 = rr[i1], a2 = rr[i2], a3 = rr[i3];
       const unsigned qa = (((a1 >> sh) & 3u) << 4) | (((a2 >> sh) & 3u) << 2) | ((a3 >> sh) & 3u);
       const unsigned nA = (a1 | a2 | a3) & CLS_N;
@@ -590,7 +608,7 @@ __global__ void __launch_bounds__(256)
       float v4[4];
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {
-        const unsigned char* rk = s_sp + (kk * 32 + lane) * SIG_PITCH + (small ? ((unsigned)((1 + 4 * kq + kk) * cols) & 3u) : 0u);
+        const unsigned char* rk = s_sp + (kk * 32 + lane) * SIG_PITCH + (windowed ? ((unsigned)((size_t)(1 + 4 * kq + kk) * cols + wlo) & 3u) : 0u);
         const unsigned b1 = rk[i1], b2 = rk[i2], b3 = rk[i3];
         const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
         const unsigned e = trow[qb];
