@@ -52,6 +52,10 @@ WORKLOADS = {
     "n14": ([(14, 3000)] * 2, 500, 13, "synthetic MAF 2 blocks x 14 species x 3000 cols, -n 500"),
     "n17s": ([(17, 150)] * 500, 100, 14, "synthetic MAF 500 blocks x 17 species x 150 cols, -n 100"),
     "mid_wide": ([(50, 800)] * 4, 250, 8, "synthetic MAF 4 blocks x 50 species x 800 cols, -n 250"),
+    # the default workload with the frameshift density of the real examples/genomic.maf (3 % of the codon pairs of its
+    # 10 x 4806 block carry a frameshift of some species; SURVEY 8(d)'s generator gives 36 %) and without any gap
+    "genomic_lowgap": (GENOMIC_SHAPES, 1000, 2, "genomic.maf block shapes, gap rate 0.0005 (frameshift density of the real file), -n 1000", 0.0005),
+    "genomic_gapfree": (GENOMIC_SHAPES, 1000, 2, "genomic.maf block shapes, gap-free (the 6-op cell of SURVEY 8(d)), -n 1000", 0.0),
 }
 METRIC = "codon_dp_cells_per_s"
 UNIT = "cells/s"
@@ -66,11 +70,12 @@ def dist_env():
 
 
 def build_workload(name, rank):
-    shapes, n, seed, desc = WORKLOADS[name]
+    shapes, n, seed, desc = WORKLOADS[name][:4]
+    gap_rate = WORKLOADS[name][4] if len(WORKLOADS[name]) > 4 else 0.0067
     blocks = []
     for i, (N, cols) in enumerate(shapes):
         idx = rank * 100000 + i
-        rows = synth.synth_block(seed, idx, N, cols)
+        rows = synth.synth_block(seed, idx, N, cols, gap_rate=gap_rate)
         sf, sr = synth.synth_scores(seed, idx, N)
         blocks.append((rows, sf, sr, idx))
     return blocks, n, seed, desc
