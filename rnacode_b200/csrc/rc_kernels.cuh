@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(256)
 // each thread produces the four sigma values of one (position, instance) and stores them as one float4, so a warp
 // writes 512 contiguous bytes of the [step][species quad][lane][4] table.
 // ---------------------------------------------------------------------------------------------
-constexpr int SIG_PCH = 252;              // reference positions per CTA (staged columns: SIG_PCH + 2)
+constexpr int SIG_PCH = 216;              // reference positions per CTA; the window of raw columns (SIG_PCH + 2 + reference gaps) should fit SIG_PITCH - 4
 constexpr int SIG_PITCH = 260;            // bytes per staged row: 65 words, odd => 32 lanes hit 32 banks
 
 __global__ void __launch_bounds__(256)

@@ -111,6 +111,9 @@ SHAPES = [
     (300, 45, 15, 0.02),
     # the same with frames too long for a resident sigma table: streamed in segments (k_dp_smps), plain and chunked
     (10, 600, 16, 0.02), (8, 1000, 15, 0.0067), (5, 1201, 31, 0.01), (26, 520, 15, 0.03), (18, 700, 17, 0.02), (50, 450, 16, 0.02),
+    # reference rows so gappy that a chunk of 216 positions spans more than 256 columns: k_sigma_smp gathers bytes instead of
+    # staging a window of raw columns
+    (6, 700, 17, 0.08), (10, 900, 16, 0.12),
     # 13-16 scored species: row-major blocks take k_dp_chain with two warps of 6-8 species (k_dp_reg<13..16> spills),
     # blocks with >= 16 instances stay on the one-launch sample-major kernels
     (14, 700, 3, 0.02), (15, 2000, 1, 0.01), (16, 450, 2, 0.03), (17, 600, 2, 0.02), (17, 1500, 20, 0.01),
