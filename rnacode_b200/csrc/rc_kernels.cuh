@@ -369,9 +369,10 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     k_sigma_rows(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned char* __restrict__ cls,
-                 const int* __restrict__ cols0, const float* __restrict__ scores, const SigmaTables* __restrict__ tables,
+                 const int* __restrict__ cols0, const float* __restrict__ scores, const PairTables* __restrict__ tables,
                  const unsigned* __restrict__ ztiles, float* __restrict__ sigma, Params prm) {
-  __shared__ SigmaTables s_tab;
+  __shared__ PairTables s_tab;
+  __shared__ float s_sc[2 * (REG_MAX_NK + 1) * 4];  // expected scores [strand][row][h], h = 0 -> 0 (see PairTables)
   __shared__ __align__(8) uint64_t s_bar;
   const Item it = items[blockIdx.x];
   const BlockDev bd = blocks[it.block];
@@ -379,9 +380,10 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
     mbar_fence_init();
-    mbar_expect_tx(&s_bar, (unsigned)sizeof(SigmaTables));
-    bulk_g2s(&s_tab, tables, (unsigned)sizeof(SigmaTables), &s_bar);
+    mbar_expect_tx(&s_bar, (unsigned)sizeof(PairTables));
+    bulk_g2s(&s_tab, tables, (unsigned)sizeof(PairTables), &s_bar);
   }
+  for (int t = threadIdx.x; t < 2 * bd.N * 4; t += blockDim.x) s_sc[t] = (t & 3) ? scores[bd.scores_off + t] : 0.0f;
   __syncthreads();
   mbar_wait(&s_bar, 0);
   const int L = bd.L, N = bd.N, NK = bd.NK, cols = bd.cols;
@@ -412,33 +414,32 @@ __global__ void __launch_bounds__(256)
     const int sh = s ? 2 : 0;
     const unsigned qa = (((a1 >> sh) & 3u) << 4) | (((a2 >> sh) & 3u) << 2) | ((a3 >> sh) & 3u);
     const unsigned nA = (a1 | a2 | a3) & CLS_N;
-    const int pepA = s_tab.transcode[qa];
-    const float* sc = scores + bd.scores_off + (size_t)s * N * 4;
+    const unsigned short* trow = s_tab.t + (qa << 6);
+    const float* sc = s_sc + s * N * 4;
     const unsigned zword = ztiles[bd.z_off[s][f] + j];  // zstride == TILE: one word per step
     for (int q = 0; q < rs / 4; q++) {
+      // the twelve bytes of the quad's codons first (independent loads in flight), then the arithmetic
+      unsigned bb[4][3];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int k = 4 * q + t;
+        const unsigned char* rowk = base + (size_t)(k < NK ? k + 1 : 0) * cols;
+        bb[t][0] = rowk[c1];
+        bb[t][1] = rowk[c2];
+        bb[t][2] = rowk[c3];
+      }
       float v4[4];
 #pragma unroll
       for (int t = 0; t < 4; t++) {
         const int k = 4 * q + t;
-        float v = 0.0f;
-        if (k < NK) {
-          const unsigned char* rowk = base + (size_t)(k + 1) * cols;
-          const unsigned b1 = rowk[c1], b2 = rowk[c2], b3 = rowk[c3];
-          const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
-          // src/score.c:394-425, see k_sigma; entries with a frameshift are never read by the recurrence: +0
-          if (!(nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X)) && qa != qb && !((zword >> (2 * k)) & 1u)) {
-            const int pepB = s_tab.transcode[qb];
-            if (pepA < 0) v = prm.stop0;
-            else if (pepB < 0) v = prm.stopk;
-            else {
-              const unsigned d = qa ^ qb;
-              const int h = ((d & 0x30u) != 0) + ((d & 0x0cu) != 0) + ((d & 0x03u) != 0);
-              v = s_tab.blosum[pepA * 24 + pepB] - sc[(k + 1) * 4 + h];
-            }
-          }
-        } else if (k == NK) {
-          v = __uint_as_float(zword);
-        }
+        const unsigned b1 = bb[t][0], b2 = bb[t][1], b3 = bb[t][2];
+        const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
+        const unsigned e = trow[qb];
+        // src/score.c:394-425 through PairTables, see k_sigma_smp; entries with a frameshift are never read by the recurrence: +0
+        float v = s_tab.val[e & 0x3ffu] - sc[(k < NK ? k + 1 : 0) * 4 + (e >> 10)];
+        const unsigned zero = nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X) | ((zword >> (2 * (k & 15))) & 1u);
+        if (zero || k > NK) v = 0.0f;
+        if (k == NK) v = __uint_as_float(zword);
         v4[t] = v;
       }
       out[q] = make_float4(v4[0], v4[1], v4[2], v4[3]);

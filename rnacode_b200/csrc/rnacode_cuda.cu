@@ -1350,7 +1350,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
         b->stats.launches++;
       }
       if (ch.n_layout[1] > 0) {
-        k_sigma_rows<<<g, 256, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores, b->d_tables,
+        k_sigma_rows<<<g, 256, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores, b->d_ptab,
                                         b->d_z, b->d_sigma, b->prm);
         RC_CUDA(cudaGetLastError());
         b->stats.launches++;
