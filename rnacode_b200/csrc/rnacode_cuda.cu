@@ -39,6 +39,7 @@ struct rc_ctx {
   long scratch_mb = 2048;
   long no_smp = 0;
   long no_chain = 0;
+  long smp_warps_forced = 0;
   long hss_thr_tasks = 3000;  // blocks with at least this many (instance, strand, frame) scans use one thread per scan for frames of up to
                               // HSS_THR_MAX_SITES codons (0: never).  10x500 n=1000: 0.89 -> 0.39 ms; 10x1200: 0.54 -> 0.37; 10x4806: 0.45 -> 1.24 (kept on warps)
   long reg_max_nk = 12;  // row-major alignments with more scored species take k_dp_chain (k_dp_reg<13..16> spills: 17x3000 14.7 vs 11.1 ms)
@@ -360,6 +361,7 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   if (const char* e = getenv("RNACODE_CUDA_NO_SMPS")) ctx->no_smps = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_SMPC_MAX_SITES")) ctx->smpc_max_sites = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_SMPS_MAX_SITES")) ctx->smps_max_sites = atol(e);
+  if (const char* e = getenv("RNACODE_CUDA_SMP_WARPS")) ctx->smp_warps_forced = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_HSS_THR_TASKS")) ctx->hss_thr_tasks = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_REG_MAX_NK")) ctx->reg_max_nk = std::max(12L, std::min<long>(REG_MAX_NK, atol(e)));
   unsigned char lut[256];
@@ -1026,6 +1028,7 @@ static int launch_dp_reg(rc_batch* b, int NK, const CtaDesc* d_ctas, size_t ncta
 // Warps per CTA of k_dp_smp: the CTA's sigma table decides how many CTAs fit an SM; with few of them, more warps
 // share each table (the launch that owns the getHSS digest also needs 2 KB of fold state per warp).
 static int smp_warps(rc_ctx* ctx, size_t smem_table, bool with_fold) {
+  if (ctx->smp_warps_forced >= 1 && ctx->smp_warps_forced <= SMP_MAX_WARPS) return (int)ctx->smp_warps_forced;  // experiments
   int best = SMP_WARPS, best_warps = 0;
   for (int nw = SMP_WARPS; nw <= SMP_MAX_WARPS; nw += 2) {
     const size_t per_cta = smem_table + (with_fold ? (size_t)nw * 64 * sizeof(RowRec) : 0) + 1024;
