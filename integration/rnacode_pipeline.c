@@ -53,6 +53,7 @@
 #include "rnacode_cuda.h"
 
 #include "rnacode_cuda_host.h"
+#include "rnacode_maf_mmap.h"
 
 extern long int hitCounter;
 void freeModels(bgModel *models, int N);
@@ -508,6 +509,8 @@ int main(int argc, char *argv[]) {
   struct aln *inputAln[MAX_NUM_NAMES];
   blk_t *blk;
   const char *e;
+  rc_maf_map map = {NULL, NULL, NULL, 0};
+  int mapped = 0;
 
   /* the reference's defaults, src/RNAcode.c:68-90 */
   pars.Delta = -10.0;
@@ -563,7 +566,11 @@ int main(int argc, char *argv[]) {
   blk = (blk_t *)calloc(win_blocks, sizeof(blk_t));
   startTime = clock();
 
-  while (readFunction(pars.inputFile, inputAln) != 0) {
+  /* (f3) MAF files are parsed in place from a mapping of the file (rnacode_maf_mmap.h); pipes, Clustal input and
+   * RNACODE_CUDA_PARSER=reference keep the reference's read functions */
+  if (readFunction == &read_maf && !((e = getenv("RNACODE_CUDA_PARSER")) && strcmp(e, "reference") == 0))
+    mapped = rc_maf_map_open(pars.inputFile, &map);
+  while ((mapped ? rc_read_maf_mapped(&map, inputAln) : readFunction(pars.inputFile, inputAln)) != 0) {
     alnCounter++;
     for (i = 0; inputAln[i] != NULL; i++)
       for (j = 0; inputAln[i]->seq[j]; j++) inputAln[i]->seq[j] = toupper(inputAln[i]->seq[j]);

@@ -1,0 +1,47 @@
+"""(f3) The memory-mapped MAF reader of the batched driver (integration/rnacode_maf_mmap.h) against the reference's
+read_maf (src/rnaz_utils.c:132-234): oracle/_ref/maf_parse_check parses a file with both and compares every block field by
+field (names, upper-cased sequences, start, length, source length, strand)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+CHECK = os.path.join(REFDIR, "maf_parse_check")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(CHECK), reason="oracle/_ref/maf_parse_check not built (needs /root/reference)")
+
+
+def _check(path):
+    res = subprocess.run([CHECK, path], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    tag, blocks, rows = res.stdout.split()
+    assert tag == "OK"
+    return int(blocks), int(rows)
+
+
+@pytest.mark.parametrize("name,blocks", [("coding.maf", 1), ("noncoding.maf", 1), ("genomic.maf", 11),
+                                         ("genomic-preprocessed.maf", 34)])
+def test_examples(name, blocks):
+    assert _check(os.path.join(REFDIR, "examples", name))[0] == blocks
+
+
+def test_synthetic_mixed(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    from rnacode_b200 import synth
+    p = os.path.join(str(tmp_path), "mixed.maf")
+    synth.to_maf(make_golden.mixed_blocks(), p)
+    assert _check(p)[0] == 36
+
+
+def test_irregular_lines(tmp_path):
+    """Comments, blank lines, i / e / q lines, unknown lines, tabs, CR LF, lower case, no newline at the end."""
+    p = os.path.join(str(tmp_path), "nasty.maf")
+    with open(p, "w") as fh:
+        fh.write("##maf version=1\n# c\n\na score=1\ns a.chr1\t10 6 + 100 acgt-NN\r\ns b.chr2 0 7 - 50 ACGTTnn\n"
+                 "i b.chr2 N 0 C 0\n\nq b.chr2 99999\n#x\na score=2\ns a 1 3 + 9 ACG\ns b 2 3 + 9 acg\ne c 0 0 + 0 I\n"
+                 "z junk line\ns c 3 3 - 9 A-G")
+    assert _check(p) == (2, 5)
