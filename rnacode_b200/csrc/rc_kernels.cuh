@@ -2077,16 +2077,25 @@ __global__ void __launch_bounds__(HSS_WARPS * 32)
       n1 = rp[2 * (i0 + 32 + lane) + 1];
     }
     // RowRec: w0 = {Emax, vF, be0, be1}, w1 = {be2, jF | n << 16, bj0 | bj1 << 16, bj2 | pad << 16}
-    unsigned mask = __ballot_sync(FULL, (w1.y >> 16) != 0u);
-    while (mask) {
+    // Rows that cannot change the scan's state are skipped 32 at a time: a row matters only if it has entries and either
+    // lies beyond the current segment (flush, :897-949) or its maximum reaches cur - 1e-4 (a larger score or a tie, :953-959;
+    // band entries never exceed the row maximum).  The state only changes at processed rows, so the test with the current
+    // (cur, segE) is the test each skipped row would have seen.
+    const bool has = (w1.y >> 16) != 0u;
+    if (__any_sync(FULL, has && ((w1.y >> 16) & 0x8000u))) overflow = true;
+    const float myE = __uint_as_float(w0.x);
+    unsigned pend = __ballot_sync(FULL, has);
+    while (pend) {
+      const bool cand = has && ((cur > 0.0f && segE < i0 + lane) || !(myE - cur < -0.0001f));
+      const unsigned mask = __ballot_sync(FULL, cand) & pend;
+      if (!mask) break;
       const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
+      pend &= ~((2u << src) - 1u);  // src and the rows before it are decided
       const int i = i0 + src;
       const float Emax = __uint_as_float(__shfl_sync(FULL, w0.x, src));
       const float vF = __uint_as_float(__shfl_sync(FULL, w0.y, src));
       const unsigned jn = __shfl_sync(FULL, w1.y, src);
       const int n = (int)(jn >> 16), jF = (int)(jn & 0xffffu);
-      if (n & 0x8000) overflow = true;
       bool take;
       if (cur > 0.0f && segE < i) {  // flush (:897-949)
         if (segE - segS >= 2) {
