@@ -335,3 +335,25 @@ def test_full_size_kernel_routes_agree(oracle):
         assert hss == ref_hss
         for a, b in zip(mx, ref_max):
             assert np.array_equal(a, b)
+
+
+def test_thread_scan_on_long_frames(oracle):
+    """getHSS scan with one thread per (instance, strand, frame) -- taken by blocks with thousands of scans -- on frames of
+    96..640 codons, forced here for a few instances (hss_thr_tasks = 1) so that the oracle can check it."""
+    from rnacode_b200 import synth
+    capi = _capi()
+    ctx = capi.Context(0)
+    ctx.set_option("hss_thr_tasks", 1)
+    try:
+        for (N, cols, n, gr) in [(10, 600, 5, 0.02), (6, 1900, 2, 0.01), (18, 700, 17, 0.02)]:
+            rows = synth.synth_block(77, cols, N, cols, gap_rate=gr)
+            sf, sr = synth.synth_scores(77, 3, N)
+            smp = synth.synth_samples(77, cols, n, N, cols)
+            bt = ctx.batch([_block(rows, sf, sr, smp)], capi.make_params(), oracle.blosum62)
+            bt.upload(); bt.run(); bt.download()
+            assert bt.native_hss(0) == oracle.score_aln(rows, sf, sr, oracle.params()), (N, cols)
+            exp = oracle.sample_maxima(rows, smp, sf, sr, oracle.params()).astype(np.float32)
+            assert np.array_equal(bt.max_scores(0).astype(np.float32), exp), (N, cols)
+            bt.close()
+    finally:
+        ctx.close()
