@@ -81,6 +81,20 @@ class Oracle:
         self.lib.orc_rev_aln(rows.ctypes.data, rows.shape[0], rows.shape[1], out.ctypes.data)
         return out
 
+    def dense_S(self, rows, scores, params, blosum=None):
+        """S[b][i] of one strand (getMultipleScoreMatrix, src/score.c:811-848) as orc_score_strand materialises it for small
+        L: array [L+1][L+1], entries outside b = 1.., i = b+2, b+5, ... are 0."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint8)
+        N, cols = rows.shape
+        L = self.lib.orc_seq_length(rows.ctypes.data, cols)
+        sc = np.ascontiguousarray(scores, dtype=np.float32)
+        bl = np.ascontiguousarray(self.blosum62 if blosum is None else blosum, dtype=np.int32)
+        S = np.zeros((L + 1, L + 1), dtype=np.float32)
+        out = (orc_hss * 4096)()
+        self.lib.orc_score_strand(rows.ctypes.data, N, cols, sc.ctypes.data, bl.ctypes.data, C.byref(params), ord("+"), out, 4096,
+                                  S.ctypes.data)
+        return S
+
     def pair_row(self, rows, scores, params, b, blosum=None):
         """Sk[k][state][b][0..L] of one strand (rows already in that strand's orientation): array [N][3][L+1]."""
         rows = np.ascontiguousarray(rows, dtype=np.uint8)

@@ -89,3 +89,23 @@ def test_pair_rows_bit_exact(oracle, name):
                     assert np.array_equal(got[k, x, b - 1:L + 1:3], e), (blk["index"], rec["strand"], b, k, x)
                     checked += len(e)
     assert checked > 1000
+
+
+def test_pair_rows_consistent_with_multiple_score_matrix(oracle):
+    """S[b][i] = max(sum_k max3(Sk[k][0..2][b][i]), Delta) / (N-1) (src/score.c:830-845): the rows orc_pair_row
+    produces must reproduce, bit for bit, the S matrix the (golden-pinned) streaming restatement materialises."""
+    from rnacode_b200 import synth
+    prm = oracle.params()
+    for idx, (N, cols, gr) in enumerate([(5, 60, 0.02), (9, 99, 0.05), (3, 33, 0.0)]):
+        rows = synth.synth_block(91, idx, N, cols, gap_rate=gr)
+        sf, _ = synth.synth_scores(91, idx, N)
+        S = oracle.dense_S(rows, sf, prm)
+        L = S.shape[0] - 1
+        for b in range(1, L - 1):
+            row = oracle.pair_row(rows, sf, prm, b)
+            for i in range(b + 2, L + 1, 3):
+                tot = np.float32(0.0)
+                for k in range(1, N):
+                    tot = np.float32(tot + np.float32(row[k, :, i].max()))
+                exp = np.float32(max(tot, np.float32(prm.Delta))) / np.float32(N - 1)
+                assert np.float32(exp) == S[b, i], (idx, b, i)
