@@ -18,6 +18,18 @@ int main(int argc, char *argv[]) {
   long blocks = 0, rows = 0;
   int na, nb, i, j;
   if (argc < 2) return 2;
+  if (argc > 2) { /* --reference-only / --mapped-only FILE: one parser alone (error paths: both exit with a message) */
+    const int mapped_only = strcmp(argv[1], "--mapped-only") == 0;
+    fa = fopen(argv[2], "r");
+    if (!fa || checkFormat(fa) != MAF) return 2;
+    if (mapped_only && !rc_maf_map_open(fa, &map)) return 2;
+    while ((na = mapped_only ? rc_read_maf_mapped(&map, a) : read_maf(fa, a)) != 0) {
+      rows += na;
+      blocks++;
+    }
+    printf("OK %ld %ld\n", blocks, rows);
+    return 0;
+  }
   fa = fopen(argv[1], "r");
   fb = fopen(argv[1], "r");
   if (!fa || !fb) return 2;

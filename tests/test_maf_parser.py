@@ -45,3 +45,23 @@ def test_irregular_lines(tmp_path):
                  "i b.chr2 N 0 C 0\n\nq b.chr2 99999\n#x\na score=2\ns a 1 3 + 9 ACG\ns b 2 3 + 9 acg\ne c 0 0 + 0 I\n"
                  "z junk line\ns c 3 3 - 9 A-G")
     assert _check(p) == (2, 5)
+
+
+@pytest.mark.parametrize("body", [
+    "a score=1\ns a 0 3 + 9 ACG extra\ns b 0 3 + 9 ACG\n",       # 8 fields
+    "a score=1\ns a 0 3 + 9\n",                                   # 6 fields
+    "a score=1\ns a x 3 + 9 ACG\ns b 0 3 + 9 ACG\n",             # start is not an integer
+    "a score=1\ns a 0 y + 9 ACG\n",                               # length is not an integer
+    "a score=1\ns a 0 3 + z ACG\n",                               # source length is not an integer
+    "a score=1\ns a 0 3 ? 9 ACG\n",                               # strand
+    "a score=1\ns a 0 3 + 9 ACG\ns b 0 4 + 9 ACGT\n",            # unequal lengths
+], ids=["8fields", "6fields", "start", "length", "srcsize", "strand", "unequal"])
+def test_malformed_input_fails_like_the_reference(body, tmp_path):
+    """Both readers stop with the same message and a non-zero exit status."""
+    p = os.path.join(str(tmp_path), "bad.maf")
+    with open(p, "w") as fh:
+        fh.write("##maf version=1\n" + body)
+    ref = subprocess.run([CHECK, "--reference-only", p], capture_output=True, text=True, timeout=60)
+    got = subprocess.run([CHECK, "--mapped-only", p], capture_output=True, text=True, timeout=60)
+    assert ref.returncode != 0 and got.returncode != 0
+    assert got.stderr == ref.stderr and ref.stderr.strip() != ""
