@@ -1,12 +1,25 @@
 """Sharding of independent alignment blocks over the GPUs of one box.
 
 Blocks carry nothing from one to the next (src/RNAcode.c:115-221) except the running hit counter of the
-printer, so the data path needs no collective: every rank scores its own blocks, and the per-block results
+printer, so the data path needs no collective: every rank scores its own units, and the per-block results
 are gathered on the host and re-serialised in input order.  torch.distributed is used for that gather only.
+
+This module is the Python mirror of the sharder inside the batched CLI (integration/rnacode_pipeline.c,
+gpu_batch / process_window): the same unit of work (a block's native alignment plus a range of its null
+alignments), the same cost model, the same cut of oversize blocks along their null alignments, the same
+heaviest-first assignment and the same two-round --stop-early sampling.  bench.py --gpus N drives it with
+libRNAcode_cuda as the scorer; tests/test_shard_gloo.py drives it with the CPU oracle.
 """
+import hashlib
 import heapq
+from collections import namedtuple
+
+import numpy as np
 
 from . import synth
+
+# want_native: this unit also reports the block's native HSS list (the first part of a cut block)
+Unit = namedtuple("Unit", "block s0 ns want_native cost")
 
 
 def block_cost(N, L, n_samples):
@@ -32,17 +45,46 @@ def loads(costs, shards):
     return [sum(costs[i] for i in s) for s in shards]
 
 
+def plan_units(per_aln, blocks, s0, ns, world_size, want_native=True):
+    """Units of GPU work for the null alignments [s0, s0+ns) (and, if want_native, the native alignment) of the listed
+    blocks, dealt out over world_size devices -- gpu_batch() of integration/rnacode_pipeline.c:
+    per_aln[i] = (N-1) * L * L is the cost of one alignment of block i; a block whose cost alone exceeds half a device's
+    fair share is cut along its null alignments into world_size parts (the native alignment goes with the first part);
+    units are assigned heaviest first, each to the device with the least work so far.
+    Returns (per-rank lists of Unit, per-rank loads)."""
+    G = world_size
+    total = sum(per_aln[i] * (ns + 1) for i in blocks)
+    units = []
+    for i in blocks:
+        parts = G if (G > 1 and ns >= 2 * G and per_aln[i] * (ns + 1) > total / (2.0 * G)) else 1
+        for p in range(parts):
+            a, e = ns * p // parts, ns * (p + 1) // parts
+            units.append(Unit(i, s0 + a, e - a, bool(want_native and p == 0), float(per_aln[i]) * (e - a + 1)))
+    order = sorted(range(len(units)), key=lambda k: (-units[k].cost, k))  # stable: equal costs keep input order
+    shards = [[] for _ in range(G)]
+    load = [0.0] * G
+    for k in order:
+        d = min(range(G), key=lambda r: (load[r], r))
+        shards[d].append(units[k])
+        load[d] += units[k].cost
+    return shards, load
+
+
+def _gather(local, group=None):
+    """all_gather_object of a python object (host-side gather; no collective on the data path)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return [local]
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, local, group=group)
+    return parts
+
+
 def gather_in_order(local, n_blocks, group=None):
     """local: {block index: result}.  Returns on every rank the list of results in input order
     (host-side gather of HSS records; all_gather_object so that any rank may print)."""
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()):
-        parts = [local]
-    else:
-        parts = [None] * dist.get_world_size(group)
-        dist.all_gather_object(parts, local, group=group)
     merged = {}
-    for p in parts:
+    for p in _gather(local, group):
         for k, v in p.items():
             if k in merged:
                 raise ValueError("block %d scored by two ranks" % k)
@@ -51,3 +93,83 @@ def gather_in_order(local, n_blocks, group=None):
     if missing:
         raise ValueError("blocks not scored by any rank: %s" % missing[:8])
     return [merged[i] for i in range(n_blocks)]
+
+
+def score_sharded(per_aln, n, rank, world_size, scorer, stop_early=False, cutoff=1.0, group=None, first_round=32):
+    """The scoring part of process_window() (integration/rnacode_pipeline.c) over world_size ranks.
+
+    scorer(units) scores this rank's units and returns {(block, s0): (native HSS list or None, maxima of the unit's null
+    alignments as float64 array)}.  Without stop_early every block gets its n null alignments in one round; with it, a first
+    round of `first_round` null alignments decides most non-coding blocks (more than int(cutoff*n) of them beat the best
+    native score, src/score.c:992, :1036-1042 -- the count is monotone in the sample index, so the verdicts are the
+    reference's) and only the others get the remaining n - first_round.
+    Returns on every rank, in input order: [(native HSS list, maxima float64[n] (unsampled entries NaN), status)], status 1 =
+    all n null alignments scored, -1 = stopped early; plus a dict of planning facts (units, loads per round)."""
+    nb = len(per_aln)
+    n1 = first_round if (stop_early and n > first_round) else n
+    stop_cut = int(cutoff * n)
+    hss = [None] * nb
+    maxima = [np.full(n, np.nan) for _ in range(nb)]
+    info = {"rounds": []}
+
+    def one_round(blocks, s0, ns, want_native):
+        shards, load = plan_units(per_aln, blocks, s0, ns, world_size, want_native)
+        local = scorer(shards[rank]) if shards[rank] else {}
+        for part in _gather(local, group):
+            for (b, u0), (h, mx) in part.items():
+                if h is not None:
+                    if hss[b] is not None:
+                        raise ValueError("native alignment of block %d scored twice" % b)
+                    hss[b] = h
+                if np.isfinite(maxima[b][u0:u0 + len(mx)]).any():
+                    raise ValueError("null alignments of block %d scored twice" % b)
+                maxima[b][u0:u0 + len(mx)] = mx
+        info["rounds"].append({"blocks": len(blocks), "units": sum(len(s) for s in shards), "samples": ns,
+                               "load_max_over_mean": (max(load) * world_size / sum(load)) if sum(load) > 0 else 1.0})
+
+    one_round(list(range(nb)), 0, n1, True)
+    status, better, best = [1] * nb, [0] * nb, [0.0] * nb
+    todo = []
+    for b in range(nb):
+        if hss[b] is None:
+            raise ValueError("block %d not scored by any rank" % b)
+        best[b] = np.float32(max([h[4] for h in hss[b]], default=-1.0))  # results[0].score after the sort, -1 when empty
+        for j in range(n1):  # src/score.c:1036-1042
+            if np.float32(maxima[b][j]) > best[b]:
+                better[b] += 1
+            if stop_early and better[b] > stop_cut:
+                status[b] = -1
+                break
+        if status[b] == 1 and n1 < n:
+            todo.append(b)
+    if todo:
+        one_round(todo, n1, n - n1, False)
+        for b in todo:
+            for j in range(n1, n):
+                if np.float32(maxima[b][j]) > best[b]:
+                    better[b] += 1
+                if stop_early and better[b] > stop_cut:
+                    status[b] = -1
+                    break
+    for b in range(nb):
+        if status[b] == 1 and not np.isfinite(maxima[b]).all():
+            raise ValueError("null alignments of block %d missing" % b)
+    info["round2_blocks"] = len(todo)
+    info["stopped_early"] = sum(1 for s in status if s < 0)
+    return [(hss[b], maxima[b], status[b]) for b in range(nb)], info
+
+
+def digest(results):
+    """SHA-256 over everything the reporting stage consumes: per block the native HSS records (strand, frame, sites, float32
+    score bits), the status, and the float32 bits of the sample maxima that the verdict depends on (all n when the block was
+    sampled in full; for a block stopped early only the decisive prefix is defined by the reference, so only the status)."""
+    h = hashlib.sha256()
+    for hss, mx, status in results:
+        h.update(np.int32(len(hss)).tobytes())
+        for s, f, a, e, sc in hss:
+            h.update(("%s%d:%d:%d:" % (s, f, a, e)).encode())
+            h.update(np.float32(sc).tobytes())
+        h.update(np.int32(status).tobytes())
+        if status == 1:
+            h.update(np.asarray(mx, dtype=np.float32).tobytes())
+    return h.hexdigest()

@@ -8,7 +8,8 @@
    on synthetic MAF written by rnacode_b200.synth (gappy, with N / lower-case / odd symbols, non-default
    --pars), and stores the JSON dumps gzip-compressed,
 3. runs the deterministic reference CLI (RNAcode_det) on the examples with several option sets and stores
-   its stdout (tests/golden/cli_*.txt.gz) for the drop-in CLI comparison.
+   its stdout (tests/golden/cli_outputs.json.gz) for the drop-in CLI comparison; with RC_GOLDEN_FULL=1 also BASELINE
+   config 2 at its full -n 1000 (see long_cases).
 The fixtures pin oracle/rnacode_oracle.c (tests/test_oracle_golden.py) and, on the GPU box, the CUDA path.
 """
 import gzip
@@ -94,6 +95,32 @@ def eps_golden(ex):
     return doc
 
 
+LONG_CLI_CASE = "genomic.maf --gtf --best-only -n 1000"  # BASELINE.json configs[1], the headline command
+
+
+def load(name):
+    with gzip.open(os.path.join(HERE, name + ".json.gz"), "rb") as fh:
+        return json.loads(fh.read())
+
+
+def long_cases(ex, cli):
+    """BASELINE config 2 at its full -n 1000 (14 minutes of one core each, the 10 x 4806 block dominates): the reference's
+    stdout for the headline command and, through ref_probe, the 1000 per-sample maxima, the Gumbel fit and the p-values of
+    every block.  Regenerated only with RC_GOLDEN_FULL=1; otherwise the committed entries are kept."""
+    if os.environ.get("RC_GOLDEN_FULL") == "1":
+        env = dict(os.environ, RNACODE_SEED="1")
+        opts = LONG_CLI_CASE.split(" ")[1:]
+        cli[LONG_CLI_CASE] = subprocess.run([DET, *opts, os.path.join(ex, "genomic.maf")], check=True, capture_output=True,
+                                            env=env).stdout.decode()
+        doc = probe(os.path.join(ex, "genomic.maf"), 1000, 0)
+        for blk in doc["blocks"]:
+            blk.pop("samples", None)
+        save("genomic_maf_n1000", doc)
+    else:
+        cli[LONG_CLI_CASE] = load("cli_outputs")[LONG_CLI_CASE]
+        print("kept the committed -n 1000 cases (set RC_GOLDEN_FULL=1 to regenerate them: 2 x 14 core-minutes)")
+
+
 def main():
     subprocess.run(["make", "-C", ORC, "-j8", "ref"], check=True, stdout=subprocess.DEVNULL)
     os.makedirs(TMP, exist_ok=True)
@@ -145,6 +172,7 @@ def main():
     env = dict(os.environ, RNACODE_SEED="1")
     cli["synthetic:mixed --tabular -n 30"] = subprocess.run([DET, "--tabular", "-n", "30", p], check=True, capture_output=True,
                                                             env=env).stdout.decode()
+    long_cases(ex, cli)
     save("cli_outputs", cli)
     save("eps_outputs", eps_golden(ex))
 

@@ -45,6 +45,36 @@ def test_exact_mode_reproduces_seqgen(rc_ctx, name):
     bt.close()
 
 
+def test_genomic_maf_full_n1000_maxima(rc_ctx):
+    """BASELINE config 2 as quoted: examples/genomic.maf at -n 1000.  The unmodified reference (ref_probe, 14 core-minutes,
+    tests/golden/make_golden.py:long_cases) gives, per block, the native HSS list and the best score of each of its 1000
+    null alignments (src/score.c:1004-1044); the library redraws those alignments from the same seeds and tree (kernel d)
+    and must reproduce all 10 x 1000 maxima and every HSS bit for bit -- the 10 x 4806 block through k_dp_reg, the short
+    ones through the sample-major kernels."""
+    from rnacode_b200 import capi
+    doc = op.golden("genomic_maf_n1000")
+    prm = capi.make_params(**op.golden_params(doc))
+    blocks, blks = [], []
+    for blk in doc["blocks"]:
+        if blk.get("skipped"):
+            continue
+        rows, sf, sr, _ = op.block_arrays(doc, blk)
+        assert len(blk["maxScores"]) == len(blk["seeds"]) == 1000
+        blocks.append(capi.Block(rows, sf, sr, None, n_samples=1000))
+        blks.append(blk)
+    assert len(blocks) == 10 and max(b.cols for b in blocks) == 4806
+    bt = rc_ctx.batch(blocks, prm, doc["blosum"])
+    for i, blk in enumerate(blks):
+        bt.set_evolve(i, _tree(capi, blk), blk["seeds"], capi.RC_RNG_MT19937)
+    bt.upload(); bt.run(); bt.download()
+    for i, blk in enumerate(blks):
+        assert bt.native_hss(i) == op.expected_hss(blk), blk["index"]
+        got = bt.max_scores(i).astype(np.float32)
+        assert np.array_equal(got, np.array(blk["maxScores"], dtype=np.float32)), blk["index"]
+    assert bt.stats()["dense_fallbacks"] == 0
+    bt.close()
+
+
 def test_oracle_evolve_matches_gpu_on_long_rows(rc_ctx, oracle):
     """Rows longer than one MT19937 batch (624 draws) and not a multiple of 32: batch-boundary handling."""
     import ctypes as C

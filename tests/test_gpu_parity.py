@@ -118,6 +118,9 @@ SHAPES = [
     # blocks with >= 16 instances stay on the one-launch sample-major kernels
     (14, 700, 3, 0.02), (15, 2000, 1, 0.01), (16, 450, 2, 0.03), (17, 600, 2, 0.02), (17, 1500, 20, 0.01),
     (14, 150, 20, 0.02), (17, 150, 33, 0.02), (15, 900, 16, 0.02),
+    # BASELINE config 5's row count (100-way): k_dp_chain with 9 chunks in two passes on rows of up to 330 codons, with few
+    # and with >= 16 instances; short 100-way blocks take the chunked sample-major route
+    (100, 1000, 2, 0.0067), (100, 1000, 17, 0.02), (100, 200, 33, 0.0067), (100, 60, 40, 0.0067),
 ]
 
 
@@ -141,6 +144,50 @@ def test_synthetic_vs_oracle(rc_ctx, oracle, shape):
         assert bt.native_hss(i) == oracle.score_aln(rows, sf, sr, oprm), (shape, i)
         exp = oracle.sample_maxima(rows, smp, sf, sr, oprm).astype(np.float32)
         assert np.array_equal(bt.max_scores(i).astype(np.float32), exp), (shape, i)
+    bt.close()
+
+
+@pytest.mark.parametrize("n", [2, 17], ids=lambda n: "n%d" % n)
+def test_config4_shape_vs_oracle(rc_ctx, oracle, n):
+    """BASELINE config 4's block shape, 50 species x 5000 columns (4.1e8 DP cells per alignment): k_dp_chain with W = 5 warps
+    over rows of up to 1666 codons (multi-stage hand-off, chain_tasks), native HSS list and the maxima of n null alignments
+    against the streaming oracle, bit for bit (src/score.c:496-535, :830-845, :864-974)."""
+    from rnacode_b200 import synth
+    capi = _capi()
+    N, cols = 50, 5000
+    rows = synth.synth_block(2, 4000 + n, N, cols, gap_rate=0.0067)
+    sf, sr = synth.synth_scores(2, n, N)
+    smp = synth.synth_samples(2, 4000 + n, n, N, cols)
+    bt = rc_ctx.batch([_block(rows, sf, sr, smp)], capi.make_params(), oracle.blosum62)
+    bt.upload(); bt.run(); bt.download()
+    hss = bt.native_hss(0)
+    assert len(hss) > 50
+    assert hss == oracle.score_aln(rows, sf, sr, oracle.params())
+    exp = oracle.sample_maxima(rows, smp, sf, sr, oracle.params()).astype(np.float32)
+    assert np.array_equal(bt.max_scores(0).astype(np.float32), exp)
+    bt.close()
+
+
+def test_config5_mixed_lengths_vs_oracle(rc_ctx, oracle):
+    """BASELINE config 5's regime: 100-way blocks of mixed length (log-uniform 60..2000 columns) in ONE batch -- the routes
+    change with the length (chunked sample-major, chain in passes) -- with 33 null alignments each, against the oracle."""
+    from rnacode_b200 import synth
+    capi = _capi()
+    rng = np.random.default_rng(5)
+    lens = [60, 2000] + [int(round(float(np.exp(rng.uniform(np.log(60), np.log(2000)))))) for _ in range(6)]
+    blocks, data = [], []
+    for idx, cols in enumerate(lens):
+        rows = synth.synth_block(3, idx, 100, cols, gap_rate=0.0067)
+        sf, sr = synth.synth_scores(3, idx, 100)
+        smp = synth.synth_samples(3, idx, 33, 100, cols)
+        blocks.append(_block(rows, sf, sr, smp))
+        data.append((rows, sf, sr, smp))
+    bt = rc_ctx.batch(blocks, capi.make_params(), oracle.blosum62)
+    bt.upload(); bt.run(); bt.download()
+    for i, (rows, sf, sr, smp) in enumerate(data):
+        assert bt.native_hss(i) == oracle.score_aln(rows, sf, sr, oracle.params()), (i, lens[i])
+        exp = oracle.sample_maxima(rows, smp, sf, sr, oracle.params()).astype(np.float32)
+        assert np.array_equal(bt.max_scores(i).astype(np.float32), exp), (i, lens[i])
     bt.close()
 
 

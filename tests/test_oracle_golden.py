@@ -109,3 +109,36 @@ def test_pair_rows_consistent_with_multiple_score_matrix(oracle):
                     tot = np.float32(tot + np.float32(row[k, :, i].max()))
                 exp = np.float32(max(tot, np.float32(prm.Delta))) / np.float32(N - 1)
                 assert np.float32(exp) == S[b, i], (idx, b, i)
+
+
+def test_genomic_maf_n1000_golden(oracle):
+    """BASELINE config 2 at its own -n 1000 (tests/golden/genomic_maf_n1000.json.gz: per-sample maxima of the unmodified
+    reference for all 1000 null alignments of every block of examples/genomic.maf, incl. the 10 x 4806 one).  The oracle
+    redraws null alignments from the dumped seeds / tree (orc_evolve = seq-gen's MT19937 + HKY walk) and scores them: every
+    native HSS list, and the maxima of the first 40 (10 x 4806 block) or 250 (short blocks) null alignments, bit for bit."""
+    import ctypes as C
+    doc = op.golden("genomic_maf_n1000")
+    prm = oracle.params(**op.golden_params(doc))
+    oracle.lib.orc_evolve.argtypes = [C.c_ulong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_int, C.c_void_p]
+    checked = 0
+    for blk in doc["blocks"]:
+        if blk.get("skipped"):
+            continue
+        rows, sf, sr, _ = op.block_arrays(doc, blk)
+        assert oracle.score_aln(rows, sf, sr, prm) == op.expected_hss(blk), blk["index"]
+        nodes = blk["evolve"]["nodes"]
+        parent = np.array([n["parent"] for n in nodes], dtype=np.int32)
+        row = np.array([n["row"] for n in nodes], dtype=np.int32)
+        cum = np.array([n["cum"] for n in nodes], dtype=np.float64)
+        af = np.array(blk["evolve"]["addFreq"], dtype=np.float64)
+        N, cols = rows.shape
+        k = 40 if cols > 2000 else 250
+        smp = np.zeros((k, N, cols), dtype=np.uint8)
+        for s in range(k):
+            oracle.lib.orc_evolve(int(blk["seeds"][s]), len(nodes), parent.ctypes.data, row.ctypes.data, cum.ctypes.data,
+                                  af.ctypes.data, N, cols, smp[s].ctypes.data)
+        got = oracle.sample_maxima(rows, smp, sf, sr, prm).astype(np.float32)
+        assert np.array_equal(got, np.array(blk["maxScores"][:k], dtype=np.float32)), blk["index"]
+        checked += k
+    assert checked == 40 + 9 * 250
