@@ -109,7 +109,8 @@ def score_sharded(per_aln, n, rank, world_size, scorer, stop_early=False, cutoff
     n1 = first_round if (stop_early and n > first_round) else n
     stop_cut = int(cutoff * n)
     hss = [None] * nb
-    maxima = [np.full(n, np.nan) for _ in range(nb)]
+    M = np.full((nb, n), np.nan)  # maxima of the null alignments, NaN = not sampled
+    maxima = [M[b] for b in range(nb)]  # row views
     info = {"rounds": []}
 
     def one_round(blocks, s0, ns, want_native):
@@ -128,35 +129,28 @@ def score_sharded(per_aln, n, rank, world_size, scorer, stop_early=False, cutoff
                                "load_max_over_mean": (max(load) * world_size / sum(load)) if sum(load) > 0 else 1.0})
 
     one_round(list(range(nb)), 0, n1, True)
-    status, better, best = [1] * nb, [0] * nb, [0.0] * nb
-    todo = []
-    for b in range(nb):
-        if hss[b] is None:
-            raise ValueError("block %d not scored by any rank" % b)
-        best[b] = np.float32(max([h[4] for h in hss[b]], default=-1.0))  # results[0].score after the sort, -1 when empty
-        for j in range(n1):  # src/score.c:1036-1042
-            if np.float32(maxima[b][j]) > best[b]:
-                better[b] += 1
-            if stop_early and better[b] > stop_cut:
-                status[b] = -1
-                break
-        if status[b] == 1 and n1 < n:
-            todo.append(b)
+    missing = [b for b in range(nb) if hss[b] is None]
+    if missing:
+        raise ValueError("blocks not scored by any rank: %s" % missing[:8])
+    # results[0].score after the sort (src/RNAcode.c:176-178), -1 when the list is empty (src/score.c:1129-1134)
+    best = np.array([max([h[4] for h in hss[b]], default=-1.0) for b in range(nb)], dtype=np.float32)
+
+    def verdicts(upto):
+        """src/score.c:1036-1042 over the first `upto` null alignments: -1 as soon as more than stop_cut of them beat the
+        native score (the running count is monotone, so "at some point" == "at the end of the prefix")."""
+        better = (M[:, :upto].astype(np.float32) > best[:, None]).sum(axis=1)
+        return np.where(stop_early & (better > stop_cut), -1, 1)
+    status = verdicts(n1)
+    todo = [b for b in range(nb) if status[b] == 1] if n1 < n else []
     if todo:
         one_round(todo, n1, n - n1, False)
-        for b in todo:
-            for j in range(n1, n):
-                if np.float32(maxima[b][j]) > best[b]:
-                    better[b] += 1
-                if stop_early and better[b] > stop_cut:
-                    status[b] = -1
-                    break
-    for b in range(nb):
-        if status[b] == 1 and not np.isfinite(maxima[b]).all():
-            raise ValueError("null alignments of block %d missing" % b)
+        status = np.where(status == 1, verdicts(n), status)
+    full = status == 1
+    if not np.isfinite(M[full]).all():
+        raise ValueError("null alignments missing for some fully sampled block")
     info["round2_blocks"] = len(todo)
-    info["stopped_early"] = sum(1 for s in status if s < 0)
-    return [(hss[b], maxima[b], status[b]) for b in range(nb)], info
+    info["stopped_early"] = int((status < 0).sum())
+    return [(hss[b], M[b], int(status[b])) for b in range(nb)], info
 
 
 def digest(results):
