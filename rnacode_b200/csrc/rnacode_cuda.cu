@@ -45,6 +45,8 @@ struct rc_ctx {
   long reg_max_nk = 12;  // row-major alignments with more scored species take k_dp_chain (k_dp_reg<13..16> spills: 17x3000 14.7 vs 11.1 ms)
   long no_smps = 0;          // never stream the sigma table in segments (k_dp_smps)
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
+  long tail_max = 12;         // a sample-major block whose instance count leaves 1..tail_max instances in its last group of 32 scores
+                              // those instances row-major (lanes = rows) instead of in a warp with that many live lanes (0: never)
   long smpc_max_sites = 0;    // longest frame (codons) for the STREAMED chunked sample-major route of wide alignments
                               // (measured slower than k_dp_chain: 50x800 11.3 vs 4.5 ms; kept as an experiment switch)
   int smem_optin = 0;
@@ -236,11 +238,27 @@ void set_layout(BlockDev& bd, int layout) {
   }
 }
 
+// what depends on the layout besides set_layout(): tasks per CTA of k_dp_chain, frame padding of k_dp_reg
+void finish_layout(BlockDev& bd) {
+  if (bd.layout == 3) {
+    // tasks per CTA: enough tiles per CTA to amortise the W-1 tiles the warp pipeline needs to fill and drain
+    // (a row group of a frame with T tiles has T - 4g tiles: about T/2 on average), but not more: long rows are
+    // better balanced with one task per CTA
+    const double avg_tiles = std::max(1.0, 0.5 * bd.ntiles[0]);
+    const int wp = chain_pass_width(bd.nchunk);  // warps per CTA = depth of the pipeline
+    bd.chain_tasks = (int)std::min<double>(CHAIN_MAX_TASKS, std::max(1.0, std::ceil(4.0 * (wp - 1) / avg_tiles)));
+  }
+  if (bd.layout == 1)  // k_dp_reg stages RC_REG_TILE end codons at a time: pad the frame to whole stages
+    for (int f = 0; f < 3; f++) bd.ntiles[f] = (bd.ntiles[f] + RC_REG_TILE / TILE - 1) / (RC_REG_TILE / TILE) * (RC_REG_TILE / TILE);
+}
+
 }  // namespace
 
 struct rc_batch {
   rc_ctx* ctx = nullptr;
-  int n_blocks = 0;
+  int n_blocks = 0;  // blocks of the caller; b->blocks may hold "tail" blocks after them (see rc_batch_create)
+  std::vector<int> tail_of;   // per caller block: index of its tail block in `blocks`, or -1
+  std::vector<int> main_inst; // per caller block: instances [0, main_inst) use the block's own layout, the rest the tail block's
   std::vector<rc_block_desc> descs;
   std::vector<BlockDev> blocks;
   std::vector<Item> items;
@@ -363,6 +381,7 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   if (const char* e = getenv("RNACODE_CUDA_SMPS_MAX_SITES")) ctx->smps_max_sites = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_SMP_WARPS")) ctx->smp_warps_forced = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_HSS_THR_TASKS")) ctx->hss_thr_tasks = atol(e);
+  if (const char* e = getenv("RNACODE_CUDA_TAIL_MAX")) ctx->tail_max = std::max(0L, std::min(31L, atol(e)));
   if (const char* e = getenv("RNACODE_CUDA_REG_MAX_NK")) ctx->reg_max_nk = std::max(12L, std::min<long>(REG_MAX_NK, atol(e)));
   unsigned char lut[256];
   build_lut(lut);
@@ -428,6 +447,9 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->smps_max_sites = value;
   } else if (k == "smpc_max_sites") {
     ctx->smpc_max_sites = value;
+  } else if (k == "tail_max") {
+    if (value < 0 || value > 31) { ctx_fail(ctx, "tail_max must be 0..31"); return RC_ERR_ARG; }
+    ctx->tail_max = value;
   } else if (k == "scratch_mb") {
     if (value < 1) { ctx_fail(ctx, "scratch_mb must be >= 1"); return RC_ERR_ARG; }
     ctx->scratch_mb = value;
@@ -624,16 +646,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       }
       set_layout(bd, layout);
       bd.smp_seg = seg;
-      if (layout == 3) {
-        // tasks per CTA: enough tiles per CTA to amortise the W-1 tiles the warp pipeline needs to fill and drain
-        // (a row group of a frame with T tiles has T - 4g tiles: about T/2 on average), but not more: long rows are
-        // better balanced with one task per CTA
-        const double avg_tiles = std::max(1.0, 0.5 * bd.ntiles[0]);
-        const int wp = chain_pass_width(bd.nchunk);  // warps per CTA = depth of the pipeline
-        bd.chain_tasks = (int)std::min<double>(CHAIN_MAX_TASKS, std::max(1.0, std::ceil(4.0 * (wp - 1) / avg_tiles)));
-      }
-      if (layout == 1)  // k_dp_reg stages RC_REG_TILE end codons at a time: pad the frame to whole stages
-        for (int f = 0; f < 3; f++) bd.ntiles[f] = (bd.ntiles[f] + RC_REG_TILE / TILE - 1) / (RC_REG_TILE / TILE) * (RC_REG_TILE / TILE);
+      finish_layout(bd);
     }
     for (int s = 0; s < 2; s++)
       for (int f = 0; f < 3; f++) {
@@ -648,6 +661,37 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     b->hsscnt_ints += 6;
   }
   b->stats.cells = cells;
+  // Tail blocks.  The sample-major kernels put 32 instances into a warp; a block with 101 instances (RNAcode's default -n 100)
+  // leaves 5 of them in a fourth warp that costs as much as a full one.  Those instances are scored by the row-major
+  // kernels instead (lanes = rows of one instance): a "tail block" is a second BlockDev of the same alignment -- same
+  // class bytes, maps, scores, results -- with a row-major sigma / z layout; the block's last instances become items of it.
+  b->tail_of.assign(n_blocks, -1);
+  b->main_inst.resize(n_blocks);
+  for (int i = 0; i < n_blocks; i++) {
+    const BlockDev bd = b->blocks[i];
+    b->main_inst[i] = bd.n_inst;
+    const int r = bd.n_inst % 32;
+    if ((bd.layout != 2 && bd.layout != 5) || bd.n_inst < 64 || r == 0 || r > ctx->tail_max || bd.L < 3) continue;
+    const int reg_max = (int)std::min<long>(REG_MAX_NK, ctx->reg_max_nk);
+    int alt = -1;
+    if (bd.NK <= reg_max) alt = 1;
+    else if (params->omega <= 0.0f && !ctx->no_chain && (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX >= 2 &&
+             (bd.NK + CHAIN_NKW_MAX - 1) / CHAIN_NKW_MAX <= CHAIN_MAX_CHUNKS) alt = 3;
+    if (alt < 0) continue;
+    BlockDev vb = bd;
+    for (int f = 0; f < 3; f++) vb.ntiles[f] = (vb.sites[f] + TILE - 1) / TILE;
+    set_layout(vb, alt);
+    vb.smp_seg = 0;
+    finish_layout(vb);
+    for (int s = 0; s < 2; s++)
+      for (int f = 0; f < 3; f++) {
+        vb.z_off[s][f] = (long long)b->z_words;
+        b->z_words += (size_t)vb.ntiles[f] * vb.zstride;
+      }
+    b->tail_of[i] = (int)b->blocks.size();
+    b->main_inst[i] = bd.n_inst - r;
+    b->blocks.push_back(vb);
+  }
   for (BlockDev& bd : b->blocks) bd.nat_off += (long long)b->raw_bytes;  // the natives follow the samples in d_raw
   b->stats.pack_chars = (double)b->cls_bytes;
 
@@ -662,7 +706,15 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     cur.item0 = b->items.size();
     cur_bytes = 0;
   };
+  // segments of instances: a caller block's instances [0, main_inst) with its own layout, the rest with its tail block's
+  struct Seg { int block, inst0, inst1; };
+  std::vector<Seg> segs;
   for (int i = 0; i < n_blocks; i++) {
+    segs.push_back(Seg{i, 0, b->main_inst[i]});
+    if (b->tail_of[i] >= 0) segs.push_back(Seg{b->tail_of[i], b->main_inst[i], b->blocks[i].n_inst});
+  }
+  for (const Seg& sg : segs) {
+    const int i = sg.block;
     const BlockDev& bd = b->blocks[i];
     if (bd.L < 3) continue;  // nothing to score (the reference skips such blocks, src/RNAcode.c:147-150)
     size_t sig_per_inst = 0, rec_per_inst = 0;
@@ -676,17 +728,17 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     if (bd.layout == 3 && chain_passes(bd.nchunk) > 1)
       for (int f = 0; f < 3; f++) part_per_inst += 2 * chain_part_entries(bd.sites[f], bd.ntiles[f]);
     const size_t bytes_per_inst = sig_per_inst * sizeof(float) + rec_per_inst * sizeof(RowRec) + part_per_inst * sizeof(float2);
-    int inst = 0;
-    while (inst < bd.n_inst) {
+    int inst = sg.inst0;
+    while (inst < sg.inst1) {
       size_t room = budget > cur_bytes ? (budget - cur_bytes) / bytes_per_inst : 0;
       if (room == 0) {
         if (cur.nitems == 0) room = 1;  // a single instance always goes through
         else { close_chunk(); continue; }
       }
-      int take = (int)std::min<size_t>(room, (size_t)(bd.n_inst - inst));
-      if ((bd.layout == 2 || bd.layout == 5) && take < bd.n_inst - inst) {  // instance groups of 32 must not straddle chunks
+      int take = (int)std::min<size_t>(room, (size_t)(sg.inst1 - inst));
+      if ((bd.layout == 2 || bd.layout == 5) && take < sg.inst1 - inst) {  // instance groups of 32 must not straddle chunks
         if (take >= 32) take = take / 32 * 32;
-        else if (cur.nitems == 0) take = std::min(32, bd.n_inst - inst);
+        else if (cur.nitems == 0) take = std::min(32, sg.inst1 - inst);
         else { close_chunk(); continue; }
       }
       Item it;
@@ -749,7 +801,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     *p = ctx_alloc(ctx, bytes);
     return *p != nullptr;
   };
-  bool ok = dalloc((void**)&b->d_blocks, sizeof(BlockDev) * n_blocks) &&
+  bool ok = dalloc((void**)&b->d_blocks, sizeof(BlockDev) * b->blocks.size()) &&
             dalloc((void**)&b->d_items, sizeof(Item) * b->items.size()) &&
             dalloc((void**)&b->d_ctas, sizeof(CtaDesc) * b->ctas.size()) &&
             dalloc((void**)&b->d_raw, b->raw_bytes + b->nat_bytes + 64) && dalloc((void**)&b->d_cls, b->cls_bytes) && dalloc((void**)&b->d_cols0, sizeof(int) * b->cols0_ints) &&
@@ -913,7 +965,7 @@ extern "C" int rc_batch_upload(rc_batch* b) {
   }
   RC_CUDA(cudaMemcpyAsync(b->d_raw + b->raw_bytes, b->h_nat.data(), b->nat_bytes, cudaMemcpyHostToDevice, st));
   RC_CUDA(cudaMemcpyAsync(b->d_scores, b->h_scores.data(), sizeof(float) * b->scores_floats, cudaMemcpyHostToDevice, st));
-  RC_CUDA(cudaMemcpyAsync(b->d_blocks, b->blocks.data(), sizeof(BlockDev) * b->n_blocks, cudaMemcpyHostToDevice, st));
+  RC_CUDA(cudaMemcpyAsync(b->d_blocks, b->blocks.data(), sizeof(BlockDev) * b->blocks.size(), cudaMemcpyHostToDevice, st));
   if (!b->items.empty())
     RC_CUDA(cudaMemcpyAsync(b->d_items, b->items.data(), sizeof(Item) * b->items.size(), cudaMemcpyHostToDevice, st));
   if (!b->ctas.empty())
@@ -939,7 +991,7 @@ extern "C" int rc_batch_upload(rc_batch* b) {
     h2d += sizeof(EvoDev) * b->evos.size() + sizeof(int) * b->evo_nodes.size() +
            sizeof(unsigned) * (b->evo_thr.size() + b->evo_seeds.size());
   }
-  h2d += sizeof(float) * b->scores_floats + sizeof(BlockDev) * b->n_blocks + sizeof(Item) * b->items.size() +
+  h2d += sizeof(float) * b->scores_floats + sizeof(BlockDev) * b->blocks.size() + sizeof(Item) * b->items.size() +
          sizeof(CtaDesc) * b->ctas.size() + sizeof(SigmaTables);
   // descriptors may go away after this call returns
   RC_CUDA(cudaStreamSynchronize(st));
@@ -1315,7 +1367,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
     // z words: a long block would keep a single CTA busy for ~0.2 ms; spread each block over several CTAs
     size_t maxz = 1;
     for (const BlockDev& bd : b->blocks) maxz = std::max(maxz, (size_t)bd.ntiles[0] * bd.zstride);
-    dim3 gz((unsigned)b->n_blocks, (unsigned)std::min<size_t>((maxz + 255) / 256, 64));
+    dim3 gz((unsigned)b->blocks.size(), (unsigned)std::min<size_t>((maxz + 255) / 256, 64));  // tail blocks have z words of their own
     k_prep<2><<<gz, 256, 0, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_z);
     RC_CUDA(cudaGetLastError());
     b->stats.launches += 3;
