@@ -696,8 +696,12 @@ def ours(args):
     torch, dist = B.torch, B.dist
     rank, world, local = B.rank, B.world, B.local
     sampler = ClockSampler(local)
-    m = B.measure(args.workload, args.steps, args.warmup, host_samples=True, e2e_steps=args.steps, n_override=args.samples,
-                  sampler=sampler)
+    m = B.measure(args.workload, args.steps, args.warmup, host_samples=not args.evolve, e2e_steps=args.steps,
+                  n_override=args.samples, sampler=sampler)
+    if args.quick and rank == 0:  # kernel iteration: one compact line on stderr
+        sys.stderr.write("[quick] %s: %.4g cells/s, %.3f ms/step, stages %s, e2e %.3f ms, launches %d\n" % (
+            args.workload, m["cells"] / (m["total_ms"] / m["steps"] * 1e-3), m["total_ms"] / m["steps"],
+            {k: round(v, 3) for k, v in m["stage_ms"].items()}, m["e2e_ms"] / m["e2e_steps"], m["launches"] // m["steps"]))
 
     # the same C-ABI sequence with the null alignments drawn on the GPU (kernel d, the CLIs' default): the host supplies the
     # native rows, the score tables, a flattened tree and one seed per sample
@@ -873,6 +877,7 @@ def main():
     ap.add_argument("--no-side", action="store_true", help="skip the other BASELINE configs (workloads) and the CLI leg")
     ap.add_argument("--no-cli", action="store_true", help="skip the CLI end-to-end leg")
     ap.add_argument("--no-sharded", action="store_true", help="skip the strong-scaling legs through the sharder")
+    ap.add_argument("--evolve", action="store_true", help="headline legs with the null alignments drawn on the GPU instead of host buffers")
     ap.add_argument("--quick", action="store_true", help="kernel iteration: headline legs only (= --no-cpu --no-side --no-sharded)")
     args = ap.parse_args()
     if args.quick:

@@ -63,6 +63,10 @@ struct BlockDev {
                             //    [chunk][group of 32 instances][step][3 quads][lane][4] (k_dp_smp<., true>, one launch per chunk)
   int chain_tasks;          // layout 3: consecutive tasks one CTA of k_dp_chain works through
   int smp_seg;              // layouts 2 / 5: 1 = the frame's sigma table does not fit shared memory, streamed in segments (k_dp_smps)
+  int smp_fused;            // layouts 2 / 5, resident table: 1 = the DP kernel builds its sigma table itself from class bytes
+                            // (k_dp_smpf; no sigma scratch, no k_sigma_smp launch for this block)
+  int smp_pitch;            // k_dp_smpf: bytes per staged row (>= cols + 6, a multiple of 4 with an odd word count)
+  float fold_B;             // k_dp_smpf: half-width of the ambiguity zone of the getHSS fold in species-sum space (see RowFoldS)
   int nchunk, nkw;          // layout 3: chunks and species per chunk (template NK of k_dp_chain); chunk g holds
   int chunk_base, chunk_rem;  //   chunk_base + (g < chunk_rem) species starting at g*chunk_base + min(g, chunk_rem)
   int sig_tile;             // floats per sigma tile

@@ -2033,6 +2033,329 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
 }
 
 // ---------------------------------------------------------------------------------------------
+// (b)+(c) k_dp_smpf: k_dp_smp with kernel (b) fused in.  The CTA (32 instances of one block, one strand, one frame) builds
+// its sigma table itself: the class bytes of its 32 reference rows and of four species rows at a time are staged in shared
+// memory with aligned word copies (lane = instance, odd row pitch => conflict-free byte reads), every (end codon, instance)
+// gets its four sigma values from the two look-ups of PairTables and stores them as one float4 into the lane-interleaved
+// table the DP loop reads -- sigma never exists in HBM (k_sigma_smp wrote and k_dp_smp re-read 0.4 KB per codon and
+// instance).  While one CTA of an SM is in its table phase (LSU / integer work) the other runs its DP phase (FP32 pipe).
+//
+// The getHSS fold (see k_dp) runs in the space of the species sums s, not of the entries e = s / (N-1):
+//   * e is a monotone function of s, so the row maximum and exact ties can be tracked on s without the division;
+//   * the record of a row only has to keep (a) the row maximum Emax with the LAST end codon that reaches it, and (b) entries
+//     AFTER that position which the lenient fold accepts, i.e. which lie within the 1e-4 band below the last accepted value.
+//     Band entries BEFORE the maximum are redundant for the replay in k_hss: they are shorter and not larger than the
+//     maximum, so whenever one of them passes the tie rule (|e - cur| <= 1e-4 and length >= current length, src/score.c:953-959)
+//     the maximum passes it too;
+//   * hence the state of almost every row is just (Ms, jF) in registers: a sum s >= Ms replaces it; a sum below Ms - B is
+//     rejected for certain, where B = (N-1) * 1.0002e-4 + 2^-21 * (largest possible sum) covers the tolerance and every
+//     rounding of the two quotients; only a positive sum in (Ms - B, Ms) -- a near tie after the maximum -- needs the exact
+//     test on the quotients.  That rare case runs the reference's rule on the quotients (folds_exact) and from then on the row
+//     is "complex": its state lives in a shared-memory RowRec handled by hss_accept_rec, as in k_dp_smp.
+// The fast path is branch-free: per entry two compares, two max, one select.
+// ---------------------------------------------------------------------------------------------
+struct RowFoldS {
+  float Ms;   // largest positive species sum so far (0: none yet); +inf: complex row, the state is in the shared-memory record
+  float lo;   // max(Ms - B, 0): a later sum in (lo, Ms) may fall into the tie band of the maximum
+  float nB;   // -B; -inf for a complex row (then lo stays 0 and every positive sum takes the exact path)
+  int jF;     // end codon of Ms
+};
+__device__ __forceinline__ void folds_init(RowFoldS& f, float B) {
+  f.Ms = 0.0f;
+  f.lo = 0.0f;
+  f.nB = -B;
+  f.jF = 0;
+}
+// sB = s + nB (computed for both rows of the lane with one packed add)
+__device__ __forceinline__ void folds_fast(RowFoldS& f, float s, float sB, int j, bool& amb) {
+  const bool p = s >= f.Ms;
+  amb = amb || (s > f.lo && !p);
+  f.Ms = fmaxf(f.Ms, s);
+  f.lo = fmaxf(f.lo, sB);
+  f.jF = p ? j : f.jF;
+}
+__device__ __forceinline__ float quot_nk(float s, float fNK, float rcpNK) {  // the correctly rounded s / (N-1), see k_dp
+  const float q = s * rcpNK;
+  return __fmaf_rn(__fmaf_rn(-fNK, q, s), rcpNK, q);
+}
+__device__ __noinline__ RowFoldS folds_exact(RowFoldS f, float s, int j, float fNK, float rcpNK, RowRec* rec, int slots) {
+  if (!(s > 0.0f)) return f;  // getHSS only looks at positive entries (src/score.c:891)
+  const float e = quot_nk(s, fNK, rcpNK);
+  if (f.Ms != INFINITY) {
+    if (s >= f.Ms) {  // what the fast path does
+      f.Ms = s;
+      f.jF = j;
+      f.lo = fmaxf(f.lo, s + f.nB);
+      return f;
+    }
+    const float Me = quot_nk(f.Ms, fNK, rcpNK);  // f.Ms > s > 0: something was accepted before
+    if (e == Me) {  // equal after rounding: an exact tie, the later (longer) entry stands for it
+      f.jF = j;
+      return f;
+    }
+    if (e - Me >= -0.0001f) {  // accepted below the maximum (src/score.c:953-954 without the length test): the band matters now
+      rec_init(rec);
+      fold_flush(rec, Me, f.jF);
+      hss_accept_rec(rec, e, j, slots);
+      f.Ms = INFINITY;
+      f.lo = 0.0f;
+      f.nB = -INFINITY;
+    }
+    return f;
+  }
+  if (e - rec->vF >= -0.0001f) hss_accept_rec(rec, e, j, slots);
+  return f;
+}
+// final record of a row: straight from the registers unless the row is complex
+__device__ __forceinline__ void folds_store(const RowFoldS& f, RowRec* grec, const RowRec* srec, float fNK, float rcpNK) {
+  uint4* g = reinterpret_cast<uint4*>(grec);
+  if (f.Ms == INFINITY) {
+    rec_copy(grec, srec);
+  } else if (f.Ms > 0.0f) {
+    const unsigned e = __float_as_uint(quot_nk(f.Ms, fNK, rcpNK));
+    g[0] = make_uint4(e, e, e, 0u);                                             // Emax, vF, be[0], be[1]
+    g[1] = make_uint4(0u, (unsigned)f.jF | (1u << 16), (unsigned)f.jF, 0u);     // be[2], jF | n << 16, bj[0] | bj[1] << 16, bj[2] | pad
+  } else {
+    const unsigned ninf = __float_as_uint(-INFINITY);
+    g[0] = make_uint4(ninf, ninf, 0u, 0u);
+    g[1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+#ifndef RC_FOLD_GATE
+#define RC_FOLD_GATE 0  // 1: skip the fold of a step pair when no lane has a sum above its row's lower bound
+#endif
+
+template <int NK>
+struct SmpfCfg {
+  static constexpr int RSB = (NK + 3) / 4 * 4;
+  static __host__ __device__ size_t align16(size_t v) { return (v + 15) / 16 * 16; }
+  // dynamic shared memory: sigma table | z words | barrier | PairTables | expected scores of a quad | codon columns |
+  // staged reference rows | staged species rows of a quad | fold records
+  static __host__ __device__ size_t off_z(int sites, int row_bytes) { return (size_t)sites * row_bytes; }
+  static __host__ __device__ size_t off_bar(int sites, int row_bytes) { return off_z(sites, row_bytes) + align16((size_t)sites * 4); }
+  static __host__ __device__ size_t off_tab(int sites, int row_bytes) { return off_bar(sites, row_bytes) + 16; }
+  static __host__ __device__ size_t off_sc(int sites, int row_bytes) { return off_tab(sites, row_bytes) + sizeof(PairTables); }
+  static __host__ __device__ size_t off_col(int sites, int row_bytes) { return off_sc(sites, row_bytes) + 64; }
+  static __host__ __device__ size_t off_ref(int sites, int row_bytes) { return off_col(sites, row_bytes) + align16((size_t)3 * sites * 4); }
+  static __host__ __device__ size_t off_sp(int sites, int row_bytes, int pitch) { return off_ref(sites, row_bytes) + (size_t)32 * pitch; }
+  static __host__ __device__ size_t off_rec(int sites, int row_bytes, int pitch) { return off_sp(sites, row_bytes, pitch) + (size_t)128 * pitch; }
+  static __host__ __device__ size_t total(int sites, int row_bytes, int pitch, int nw) {
+    return off_rec(sites, row_bytes, pitch) + (size_t)nw * 64 * sizeof(RowRec);
+  }
+};
+
+template <int NK, bool CHAINED>
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
+    k_dp_smpf(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
+              const unsigned char* __restrict__ cls, const int* __restrict__ cols0, const float* __restrict__ scores,
+              const PairTables* __restrict__ tables, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm,
+              int band_slots, int chunk, float2* __restrict__ partial) {
+  constexpr int RS = RegCfg<NK>::RS;
+  constexpr int RSB = (NK + 3) / 4 * 4;
+  constexpr int ROW_BYTES = (CHAINED ? 12 : RSB) * 32 * 4;  // one end codon, 32 lanes (chained: always room for three quads)
+  using Cfg = SmpfCfg<NK>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const CtaDesc cd = ctas[blockIdx.x];
+  const Item& it = items[cd.item];
+  const BlockDev& bd = blocks[it.block];
+  const int strand = cd.sf / 3, frame = cd.sf % 3;
+  const int sites = bd.sites[frame];
+  const int group = cd.task0;  // group of 32 instances inside the item
+  const int inst_l = group * 32 + lane;
+  const bool valid = inst_l < it.ninst;
+  const bool first = !CHAINED || chunk == 0, last = !CHAINED || chunk == bd.nchunk - 1;
+  const int N = bd.N, cols = bd.cols, L = bd.L, pitch = bd.smp_pitch;
+
+  unsigned* zs = reinterpret_cast<unsigned*>(smem + Cfg::off_z(sites, ROW_BYTES));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::off_bar(sites, ROW_BYTES));
+  const PairTables& s_tab = *reinterpret_cast<const PairTables*>(smem + Cfg::off_tab(sites, ROW_BYTES));
+  float* s_sc = reinterpret_cast<float*>(smem + Cfg::off_sc(sites, ROW_BYTES));  // [species of the quad][h], h = 0 -> 0
+  int* s_col = reinterpret_cast<int*>(smem + Cfg::off_col(sites, ROW_BYTES));   // columns of the frame's codons: site j at 3j .. 3j+2
+  unsigned char* s_ref = smem + Cfg::off_ref(sites, ROW_BYTES);
+  unsigned char* s_sp = smem + Cfg::off_sp(sites, ROW_BYTES, pitch);
+  RowRec* srec = reinterpret_cast<RowRec*>(smem + Cfg::off_rec(sites, ROW_BYTES, pitch));
+
+  // ---- table phase: kernel (b) for this CTA's (instances, strand, frame, species of the chunk) ------------------------
+  const size_t z_bytes = Cfg::align16((size_t)sites * 4);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(bar, (unsigned)(sizeof(PairTables) + z_bytes));
+    bulk_g2s(smem + Cfg::off_tab(sites, ROW_BYTES), tables, (unsigned)sizeof(PairTables), bar);
+    bulk_g2s(zs, ztiles + bd.z_off[strand][frame] + (CHAINED ? (size_t)chunk * bd.ntiles[frame] * TILE : 0), (unsigned)z_bytes, bar);
+  }
+  // codon of site j: reference positions x-2 .. x with x = 3j + 3 + frame, i.e. entries frame+1+3j .. frame+3+3j of cols0
+  const int* c0 = cols0 + bd.cols0_off + (size_t)strand * (L + 1) + frame + 1;
+  for (int t = threadIdx.x; t < 3 * sites; t += blockDim.x) s_col[t] = c0[t];
+  const int ninst_g = min(32, it.ninst - group * 32);
+  const unsigned char* gbase = cls + bd.cls_off + (size_t)(it.inst0 + group * 32) * bd.inst_stride;
+  // reference rows of the 32 instances: one warp per row, aligned word copies (instances start 16-byte aligned)
+  for (int li = warp; li < 32; li += nw) {
+    const unsigned* src4 = reinterpret_cast<const unsigned*>(gbase + (size_t)li * bd.inst_stride);
+    unsigned* dst4 = reinterpret_cast<unsigned*>(s_ref + li * pitch);
+    for (int w = lane; w < (cols + 3) / 4; w += 32) dst4[w] = (li < ninst_g) ? src4[w] : 0u;
+  }
+  // species quads of this launch: all of them, or the quads of the chunk (layout 5)
+  int q_first = 0, q_count = RSB / 4;
+  if (CHAINED) {
+    q_first = chunk * bd.chunk_base + min(chunk, bd.chunk_rem);
+    q_count = bd.chunk_base + (chunk < bd.chunk_rem ? 1 : 0);
+  }
+  const int sh = strand ? 2 : 0;
+  __syncthreads();  // barrier initialised, s_col and the reference rows staged
+  mbar_wait(bar, 0);
+  for (int kq = 0; kq < q_count; kq++) {
+    const int k0 = 4 * (q_first + kq);  // first species (0-based among the scored ones) of the quad
+    for (int pr = warp; pr < 128; pr += nw) {  // (species of the quad, instance): one warp per row
+      const int kk = pr >> 5, li = pr & 31;
+      const int row = 1 + k0 + kk;
+      const bool ok = li < ninst_g && row < N;
+      const size_t roff = (size_t)row * cols;
+      const unsigned shift = (unsigned)roff & 3u;  // rows start at any byte: staged column c sits at dst[shift + c]
+      const unsigned* src4 = reinterpret_cast<const unsigned*>(gbase + (size_t)li * bd.inst_stride + (ok ? roff - shift : 0));
+      unsigned* dst4 = reinterpret_cast<unsigned*>(s_sp + pr * pitch);
+      for (int w = lane; w < (int)(shift + cols + 3) / 4; w += 32) dst4[w] = ok ? src4[w] : 0u;
+    }
+    if (threadIdx.x < 16) {  // expected scores of the quad's species on this strand, [species][h], h = 0 -> 0 (see PairTables)
+      const int kk = threadIdx.x >> 2, h = threadIdx.x & 3, row = 1 + k0 + kk;
+      s_sc[threadIdx.x] = (h > 0 && row < N) ? scores[bd.scores_off + ((size_t)strand * N + row) * 4 + h] : 0.0f;
+    }
+    __syncthreads();
+    const unsigned char* rr = s_ref + lane * pitch;
+    unsigned shk[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) shk[kk] = (unsigned)((size_t)(1 + k0 + kk) * cols) & 3u;
+    for (int j = warp; j < sites; j += nw) {
+      const int i1 = s_col[3 * j], i2 = s_col[3 * j + 1], i3 = s_col[3 * j + 2];
+      const unsigned a1 = rr[i1], a2 = rr[i2], a3 = rr[i3];
+      const unsigned qa = (((a1 >> sh) & 3u) << 4) | (((a2 >> sh) & 3u) << 2) | ((a3 >> sh) & 3u);
+      const unsigned nA = (a1 | a2 | a3) & CLS_N;
+      const unsigned short* trow = s_tab.t + (qa << 6);
+      float v4[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const unsigned char* rk = s_sp + (kk * 32 + lane) * pitch + shk[kk];
+        const unsigned b1 = rk[i1], b2 = rk[i2], b3 = rk[i3];
+        const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
+        const unsigned e = trow[qb];
+        const float v = s_tab.val[e & 0x3ffu] - s_sc[kk * 4 + (e >> 10)];  // observed - expected (src/score.c:422-425), or constant - 0
+        const unsigned zero = nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X);  // src/score.c:394-404
+        v4[kk] = (zero || k0 + kk >= bd.NK) ? 0.0f : v;
+      }
+      *reinterpret_cast<float4*>(smem + (size_t)j * ROW_BYTES + kq * 512 + lane * 16) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+    }
+    __syncthreads();  // the staged rows are free for the next quad; after the last quad: the table is complete
+  }
+
+  // ---- DP phase: k_dp_smp's loop with the fold in species-sum space ------------------------------------------------------
+  unsigned sig_a = smem_u32(smem) + lane * 16;
+  asm volatile("" : "+r"(sig_a));
+  const float Delta = prm.Delta, Omega = prm.Omega;
+  float omega = prm.omega;
+  asm volatile("" : "+f"(omega));
+  const float fNK = bd.fNK, rcpNK = bd.rcpNK, foldB = bd.fold_B;
+  RowRec* rec_inst = recs + it.rec_off[strand][frame] + (size_t)(valid ? inst_l : 0) * sites;
+  const int npairs = (sites + 1) / 2;
+  float2* part = nullptr;
+  if (CHAINED) {
+    const size_t per_group = ((size_t)npairs * sites - (size_t)npairs * (npairs - 1)) * 32;
+    part = partial + it.part_off[strand][frame] + (size_t)group * per_group + lane;
+  }
+#pragma unroll 1
+  for (int turn = 0;; turn++) {
+    const int p = (turn & 1) ? (turn + 1) * nw - 1 - warp : turn * nw + warp;  // boustrophedon, see k_dp_smp
+    if (turn * nw >= npairs) break;
+    if (p >= npairs) continue;
+    const int r0 = 2 * p;
+    RowRec* rec0 = srec + (warp * 32 + lane) * 2;
+    float2* pp = CHAINED ? part + ((size_t)p * sites - (size_t)p * (p - 1) - r0) * 32 : nullptr;
+    float2 S0[NK], S1[NK], S2[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
+    RowFoldS fx, fy;
+    folds_init(fx, foldB);
+    folds_init(fy, foldB);
+    int j = r0;
+#pragma unroll 1
+    while (j < sites) {
+      float svA[RS];
+      const unsigned zA = zs[j];
+      smp_load_row<NK>(sig_a + j * ROW_BYTES, zA, svA);
+      if (j >= r0 + 2 && j + 1 < sites) {
+        const unsigned zB = zs[j + 1];
+        if ((zA | zB) == 0u) {
+          float svB[RS];
+          smp_load_row<NK>(sig_a + (j + 1) * ROW_BYTES, zB, svB);
+          float2 sumA, sumB, sinA = make_float2(0.0f, 0.0f), sinB = make_float2(0.0f, 0.0f);
+          if (CHAINED && !first) {
+            sinA = pp[(size_t)j * 32];
+            sinB = pp[(size_t)(j + 1) * 32];
+          }
+          reg_pair_fast<NK, CHAINED>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
+          if (CHAINED && !last) {
+            pp[(size_t)j * 32] = sumA;
+            pp[(size_t)(j + 1) * 32] = sumB;
+          } else {
+#if RC_FOLD_GATE
+            if (fmaxf(sumA.x, sumB.x) > fx.lo || fmaxf(sumA.y, sumB.y) > fy.lo)
+#endif
+            {
+              RowFoldS nx = fx, ny = fy;
+              bool amb = false;
+              const float2 aB = add2(sumA, make_float2(fx.nB, fy.nB)), bB = add2(sumB, make_float2(fx.nB, fy.nB));
+              folds_fast(nx, sumA.x, aB.x, j, amb);
+              folds_fast(ny, sumA.y, aB.y, j, amb);
+              folds_fast(nx, sumB.x, bB.x, j + 1, amb);
+              folds_fast(ny, sumB.y, bB.y, j + 1, amb);
+              if (amb) {  // a possible near tie after some row's maximum: the two rows again, entry by entry, exactly
+                fx = folds_exact(fx, sumA.x, j, fNK, rcpNK, rec0, band_slots);
+                fx = folds_exact(fx, sumB.x, j + 1, fNK, rcpNK, rec0, band_slots);
+                fy = folds_exact(fy, sumA.y, j, fNK, rcpNK, rec0 + 1, band_slots);
+                fy = folds_exact(fy, sumB.y, j + 1, fNK, rcpNK, rec0 + 1, band_slots);
+              } else {
+                fx = nx;
+                fy = ny;
+              }
+            }
+          }
+          j += 2;
+          continue;
+        }
+      }
+      float2 sin = make_float2(0.0f, 0.0f);
+      if (CHAINED && !first) sin = pp[(size_t)j * 32];
+      const float2 sum = reg_update<NK, CHAINED>(S0, S1, S2, svA, j < r0 + 2, j, r0, Delta, Omega, omega, sin);
+      if (CHAINED && !last) {
+        pp[(size_t)j * 32] = sum;
+      } else {
+        // single end codon (start of the rows, or some species has a frameshift): the exact path is cheap enough here
+        // when it is needed, the fast one otherwise; row r0 + 1 starts one codon later
+        RowFoldS nx = fx, ny = fy;
+        bool amb = false;
+        const float2 sB = add2(sum, make_float2(fx.nB, fy.nB));
+        const bool ylive = j > r0;
+        folds_fast(nx, sum.x, sB.x, j, amb);
+        if (ylive) folds_fast(ny, sum.y, sB.y, j, amb);
+        if (amb) {
+          fx = folds_exact(fx, sum.x, j, fNK, rcpNK, rec0, band_slots);
+          if (ylive) fy = folds_exact(fy, sum.y, j, fNK, rcpNK, rec0 + 1, band_slots);
+        } else {
+          fx = nx;
+          fy = ny;
+        }
+      }
+      j += 1;
+    }
+    if (valid && last) {
+      folds_store(fx, rec_inst + r0, rec0, fNK, rcpNK);
+      if (r0 + 1 < sites) folds_store(fy, rec_inst + r0 + 1, rec0 + 1, fNK, rcpNK);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // (c) k_hss: the sequential scan of getHSS (src/score.c:888-961) over row digests.
 // One WARP per (instance, strand, frame): the lanes fetch 32 row records at a time (coalesced 1 KB), rows without
 // a positive entry are skipped by ballot, the others are replayed in row order with their fields broadcast by
@@ -2288,8 +2611,10 @@ __global__ void __launch_bounds__(128)
 // (src/treeSimulate.c:52-97, :254-283, src/misc.c:150-171; seq-gen HKY, no rate heterogeneity:
 // seqgen/evolve.c:167-199, :291-308, :400-433).
 //
-// rng 0 (exact): one warp per (block, sample) owns a bit-exact MT19937 (seqgen/twister.c:73-146), seeded with
-// the sample's seed, and consumes it in seq-gen's order: nodes in evolution order, one genrand_real1 per site.
+// rng 0 (exact): every (block, sample) has a bit-exact MT19937 (seqgen/twister.c:73-146), seeded with the sample's
+// seed and consumed in seq-gen's order: nodes in evolution order, one genrand_real1 per site.  A warp owns EVO_SPW
+// consecutive samples: their generators are seeded side by side (init_genrand is a serial chain of 624 steps, lane q
+// runs it for sample q), then the warp draws the samples one after the other with all 32 lanes.
 // The 624-word state lives in shared memory and is regenerated by the 32 lanes in place (each lane reads its
 // three source words before any lane writes; the recurrence only reaches words of earlier batches or old words
 // of later ones).  SetState's `r > P[j]` on doubles (r = u * (1/4294967295.0)) is evaluated as `u > thr[j]`
@@ -2350,68 +2675,81 @@ __device__ __forceinline__ unsigned philox_draw(unsigned seed, unsigned node, un
 }
 
 constexpr int EVO_WARPS = 4;
+constexpr int EVO_SPW = 8;          // samples per warp: their MT19937 states are seeded side by side, one lane each
+constexpr int EVO_MT_PITCH = 625;   // words per state in shared memory (odd: the seeding lanes hit distinct banks)
+constexpr int EVO_SMEM = EVO_WARPS * EVO_SPW * EVO_MT_PITCH * 4;
 
 __global__ void __launch_bounds__(EVO_WARPS * 32)
     k_evolve(const BlockDev* __restrict__ blocks, const EvoDev* __restrict__ evos, const int* __restrict__ nodes,
              const unsigned* __restrict__ thr, const unsigned* __restrict__ seeds, unsigned char* __restrict__ seqs,
-             unsigned char* __restrict__ raw) {
-  __shared__ unsigned s_mt[EVO_WARPS][624];
+             unsigned char* __restrict__ raw, int evo0) {
+  extern __shared__ unsigned s_mt[];  // [EVO_WARPS][EVO_SPW][EVO_MT_PITCH]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const EvoDev ev = evos[blockIdx.y];
+  const EvoDev ev = evos[evo0 + blockIdx.y];
   const BlockDev& bd = blocks[ev.block];
-  const int sample = blockIdx.x * EVO_WARPS + warp;
-  if (sample >= bd.n_inst - 1) return;
+  const int n_samp = bd.n_inst - 1;
+  const int s_base = (blockIdx.x * EVO_WARPS + warp) * EVO_SPW;  // the warp draws samples s_base .. s_base + EVO_SPW - 1, one after the other
+  if (s_base >= n_samp) return;
+  const int n_mine = min(EVO_SPW, n_samp - s_base);
   const int cols = bd.cols;
-  const unsigned seed = seeds[ev.seed_off + sample];
   const int* nd = nodes + ev.node_off;
   const unsigned* th = thr + ev.thr_off;
-  unsigned char* myseq = seqs + ev.seq_off + (size_t)sample * ev.n_internal * cols;
-  unsigned char* myraw = raw + bd.raw_off + (size_t)sample * bd.N * cols;
-  unsigned* mt = s_mt[warp];
-  int pos = 624;  // next unread word of the current 624-word batch
+  unsigned* wmt = s_mt + warp * (EVO_SPW * EVO_MT_PITCH);
   if (ev.rng == 0) {
-    // init_genrand (seqgen/twister.c:73-86) is a serial recurrence: every lane runs it redundantly in
-    // registers, lane l keeps the words it owns
-    unsigned x = seed;
-    for (int i = 0; i < 624; i++) {
-      if ((i & 31) == lane) mt[i] = x;
-      x = 1812433253u * (x ^ (x >> 30)) + (unsigned)(i + 1);
+    // init_genrand (seqgen/twister.c:73-86) is a serial recurrence of 624 steps: lane q runs it for sample s_base + q, so
+    // the warp seeds its EVO_SPW generators in the time of one
+    if (lane < n_mine) {
+      unsigned x = seeds[ev.seed_off + s_base + lane];
+      unsigned* m = wmt + lane * EVO_MT_PITCH;
+      for (int i = 0; i < 624; i++) {
+        m[i] = x;
+        x = 1812433253u * (x ^ (x >> 30)) + (unsigned)(i + 1);
+      }
     }
     __syncwarp();
   }
-  for (int n = 0; n < ev.n_nodes; n++) {
-    const int parent = nd[4 * n], row = nd[4 * n + 1], slot = nd[4 * n + 2];
-    const unsigned char* pseq = parent >= 0 ? myseq + (size_t)nd[4 * parent + 2] * cols : nullptr;
-    const unsigned* tn = th + (size_t)n * 16;
-    for (int c0 = 0; c0 < cols; c0 += 32) {
-      const int site = c0 + lane;
-      const int cnt = min(32, cols - c0);  // draws consumed by this chunk
-      unsigned u;
-      if (ev.rng == 0) {
-        // lanes 0..cnt-1 take the next cnt outputs of the generator, in order
-        int idx = pos + lane;
-        unsigned v = 0;
-        if (lane < cnt && idx < 624) v = mt[idx];
-        if (pos + cnt > 624) {  // the chunk crosses a batch boundary (warp-uniform)
-          __syncwarp();
-          mt_twist(mt, lane);
-          if (lane < cnt && idx >= 624) v = mt[idx - 624];
-          pos -= 624;
+#pragma unroll 1
+  for (int q = 0; q < n_mine; q++) {
+    const int sample = s_base + q;
+    const unsigned seed = seeds[ev.seed_off + sample];
+    unsigned char* myseq = seqs + ev.seq_off + (size_t)sample * ev.n_internal * cols;
+    unsigned char* myraw = raw + bd.raw_off + (size_t)sample * bd.N * cols;
+    unsigned* mt = wmt + q * EVO_MT_PITCH;
+    int pos = 624;  // next unread word of the current 624-word batch
+    for (int n = 0; n < ev.n_nodes; n++) {
+      const int parent = nd[4 * n], row = nd[4 * n + 1], slot = nd[4 * n + 2];
+      const unsigned char* pseq = parent >= 0 ? myseq + (size_t)nd[4 * parent + 2] * cols : nullptr;
+      const unsigned* tn = th + (size_t)n * 16;
+      for (int c0 = 0; c0 < cols; c0 += 32) {
+        const int site = c0 + lane;
+        const int cnt = min(32, cols - c0);  // draws consumed by this chunk
+        unsigned u;
+        if (ev.rng == 0) {
+          // lanes 0..cnt-1 take the next cnt outputs of the generator, in order
+          int idx = pos + lane;
+          unsigned v = 0;
+          if (lane < cnt && idx < 624) v = mt[idx];
+          if (pos + cnt > 624) {  // the chunk crosses a batch boundary (warp-uniform)
+            __syncwarp();
+            mt_twist(mt, lane);
+            if (lane < cnt && idx >= 624) v = mt[idx - 624];
+            pos -= 624;
+          }
+          pos += cnt;
+          u = mt_temper(v);
+        } else {
+          u = philox_draw(seed, (unsigned)n, (unsigned)site);
         }
-        pos += cnt;
-        u = mt_temper(v);
-      } else {
-        u = philox_draw(seed, (unsigned)n, (unsigned)site);
+        if (site < cols) {
+          const int ps = parent >= 0 ? (int)pseq[site] : 0;  // root: row 0 of its table holds the cumulative frequencies
+          const unsigned* t = tn + ps * 4;
+          const int state = (u > t[0]) + (u > t[1]) + (u > t[2]);
+          if (slot >= 0) myseq[(size_t)slot * cols + site] = (unsigned char)state;
+          if (row >= 0) myraw[(size_t)row * cols + site] = (unsigned char)("ACGT"[state]);
+        }
       }
-      if (site < cols) {
-        const int ps = parent >= 0 ? (int)pseq[site] : 0;  // root: row 0 of its table holds the cumulative frequencies
-        const unsigned* t = tn + ps * 4;
-        const int state = (u > t[0]) + (u > t[1]) + (u > t[2]);
-        if (slot >= 0) myseq[(size_t)slot * cols + site] = (unsigned char)state;
-        if (row >= 0) myraw[(size_t)row * cols + site] = (unsigned char)("ACGT"[state]);
-      }
+      __syncwarp();  // a child reads its parent's sequence written by other lanes
     }
-    __syncwarp();  // a child reads its parent's sequence written by other lanes
   }
 }
 

@@ -45,6 +45,7 @@ struct rc_ctx {
   long reg_max_nk = 12;  // row-major alignments with more scored species take k_dp_chain (k_dp_reg<13..16> spills: 17x3000 14.7 vs 11.1 ms)
   long no_smps = 0;          // never stream the sigma table in segments (k_dp_smps)
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
+  long no_fused = 0;          // never build the sigma table inside the sample-major DP kernel (k_dp_smpf)
   long tail_max = 12;         // a sample-major block whose instance count leaves 1..tail_max instances in its last group of 32 scores
                               // those instances row-major (lanes = rows) instead of in a warp with that many live lanes (0: never)
   long smpc_max_sites = 0;    // longest frame (codons) for the STREAMED chunked sample-major route of wide alignments
@@ -126,7 +127,10 @@ constexpr int SMPC_Q_MIN = 4, SMPC_Q_MAX = 125;
 // and the segmented (streaming) variants k_dp_smps of both sample-major kinds
 constexpr int SMPS_CLASS0 = SMPC_CLASS0 + (SMPC_Q_MAX - SMPC_Q_MIN + 1);
 constexpr int SMPCS_CLASS0 = SMPS_CLASS0 + REG_MAX_NK;
-constexpr int N_CLASSES = SMPCS_CLASS0 + (SMPC_Q_MAX - SMPC_Q_MIN + 1);
+// and the fused variants k_dp_smpf (sigma table built inside the DP kernel) of the resident-table kinds
+constexpr int SMPF_CLASS0 = SMPCS_CLASS0 + (SMPC_Q_MAX - SMPC_Q_MIN + 1);
+constexpr int SMPCF_CLASS0 = SMPF_CLASS0 + REG_MAX_NK;
+constexpr int N_CLASSES = SMPCF_CLASS0 + (SMPC_Q_MAX - SMPC_Q_MIN + 1);
 constexpr size_t SMP_SMEM_MAX = 200 * 1024;  // sigma table + z words of one CTA of k_dp_smp
 constexpr int SMP_MIN_INST = 16;             // fewer instances than this: the row-major kernels are the better fit
 
@@ -135,6 +139,8 @@ struct Chunk {
   size_t cta0[N_CLASSES] = {}, ncta[N_CLASSES] = {};  // per class range in the CTA array
   int maxNK[N_CLASSES] = {}, maxZs[N_CLASSES] = {};
   size_t sigma_floats = 0, rec_count = 0, part_count = 0, max_smp_smem = 0, max_smps_smem = 0;
+  size_t max_smpf_smem = 0;  // k_dp_smpf: shared memory of a CTA without the fold records
+  int n_smp_unfused = 0;     // sample-major items that still need k_sigma_smp
   long long max_sigma_work = 0;  // largest ninst*2*(L-2) of an item, for the k_sigma grid
   int max_ninst = 0;
   int n_layout[6] = {0, 0, 0, 0, 0, 0};  // items per sigma layout
@@ -152,8 +158,8 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int class_of(const BlockDev& bd) {
   if (bd.layout == 3) return CHAIN_CLASS0 + (bd.nchunk - 2) * CHAIN_NKW_SPAN + (bd.nkw - CHAIN_NKW_MIN);
-  if (bd.layout == 5) return (bd.smp_seg ? SMPCS_CLASS0 : SMPC_CLASS0) + ((bd.NK + 3) / 4 - SMPC_Q_MIN);
-  if (bd.layout == 2) return bd.smp_seg ? SMPS_CLASS0 + bd.NK - 1 : SMP_CLASS0 + bd.NK - 1;
+  if (bd.layout == 5) return (bd.smp_seg ? SMPCS_CLASS0 : (bd.smp_fused ? SMPCF_CLASS0 : SMPC_CLASS0)) + ((bd.NK + 3) / 4 - SMPC_Q_MIN);
+  if (bd.layout == 2) return (bd.smp_seg ? SMPS_CLASS0 : (bd.smp_fused ? SMPF_CLASS0 : SMP_CLASS0)) + bd.NK - 1;
   if (bd.layout == 1) return bd.NK - 1;
   return bd.NK <= 24 ? REG_MAX_NK : REG_MAX_NK + 1;
 }
@@ -185,8 +191,20 @@ size_t smp_smem_bytes(const BlockDev& bd, int f, int layout, int seg) {
   return (size_t)bd.sites[f] * rsb * 32 * 4 + zb + 16;
 }
 
+// k_dp_smpf: staged row pitch and shared memory of a CTA (frame 0 is the longest) without the fold records
+int smpf_pitch(int cols) {
+  int p = (cols + 6 + 3) / 4 * 4;
+  if (((p / 4) & 1) == 0) p += 4;  // odd word count: 32 lanes (rows) hit 32 banks
+  return p;
+}
+size_t smpf_smem_bytes(const BlockDev& bd, int layout) {
+  const int row_bytes = (layout == 5 ? 12 : (bd.NK + 3) / 4 * 4) * 32 * 4;
+  return SmpfCfg<1>::off_rec(bd.sites[0], row_bytes, smpf_pitch(bd.cols));
+}
+
 // floats of sigma scratch for `ninst` instances of one (strand, frame) of a block
 size_t sigma_floats_sf(const BlockDev& bd, int f, int ninst) {
+  if ((bd.layout == 2 || bd.layout == 5) && bd.smp_fused) return 0;  // the table only ever exists in shared memory
   if (bd.layout == 2) {
     const size_t rsb = (size_t)(bd.NK + 3) / 4 * 4;
     return (size_t)((ninst + 31) / 32) * bd.sites[f] * rsb * 32;
@@ -381,6 +399,7 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   if (const char* e = getenv("RNACODE_CUDA_SMPS_MAX_SITES")) ctx->smps_max_sites = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_SMP_WARPS")) ctx->smp_warps_forced = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_HSS_THR_TASKS")) ctx->hss_thr_tasks = atol(e);
+  if (const char* e = getenv("RNACODE_CUDA_NO_FUSED")) ctx->no_fused = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_TAIL_MAX")) ctx->tail_max = std::max(0L, std::min(31L, atol(e)));
   if (const char* e = getenv("RNACODE_CUDA_REG_MAX_NK")) ctx->reg_max_nk = std::max(12L, std::min<long>(REG_MAX_NK, atol(e)));
   unsigned char lut[256];
@@ -447,6 +466,8 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->smps_max_sites = value;
   } else if (k == "smpc_max_sites") {
     ctx->smpc_max_sites = value;
+  } else if (k == "no_fused") {
+    ctx->no_fused = value ? 1 : 0;
   } else if (k == "tail_max") {
     if (value < 0 || value > 31) { ctx_fail(ctx, "tail_max must be 0..31"); return RC_ERR_ARG; }
     ctx->tail_max = value;
@@ -647,6 +668,27 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       set_layout(bd, layout);
       bd.smp_seg = seg;
       finish_layout(bd);
+      // resident-table sample-major blocks build their sigma table inside the DP kernel when the staged rows fit as well
+      if ((layout == 2 || layout == 5) && !seg && !ctx->no_fused && params->Delta <= 0.0f &&
+          smpf_smem_bytes(bd, layout) + (size_t)SMP_WARPS * 64 * sizeof(RowRec) <= (size_t)ctx->smem_optin) {
+        bd.smp_fused = 1;
+        bd.smp_pitch = smpf_pitch(bd.cols);
+        // B of RowFoldS: (N-1) * 1.0002e-4 for the tolerance of getHSS's tie rule plus 2^-21 of the largest species sum a
+        // row can reach (per end codon and species at most the largest sigma -- BLOSUM entry or stop penalty minus the
+        // smallest expected score -- or a positive penalty) for the roundings of the two quotients and of the bound itself
+        int bmax = 0;
+        for (int q = 0; q < 576; q++) bmax = std::max(bmax, blosum[q]);
+        double smax = 0.0;
+        for (int k = 1; k < d.N; k++) {
+          double lo = 0.0;
+          for (int h = 1; h < 4; h++) lo = std::min(lo, (double)std::min(d.scores_fwd[4 * k + h], d.scores_rev[4 * k + h]));
+          double g = std::max({(double)bmax, (double)params->stopPenalty_0, (double)params->stopPenalty_k}) - lo;
+          g = std::max({g, (double)params->omega, (double)params->Omega, 0.0});
+          smax += g;
+        }
+        smax *= std::max(1, bd.sites[0]);
+        bd.fold_B = (float)(bd.NK * 1.0002e-4 + smax / 2097152.0);
+      }
     }
     for (int s = 0; s < 2; s++)
       for (int f = 0; f < 3; f++) {
@@ -763,7 +805,10 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
         }
       const int cl = class_of(bd);
       cur.maxNK[cl] = std::max(cur.maxNK[cl], bd.NK);
-      if (bd.layout == 2 || bd.layout == 5) {
+      if ((bd.layout == 2 || bd.layout == 5) && bd.smp_fused) {
+        cur.max_smpf_smem = std::max(cur.max_smpf_smem, smpf_smem_bytes(bd, bd.layout));
+      } else if (bd.layout == 2 || bd.layout == 5) {
+        cur.n_smp_unfused++;
         if (!bd.smp_seg) cur.max_smp_smem = std::max(cur.max_smp_smem, smp_smem_bytes(bd, 0, bd.layout, 0));
         if (bd.smp_seg) cur.max_smps_smem = std::max(cur.max_smps_smem, smp_smem_bytes(bd, 0, bd.layout, 1));
         cur.max_smp_quads = std::max(cur.max_smp_quads, (bd.NK + 3) / 4);
@@ -804,7 +849,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
   bool ok = dalloc((void**)&b->d_blocks, sizeof(BlockDev) * b->blocks.size()) &&
             dalloc((void**)&b->d_items, sizeof(Item) * b->items.size()) &&
             dalloc((void**)&b->d_ctas, sizeof(CtaDesc) * b->ctas.size()) &&
-            dalloc((void**)&b->d_raw, b->raw_bytes + b->nat_bytes + 64) && dalloc((void**)&b->d_cls, b->cls_bytes) && dalloc((void**)&b->d_cols0, sizeof(int) * b->cols0_ints) &&
+            dalloc((void**)&b->d_raw, b->raw_bytes + b->nat_bytes + 64) && dalloc((void**)&b->d_cls, b->cls_bytes + 64) && dalloc((void**)&b->d_cols0, sizeof(int) * b->cols0_ints) &&
             dalloc((void**)&b->d_scores, sizeof(float) * b->scores_floats) &&
             dalloc((void**)&b->d_z, sizeof(unsigned) * b->z_words) && dalloc((void**)&b->d_res, sizeof(float) * b->res_floats) &&
             dalloc((void**)&b->d_hss, sizeof(HssDev) * b->hss_count) &&
@@ -1177,6 +1222,64 @@ static int launch_dp_smp(rc_batch* b, int NK, bool seg, const CtaDesc* d_ctas, s
   }
 }
 
+// k_dp_smpf: the fused kernels (sigma table built in shared memory by the DP CTA itself)
+template <int NK, bool CHAINED>
+static int launch_dp_smpf_nk(rc_batch* b, int chunk, bool last, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
+  rc_ctx* ctx = b->ctx;
+  (void)last;
+  const int nw = smp_warps(ctx, smem, true);
+  smem += (size_t)nw * 64 * sizeof(RowRec);  // the carve-up always has the records at the end (SmpfCfg::off_rec)
+  RC_CUDA(cudaFuncSetAttribute(k_dp_smpf<NK, CHAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dp_smpf<NK, CHAINED><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_cls, b->d_cols0,
+                                                                         b->d_scores, b->d_ptab, b->d_z, b->d_recs, b->prm,
+                                                                         (int)ctx->band_slots, chunk, b->d_partial);
+  RC_CUDA(cudaGetLastError());
+  b->stats.launches++;
+  b->stats.dp_launches++;
+  return RC_OK;
+}
+
+static int launch_dp_smpf(rc_batch* b, int NK, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
+  if (ncta == 0) return RC_OK;
+  switch (NK) {
+    case 1: return launch_dp_smpf_nk<1, false>(b, 0, true, d_ctas, ncta, smem);
+    case 2: return launch_dp_smpf_nk<2, false>(b, 0, true, d_ctas, ncta, smem);
+    case 3: return launch_dp_smpf_nk<3, false>(b, 0, true, d_ctas, ncta, smem);
+    case 4: return launch_dp_smpf_nk<4, false>(b, 0, true, d_ctas, ncta, smem);
+    case 5: return launch_dp_smpf_nk<5, false>(b, 0, true, d_ctas, ncta, smem);
+    case 6: return launch_dp_smpf_nk<6, false>(b, 0, true, d_ctas, ncta, smem);
+    case 7: return launch_dp_smpf_nk<7, false>(b, 0, true, d_ctas, ncta, smem);
+    case 8: return launch_dp_smpf_nk<8, false>(b, 0, true, d_ctas, ncta, smem);
+    case 9: return launch_dp_smpf_nk<9, false>(b, 0, true, d_ctas, ncta, smem);
+    case 10: return launch_dp_smpf_nk<10, false>(b, 0, true, d_ctas, ncta, smem);
+    case 11: return launch_dp_smpf_nk<11, false>(b, 0, true, d_ctas, ncta, smem);
+    case 12: return launch_dp_smpf_nk<12, false>(b, 0, true, d_ctas, ncta, smem);
+    case 13: return launch_dp_smpf_nk<13, false>(b, 0, true, d_ctas, ncta, smem);
+    case 14: return launch_dp_smpf_nk<14, false>(b, 0, true, d_ctas, ncta, smem);
+    case 15: return launch_dp_smpf_nk<15, false>(b, 0, true, d_ctas, ncta, smem);
+    case 16: return launch_dp_smpf_nk<16, false>(b, 0, true, d_ctas, ncta, smem);
+    default: ctx_fail(b->ctx, "internal: k_dp_smpf NK out of range"); return RC_ERR_STATE;
+  }
+}
+
+// layout 5, fused: one launch per species chunk (1-3 quads each), as launch_dp_smpc
+static int launch_dp_smpcf(rc_batch* b, int Q, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
+  if (ncta == 0) return RC_OK;
+  const int W = (Q + 2) / 3, base = Q / W, rem = Q % W;
+  for (int g = 0; g < W; g++) {
+    const int quads = base + (g < rem ? 1 : 0);
+    int rc;
+    switch (quads) {
+      case 1: rc = launch_dp_smpf_nk<4, true>(b, g, g == W - 1, d_ctas, ncta, smem); break;
+      case 2: rc = launch_dp_smpf_nk<8, true>(b, g, g == W - 1, d_ctas, ncta, smem); break;
+      case 3: rc = launch_dp_smpf_nk<12, true>(b, g, g == W - 1, d_ctas, ncta, smem); break;
+      default: ctx_fail(b->ctx, "internal: k_dp_smpf chunk size out of range"); return RC_ERR_STATE;
+    }
+    if (rc != RC_OK) return rc;
+  }
+  return RC_OK;
+}
+
 template <int NKW>
 static int launch_dp_chain_nk(rc_batch* b, int W, const CtaDesc* d_ctas, size_t ncta) {
   rc_ctx* ctx = b->ctx;
@@ -1350,11 +1453,15 @@ extern "C" int rc_batch_run(rc_batch* b) {
   for (const BlockDev& bd : b->blocks) maxchunks = std::max(maxchunks, (int)(((size_t)bd.inst_stride >> 4) * bd.n_inst / 256 + 1));
   int ev = ev_begin(b, 0);
   if (!b->evos.empty()) {
-    dim3 ge((unsigned)((b->evo_max_samples + EVO_WARPS - 1) / EVO_WARPS), (unsigned)b->evos.size());
-    k_evolve<<<ge, EVO_WARPS * 32, 0, st>>>(b->d_blocks, b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds,
-                                            b->d_evo_seq, b->d_raw);
-    RC_CUDA(cudaGetLastError());
-    b->stats.launches++;
+    RC_CUDA(cudaFuncSetAttribute(k_evolve, cudaFuncAttributeMaxDynamicSharedMemorySize, EVO_SMEM));
+    const unsigned gx = (unsigned)((b->evo_max_samples + EVO_WARPS * EVO_SPW - 1) / (EVO_WARPS * EVO_SPW));
+    for (size_t e0 = 0; e0 < b->evos.size(); e0 += 65535) {  // gridDim.y is limited to 65535
+      dim3 ge(gx, (unsigned)std::min<size_t>(65535, b->evos.size() - e0));
+      k_evolve<<<ge, EVO_WARPS * 32, EVO_SMEM, st>>>(b->d_blocks, b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds,
+                                                    b->d_evo_seq, b->d_raw, (int)e0);
+      RC_CUDA(cudaGetLastError());
+      b->stats.launches++;
+    }
   }
   {
     dim3 g((unsigned)b->n_blocks, (unsigned)std::min(maxchunks, 2048));
@@ -1410,7 +1517,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
         RC_CUDA(cudaGetLastError());
         b->stats.launches++;
       }
-      if (ch.max_smp_smem > 0 || ch.max_smps_smem > 0) {  // some items use the sample-major layouts
+      if (ch.n_smp_unfused > 0) {  // some items use the sample-major layouts with a sigma table in HBM
         const int nqz = std::min(16, std::max(1, ch.max_smp_quads / 3));
         const int npc = (ch.max_smp_npos + SIG_PCH - 1) / SIG_PCH;
         dim3 g2((unsigned)ch.nitems, (unsigned)((ch.max_ninst + 31) / 32), (unsigned)(npc * 2 * nqz));
@@ -1429,7 +1536,11 @@ extern "C" int rc_batch_run(rc_batch* b) {
       for (int cl = 0; cl < N_CLASSES; cl++) {
         if (ch.ncta[cl] == 0) continue;
         int rcode;
-        if (cl >= SMPCS_CLASS0)
+        if (cl >= SMPCF_CLASS0)
+          rcode = launch_dp_smpcf(b, SMPC_Q_MIN + (cl - SMPCF_CLASS0), b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smpf_smem);
+        else if (cl >= SMPF_CLASS0)
+          rcode = launch_dp_smpf(b, cl - SMPF_CLASS0 + 1, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smpf_smem);
+        else if (cl >= SMPCS_CLASS0)
           rcode = launch_dp_smpc(b, SMPC_Q_MIN + (cl - SMPCS_CLASS0), true, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smps_smem);
         else if (cl >= SMPS_CLASS0)
           rcode = launch_dp_smp(b, cl - SMPS_CLASS0 + 1, true, b->d_ctas + ch.cta0[cl], ch.ncta[cl], ch.max_smps_smem);
