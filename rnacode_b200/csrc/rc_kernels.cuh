@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(256)
   const Item it = items[blockIdx.x];
   const BlockDev bd = blocks[it.block];
   const int group = blockIdx.y;
-  if ((bd.layout != 2 && bd.layout != 5) || group * 32 >= it.ninst) return;
+  if ((bd.layout != 2 && bd.layout != 5) || bd.smp_fused || group * 32 >= it.ninst) return;  // fused: k_dp_smpf builds its own table
   // blockIdx.z = ((position chunk * 2) + strand) * nqz + quad share
   const int qz = blockIdx.z % nqz, s_cta = (blockIdx.z / nqz) & 1, pc = blockIdx.z / (2 * nqz);
   const int L = bd.L, N = bd.N, NK = bd.NK, cols = bd.cols;
@@ -1719,6 +1719,124 @@ __global__ void
 }
 
 // ---------------------------------------------------------------------------------------------
+// getHSS fold of the sample-major kernels in the space of the species sums (see k_dp_smpf for the argument)
+// ---------------------------------------------------------------------------------------------
+#ifndef RC_SMP_FOLDS
+#define RC_SMP_FOLDS 1  // 0: the round-1 fold on the quotients (fold_entry) in k_dp_smp / k_dp_smps
+#endif
+struct RowFoldS {
+  float Ms;   // largest positive species sum so far (0: none yet); +inf: complex row, the state is in the shared-memory record
+  float lo;   // max(Ms - B, 0): a later sum in (lo, Ms) may fall into the tie band of the maximum
+  float nB;   // -B; -inf for a complex row (then lo stays 0 and every positive sum takes the exact path)
+  int jF;     // end codon of Ms
+};
+__device__ __forceinline__ void folds_init(RowFoldS& f, float B) {
+  f.Ms = 0.0f;
+  f.lo = 0.0f;
+  f.nB = -B;
+  f.jF = 0;
+}
+// sB = s + nB (computed for both rows of the lane with one packed add)
+__device__ __forceinline__ void folds_fast(RowFoldS& f, float s, float sB, int j, bool& amb) {
+  const bool p = s >= f.Ms;
+  amb = amb || (s > f.lo && !p);
+  f.Ms = fmaxf(f.Ms, s);
+  f.lo = fmaxf(f.lo, sB);
+  f.jF = p ? j : f.jF;
+}
+__device__ __forceinline__ float quot_nk(float s, float fNK, float rcpNK) {  // the correctly rounded s / (N-1), see k_dp
+  const float q = s * rcpNK;
+  return __fmaf_rn(__fmaf_rn(-fNK, q, s), rcpNK, q);
+}
+__device__ __noinline__ RowFoldS folds_exact(RowFoldS f, float s, int j, float fNK, float rcpNK, RowRec* rec, int slots) {
+  if (!(s > 0.0f)) return f;  // getHSS only looks at positive entries (src/score.c:891)
+  const float e = quot_nk(s, fNK, rcpNK);
+  if (f.Ms != INFINITY) {
+    if (s >= f.Ms) {  // what the fast path does
+      f.Ms = s;
+      f.jF = j;
+      f.lo = fmaxf(f.lo, s + f.nB);
+      return f;
+    }
+    const float Me = quot_nk(f.Ms, fNK, rcpNK);  // f.Ms > s > 0: something was accepted before
+    if (e == Me) {  // equal after rounding: an exact tie, the later (longer) entry stands for it
+      f.jF = j;
+      return f;
+    }
+    if (e - Me >= -0.0001f) {  // accepted below the maximum (src/score.c:953-954 without the length test): the band matters now
+      rec_init(rec);
+      fold_flush(rec, Me, f.jF);
+      hss_accept_rec(rec, e, j, slots);
+      f.Ms = INFINITY;
+      f.lo = 0.0f;
+      f.nB = -INFINITY;
+    }
+    return f;
+  }
+  if (e - rec->vF >= -0.0001f) hss_accept_rec(rec, e, j, slots);
+  return f;
+}
+// final record of a row: straight from the registers unless the row is complex
+__device__ __forceinline__ void folds_store(const RowFoldS& f, RowRec* grec, const RowRec* srec, float fNK, float rcpNK) {
+  uint4* g = reinterpret_cast<uint4*>(grec);
+  if (f.Ms == INFINITY) {
+    rec_copy(grec, srec);
+  } else if (f.Ms > 0.0f) {
+    const unsigned e = __float_as_uint(quot_nk(f.Ms, fNK, rcpNK));
+    g[0] = make_uint4(e, e, e, 0u);                                             // Emax, vF, be[0], be[1]
+    g[1] = make_uint4(0u, (unsigned)f.jF | (1u << 16), (unsigned)f.jF, 0u);     // be[2], jF | n << 16, bj[0] | bj[1] << 16, bj[2] | pad
+  } else {
+    const unsigned ninf = __float_as_uint(-INFINITY);
+    g[0] = make_uint4(ninf, ninf, 0u, 0u);
+    g[1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+#ifndef RC_FOLD_GATE
+#define RC_FOLD_GATE 0  // 1: skip the fold of a step pair when no lane has a sum above its row's lower bound
+#endif
+// two end codons (j, j+1) of the lane's two rows; the rows' states before the pair are kept for the exact path
+__device__ __forceinline__ void folds_pair(RowFoldS& fx, RowFoldS& fy, float2 sumA, float2 sumB, int j, float fNK, float rcpNK,
+                                           RowRec* rec0, int band_slots) {
+#if RC_FOLD_GATE
+  if (!(fmaxf(sumA.x, sumB.x) > fx.lo || fmaxf(sumA.y, sumB.y) > fy.lo)) return;
+#endif
+  RowFoldS nx = fx, ny = fy;
+  bool amb = false;
+  const float2 nB = make_float2(fx.nB, fy.nB);
+  const float2 aB = add2(sumA, nB), bB = add2(sumB, nB);
+  folds_fast(nx, sumA.x, aB.x, j, amb);
+  folds_fast(ny, sumA.y, aB.y, j, amb);
+  folds_fast(nx, sumB.x, bB.x, j + 1, amb);
+  folds_fast(ny, sumB.y, bB.y, j + 1, amb);
+  if (amb) {  // a possible near tie after some row's maximum: the two rows again, entry by entry, exactly
+    fx = folds_exact(fx, sumA.x, j, fNK, rcpNK, rec0, band_slots);
+    fx = folds_exact(fx, sumB.x, j + 1, fNK, rcpNK, rec0, band_slots);
+    fy = folds_exact(fy, sumA.y, j, fNK, rcpNK, rec0 + 1, band_slots);
+    fy = folds_exact(fy, sumB.y, j + 1, fNK, rcpNK, rec0 + 1, band_slots);
+  } else {
+    fx = nx;
+    fy = ny;
+  }
+}
+// one end codon; ylive: the lane's second row has started (it starts one codon after the first)
+__device__ __forceinline__ void folds_single(RowFoldS& fx, RowFoldS& fy, float2 sum, int j, bool ylive, float fNK, float rcpNK,
+                                             RowRec* rec0, int band_slots) {
+  RowFoldS nx = fx, ny = fy;
+  bool amb = false;
+  const float2 sB = add2(sum, make_float2(fx.nB, fy.nB));
+  folds_fast(nx, sum.x, sB.x, j, amb);
+  if (ylive) folds_fast(ny, sum.y, sB.y, j, amb);
+  if (amb) {
+    fx = folds_exact(fx, sum.x, j, fNK, rcpNK, rec0, band_slots);
+    if (ylive) fy = folds_exact(fy, sum.y, j, fNK, rcpNK, rec0 + 1, band_slots);
+  } else {
+    fx = nx;
+    fy = ny;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // (c) k_dp_smp: the DP for SHORT blocks with many null alignments (N-1 <= 16, sites*RSB*128 B fits in shared
 // memory).  Lane = one alignment instance (native or null sample), warp = 32 instances of the same block,
 // strand and frame, working on the same pair of start codons: the gap pattern and hence z, the row starts and
@@ -1810,17 +1928,25 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
     if (p >= npairs) continue;
     const int r0 = 2 * p;
     RowRec* rec0 = srec + (warp * 32 + lane) * 2;
+#if !RC_SMP_FOLDS
     if (last) {
       rec_init(rec0);
       rec_init(rec0 + 1);
     }
+#endif
     float2* pp = CHAINED ? part + ((size_t)p * sites - (size_t)p * (p - 1) - r0) * 32 : nullptr;  // pp[j * 32] = entry of end codon j
     float2 S0[NK], S1[NK], S2[NK];
 #pragma unroll
     for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
+#if RC_SMP_FOLDS
+    RowFoldS sx, sy;
+    folds_init(sx, bd.fold_B);
+    folds_init(sy, bd.fold_B);
+#else
     RowFold fx, fy;
     fold_init(fx);
     fold_init(fy);
+#endif
     int j = r0;
 #pragma unroll 1
     while (j < sites) {
@@ -1843,12 +1969,19 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
           if (CHAINED && !last) {
             pp[(size_t)j * 32] = sumA;
             pp[(size_t)(j + 1) * 32] = sumB;
-          } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
+          }
+#if RC_SMP_FOLDS
+          else {
+            folds_pair(sx, sy, sumA, sumB, j, fNK, rcpNK, rec0, band_slots);
+          }
+#else
+          else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
             fold_entry(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
             fold_entry(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
             fold_entry(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
             fold_entry(sumB.y, j + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
           }
+#endif
           j += 2;
           continue;
         }
@@ -1858,12 +1991,25 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
       const float2 sum = reg_update<NK, CHAINED>(S0, S1, S2, svA, j < r0 + 2, j, r0, Delta, Omega, omega, sin);
       if (CHAINED && !last) {
         pp[(size_t)j * 32] = sum;
-      } else if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
+      }
+#if RC_SMP_FOLDS
+      else {
+        folds_single(sx, sy, sum, j, j > r0, fNK, rcpNK, rec0, band_slots);
+      }
+#else
+      else if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
         fold_entry(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
         if (r0 + 1 < sites) fold_entry(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
       }
+#endif
       j += 1;
     }
+#if RC_SMP_FOLDS
+    if (valid && last) {
+      folds_store(sx, rec_inst + r0, rec0, fNK, rcpNK);
+      if (r0 + 1 < sites) folds_store(sy, rec_inst + r0 + 1, rec0 + 1, fNK, rcpNK);
+    }
+#else
     if (valid && last) {
 #pragma unroll
       for (int t = 0; t < 2; t++)
@@ -1873,6 +2019,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
           rec_copy(rec_inst + r0 + t, rec0 + t);
         }
     }
+#endif
   }
 }
 
@@ -1953,17 +2100,25 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
       }
     }
     RowRec* rec0 = srec + (warp * 32 + lane) * 2;
+#if !RC_SMP_FOLDS
     if (last && active) {
       rec_init(rec0);
       rec_init(rec0 + 1);
     }
+#endif
     float2* pp = CHAINED ? part + ((size_t)p * sites - (size_t)p * (p - 1) - r0) * 32 : nullptr;  // pp[j * 32] = entry of end codon j
     float2 S0[NK], S1[NK], S2[NK];
 #pragma unroll
     for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
+#if RC_SMP_FOLDS
+    RowFoldS sx, sy;
+    folds_init(sx, bd.fold_B);
+    folds_init(sy, bd.fold_B);
+#else
     RowFold fx, fy;
     fold_init(fx);
     fold_init(fy);
+#endif
     int j = r0;
 #pragma unroll 1
     for (int seg = seg0; seg < nseg; seg++, it_count++) {
@@ -1991,12 +2146,19 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
               if (CHAINED && !last) {
                 pp[(size_t)j * 32] = sumA;
                 pp[(size_t)(j + 1) * 32] = sumB;
-              } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
+              }
+#if RC_SMP_FOLDS
+              else {
+                folds_pair(sx, sy, sumA, sumB, j, fNK, rcpNK, rec0, band_slots);
+              }
+#else
+              else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
                 fold_entry(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
                 fold_entry(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
                 fold_entry(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
                 fold_entry(sumB.y, j + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
               }
+#endif
               j += 2;
               continue;
             }
@@ -2006,10 +2168,17 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
           const float2 sum = reg_update<NK, CHAINED>(S0, S1, S2, svA, j < r0 + 2, j, r0, Delta, Omega, omega, sin);
           if (CHAINED && !last) {
             pp[(size_t)j * 32] = sum;
-          } else if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
+          }
+#if RC_SMP_FOLDS
+          else {
+            folds_single(sx, sy, sum, j, j > r0, fNK, rcpNK, rec0, band_slots);
+          }
+#else
+          else if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
             fold_entry(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
             if (r0 + 1 < sites) fold_entry(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
           }
+#endif
           j += 1;
         }
       }
@@ -2020,6 +2189,12 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
         bulk_g2s(smem + st * STAGE_BYTES, sig_src + (size_t)(seg + 2) * T * (ROW_BYTES / 4), bytes, &bars[st]);
       }
     }
+#if RC_SMP_FOLDS
+    if (active && valid && last) {
+      folds_store(sx, rec_inst + r0, rec0, fNK, rcpNK);
+      if (r0 + 1 < sites) folds_store(sy, rec_inst + r0 + 1, rec0 + 1, fNK, rcpNK);
+    }
+#else
     if (active && valid && last) {
 #pragma unroll
       for (int t = 0; t < 2; t++)
@@ -2029,6 +2204,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
           rec_copy(rec_inst + r0 + t, rec0 + t);
         }
     }
+#endif
   }
 }
 
@@ -2054,78 +2230,6 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
 //     is "complex": its state lives in a shared-memory RowRec handled by hss_accept_rec, as in k_dp_smp.
 // The fast path is branch-free: per entry two compares, two max, one select.
 // ---------------------------------------------------------------------------------------------
-struct RowFoldS {
-  float Ms;   // largest positive species sum so far (0: none yet); +inf: complex row, the state is in the shared-memory record
-  float lo;   // max(Ms - B, 0): a later sum in (lo, Ms) may fall into the tie band of the maximum
-  float nB;   // -B; -inf for a complex row (then lo stays 0 and every positive sum takes the exact path)
-  int jF;     // end codon of Ms
-};
-__device__ __forceinline__ void folds_init(RowFoldS& f, float B) {
-  f.Ms = 0.0f;
-  f.lo = 0.0f;
-  f.nB = -B;
-  f.jF = 0;
-}
-// sB = s + nB (computed for both rows of the lane with one packed add)
-__device__ __forceinline__ void folds_fast(RowFoldS& f, float s, float sB, int j, bool& amb) {
-  const bool p = s >= f.Ms;
-  amb = amb || (s > f.lo && !p);
-  f.Ms = fmaxf(f.Ms, s);
-  f.lo = fmaxf(f.lo, sB);
-  f.jF = p ? j : f.jF;
-}
-__device__ __forceinline__ float quot_nk(float s, float fNK, float rcpNK) {  // the correctly rounded s / (N-1), see k_dp
-  const float q = s * rcpNK;
-  return __fmaf_rn(__fmaf_rn(-fNK, q, s), rcpNK, q);
-}
-__device__ __noinline__ RowFoldS folds_exact(RowFoldS f, float s, int j, float fNK, float rcpNK, RowRec* rec, int slots) {
-  if (!(s > 0.0f)) return f;  // getHSS only looks at positive entries (src/score.c:891)
-  const float e = quot_nk(s, fNK, rcpNK);
-  if (f.Ms != INFINITY) {
-    if (s >= f.Ms) {  // what the fast path does
-      f.Ms = s;
-      f.jF = j;
-      f.lo = fmaxf(f.lo, s + f.nB);
-      return f;
-    }
-    const float Me = quot_nk(f.Ms, fNK, rcpNK);  // f.Ms > s > 0: something was accepted before
-    if (e == Me) {  // equal after rounding: an exact tie, the later (longer) entry stands for it
-      f.jF = j;
-      return f;
-    }
-    if (e - Me >= -0.0001f) {  // accepted below the maximum (src/score.c:953-954 without the length test): the band matters now
-      rec_init(rec);
-      fold_flush(rec, Me, f.jF);
-      hss_accept_rec(rec, e, j, slots);
-      f.Ms = INFINITY;
-      f.lo = 0.0f;
-      f.nB = -INFINITY;
-    }
-    return f;
-  }
-  if (e - rec->vF >= -0.0001f) hss_accept_rec(rec, e, j, slots);
-  return f;
-}
-// final record of a row: straight from the registers unless the row is complex
-__device__ __forceinline__ void folds_store(const RowFoldS& f, RowRec* grec, const RowRec* srec, float fNK, float rcpNK) {
-  uint4* g = reinterpret_cast<uint4*>(grec);
-  if (f.Ms == INFINITY) {
-    rec_copy(grec, srec);
-  } else if (f.Ms > 0.0f) {
-    const unsigned e = __float_as_uint(quot_nk(f.Ms, fNK, rcpNK));
-    g[0] = make_uint4(e, e, e, 0u);                                             // Emax, vF, be[0], be[1]
-    g[1] = make_uint4(0u, (unsigned)f.jF | (1u << 16), (unsigned)f.jF, 0u);     // be[2], jF | n << 16, bj[0] | bj[1] << 16, bj[2] | pad
-  } else {
-    const unsigned ninf = __float_as_uint(-INFINITY);
-    g[0] = make_uint4(ninf, ninf, 0u, 0u);
-    g[1] = make_uint4(0u, 0u, 0u, 0u);
-  }
-}
-
-#ifndef RC_FOLD_GATE
-#define RC_FOLD_GATE 0  // 1: skip the fold of a step pair when no lane has a sum above its row's lower bound
-#endif
-
 template <int NK>
 struct SmpfCfg {
   static constexpr int RSB = (NK + 3) / 4 * 4;
@@ -2298,27 +2402,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
             pp[(size_t)j * 32] = sumA;
             pp[(size_t)(j + 1) * 32] = sumB;
           } else {
-#if RC_FOLD_GATE
-            if (fmaxf(sumA.x, sumB.x) > fx.lo || fmaxf(sumA.y, sumB.y) > fy.lo)
-#endif
-            {
-              RowFoldS nx = fx, ny = fy;
-              bool amb = false;
-              const float2 aB = add2(sumA, make_float2(fx.nB, fy.nB)), bB = add2(sumB, make_float2(fx.nB, fy.nB));
-              folds_fast(nx, sumA.x, aB.x, j, amb);
-              folds_fast(ny, sumA.y, aB.y, j, amb);
-              folds_fast(nx, sumB.x, bB.x, j + 1, amb);
-              folds_fast(ny, sumB.y, bB.y, j + 1, amb);
-              if (amb) {  // a possible near tie after some row's maximum: the two rows again, entry by entry, exactly
-                fx = folds_exact(fx, sumA.x, j, fNK, rcpNK, rec0, band_slots);
-                fx = folds_exact(fx, sumB.x, j + 1, fNK, rcpNK, rec0, band_slots);
-                fy = folds_exact(fy, sumA.y, j, fNK, rcpNK, rec0 + 1, band_slots);
-                fy = folds_exact(fy, sumB.y, j + 1, fNK, rcpNK, rec0 + 1, band_slots);
-              } else {
-                fx = nx;
-                fy = ny;
-              }
-            }
+            folds_pair(fx, fy, sumA, sumB, j, fNK, rcpNK, rec0, band_slots);
           }
           j += 2;
           continue;
@@ -2330,21 +2414,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
       if (CHAINED && !last) {
         pp[(size_t)j * 32] = sum;
       } else {
-        // single end codon (start of the rows, or some species has a frameshift): the exact path is cheap enough here
-        // when it is needed, the fast one otherwise; row r0 + 1 starts one codon later
-        RowFoldS nx = fx, ny = fy;
-        bool amb = false;
-        const float2 sB = add2(sum, make_float2(fx.nB, fy.nB));
-        const bool ylive = j > r0;
-        folds_fast(nx, sum.x, sB.x, j, amb);
-        if (ylive) folds_fast(ny, sum.y, sB.y, j, amb);
-        if (amb) {
-          fx = folds_exact(fx, sum.x, j, fNK, rcpNK, rec0, band_slots);
-          if (ylive) fy = folds_exact(fy, sum.y, j, fNK, rcpNK, rec0 + 1, band_slots);
-        } else {
-          fx = nx;
-          fy = ny;
-        }
+        folds_single(fx, fy, sum, j, j > r0, fNK, rcpNK, rec0, band_slots);
       }
       j += 1;
     }
@@ -2675,7 +2745,11 @@ __device__ __forceinline__ unsigned philox_draw(unsigned seed, unsigned node, un
 }
 
 constexpr int EVO_WARPS = 4;
-constexpr int EVO_SPW = 8;          // samples per warp: their MT19937 states are seeded side by side, one lane each
+#ifndef RC_EVO_SPW
+#define RC_EVO_SPW 2
+#endif
+constexpr int EVO_SPW = RC_EVO_SPW;  // samples per warp: their MT19937 states are seeded side by side, one lane each (more: fewer
+                                     // seeding passes per sample, but 2.5 KB of shared memory per sample limit the resident warps)
 constexpr int EVO_MT_PITCH = 625;   // words per state in shared memory (odd: the seeding lanes hit distinct banks)
 constexpr int EVO_SMEM = EVO_WARPS * EVO_SPW * EVO_MT_PITCH * 4;
 

@@ -46,7 +46,7 @@ struct rc_ctx {
   long no_smps = 0;          // never stream the sigma table in segments (k_dp_smps)
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
   long no_fused = 0;          // never build the sigma table inside the sample-major DP kernel (k_dp_smpf)
-  long tail_max = 12;         // a sample-major block whose instance count leaves 1..tail_max instances in its last group of 32 scores
+  long tail_max = 0;          // a sample-major block whose instance count leaves 1..tail_max instances in its last group of 32 scores
                               // those instances row-major (lanes = rows) instead of in a warp with that many live lanes (0: never)
   long smpc_max_sites = 0;    // longest frame (codons) for the STREAMED chunked sample-major route of wide alignments
                               // (measured slower than k_dp_chain: 50x800 11.3 vs 4.5 ms; kept as an experiment switch)
@@ -669,10 +669,12 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       bd.smp_seg = seg;
       finish_layout(bd);
       // resident-table sample-major blocks build their sigma table inside the DP kernel when the staged rows fit as well
-      if ((layout == 2 || layout == 5) && !seg && !ctx->no_fused && params->Delta <= 0.0f &&
+      if ((layout == 2 || layout == 5) && !seg && !ctx->no_fused && !ctx->force_dense &&
           smpf_smem_bytes(bd, layout) + (size_t)SMP_WARPS * 64 * sizeof(RowRec) <= (size_t)ctx->smem_optin) {
         bd.smp_fused = 1;
         bd.smp_pitch = smpf_pitch(bd.cols);
+      }
+      if (layout == 2 || layout == 5) {
         // B of RowFoldS: (N-1) * 1.0002e-4 for the tolerance of getHSS's tie rule plus 2^-21 of the largest species sum a
         // row can reach (per end codon and species at most the largest sigma -- BLOSUM entry or stop penalty minus the
         // smallest expected score -- or a positive penalty) for the roundings of the two quotients and of the bound itself
@@ -815,7 +817,8 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
         cur.max_smp_npos = std::max(cur.max_smp_npos, bd.L - 2);
       }
       cur.maxZs[cl] = std::max(cur.maxZs[cl], bd.zstride);
-      cur.max_sigma_work = std::max(cur.max_sigma_work, (long long)take * 2 * (bd.L - 2));
+      if (bd.layout != 2 && bd.layout != 5)  // grid of k_sigma / k_sigma_rows (sample-major items have kernels of their own)
+        cur.max_sigma_work = std::max(cur.max_sigma_work, (long long)take * 2 * (bd.L - 2 + 3 * RC_REG_TILE));
       cur.max_ninst = std::max(cur.max_ninst, take);
       if (bd.hss_warp) cur.hss_warp_items++;
       cur.n_layout[bd.layout]++;
