@@ -65,7 +65,9 @@ struct BlockDev {
   int smp_seg;              // layouts 2 / 5: 1 = the frame's sigma table does not fit shared memory, streamed in segments (k_dp_smps)
   int smp_fused;            // layouts 2 / 5, resident table: 1 = the DP kernel builds its sigma table itself from class bytes
                             // (k_dp_smpf; no sigma scratch, no k_sigma_smp launch for this block)
-  int smp_pitch;            // k_dp_smpf: bytes per staged row (>= cols + 6, a multiple of 4 with an odd word count)
+  int smp_pitch;            // (unused by the TMA-staged k_dp_smpf; kept for the record of the first fused variant)
+  long long il_off;         // k_dp_smpf: byte offset of the block's instance-interleaved class bytes (k_pack_il):
+                            // [group of 32 instances][flat byte q = row*cols + col of an instance][lane], groups padded with zeros
   float fold_B;             // k_dp_smpf: half-width of the ambiguity zone of the getHSS fold in species-sum space (see RowFoldS)
   int nchunk, nkw;          // layout 3: chunks and species per chunk (template NK of k_dp_chain); chunk g holds
   int chunk_base, chunk_rem;  //   chunk_base + (g < chunk_rem) species starting at g*chunk_base + min(g, chunk_rem)

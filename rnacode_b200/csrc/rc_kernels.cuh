@@ -105,6 +105,39 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDev* __restrict__ block
 }
 
 // ---------------------------------------------------------------------------------------------
+// (a) k_pack_il: instance-interleaved copy of the class bytes for the blocks whose DP kernel builds its own sigma table
+// (k_dp_smpf): il[group][q][lane] = cls[instance group*32 + lane][q], q = row*cols + col.  A row of 32 instances is then one
+// contiguous, 32-byte aligned run of cols*32 bytes -- one TMA bulk copy into shared memory, where lane = instance reads its
+// byte of a column without bank conflicts (32 consecutive bytes).  One warp per (group, 16-byte chunk of q): every lane loads
+// 16 bytes of its instance, the 32 x 16 byte tile is transposed through shared memory, every lane stores 16 bytes.
+// grid = (x: block, y: grid-stride over warps).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_il(const BlockDev* __restrict__ blocks, const unsigned char* __restrict__ cls,
+                                                 unsigned char* __restrict__ il) {
+  __shared__ __align__(16) unsigned char tile[8][16][32];
+  const BlockDev bd = blocks[blockIdx.x];
+  if (!bd.smp_fused) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = bd.inst_stride >> 4;                 // 16-byte chunks of one instance (N*cols rounded up)
+  const int groups = (bd.n_inst + 31) >> 5;
+  const size_t il_group = (size_t)chunks * 16 * 32;       // bytes of one group
+  const long long total = (long long)groups * chunks;
+  for (long long w = (long long)blockIdx.y * 8 + warp; w < total; w += (long long)gridDim.y * 8) {
+    const int g = (int)(w / chunks), ch = (int)(w % chunks);
+    const int inst = g * 32 + lane;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (inst < bd.n_inst) v = *reinterpret_cast<const uint4*>(cls + bd.cls_off + (size_t)inst * bd.inst_stride + (size_t)ch * 16);
+    const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int t = 0; t < 16; t++) tile[warp][t][lane] = (unsigned char)(wv[t >> 2] >> (8 * (t & 3)));
+    __syncwarp();
+    const uint4 o = *reinterpret_cast<const uint4*>(&tile[warp][lane >> 1][(lane & 1) * 16]);
+    *reinterpret_cast<uint4*>(il + bd.il_off + (size_t)g * il_group + (size_t)ch * 512 + lane * 16) = o;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // (a) k_prep: one CTA per block.
 //   cols0[strand][x], x = 1..L : forward 0-based column of the x-th non-gap character of the reference
 //   row when read in that strand's direction (pos2col, src/misc.c:250-269, as a prefix sum).
@@ -1866,8 +1899,10 @@ __device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv
 #ifndef RC_SMP_DIAG_PAIR
 #define RC_SMP_DIAG_PAIR 0  // measured: no gain on 40-codon frames (4.54 vs 4.56 ms), 10-20 registers more
 #endif
+// CHAINED: two CTAs of 8 warps per SM need at most 128 registers per thread (the 12-species chunk with partial sums coming in
+// and the fold state would take 138)
 template <int NK, bool CHAINED>
-__global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
     k_dp_smp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
              const float* __restrict__ sigma, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm,
              int band_slots, int chunk, float2* __restrict__ partial) {
@@ -2234,25 +2269,25 @@ template <int NK>
 struct SmpfCfg {
   static constexpr int RSB = (NK + 3) / 4 * 4;
   static __host__ __device__ size_t align16(size_t v) { return (v + 15) / 16 * 16; }
-  // dynamic shared memory: sigma table | z words | barrier | PairTables | expected scores of a quad | codon columns |
-  // staged reference rows | staged species rows of a quad | fold records
+  // dynamic shared memory: sigma table | z words | barriers | PairTables | expected scores of a quad | codon columns |
+  // staged reference row of the 32 instances | staged species rows of a quad | fold records
   static __host__ __device__ size_t off_z(int sites, int row_bytes) { return (size_t)sites * row_bytes; }
   static __host__ __device__ size_t off_bar(int sites, int row_bytes) { return off_z(sites, row_bytes) + align16((size_t)sites * 4); }
-  static __host__ __device__ size_t off_tab(int sites, int row_bytes) { return off_bar(sites, row_bytes) + 16; }
+  static __host__ __device__ size_t off_tab(int sites, int row_bytes) { return off_bar(sites, row_bytes) + 32; }
   static __host__ __device__ size_t off_sc(int sites, int row_bytes) { return off_tab(sites, row_bytes) + sizeof(PairTables); }
   static __host__ __device__ size_t off_col(int sites, int row_bytes) { return off_sc(sites, row_bytes) + 64; }
   static __host__ __device__ size_t off_ref(int sites, int row_bytes) { return off_col(sites, row_bytes) + align16((size_t)3 * sites * 4); }
-  static __host__ __device__ size_t off_sp(int sites, int row_bytes, int pitch) { return off_ref(sites, row_bytes) + (size_t)32 * pitch; }
-  static __host__ __device__ size_t off_rec(int sites, int row_bytes, int pitch) { return off_sp(sites, row_bytes, pitch) + (size_t)128 * pitch; }
-  static __host__ __device__ size_t total(int sites, int row_bytes, int pitch, int nw) {
-    return off_rec(sites, row_bytes, pitch) + (size_t)nw * 64 * sizeof(RowRec);
+  static __host__ __device__ size_t off_sp(int sites, int row_bytes, int cols) { return off_ref(sites, row_bytes) + (size_t)32 * cols; }
+  static __host__ __device__ size_t off_rec(int sites, int row_bytes, int cols) { return off_sp(sites, row_bytes, cols) + (size_t)128 * cols; }
+  static __host__ __device__ size_t total(int sites, int row_bytes, int cols, int nw) {
+    return off_rec(sites, row_bytes, cols) + (size_t)nw * 64 * sizeof(RowRec);
   }
 };
 
 template <int NK, bool CHAINED>
-__global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
     k_dp_smpf(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
-              const unsigned char* __restrict__ cls, const int* __restrict__ cols0, const float* __restrict__ scores,
+              const unsigned char* __restrict__ il, const int* __restrict__ cols0, const float* __restrict__ scores,
               const PairTables* __restrict__ tables, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm,
               int band_slots, int chunk, float2* __restrict__ partial) {
   constexpr int RS = RegCfg<NK>::RS;
@@ -2270,67 +2305,57 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
   const int inst_l = group * 32 + lane;
   const bool valid = inst_l < it.ninst;
   const bool first = !CHAINED || chunk == 0, last = !CHAINED || chunk == bd.nchunk - 1;
-  const int N = bd.N, cols = bd.cols, L = bd.L, pitch = bd.smp_pitch;
+  const int N = bd.N, cols = bd.cols, L = bd.L;
 
   unsigned* zs = reinterpret_cast<unsigned*>(smem + Cfg::off_z(sites, ROW_BYTES));
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::off_bar(sites, ROW_BYTES));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::off_bar(sites, ROW_BYTES));  // [0]: tables, z, reference row; [1]: species rows
   const PairTables& s_tab = *reinterpret_cast<const PairTables*>(smem + Cfg::off_tab(sites, ROW_BYTES));
   float* s_sc = reinterpret_cast<float*>(smem + Cfg::off_sc(sites, ROW_BYTES));  // [species of the quad][h], h = 0 -> 0
   int* s_col = reinterpret_cast<int*>(smem + Cfg::off_col(sites, ROW_BYTES));   // columns of the frame's codons: site j at 3j .. 3j+2
-  unsigned char* s_ref = smem + Cfg::off_ref(sites, ROW_BYTES);
-  unsigned char* s_sp = smem + Cfg::off_sp(sites, ROW_BYTES, pitch);
-  RowRec* srec = reinterpret_cast<RowRec*>(smem + Cfg::off_rec(sites, ROW_BYTES, pitch));
+  unsigned char* s_ref = smem + Cfg::off_ref(sites, ROW_BYTES);                 // [col][lane]
+  unsigned char* s_sp = smem + Cfg::off_sp(sites, ROW_BYTES, cols);             // [species of the quad][col][lane]
+  RowRec* srec = reinterpret_cast<RowRec*>(smem + Cfg::off_rec(sites, ROW_BYTES, cols));
 
   // ---- table phase: kernel (b) for this CTA's (instances, strand, frame, species of the chunk) ------------------------
-  const size_t z_bytes = Cfg::align16((size_t)sites * 4);
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    mbar_fence_init();
-    mbar_expect_tx(bar, (unsigned)(sizeof(PairTables) + z_bytes));
-    bulk_g2s(smem + Cfg::off_tab(sites, ROW_BYTES), tables, (unsigned)sizeof(PairTables), bar);
-    bulk_g2s(zs, ztiles + bd.z_off[strand][frame] + (CHAINED ? (size_t)chunk * bd.ntiles[frame] * TILE : 0), (unsigned)z_bytes, bar);
-  }
-  // codon of site j: reference positions x-2 .. x with x = 3j + 3 + frame, i.e. entries frame+1+3j .. frame+3+3j of cols0
-  const int* c0 = cols0 + bd.cols0_off + (size_t)strand * (L + 1) + frame + 1;
-  for (int t = threadIdx.x; t < 3 * sites; t += blockDim.x) s_col[t] = c0[t];
-  const int ninst_g = min(32, it.ninst - group * 32);
-  const unsigned char* gbase = cls + bd.cls_off + (size_t)(it.inst0 + group * 32) * bd.inst_stride;
-  // reference rows of the 32 instances: one warp per row, aligned word copies (instances start 16-byte aligned)
-  for (int li = warp; li < 32; li += nw) {
-    const unsigned* src4 = reinterpret_cast<const unsigned*>(gbase + (size_t)li * bd.inst_stride);
-    unsigned* dst4 = reinterpret_cast<unsigned*>(s_ref + li * pitch);
-    for (int w = lane; w < (cols + 3) / 4; w += 32) dst4[w] = (li < ninst_g) ? src4[w] : 0u;
-  }
   // species quads of this launch: all of them, or the quads of the chunk (layout 5)
   int q_first = 0, q_count = RSB / 4;
   if (CHAINED) {
     q_first = chunk * bd.chunk_base + min(chunk, bd.chunk_rem);
     q_count = bd.chunk_base + (chunk < bd.chunk_rem ? 1 : 0);
   }
+  const size_t z_bytes = Cfg::align16((size_t)sites * 4);
+  // interleaved class bytes of the group: row r of the 32 instances = cols*32 contiguous bytes
+  const size_t row_bytes_il = (size_t)cols * 32;
+  const unsigned char* gil = il + bd.il_off + (size_t)((it.inst0 >> 5) + group) * ((size_t)bd.inst_stride * 32);
+  auto quad_rows = [&](int kq) { return min(4, N - 1 - 4 * (q_first + kq)); };  // species rows the quad really has (>= 1)
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+    mbar_expect_tx(&bar[0], (unsigned)(sizeof(PairTables) + z_bytes + row_bytes_il));
+    bulk_g2s(smem + Cfg::off_tab(sites, ROW_BYTES), tables, (unsigned)sizeof(PairTables), &bar[0]);
+    bulk_g2s(zs, ztiles + bd.z_off[strand][frame] + (CHAINED ? (size_t)chunk * bd.ntiles[frame] * TILE : 0), (unsigned)z_bytes, &bar[0]);
+    bulk_g2s(s_ref, gil, (unsigned)row_bytes_il, &bar[0]);
+    const unsigned b0 = (unsigned)(quad_rows(0) * row_bytes_il);
+    mbar_expect_tx(&bar[1], b0);
+    bulk_g2s(s_sp, gil + (size_t)(1 + 4 * q_first) * row_bytes_il, b0, &bar[1]);
+  }
+  // codon of site j: reference positions x-2 .. x with x = 3j + 3 + frame, i.e. entries frame+1+3j .. frame+3+3j of cols0
+  const int* c0 = cols0 + bd.cols0_off + (size_t)strand * (L + 1) + frame + 1;
+  for (int t = threadIdx.x; t < 3 * sites; t += blockDim.x) s_col[t] = c0[t] * 32;  // byte offset of the column in a staged row
   const int sh = strand ? 2 : 0;
-  __syncthreads();  // barrier initialised, s_col and the reference rows staged
-  mbar_wait(bar, 0);
+  __syncthreads();  // barriers initialised, s_col written
+  mbar_wait(&bar[0], 0);
   for (int kq = 0; kq < q_count; kq++) {
     const int k0 = 4 * (q_first + kq);  // first species (0-based among the scored ones) of the quad
-    for (int pr = warp; pr < 128; pr += nw) {  // (species of the quad, instance): one warp per row
-      const int kk = pr >> 5, li = pr & 31;
-      const int row = 1 + k0 + kk;
-      const bool ok = li < ninst_g && row < N;
-      const size_t roff = (size_t)row * cols;
-      const unsigned shift = (unsigned)roff & 3u;  // rows start at any byte: staged column c sits at dst[shift + c]
-      const unsigned* src4 = reinterpret_cast<const unsigned*>(gbase + (size_t)li * bd.inst_stride + (ok ? roff - shift : 0));
-      unsigned* dst4 = reinterpret_cast<unsigned*>(s_sp + pr * pitch);
-      for (int w = lane; w < (int)(shift + cols + 3) / 4; w += 32) dst4[w] = ok ? src4[w] : 0u;
-    }
+    const int nrow = quad_rows(kq);
     if (threadIdx.x < 16) {  // expected scores of the quad's species on this strand, [species][h], h = 0 -> 0 (see PairTables)
       const int kk = threadIdx.x >> 2, h = threadIdx.x & 3, row = 1 + k0 + kk;
       s_sc[threadIdx.x] = (h > 0 && row < N) ? scores[bd.scores_off + ((size_t)strand * N + row) * 4 + h] : 0.0f;
     }
-    __syncthreads();
-    const unsigned char* rr = s_ref + lane * pitch;
-    unsigned shk[4];
-#pragma unroll
-    for (int kk = 0; kk < 4; kk++) shk[kk] = (unsigned)((size_t)(1 + k0 + kk) * cols) & 3u;
+    __syncthreads();                  // s_sc of this quad written (and, for kq > 0, nobody reads the previous quad's any more)
+    mbar_wait(&bar[1], kq & 1);       // the quad's species rows have landed
+    const unsigned char* rr = s_ref + lane;
     for (int j = warp; j < sites; j += nw) {
       const int i1 = s_col[3 * j], i2 = s_col[3 * j + 1], i3 = s_col[3 * j + 2];
       const unsigned a1 = rr[i1], a2 = rr[i2], a3 = rr[i3];
@@ -2340,17 +2365,26 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32)
       float v4[4];
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {
-        const unsigned char* rk = s_sp + (kk * 32 + lane) * pitch + shk[kk];
-        const unsigned b1 = rk[i1], b2 = rk[i2], b3 = rk[i3];
-        const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
-        const unsigned e = trow[qb];
-        const float v = s_tab.val[e & 0x3ffu] - s_sc[kk * 4 + (e >> 10)];  // observed - expected (src/score.c:422-425), or constant - 0
-        const unsigned zero = nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X);  // src/score.c:394-404
-        v4[kk] = (zero || k0 + kk >= bd.NK) ? 0.0f : v;
+        float v = 0.0f;
+        if (kk < nrow) {  // warp-uniform
+          const unsigned char* rk = s_sp + (size_t)kk * row_bytes_il + lane;
+          const unsigned b1 = rk[i1], b2 = rk[i2], b3 = rk[i3];
+          const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
+          const unsigned e = trow[qb];
+          v = s_tab.val[e & 0x3ffu] - s_sc[kk * 4 + (e >> 10)];  // observed - expected (src/score.c:422-425), or constant - 0
+          const unsigned zero = nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X);  // src/score.c:394-404
+          if (zero) v = 0.0f;
+        }
+        v4[kk] = v;
       }
       *reinterpret_cast<float4*>(smem + (size_t)j * ROW_BYTES + kq * 512 + lane * 16) = make_float4(v4[0], v4[1], v4[2], v4[3]);
     }
-    __syncthreads();  // the staged rows are free for the next quad; after the last quad: the table is complete
+    __syncthreads();  // the staged species rows are free; after the last quad: the table is complete
+    if (threadIdx.x == 0 && kq + 1 < q_count) {
+      const unsigned bn = (unsigned)(quad_rows(kq + 1) * row_bytes_il);
+      mbar_expect_tx(&bar[1], bn);
+      bulk_g2s(s_sp, gil + (size_t)(1 + k0 + 4) * row_bytes_il, bn, &bar[1]);
+    }
   }
 
   // ---- DP phase: k_dp_smp's loop with the fold in species-sum space ------------------------------------------------------

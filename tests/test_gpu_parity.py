@@ -191,6 +191,64 @@ def test_config5_mixed_lengths_vs_oracle(rc_ctx, oracle):
     bt.close()
 
 
+@pytest.mark.parametrize("opts", [{"no_fused": 0}, {"tail_max": 12}, {"no_fused": 0, "tail_max": 12}],
+                         ids=lambda o: "+".join("%s%d" % kv for kv in sorted(o.items())))
+def test_optional_sample_major_routes_vs_oracle(oracle, opts):
+    """Two routes that are off by default: k_dp_smpf (the DP CTA builds its sigma table itself, plain and chunked) and the tail
+    split (the last 1..12 instances of a sample-major block scored row-major).  Same answers as the oracle, bit for bit."""
+    from rnacode_b200 import synth
+    capi = _capi()
+    ctx = capi.Context(0)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    try:
+        shapes = [(10, 120, 100), (10, 121, 69), (4, 45, 70), (17, 150, 33), (6, 250, 40), (26, 150, 40), (100, 96, 36), (50, 130, 75)]
+        blocks, data = [], []
+        for idx, (N, cols, n) in enumerate(shapes):
+            rows = synth.synth_block(8, idx, N, cols, gap_rate=0.02)
+            sf, sr = synth.synth_scores(8, idx, N)
+            smp = synth.synth_samples(8, idx, n, N, cols)
+            blocks.append(_block(rows, sf, sr, smp))
+            data.append((rows, sf, sr, smp))
+        bt = ctx.batch(blocks, capi.make_params(), oracle.blosum62)
+        bt.upload(); bt.run(); bt.download()
+        for i, (rows, sf, sr, smp) in enumerate(data):
+            assert bt.native_hss(i) == oracle.score_aln(rows, sf, sr, oracle.params()), (opts, shapes[i])
+            exp = oracle.sample_maxima(rows, smp, sf, sr, oracle.params()).astype(np.float32)
+            assert np.array_equal(bt.max_scores(i).astype(np.float32), exp), (opts, shapes[i])
+        bt.close()
+    finally:
+        ctx.close()
+
+
+def test_near_ties_after_the_row_maximum(rc_ctx, oracle):
+    """The species-sum fold of the sample-major kernels treats a positive sum just below a row's maximum exactly (folds_exact).
+    Alignments made of a few repeated columns give rows full of exact ties and of near ties (sums that differ by rounding
+    only); gap-free and gappy, short and streamed frames."""
+    from rnacode_b200 import synth
+    capi = _capi()
+    rng = np.random.default_rng(99)
+    blocks, data = [], []
+    for idx, (N, cols, n) in enumerate([(6, 90, 40), (10, 120, 33), (10, 600, 20), (4, 300, 64)]):
+        base = synth.synth_block(9, idx, N, 9, gap_rate=0.0)          # nine columns, tiled: periodic sigma, many equal sums
+        rows = np.tile(base, (1, cols // 9 + 1))[:, :cols].copy()
+        if idx % 2:
+            rows[1, 30:32] = synth.GAP
+        sf, sr = synth.synth_scores(9, idx, N)
+        sf[:, 1:] = np.round(sf[:, 1:] * 4) / 4                       # quarter-valued expected scores: exact cancellations
+        sr[:, 1:] = np.round(sr[:, 1:] * 4) / 4
+        smp = np.stack([np.tile(synth.synth_block(10 + s, idx, N, 9, gap_rate=0.0), (1, cols // 9 + 1))[:, :cols] for s in range(n)])
+        blocks.append(_block(rows, sf, sr, smp))
+        data.append((rows, sf, sr, smp))
+    bt = rc_ctx.batch(blocks, capi.make_params(), oracle.blosum62)
+    bt.upload(); bt.run(); bt.download()
+    for i, (rows, sf, sr, smp) in enumerate(data):
+        assert bt.native_hss(i) == oracle.score_aln(rows, sf, sr, oracle.params()), i
+        exp = oracle.sample_maxima(rows, smp, sf, sr, oracle.params()).astype(np.float32)
+        assert np.array_equal(bt.max_scores(i).astype(np.float32), exp), i
+    bt.close()
+
+
 def test_mixed_batch_and_chunking(oracle):
     """Blocks of different shapes in one batch, with a scratch budget so small that instances of one block
     are split across chunks."""
