@@ -63,6 +63,7 @@ static int rc_maf_int(const char *s, int n, const char *what, const char *fmt_ms
 static int rc_read_maf_mapped(rc_maf_map *m, struct aln *alignedSeqs[]) {
   int num_seq = 0, nn;
   size_t n;
+again:
   if (m->p >= m->end) return 0;
   while (m->p < m->end) {
     const char *line = m->p, *eol = (const char *)memchr(line, '\n', (size_t)(m->end - line));
@@ -115,7 +116,12 @@ static int rc_read_maf_mapped(rc_maf_map *m, struct aln *alignedSeqs[]) {
     if (fl[0] == 1 && fs[0][0] == 'a') break; /* next block */
   }
   alignedSeqs[num_seq] = NULL;
-  if (num_seq == 0) return 0; /* nothing but blank / comment lines were left */
+  if (num_seq == 0) {
+    /* an 'a' line without any 's' line (the reference's read_maf hands an empty block to main(), which then crashes on it):
+     * not the end of the input -- go on with the next block instead of silently dropping the rest of the file */
+    if (m->p < m->end) goto again;
+    return 0; /* nothing but blank / comment lines were left */
+  }
   n = strlen(alignedSeqs[0]->seq);
   for (nn = 1; nn < num_seq; nn++)
     if (strlen(alignedSeqs[nn]->seq) != n) nrerror("ERROR: Sequences are of unequal length.");

@@ -13,6 +13,11 @@
  *      simulated (kernel d), packed, scored and reduced on the GPU (rc_batch_*);
  *   5. in input order: sort, EVDMaxLikelyFit, p-values, printResults -- all the reference's own code.
  *
+ * Windows overlap: the workers of window w+1 are forked before the parent waits for those of window w, so while the parent
+ * collects, scores (GPU), fits and prints window w -- and parses window w+2 -- the host cores are already busy with the
+ * trees of window w+1.  A worker that ends abnormally (PhyML's Warn_And_Exit, a signal) is fatal for the run, as it is for
+ * the reference; its records are flushed block by block, so nothing a live worker has finished is lost before that.
+ *
  * --stop-early (p = 99.0 as soon as more than cutoff*n null alignments beat the native score,
  * src/score.c:1036-1042): the count is monotone in the sample index, so it is evaluated in two rounds -- 32 null
  * alignments for every block, the remaining n-32 only for the blocks still undecided -- with the same outcome.
@@ -26,6 +31,7 @@
 #include <ctype.h>
 #include <math.h>
 #include <pthread.h>
+#include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -137,78 +143,134 @@ static int host_prepare(blk_t *b) {
   return 1;
 }
 
-/* phase 2: host_prepare for blocks w, w+P, ... in child w (PhyML and seq-gen keep global state: processes, not
- * threads); the results come back through one temporary file per child */
-static void run_host_stage(blk_t *blk, int nb) {
-  int P = n_workers(nb), w, i, *next;
+/* phase 2: host_prepare in forked workers (PhyML and seq-gen keep global state: processes, not threads); the workers pull
+ * the next block from a shared counter and send their results back through one temporary file each.  host_stage_start()
+ * forks and returns; host_stage_finish() waits for the workers and reads the results. */
+typedef struct {
+  blk_t *blk;
+  int nb, P;
   FILE **chan;
   pid_t *pid;
-  if (nb == 0) return;
-  if (P == 1) { /* no need to fork */
-    for (i = 0; i < nb; i++) blk[i].ok = host_prepare(&blk[i]);
-    return;
+  int *next;
+  double t_start, t_done;
+} host_job;
+
+static int g_in_worker = 0;
+/* PhyML leaves through exit() (Warn_And_Exit); in a forked worker that must not run the parent's atexit handlers (the CUDA
+ * runtime's teardown among them).  Linked with -Wl,--wrap=exit. */
+void __real_exit(int status);
+void __wrap_exit(int status) {
+  if (g_in_worker) {
+    fflush(NULL);
+    _exit(status ? status : 3);
   }
-  chan = (FILE **)malloc(sizeof(FILE *) * P);
-  pid = (pid_t *)malloc(sizeof(pid_t) * P);
+  __real_exit(status);
+}
+
+static void host_stage_start(host_job *j, blk_t *blk, int nb) {
+  int w, i;
+  const char *ke = getenv("RNACODE_CUDA_TEST_KILL_WORKER_AT");
+  const long kill_at = ke ? atol(ke) : -1;
+  memset(j, 0, sizeof(*j));
+  j->blk = blk;
+  j->nb = nb;
+  j->P = nb > 0 ? n_workers(nb) : 0;
+  j->t_start = now_s();
+  if (j->P <= 1) return; /* no fork: host_stage_finish() prepares the blocks itself */
+  j->chan = (FILE **)malloc(sizeof(FILE *) * j->P);
+  j->pid = (pid_t *)malloc(sizeof(pid_t) * j->P);
   /* blocks differ a lot in cost (PhyML is about N^2 * cols): the workers pull the next block from a shared counter */
-  next = (int *)mmap(NULL, 4096, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
-  if (next == MAP_FAILED) nrerror("ERROR: mmap failed.\n");
-  *next = 0;
+  j->next = (int *)mmap(NULL, 4096, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+  if (j->next == MAP_FAILED) nrerror("ERROR: mmap failed.\n");
+  *j->next = 0;
   fflush(NULL);
-  for (w = 0; w < P; w++) {
-    chan[w] = tmpfile();
-    if (!chan[w]) nrerror("ERROR: could not create a temporary file for the tree workers.\n");
-    pid[w] = fork();
-    if (pid[w] < 0) nrerror("ERROR: fork failed.\n");
-    if (pid[w] == 0) {
-      while ((i = __sync_fetch_and_add(next, 1)) < nb) {
+  for (w = 0; w < j->P; w++) {
+    j->chan[w] = tmpfile();
+    if (!j->chan[w]) nrerror("ERROR: could not create a temporary file for the tree workers.\n");
+    j->pid[w] = fork();
+    if (j->pid[w] < 0) nrerror("ERROR: fork failed.\n");
+    if (j->pid[w] == 0) {
+      g_in_worker = 1;
+      while ((i = __sync_fetch_and_add(j->next, 1)) < nb) {
         blk_t *b = &blk[i];
-        int ok = host_prepare(b);
-        fwrite(&i, sizeof(int), 1, chan[w]);
-        fwrite(&ok, sizeof(int), 1, chan[w]);
-        if (!ok) continue;
-        fwrite(&b->n_nodes, sizeof(int), 1, chan[w]);
-        fwrite(b->sf, sizeof(float), 4 * b->N, chan[w]);
-        fwrite(b->sr, sizeof(float), 4 * b->N, chan[w]);
-        fwrite(b->tpar, sizeof(int), b->n_nodes, chan[w]);
-        fwrite(b->trow, sizeof(int), b->n_nodes, chan[w]);
-        fwrite(b->tcum, sizeof(double), 16 * (size_t)b->n_nodes, chan[w]);
+        int ok;
+        if (kill_at >= 0 && b->scored_idx == kill_at) raise(SIGKILL); /* test hook: a worker dies mid-window */
+        ok = host_prepare(b);
+        fwrite(&i, sizeof(int), 1, j->chan[w]);
+        fwrite(&ok, sizeof(int), 1, j->chan[w]);
+        if (ok) {
+          fwrite(&b->n_nodes, sizeof(int), 1, j->chan[w]);
+          fwrite(b->sf, sizeof(float), 4 * b->N, j->chan[w]);
+          fwrite(b->sr, sizeof(float), 4 * b->N, j->chan[w]);
+          fwrite(b->tpar, sizeof(int), b->n_nodes, j->chan[w]);
+          fwrite(b->trow, sizeof(int), b->n_nodes, j->chan[w]);
+          fwrite(b->tcum, sizeof(double), 16 * (size_t)b->n_nodes, j->chan[w]);
+        }
+        fflush(j->chan[w]); /* a record per block: what this worker has finished survives its death */
       }
-      fflush(chan[w]);
       _exit(0);
     }
   }
+}
+
+static void host_stage_finish(host_job *j) {
+  blk_t *blk = j->blk;
+  const int nb = j->nb;
+  int w, i, *seen;
+  if (nb == 0) return;
+  if (j->P <= 1) {
+    for (i = 0; i < nb; i++) blk[i].ok = host_prepare(&blk[i]);
+    init_gpus();
+    j->t_done = now_s();
+    return;
+  }
   init_gpus(); /* bring the CUDA contexts up while the workers run PhyML (the children never touch CUDA) */
-  for (w = 0; w < P; w++) {
+  seen = (int *)calloc(nb, sizeof(int));
+  for (w = 0; w < j->P; w++) {
     int status = 0, idx, ok;
-    waitpid(pid[w], &status, 0);
-    rewind(chan[w]);
-    while (fread(&idx, sizeof(int), 1, chan[w]) == 1) {
+    if (waitpid(j->pid[w], &status, 0) < 0 || !WIFEXITED(status) || WEXITSTATUS(status) != 0) {
+      /* the reference ends with an error when PhyML gives up on an alignment (Warn_And_Exit) or crashes: so do we,
+       * instead of reporting the worker's remaining blocks as failed trees */
+      if (WIFSIGNALED(status))
+        fprintf(stderr, "ERROR: a tree worker was killed by signal %d.\n", WTERMSIG(status));
+      else
+        fprintf(stderr, "ERROR: a tree worker ended abnormally (exit status %d).\n", WIFEXITED(status) ? WEXITSTATUS(status) : -1);
+      for (i = 0; i < j->P; i++)
+        if (i != w) kill(j->pid[i], SIGTERM);
+      exit(EXIT_FAILURE);
+    }
+    rewind(j->chan[w]);
+    while (fread(&idx, sizeof(int), 1, j->chan[w]) == 1) {
       blk_t *b;
       int good;
-      if (fread(&ok, sizeof(int), 1, chan[w]) != 1 || idx < 0 || idx >= nb) break;
+      if (fread(&ok, sizeof(int), 1, j->chan[w]) != 1 || idx < 0 || idx >= nb) nrerror("ERROR: corrupt record from a tree worker.\n");
+      seen[idx] = 1;
       if (!ok) continue;
       b = &blk[idx];
-      if (fread(&b->n_nodes, sizeof(int), 1, chan[w]) != 1 || b->n_nodes < 2 || b->n_nodes > 2 * MAX_NUM_NAMES + 2) break;
+      if (fread(&b->n_nodes, sizeof(int), 1, j->chan[w]) != 1 || b->n_nodes < 2 || b->n_nodes > 2 * MAX_NUM_NAMES + 2)
+        nrerror("ERROR: corrupt record from a tree worker.\n");
       b->sf = (float *)malloc(sizeof(float) * 4 * b->N);
       b->sr = (float *)malloc(sizeof(float) * 4 * b->N);
       b->tpar = (int *)malloc(sizeof(int) * b->n_nodes);
       b->trow = (int *)malloc(sizeof(int) * b->n_nodes);
       b->tcum = (double *)malloc(sizeof(double) * 16 * b->n_nodes);
-      good = fread(b->sf, sizeof(float), 4 * b->N, chan[w]) == (size_t)(4 * b->N) &&
-             fread(b->sr, sizeof(float), 4 * b->N, chan[w]) == (size_t)(4 * b->N) &&
-             fread(b->tpar, sizeof(int), b->n_nodes, chan[w]) == (size_t)b->n_nodes &&
-             fread(b->trow, sizeof(int), b->n_nodes, chan[w]) == (size_t)b->n_nodes &&
-             fread(b->tcum, sizeof(double), 16 * (size_t)b->n_nodes, chan[w]) == 16 * (size_t)b->n_nodes;
-      if (!good) break; /* truncated: the worker died */
+      good = fread(b->sf, sizeof(float), 4 * b->N, j->chan[w]) == (size_t)(4 * b->N) &&
+             fread(b->sr, sizeof(float), 4 * b->N, j->chan[w]) == (size_t)(4 * b->N) &&
+             fread(b->tpar, sizeof(int), b->n_nodes, j->chan[w]) == (size_t)b->n_nodes &&
+             fread(b->trow, sizeof(int), b->n_nodes, j->chan[w]) == (size_t)b->n_nodes &&
+             fread(b->tcum, sizeof(double), 16 * (size_t)b->n_nodes, j->chan[w]) == 16 * (size_t)b->n_nodes;
+      if (!good) nrerror("ERROR: truncated record from a tree worker.\n");
       b->ok = 1;
     }
-    fclose(chan[w]);
-    /* a worker that died leaves its remaining blocks with ok == 0: they are reported like a failed tree */
+    fclose(j->chan[w]);
   }
-  munmap(next, 4096);
-  free(chan);
-  free(pid);
+  for (i = 0; i < nb; i++)
+    if (!seen[i]) nrerror("ERROR: a block was not processed by any tree worker.\n");
+  free(seen);
+  munmap(j->next, 4096);
+  free(j->chan);
+  free(j->pid);
+  j->t_done = now_s();
 }
 
 /* ---- GPUs: blocks are independent, so a window is dealt out over the devices by cost; no exchange between them ---- */
@@ -402,7 +464,12 @@ static void gpu_batch(blk_t *blk, const int *list, int nlist, int s0, int ns, co
 
 static float ***g_sk_fwd_tag[1], ***g_sk_rev_tag[1]; /* stand-ins for Sk_native / Sk_native_rev: colorAln only passes them on */
 
-static void process_window(blk_t *blk, int nb, int *blosum) {
+static double g_wall0 = 0.0;
+static int g_window_no = 0;
+
+static void process_window(host_job *job, int *blosum) {
+  blk_t *blk = job->blk;
+  const int nb = job->nb;
   const int n = pars.sampleN > 0 ? pars.sampleN : 0;
   /* --stop-early: a first round of few null alignments per block decides most non-coding blocks
    * (src/score.c:1036-1042: more than cutoff*n of them beat the native score); only the others get the rest */
@@ -412,7 +479,7 @@ static void process_window(blk_t *blk, int nb, int *blosum) {
   double t0 = now_s(), t1, t3, t_seeds = 0, t_gpu = 0;
   const int verbose = getenv("RNACODE_CUDA_VERBOSE") != NULL;
 
-  run_host_stage(blk, nb);
+  host_stage_finish(job);
   t1 = now_s();
 
   list = (int *)malloc(sizeof(int) * (nb > 0 ? nb : 1));
@@ -444,6 +511,8 @@ static void process_window(blk_t *blk, int nb, int *blosum) {
     if (b->status == 1 && n1 < n) list[nlist2++] = list[k];
   }
   if (nlist2 > 0) {
+    /* (the library scores instance 0 = the native alignment of every unit again in this round and the result is dropped:
+     * one alignment in n - 31 per block that is still undecided, accepted for the sake of one batch layout) */
     gpu_batch(blk, list, nlist2, n1, n - n1, blosum, 0, &t_seeds, &t_gpu);
     for (k = 0; k < nlist2; k++) {
       blk_t *b = &blk[list[k]];
@@ -494,9 +563,12 @@ static void process_window(blk_t *blk, int nb, int *blosum) {
   free(list);
   if (verbose)
     fprintf(stderr,
-            "[RNAcode_b200] window of %d blocks (%d scored, %d in the second sampling round): trees+models (workers) %.3f s, "
-            "batch set-up+seeds %.3f s, GPU upload+run+download %.3f s, fit+report %.3f s\n",
-            nb, nok, nlist2, t1 - t0, t_seeds, t_gpu, now_s() - t3);
+            "[RNAcode_b200] window %d of %d blocks (%d scored, %d in the second sampling round): workers forked at %.3f s, done by "
+            "%.3f s (waited %.3f s for them), batch set-up+seeds %.3f s, GPU upload+run+download %.3f s (from %.3f s), fit+report "
+            "%.3f s, window done at %.3f s\n",
+            g_window_no, nb, nok, nlist2, job->t_start - g_wall0, job->t_done - g_wall0, t1 - t0, t_seeds, t_gpu, t1 - g_wall0,
+            now_s() - t3, now_s() - g_wall0);
+  g_window_no++;
 }
 
 int main(int argc, char *argv[]) {
@@ -507,7 +579,9 @@ int main(int argc, char *argv[]) {
   double wall0 = now_s();
   int (*readFunction)(FILE * clust, struct aln * alignedSeqs[]) = NULL;
   struct aln *inputAln[MAX_NUM_NAMES];
-  blk_t *blk;
+  blk_t *blk, *blk_prev;
+  host_job job;
+  int have_job = 0;
   const char *e;
   rc_maf_map map = {NULL, NULL, NULL, 0};
   int mapped = 0;
@@ -564,7 +638,9 @@ int main(int argc, char *argv[]) {
   e = getenv("RNACODE_CUDA_WINDOW_MB"); /* bound on the bytes of simulated alignments per window */
   max_bytes = (size_t)(e ? atol(e) : 4096) << 20;
   blk = (blk_t *)calloc(win_blocks, sizeof(blk_t));
+  blk_prev = (blk_t *)calloc(win_blocks, sizeof(blk_t));
   startTime = clock();
+  g_wall0 = wall0;
 
   /* (f3) MAF files are parsed in place from a mapping of the file (rnacode_maf_mmap.h); pipes, Clustal input and
    * RNACODE_CUDA_PARSER=reference keep the reference's read functions */
@@ -595,12 +671,28 @@ int main(int argc, char *argv[]) {
     win_bytes += (size_t)N * blk[nb].cols * (size_t)(pars.sampleN + 1) * 2;
     nb++;
     if (nb == win_blocks || win_bytes >= max_bytes) {
-      process_window(blk, nb, blosum);
+      /* fork the workers of this window, then finish the previous one (its workers have been running since it was parsed) */
+      host_job next_job;
+      blk_t *tmp;
+      host_stage_start(&next_job, blk, nb);
+      if (have_job) process_window(&job, blosum);
+      job = next_job;
+      have_job = 1;
+      tmp = blk_prev;
+      blk_prev = blk;
+      blk = tmp;
       nb = 0;
       win_bytes = 0;
     }
   }
-  if (nb > 0) process_window(blk, nb, blosum);
+  if (nb > 0) {
+    host_job next_job;
+    host_stage_start(&next_job, blk, nb);
+    if (have_job) process_window(&job, blosum);
+    job = next_job;
+    have_job = 1;
+  }
+  if (have_job) process_window(&job, blosum);
 
   if (pars.outputFormat == 0) {
     float runtime = (float)(clock() - startTime) / CLOCKS_PER_SEC;
@@ -612,5 +704,6 @@ int main(int argc, char *argv[]) {
     fprintf(stderr, "[RNAcode_b200] %d alignments in %.3f s wall (%.1f blocks/s)\n", alnCounter, now_s() - wall0,
             alnCounter / (now_s() - wall0));
   free(blk);
+  free(blk_prev);
   exit(EXIT_SUCCESS);
 }

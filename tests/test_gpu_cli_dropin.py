@@ -93,6 +93,36 @@ def test_batched_pipeline_sharded_over_gpus(case):
     assert _norm(res.stdout) == _norm(op.golden("cli_outputs")[case])
 
 
+def test_dead_tree_worker_is_fatal():
+    """A PhyML worker that dies (here: killed while it holds block 3) ends the run with an error and a non-zero status, as a
+    failing treeML ends the reference -- no silently missing blocks (round-1 advice)."""
+    if not (os.path.exists(PIPELINE) and os.path.isdir(EXAMPLES)):
+        pytest.skip("oracle/_ref/RNAcode_b200_det not built (needs /root/reference at build time)")
+    env = dict(os.environ, RNACODE_SEED="1", RNACODE_CUDA_WORKERS="4", RNACODE_CUDA_TEST_KILL_WORKER_AT="3")
+    res = subprocess.run([PIPELINE, "--tabular", "-n", "20", os.path.join(EXAMPLES, "genomic-preprocessed.maf")],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode != 0
+    assert "tree worker was killed by signal 9" in res.stderr
+    assert res.stdout == ""  # the window was not reported
+
+
+def test_windows_overlap_in_the_batched_pipeline(tmp_path):
+    """The workers of window w+1 are forked before window w is collected: in the verbose stage log every window but the
+    first has its workers started before the previous window is done, and the output is still the reference's."""
+    if not (os.path.exists(PIPELINE) and os.path.isdir(EXAMPLES)):
+        pytest.skip("oracle/_ref/RNAcode_b200_det not built (needs /root/reference at build time)")
+    case = "genomic-preprocessed.maf --tabular -n 20"
+    env = dict(os.environ, RNACODE_SEED="1", RNACODE_CUDA_WORKERS="3", RNACODE_CUDA_WINDOW="6", RNACODE_CUDA_VERBOSE="1")
+    res = subprocess.run([PIPELINE, "--tabular", "-n", "20", os.path.join(EXAMPLES, "genomic-preprocessed.maf")],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr
+    assert _norm(res.stdout) == _norm(op.golden("cli_outputs")[case])
+    wins = re.findall(r"window (\d+) of .*?workers forked at ([0-9.]+) s.*?window done at ([0-9.]+) s", res.stderr)
+    assert len(wins) >= 5
+    for (k, forked, _), (_, _, prev_done) in zip(wins[1:], wins[:-1]):
+        assert float(forked) < float(prev_done), (k, forked, prev_done)
+
+
 def test_gpu_rng_mode_pvalues_within_sampling_error():
     """GPU-RNG mode (RNACODE_CUDA_EVOLVE=philox): the HSS and their scores do not depend on the generator, and the
     p-values from the Gumbel fit of 2000 Philox-drawn null alignments agree with those of 2000 MT19937-drawn ones

@@ -65,3 +65,14 @@ def test_malformed_input_fails_like_the_reference(body, tmp_path):
     got = subprocess.run([CHECK, "--mapped-only", p], capture_output=True, text=True, timeout=60)
     assert ref.returncode != 0 and got.returncode != 0
     assert got.stderr == ref.stderr and ref.stderr.strip() != ""
+
+
+def test_block_without_sequences_does_not_end_the_file(tmp_path):
+    """Two consecutive 'a' lines: the reference's read_maf dereferences the empty block and crashes; the mapped reader skips
+    it and goes on with the blocks that follow instead of treating it as the end of the input."""
+    p = os.path.join(str(tmp_path), "empty_block.maf")
+    with open(p, "w") as fh:
+        fh.write("##maf version=1\na score=0\na score=1\ns a.c 0 6 + 100 ACGTAC\ns b.c 0 6 + 100 ACGTAC\ns c.c 0 6 + 100 ACGTAA\n\n"
+                 "a score=2\n\na score=3\ns a.c 0 3 + 100 ACG\ns b.c 0 3 + 100 ACG\n")
+    got = subprocess.run([CHECK, "--mapped-only", p], capture_output=True, text=True, timeout=60)
+    assert got.returncode == 0 and got.stdout.split() == ["OK", "2", "5"], got.stdout + got.stderr
