@@ -65,9 +65,13 @@ struct BlockDev {
   int smp_seg;              // layouts 2 / 5: 1 = the frame's sigma table does not fit shared memory, streamed in segments (k_dp_smps)
   int smp_fused;            // layouts 2 / 5, resident table: 1 = the DP kernel builds its sigma table itself from class bytes
                             // (k_dp_smpf; no sigma scratch, no k_sigma_smp launch for this block)
-  int smp_pitch;            // (unused by the TMA-staged k_dp_smpf; kept for the record of the first fused variant)
-  long long il_off;         // k_dp_smpf: byte offset of the block's instance-interleaved class bytes (k_pack_il):
-                            // [group of 32 instances][flat byte q = row*cols + col of an instance][lane], groups padded with zeros
+  int p2_words;             // k_dp_smpf: 32-bit words per packed row = ceil(L / 16)
+  long long p2_off;         // k_dp_smpf: u32 offset of the block's packed rows (k_pack2):
+                            // [group of 32 instances][strand][row][word w][lane]: 2-bit nucleotide codes of the row's characters at
+                            // the reference's non-gap columns, 16 positions per word (position 16w + t of the strand's reading
+                            // direction in bits 2t, 2t+1), groups padded with zero lanes
+  long long p2f_off;        // k_dp_smpf: u32 offset of the rows' flag words [group][strand][row]: bit = lane whose row holds an
+                            // 'N' or 'X' at some reference position (such codons take the byte-wise path)
   float fold_B;             // k_dp_smpf: half-width of the ambiguity zone of the getHSS fold in species-sum space (see RowFoldS)
   int nchunk, nkw;          // layout 3: chunks and species per chunk (template NK of k_dp_chain); chunk g holds
   int chunk_base, chunk_rem;  //   chunk_base + (g < chunk_rem) species starting at g*chunk_base + min(g, chunk_rem)

@@ -105,35 +105,48 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDev* __restrict__ block
 }
 
 // ---------------------------------------------------------------------------------------------
-// (a) k_pack_il: instance-interleaved copy of the class bytes for the blocks whose DP kernel builds its own sigma table
-// (k_dp_smpf): il[group][q][lane] = cls[instance group*32 + lane][q], q = row*cols + col.  A row of 32 instances is then one
-// contiguous, 32-byte aligned run of cols*32 bytes -- one TMA bulk copy into shared memory, where lane = instance reads its
-// byte of a column without bank conflicts (32 consecutive bytes).  One warp per (group, 16-byte chunk of q): every lane loads
-// 16 bytes of its instance, the 32 x 16 byte tile is transposed through shared memory, every lane stores 16 bytes.
-// grid = (x: block, y: grid-stride over warps).
+// (a) k_pack2: the packed form of the alignment rows that kernel (b) inside k_dp_smpf consumes: per (group of 32 instances,
+// strand, row) the 2-bit nucleotide codes of the row's characters at the reference's non-gap columns, in the strand's reading
+// direction, 16 positions per 32-bit word, lane-interleaved ([word][lane]) -- so that a row of 32 instances is one contiguous
+// run for a TMA bulk copy, lane = instance reads its own word without bank conflicts, and a codon (three consecutive
+// reference positions) is six adjacent bits: one funnel shift and one mask instead of three byte loads and their shifts.
+// calculateSigma only ever looks at those columns (src/score.c:384-391), a '-' or any other symbol there counts as 'A'
+// (code 0, ntMap), and the reverse strand complements upper-case ACGTU only (revAln) -- all of which the class byte already
+// encodes.  'N' / 'X' (src/score.c:394-404) cannot be expressed in two bits: rows that hold one at a reference position are
+// marked per lane in a flag word, their codons take the byte-wise path.
+// One warp per (group, strand, row, word); lane = instance.  grid = (x: block, y: grid-stride over warps).  cols0 must exist
+// (k_prep<1>).  0.5 byte per character and strand.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pack_il(const BlockDev* __restrict__ blocks, const unsigned char* __restrict__ cls,
-                                                 unsigned char* __restrict__ il) {
-  __shared__ __align__(16) unsigned char tile[8][16][32];
+__global__ void __launch_bounds__(256) k_pack2(const BlockDev* __restrict__ blocks, const unsigned char* __restrict__ cls,
+                                               const int* __restrict__ cols0, unsigned* __restrict__ p2, unsigned* __restrict__ p2f) {
   const BlockDev bd = blocks[blockIdx.x];
   if (!bd.smp_fused) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunks = bd.inst_stride >> 4;                 // 16-byte chunks of one instance (N*cols rounded up)
+  const int N = bd.N, L = bd.L, W = bd.p2_words, cols = bd.cols;
   const int groups = (bd.n_inst + 31) >> 5;
-  const size_t il_group = (size_t)chunks * 16 * 32;       // bytes of one group
-  const long long total = (long long)groups * chunks;
-  for (long long w = (long long)blockIdx.y * 8 + warp; w < total; w += (long long)gridDim.y * 8) {
-    const int g = (int)(w / chunks), ch = (int)(w % chunks);
+  const long long total = (long long)groups * 2 * N * W;
+  for (long long task = (long long)blockIdx.y * 8 + warp; task < total; task += (long long)gridDim.y * 8) {
+    const int w = (int)(task % W);
+    long long rest = task / W;
+    const int r = (int)(rest % N);
+    rest /= N;
+    const int s = (int)(rest & 1), g = (int)(rest >> 1);
     const int inst = g * 32 + lane;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (inst < bd.n_inst) v = *reinterpret_cast<const uint4*>(cls + bd.cls_off + (size_t)inst * bd.inst_stride + (size_t)ch * 16);
-    const unsigned wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int t = 0; t < 16; t++) tile[warp][t][lane] = (unsigned char)(wv[t >> 2] >> (8 * (t & 3)));
-    __syncwarp();
-    const uint4 o = *reinterpret_cast<const uint4*>(&tile[warp][lane >> 1][(lane & 1) * 16]);
-    *reinterpret_cast<uint4*>(il + bd.il_off + (size_t)g * il_group + (size_t)ch * 512 + lane * 16) = o;
-    __syncwarp();
+    const int* c0 = cols0 + bd.cols0_off + (size_t)s * (L + 1) + 1 + 16 * w;  // columns of positions 16w .. 16w+15 (0-based)
+    const int npos = min(16, L - 16 * w);
+    unsigned word = 0u, flag = 0u;
+    if (inst < bd.n_inst) {
+      const unsigned char* row = cls + bd.cls_off + (size_t)inst * bd.inst_stride + (size_t)r * cols;
+      const int sh = s ? 2 : 0;
+      for (int t = 0; t < npos; t++) {
+        const unsigned b = row[c0[t]];
+        word |= ((b >> sh) & 3u) << (2 * t);
+        flag |= b & (CLS_N | CLS_X);
+      }
+    }
+    p2[bd.p2_off + (size_t)task * 32 + lane] = word;
+    const unsigned m = __ballot_sync(0xffffffffu, flag != 0u);
+    if (lane == 0 && m) atomicOr(&p2f[bd.p2f_off + ((size_t)g * 2 + s) * N + r], m);
   }
 }
 
@@ -266,6 +279,9 @@ struct __align__(16) PairTables {
   unsigned short t[4096];
   float val[580];
 };
+// PairTables for codons taken from the packed rows of k_pack2, where the codon's FIRST position sits in the low bits:
+// t[qa'*64 + qb'] with q' = c1 | c2 << 2 | c3 << 4 (PairTables: q = c1 << 4 | c2 << 2 | c3).
+__host__ __device__ inline unsigned pt_swap(unsigned q) { return ((q & 3u) << 4) | (q & 0xcu) | ((q >> 4) & 3u); }
 
 __global__ void __launch_bounds__(256)
     k_sigma(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned char* __restrict__ cls,
@@ -2269,27 +2285,41 @@ template <int NK>
 struct SmpfCfg {
   static constexpr int RSB = (NK + 3) / 4 * 4;
   static __host__ __device__ size_t align16(size_t v) { return (v + 15) / 16 * 16; }
-  // dynamic shared memory: sigma table | z words | barriers | PairTables | expected scores of a quad | codon columns |
-  // staged reference row of the 32 instances | staged species rows of a quad | fold records
+  // dynamic shared memory: sigma table | z words | barrier | PairTables (packed-codon order) | expected scores of the staged
+  // species | flag words of the staged rows | codon columns (byte-wise path) | packed reference row | packed species rows |
+  // fold records.  nsp = species rows staged at once (all of the launch's quads)
   static __host__ __device__ size_t off_z(int sites, int row_bytes) { return (size_t)sites * row_bytes; }
   static __host__ __device__ size_t off_bar(int sites, int row_bytes) { return off_z(sites, row_bytes) + align16((size_t)sites * 4); }
-  static __host__ __device__ size_t off_tab(int sites, int row_bytes) { return off_bar(sites, row_bytes) + 32; }
+  static __host__ __device__ size_t off_tab(int sites, int row_bytes) { return off_bar(sites, row_bytes) + 16; }
   static __host__ __device__ size_t off_sc(int sites, int row_bytes) { return off_tab(sites, row_bytes) + sizeof(PairTables); }
-  static __host__ __device__ size_t off_col(int sites, int row_bytes) { return off_sc(sites, row_bytes) + 64; }
-  static __host__ __device__ size_t off_ref(int sites, int row_bytes) { return off_col(sites, row_bytes) + align16((size_t)3 * sites * 4); }
-  static __host__ __device__ size_t off_sp(int sites, int row_bytes, int cols) { return off_ref(sites, row_bytes) + (size_t)32 * cols; }
-  static __host__ __device__ size_t off_rec(int sites, int row_bytes, int cols) { return off_sp(sites, row_bytes, cols) + (size_t)128 * cols; }
-  static __host__ __device__ size_t total(int sites, int row_bytes, int cols, int nw) {
-    return off_rec(sites, row_bytes, cols) + (size_t)nw * 64 * sizeof(RowRec);
+  static __host__ __device__ size_t off_flag(int sites, int row_bytes, int nsp) { return off_sc(sites, row_bytes) + align16((size_t)nsp * 16); }
+  static __host__ __device__ size_t off_col(int sites, int row_bytes, int nsp) { return off_flag(sites, row_bytes, nsp) + align16((size_t)(nsp + 1) * 4); }
+  static __host__ __device__ size_t off_ref(int sites, int row_bytes, int nsp) { return off_col(sites, row_bytes, nsp) + align16((size_t)3 * sites * 4); }
+  static __host__ __device__ size_t off_sp(int sites, int row_bytes, int nsp, int words) { return off_ref(sites, row_bytes, nsp) + (size_t)(words + 1) * 128; }
+  static __host__ __device__ size_t off_rec(int sites, int row_bytes, int nsp, int words) {
+    return off_sp(sites, row_bytes, nsp, words) + ((size_t)nsp * words + 1) * 128;
+  }
+  static __host__ __device__ size_t total(int sites, int row_bytes, int nsp, int words, int nw) {
+    return off_rec(sites, row_bytes, nsp, words) + (size_t)nw * 64 * sizeof(RowRec);
   }
 };
+
+// six adjacent bits of a packed row: the codon whose first position is p0 (see k_pack2); row = shared address of the lane's
+// word 0, words 128 bytes apart
+__device__ __forceinline__ unsigned p2_codon(const unsigned char* row, int p0) {
+  const int w = p0 >> 4, sh = 2 * (p0 & 15);
+  const unsigned lo = *reinterpret_cast<const unsigned*>(row + (size_t)w * 128);
+  const unsigned hi = *reinterpret_cast<const unsigned*>(row + (size_t)(w + 1) * 128);  // the staged rows have one word of slack
+  return __funnelshift_r(lo, hi, sh) & 63u;
+}
 
 template <int NK, bool CHAINED>
 __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
     k_dp_smpf(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
-              const unsigned char* __restrict__ il, const int* __restrict__ cols0, const float* __restrict__ scores,
-              const PairTables* __restrict__ tables, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm,
-              int band_slots, int chunk, float2* __restrict__ partial) {
+              const unsigned* __restrict__ p2, const unsigned* __restrict__ p2f, const unsigned char* __restrict__ cls,
+              const int* __restrict__ cols0, const float* __restrict__ scores, const PairTables* __restrict__ tables,
+              const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm, int band_slots, int chunk,
+              float2* __restrict__ partial) {
   constexpr int RS = RegCfg<NK>::RS;
   constexpr int RSB = (NK + 3) / 4 * 4;
   constexpr int ROW_BYTES = (CHAINED ? 12 : RSB) * 32 * 4;  // one end codon, 32 lanes (chained: always room for three quads)
@@ -2305,87 +2335,102 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
   const int inst_l = group * 32 + lane;
   const bool valid = inst_l < it.ninst;
   const bool first = !CHAINED || chunk == 0, last = !CHAINED || chunk == bd.nchunk - 1;
-  const int N = bd.N, cols = bd.cols, L = bd.L;
+  const int N = bd.N, cols = bd.cols, L = bd.L, W = bd.p2_words;
 
-  unsigned* zs = reinterpret_cast<unsigned*>(smem + Cfg::off_z(sites, ROW_BYTES));
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::off_bar(sites, ROW_BYTES));  // [0]: tables, z, reference row; [1]: species rows
-  const PairTables& s_tab = *reinterpret_cast<const PairTables*>(smem + Cfg::off_tab(sites, ROW_BYTES));
-  float* s_sc = reinterpret_cast<float*>(smem + Cfg::off_sc(sites, ROW_BYTES));  // [species of the quad][h], h = 0 -> 0
-  int* s_col = reinterpret_cast<int*>(smem + Cfg::off_col(sites, ROW_BYTES));   // columns of the frame's codons: site j at 3j .. 3j+2
-  unsigned char* s_ref = smem + Cfg::off_ref(sites, ROW_BYTES);                 // [col][lane]
-  unsigned char* s_sp = smem + Cfg::off_sp(sites, ROW_BYTES, cols);             // [species of the quad][col][lane]
-  RowRec* srec = reinterpret_cast<RowRec*>(smem + Cfg::off_rec(sites, ROW_BYTES, cols));
-
-  // ---- table phase: kernel (b) for this CTA's (instances, strand, frame, species of the chunk) ------------------------
-  // species quads of this launch: all of them, or the quads of the chunk (layout 5)
+  // species of this launch: all of them, or the quads of the chunk (layout 5)
   int q_first = 0, q_count = RSB / 4;
   if (CHAINED) {
     q_first = chunk * bd.chunk_base + min(chunk, bd.chunk_rem);
     q_count = bd.chunk_base + (chunk < bd.chunk_rem ? 1 : 0);
   }
+  const int NSP = CHAINED ? 12 : RSB;                      // species slots the carve-up provides for
+  const int k_first = 4 * q_first;                         // first scored species (0-based) of the launch
+  const int n_real = min(4 * q_count, bd.NK - k_first);    // species rows that exist
+
+  unsigned* zs = reinterpret_cast<unsigned*>(smem + Cfg::off_z(sites, ROW_BYTES));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::off_bar(sites, ROW_BYTES));
+  const PairTables& s_tab = *reinterpret_cast<const PairTables*>(smem + Cfg::off_tab(sites, ROW_BYTES));
+  float* s_sc = reinterpret_cast<float*>(smem + Cfg::off_sc(sites, ROW_BYTES));            // [species of the launch][h], h = 0 -> 0
+  unsigned* s_flag = reinterpret_cast<unsigned*>(smem + Cfg::off_flag(sites, ROW_BYTES, NSP));  // [0]: reference row, [1 + k]: species
+  int* s_col = reinterpret_cast<int*>(smem + Cfg::off_col(sites, ROW_BYTES, NSP));      // columns of the frame's codons (byte-wise path)
+  unsigned char* s_ref = smem + Cfg::off_ref(sites, ROW_BYTES, NSP);                    // packed reference row [word][lane]
+  unsigned char* s_sp = smem + Cfg::off_sp(sites, ROW_BYTES, NSP, W);                   // packed species rows [species][word][lane]
+  RowRec* srec = reinterpret_cast<RowRec*>(smem + Cfg::off_rec(sites, ROW_BYTES, NSP, W));
+
+  // ---- table phase: kernel (b) for this CTA's (instances, strand, frame, species of the launch) ------------------------
   const size_t z_bytes = Cfg::align16((size_t)sites * 4);
-  // interleaved class bytes of the group: row r of the 32 instances = cols*32 contiguous bytes
-  const size_t row_bytes_il = (size_t)cols * 32;
-  const unsigned char* gil = il + bd.il_off + (size_t)((it.inst0 >> 5) + group) * ((size_t)bd.inst_stride * 32);
-  auto quad_rows = [&](int kq) { return min(4, N - 1 - 4 * (q_first + kq)); };  // species rows the quad really has (>= 1)
+  const size_t prow = (size_t)W * 128;  // bytes of one packed row of 32 instances
+  const size_t grp = (size_t)(it.inst0 >> 5) + group;
+  const unsigned* gp2 = p2 + bd.p2_off + ((grp * 2 + strand) * N) * (size_t)W * 32;
+  const unsigned* gfl = p2f + bd.p2f_off + (grp * 2 + strand) * N;
   if (threadIdx.x == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    mbar_init(bar, 1);
     mbar_fence_init();
-    mbar_expect_tx(&bar[0], (unsigned)(sizeof(PairTables) + z_bytes + row_bytes_il));
-    bulk_g2s(smem + Cfg::off_tab(sites, ROW_BYTES), tables, (unsigned)sizeof(PairTables), &bar[0]);
-    bulk_g2s(zs, ztiles + bd.z_off[strand][frame] + (CHAINED ? (size_t)chunk * bd.ntiles[frame] * TILE : 0), (unsigned)z_bytes, &bar[0]);
-    bulk_g2s(s_ref, gil, (unsigned)row_bytes_il, &bar[0]);
-    const unsigned b0 = (unsigned)(quad_rows(0) * row_bytes_il);
-    mbar_expect_tx(&bar[1], b0);
-    bulk_g2s(s_sp, gil + (size_t)(1 + 4 * q_first) * row_bytes_il, b0, &bar[1]);
+    mbar_expect_tx(bar, (unsigned)(sizeof(PairTables) + z_bytes + prow + (size_t)n_real * prow));
+    bulk_g2s(smem + Cfg::off_tab(sites, ROW_BYTES), tables, (unsigned)sizeof(PairTables), bar);
+    bulk_g2s(zs, ztiles + bd.z_off[strand][frame] + (CHAINED ? (size_t)chunk * bd.ntiles[frame] * TILE : 0), (unsigned)z_bytes, bar);
+    bulk_g2s(s_ref, gp2, (unsigned)prow, bar);
+    bulk_g2s(s_sp, gp2 + (size_t)(1 + k_first) * W * 32, (unsigned)((size_t)n_real * prow), bar);
   }
+  // expected scores of the launch's species on this strand, [species][h], h = 0 -> 0 (see PairTables); flag words of the rows
+  for (int t = threadIdx.x; t < 4 * NSP; t += blockDim.x) {
+    const int kk = t >> 2, h = t & 3, row = 1 + k_first + kk;
+    s_sc[t] = (h > 0 && kk < n_real) ? scores[bd.scores_off + ((size_t)strand * N + row) * 4 + h] : 0.0f;
+  }
+  for (int t = threadIdx.x; t <= NSP; t += blockDim.x) s_flag[t] = t == 0 ? gfl[0] : (t - 1 < n_real ? gfl[k_first + t] : 0u);
   // codon of site j: reference positions x-2 .. x with x = 3j + 3 + frame, i.e. entries frame+1+3j .. frame+3+3j of cols0
   const int* c0 = cols0 + bd.cols0_off + (size_t)strand * (L + 1) + frame + 1;
-  for (int t = threadIdx.x; t < 3 * sites; t += blockDim.x) s_col[t] = c0[t] * 32;  // byte offset of the column in a staged row
-  const int sh = strand ? 2 : 0;
-  __syncthreads();  // barriers initialised, s_col written
-  mbar_wait(&bar[0], 0);
-  for (int kq = 0; kq < q_count; kq++) {
-    const int k0 = 4 * (q_first + kq);  // first species (0-based among the scored ones) of the quad
-    const int nrow = quad_rows(kq);
-    if (threadIdx.x < 16) {  // expected scores of the quad's species on this strand, [species][h], h = 0 -> 0 (see PairTables)
-      const int kk = threadIdx.x >> 2, h = threadIdx.x & 3, row = 1 + k0 + kk;
-      s_sc[threadIdx.x] = (h > 0 && row < N) ? scores[bd.scores_off + ((size_t)strand * N + row) * 4 + h] : 0.0f;
-    }
-    __syncthreads();                  // s_sc of this quad written (and, for kq > 0, nobody reads the previous quad's any more)
-    mbar_wait(&bar[1], kq & 1);       // the quad's species rows have landed
-    const unsigned char* rr = s_ref + lane;
-    for (int j = warp; j < sites; j += nw) {
-      const int i1 = s_col[3 * j], i2 = s_col[3 * j + 1], i3 = s_col[3 * j + 2];
-      const unsigned a1 = rr[i1], a2 = rr[i2], a3 = rr[i3];
-      const unsigned qa = (((a1 >> sh) & 3u) << 4) | (((a2 >> sh) & 3u) << 2) | ((a3 >> sh) & 3u);
-      const unsigned nA = (a1 | a2 | a3) & CLS_N;
-      const unsigned short* trow = s_tab.t + (qa << 6);
-      float v4[4];
+  for (int t = threadIdx.x; t < 3 * sites; t += blockDim.x) s_col[t] = c0[t];
+  __syncthreads();  // barrier initialised; s_sc, s_flag, s_col written
+  mbar_wait(bar, 0);
+  {
+    const unsigned char* rr = s_ref + lane * 4;
+    const unsigned lane_bit = 1u << lane;
+    const unsigned fl_ref = s_flag[0];
+    // class bytes of this lane's instance, for codons of rows with 'N' / 'X' (rare)
+    const unsigned char* cbase = cls + bd.cls_off + (size_t)(it.inst0 + (valid ? inst_l : 0)) * bd.inst_stride;
+    const int sh = strand ? 2 : 0;
+    for (int kq = 0; kq < q_count; kq++) {
+      unsigned fl_any = fl_ref;
 #pragma unroll
-      for (int kk = 0; kk < 4; kk++) {
-        float v = 0.0f;
-        if (kk < nrow) {  // warp-uniform
-          const unsigned char* rk = s_sp + (size_t)kk * row_bytes_il + lane;
-          const unsigned b1 = rk[i1], b2 = rk[i2], b3 = rk[i3];
-          const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
-          const unsigned e = trow[qb];
-          v = s_tab.val[e & 0x3ffu] - s_sc[kk * 4 + (e >> 10)];  // observed - expected (src/score.c:422-425), or constant - 0
-          const unsigned zero = nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X);  // src/score.c:394-404
-          if (zero) v = 0.0f;
+      for (int kk = 0; kk < 4; kk++) fl_any |= s_flag[1 + 4 * kq + kk];
+      const bool slow_lane = (fl_any & lane_bit) != 0u;
+      const bool slow_warp = fl_any != 0u;  // warp-uniform (every lane reads the same words)
+      for (int j = warp; j < sites; j += nw) {
+        const int p0 = 3 * j + frame;
+        const unsigned qa = p2_codon(rr, p0);
+        const unsigned short* trow = s_tab.t + (qa << 6);
+        float v4[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          float v = 0.0f;
+          if (4 * kq + kk < n_real) {  // warp-uniform
+            const unsigned qb = p2_codon(s_sp + (size_t)(4 * kq + kk) * prow + lane * 4, p0);
+            const unsigned e = trow[qb];
+            v = s_tab.val[e & 0x3ffu] - s_sc[(4 * kq + kk) * 4 + (e >> 10)];  // observed - expected (src/score.c:422-425), or constant - 0
+          }
+          v4[kk] = v;
         }
-        v4[kk] = v;
+        if (slow_warp) {  // some lane's rows hold an 'N' or 'X': those lanes test the six characters (src/score.c:394-404)
+          if (slow_lane && valid) {
+            const int i1 = s_col[3 * j], i2 = s_col[3 * j + 1], i3 = s_col[3 * j + 2];
+            const unsigned a1 = cbase[i1], a2 = cbase[i2], a3 = cbase[i3];
+            const unsigned nA = (a1 | a2 | a3) & CLS_N;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++)
+              if (4 * kq + kk < n_real) {
+                const unsigned char* rk = cbase + (size_t)(1 + k_first + 4 * kq + kk) * cols;
+                const unsigned b1 = rk[i1], b2 = rk[i2], b3 = rk[i3];
+                if (nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X)) v4[kk] = 0.0f;
+              }
+          }
+        }
+        *reinterpret_cast<float4*>(smem + (size_t)j * ROW_BYTES + kq * 512 + lane * 16) = make_float4(v4[0], v4[1], v4[2], v4[3]);
       }
-      *reinterpret_cast<float4*>(smem + (size_t)j * ROW_BYTES + kq * 512 + lane * 16) = make_float4(v4[0], v4[1], v4[2], v4[3]);
     }
-    __syncthreads();  // the staged species rows are free; after the last quad: the table is complete
-    if (threadIdx.x == 0 && kq + 1 < q_count) {
-      const unsigned bn = (unsigned)(quad_rows(kq + 1) * row_bytes_il);
-      mbar_expect_tx(&bar[1], bn);
-      bulk_g2s(s_sp, gil + (size_t)(1 + k0 + 4) * row_bytes_il, bn, &bar[1]);
-    }
+    (void)sh;
   }
+  __syncthreads();  // the table is complete
 
   // ---- DP phase: k_dp_smp's loop with the fold in species-sum space ------------------------------------------------------
   unsigned sig_a = smem_u32(smem) + lane * 16;

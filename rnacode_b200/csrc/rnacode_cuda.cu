@@ -45,9 +45,7 @@ struct rc_ctx {
   long reg_max_nk = 12;  // row-major alignments with more scored species take k_dp_chain (k_dp_reg<13..16> spills: 17x3000 14.7 vs 11.1 ms)
   long no_smps = 0;          // never stream the sigma table in segments (k_dp_smps)
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
-  long no_fused = 1;          // 0: build the sigma table inside the sample-major DP kernel (k_dp_smpf).  Off by default: staging the
-                              // class bytes with ordinary loads exposes their latency at two CTAs per SM (2000 x 10x120, n=100:
-                              // 7.1 ms fused against 1.8 + 3.1 ms for k_sigma_smp + k_dp_smp)
+  long no_fused = 0;          // 1: never build the sigma table inside the sample-major DP kernel (k_dp_smpf)
   long tail_max = 0;          // a sample-major block whose instance count leaves 1..tail_max instances in its last group of 32 scores
                               // those instances row-major (lanes = rows) instead of in a warp with that many live lanes (0: never)
   long smpc_max_sites = 0;    // longest frame (codons) for the STREAMED chunked sample-major route of wide alignments
@@ -195,8 +193,8 @@ size_t smp_smem_bytes(const BlockDev& bd, int f, int layout, int seg) {
 
 // k_dp_smpf: shared memory of a CTA (frame 0 is the longest) without the fold records
 size_t smpf_smem_bytes(const BlockDev& bd, int layout) {
-  const int row_bytes = (layout == 5 ? 12 : (bd.NK + 3) / 4 * 4) * 32 * 4;
-  return SmpfCfg<1>::off_rec(bd.sites[0], row_bytes, bd.cols);
+  const int nsp = layout == 5 ? 12 : (bd.NK + 3) / 4 * 4;
+  return SmpfCfg<1>::off_rec(bd.sites[0], nsp * 32 * 4, nsp, (bd.L + 15) / 16);
 }
 
 // floats of sigma scratch for `ninst` instances of one (strand, frame) of a block
@@ -287,8 +285,10 @@ struct rc_batch {
   Item* d_items = nullptr;
   CtaDesc* d_ctas = nullptr;
   unsigned char *d_raw = nullptr, *d_cls = nullptr;
-  unsigned char* d_il = nullptr;  // instance-interleaved class bytes of the blocks scored by k_dp_smpf
-  size_t il_bytes = 0;
+  unsigned *d_p2 = nullptr, *d_p2f = nullptr;  // packed rows (k_pack2) and their flag words, for the blocks scored by k_dp_smpf
+  size_t p2_words = 0, p2f_words = 0;
+  PairTables ptab2{};             // PairTables indexed by packed codons (first position in the low bits)
+  PairTables* d_ptab2 = nullptr;
   int* d_cols0 = nullptr;
   float* d_scores = nullptr;
   unsigned* d_z = nullptr;
@@ -513,7 +513,7 @@ extern "C" int rc_calibrate_issue(rc_ctx* ctx, double* lane_ops_per_s) {
 static void free_batch_device(rc_batch* b) {
   rc_ctx* ctx = b->ctx;
   void* ptrs[] = {b->d_blocks, b->d_items, b->d_ctas, b->d_raw, b->d_cls, b->d_cols0, b->d_scores, b->d_z, b->d_res,
-                  b->d_hss, b->d_hsscnt, b->d_ovf, b->d_tables, b->d_ptab, b->d_sigma, b->d_recs, b->d_dense, b->d_partial, b->d_il,
+                  b->d_hss, b->d_hsscnt, b->d_ovf, b->d_tables, b->d_ptab, b->d_sigma, b->d_recs, b->d_dense, b->d_partial, b->d_p2, b->d_p2f, b->d_ptab2,
                   b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq};
   for (void* p : ptrs) ctx_free(ctx, p);
   for (auto& e : b->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -595,6 +595,9 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
   b->prm = Params{params->Delta, params->Omega, params->omega, params->stopPenalty_0, params->stopPenalty_k};
   fill_tables(b->tables, blosum);
   fill_pair_tables(b->ptab, b->tables, b->prm);
+  b->ptab2 = b->ptab;
+  for (unsigned qa = 0; qa < 64; qa++)
+    for (unsigned qb = 0; qb < 64; qb++) b->ptab2.t[qa * 64 + qb] = b->ptab.t[pt_swap(qa) * 64 + pt_swap(qb)];
 
   b->blocks.resize(n_blocks);
   double cells = 0;
@@ -668,11 +671,20 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       bd.smp_seg = seg;
       finish_layout(bd);
       // resident-table sample-major blocks build their sigma table inside the DP kernel when the staged rows fit as well
-      if ((layout == 2 || layout == 5) && !seg && !ctx->no_fused && !ctx->force_dense &&
+      // ... unless that costs a resident CTA (two CTAs of 8 warps per SM need <= 113 KB each): wide alignments in chunks have
+      // a 100 KB table already and stay with k_sigma_smp + k_dp_smp
+      const size_t sm_bytes = (size_t)228 * 1024;
+      const bool two_fused = 2 * (smpf_smem_bytes(bd, layout) + (size_t)SMP_MAX_WARPS * 64 * sizeof(RowRec) + 1024) <= sm_bytes;
+      const bool two_unfused = 2 * (smp_smem_bytes(bd, 0, layout, 0) + (size_t)SMP_WARPS * 64 * sizeof(RowRec) + 1024) <= sm_bytes;
+      if ((layout == 2 || layout == 5) && !seg && !ctx->no_fused && !ctx->force_dense && (two_fused || !two_unfused) &&
           smpf_smem_bytes(bd, layout) + (size_t)SMP_WARPS * 64 * sizeof(RowRec) <= (size_t)ctx->smem_optin) {
         bd.smp_fused = 1;
-        bd.il_off = (long long)b->il_bytes;
-        b->il_bytes += (size_t)((bd.n_inst + 31) / 32) * bd.inst_stride * 32;
+        bd.p2_words = (bd.L + 15) / 16;
+        const size_t groups = (size_t)(bd.n_inst + 31) / 32;
+        bd.p2_off = (long long)b->p2_words;
+        b->p2_words += groups * 2 * bd.N * bd.p2_words * 32 + 64;  // + slack: the last row's codon look-ups read one word ahead
+        bd.p2f_off = (long long)b->p2f_words;
+        b->p2f_words += groups * 2 * bd.N;
       }
       if (layout == 2 || layout == 5) {
         // B of RowFoldS: (N-1) * 1.0002e-4 for the tolerance of getHSS's tie rule plus 2^-21 of the largest species sum a
@@ -860,7 +872,9 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
             dalloc((void**)&b->d_tables, sizeof(SigmaTables)) && dalloc((void**)&b->d_ptab, sizeof(PairTables)) && dalloc((void**)&b->d_sigma, sizeof(float) * b->sigma_floats) &&
             dalloc((void**)&b->d_recs, sizeof(RowRec) * b->rec_count) &&
             (b->part_count == 0 || dalloc((void**)&b->d_partial, sizeof(float2) * b->part_count)) &&
-            (b->il_bytes == 0 || dalloc((void**)&b->d_il, b->il_bytes));
+            (b->p2_words == 0 || (dalloc((void**)&b->d_p2, sizeof(unsigned) * b->p2_words) &&
+                                  dalloc((void**)&b->d_p2f, sizeof(unsigned) * b->p2f_words) &&
+                                  dalloc((void**)&b->d_ptab2, sizeof(PairTables))));
   if (!ok) {
     ctx_fail(ctx, std::string("rc_batch_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     free_batch_device(b);
@@ -1021,6 +1035,7 @@ extern "C" int rc_batch_upload(rc_batch* b) {
     RC_CUDA(cudaMemcpyAsync(b->d_ctas, b->ctas.data(), sizeof(CtaDesc) * b->ctas.size(), cudaMemcpyHostToDevice, st));
   RC_CUDA(cudaMemcpyAsync(b->d_tables, &b->tables, sizeof(SigmaTables), cudaMemcpyHostToDevice, st));
   RC_CUDA(cudaMemcpyAsync(b->d_ptab, &b->ptab, sizeof(PairTables), cudaMemcpyHostToDevice, st));
+  if (b->d_ptab2) RC_CUDA(cudaMemcpyAsync(b->d_ptab2, &b->ptab2, sizeof(PairTables), cudaMemcpyHostToDevice, st));
   if (!b->evos.empty()) {
     void* ptrs[] = {b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq};
     for (void* p : ptrs) ctx_free(ctx, p);
@@ -1234,9 +1249,9 @@ static int launch_dp_smpf_nk(rc_batch* b, int chunk, bool last, const CtaDesc* d
   const int nw = smp_warps(ctx, smem, true);
   smem += (size_t)nw * 64 * sizeof(RowRec);  // the carve-up always has the records at the end (SmpfCfg::off_rec)
   RC_CUDA(cudaFuncSetAttribute(k_dp_smpf<NK, CHAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dp_smpf<NK, CHAINED><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_il, b->d_cols0,
-                                                                         b->d_scores, b->d_ptab, b->d_z, b->d_recs, b->prm,
-                                                                         (int)ctx->band_slots, chunk, b->d_partial);
+  k_dp_smpf<NK, CHAINED><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_p2, b->d_p2f, b->d_cls,
+                                                                         b->d_cols0, b->d_scores, b->d_ptab2, b->d_z, b->d_recs,
+                                                                         b->prm, (int)ctx->band_slots, chunk, b->d_partial);
   RC_CUDA(cudaGetLastError());
   b->stats.launches++;
   b->stats.dp_launches++;
@@ -1472,14 +1487,15 @@ extern "C" int rc_batch_run(rc_batch* b) {
     const int evk = ev_begin(b, 4);  // k_pack alone (HBM roofline of subsystem (a))
     k_pack<<<g, 256, 0, st>>>(b->d_blocks, b->d_raw, b->d_cls, ctx->d_lut);
     RC_CUDA(cudaGetLastError());
-    if (b->il_bytes > 0) {  // instance-interleaved copy for the blocks whose DP kernel builds its own sigma table
-      k_pack_il<<<g, 256, 0, st>>>(b->d_blocks, b->d_cls, b->d_il);
-      RC_CUDA(cudaGetLastError());
-      b->stats.launches++;
-    }
     ev_end(b, evk);
     k_prep<1><<<b->n_blocks, 256, 0, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_z);
     RC_CUDA(cudaGetLastError());
+    if (b->p2_words > 0) {  // packed rows for the blocks whose DP kernel builds its own sigma table (needs cols0)
+      RC_CUDA(cudaMemsetAsync(b->d_p2f, 0, sizeof(unsigned) * b->p2f_words, st));
+      k_pack2<<<g, 256, 0, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_p2, b->d_p2f);
+      RC_CUDA(cudaGetLastError());
+      b->stats.launches++;
+    }
     // z words: a long block would keep a single CTA busy for ~0.2 ms; spread each block over several CTAs
     size_t maxz = 1;
     for (const BlockDev& bd : b->blocks) maxz = std::max(maxz, (size_t)bd.ntiles[0] * bd.zstride);
