@@ -114,39 +114,56 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDev* __restrict__ block
 // (code 0, ntMap), and the reverse strand complements upper-case ACGTU only (revAln) -- all of which the class byte already
 // encodes.  'N' / 'X' (src/score.c:394-404) cannot be expressed in two bits: rows that hold one at a reference position are
 // marked per lane in a flag word, their codons take the byte-wise path.
-// One warp per (group, strand, row, word); lane = instance.  grid = (x: block, y: grid-stride over warps).  cols0 must exist
-// (k_prep<1>).  0.5 byte per character and strand.
+// One CTA pass per (group, row): the class bytes of the row of the group's 32 instances are staged in shared memory with
+// coalesced word loads (odd word pitch), then every thread packs the sixteen positions of one (strand, word, instance) from
+// its instance's staged bytes -- lane = instance, so the 128-byte lines of the output are written whole.
+// grid = (x: block, y: grid-stride over (group, row)).  cols0 must exist (k_prep<1>).  0.5 byte per character and strand.
 // ---------------------------------------------------------------------------------------------
+constexpr int P2_MAX_COLS = 1020;  // longest row k_pack2 stages (blocks scored by k_dp_smpf are far shorter: their sigma table fits smem)
+
 __global__ void __launch_bounds__(256) k_pack2(const BlockDev* __restrict__ blocks, const unsigned char* __restrict__ cls,
                                                const int* __restrict__ cols0, unsigned* __restrict__ p2, unsigned* __restrict__ p2f) {
+  __shared__ __align__(16) unsigned char s_row[32 * (P2_MAX_COLS + 16)];
+  __shared__ int s_c0[2][P2_MAX_COLS];
   const BlockDev bd = blocks[blockIdx.x];
   if (!bd.smp_fused) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = bd.N, L = bd.L, W = bd.p2_words, cols = bd.cols;
   const int groups = (bd.n_inst + 31) >> 5;
-  const long long total = (long long)groups * 2 * N * W;
-  for (long long task = (long long)blockIdx.y * 8 + warp; task < total; task += (long long)gridDim.y * 8) {
-    const int w = (int)(task % W);
-    long long rest = task / W;
-    const int r = (int)(rest % N);
-    rest /= N;
-    const int s = (int)(rest & 1), g = (int)(rest >> 1);
-    const int inst = g * 32 + lane;
-    const int* c0 = cols0 + bd.cols0_off + (size_t)s * (L + 1) + 1 + 16 * w;  // columns of positions 16w .. 16w+15 (0-based)
-    const int npos = min(16, L - 16 * w);
-    unsigned word = 0u, flag = 0u;
-    if (inst < bd.n_inst) {
-      const unsigned char* row = cls + bd.cls_off + (size_t)inst * bd.inst_stride + (size_t)r * cols;
-      const int sh = s ? 2 : 0;
-      for (int t = 0; t < npos; t++) {
-        const unsigned b = row[c0[t]];
-        word |= ((b >> sh) & 3u) << (2 * t);
-        flag |= b & (CLS_N | CLS_X);
-      }
+  int pitch = (cols + 6 + 3) / 4 * 4;
+  if (((pitch / 4) & 1) == 0) pitch += 4;  // odd word count: the 32 instances' bytes of a column sit in 32 banks
+  for (int t = threadIdx.x; t < 2 * L; t += blockDim.x) s_c0[t / L][t % L] = cols0[bd.cols0_off + (size_t)(t / L) * (L + 1) + 1 + t % L];
+  for (int gr = blockIdx.y; gr < groups * N; gr += gridDim.y) {
+    const int g = gr / N, r = gr % N;
+    __syncthreads();  // s_c0 written; the previous pass is done with s_row
+    // stage row r of the 32 instances: one warp per instance, aligned word copies; column c of instance li at s_row[li*pitch + shift + c]
+    const size_t roff = (size_t)r * cols;
+    const unsigned shift = (unsigned)roff & 3u;
+    for (int li = warp; li < 32; li += 8) {
+      const int inst = g * 32 + li;
+      const unsigned* src4 = reinterpret_cast<const unsigned*>(cls + bd.cls_off + (size_t)(inst < bd.n_inst ? inst : 0) * bd.inst_stride + roff - shift);
+      unsigned* dst4 = reinterpret_cast<unsigned*>(s_row + li * pitch);
+      for (int w = lane; w < (int)(shift + cols + 3) / 4; w += 32) dst4[w] = inst < bd.n_inst ? src4[w] : 0u;
     }
-    p2[bd.p2_off + (size_t)task * 32 + lane] = word;
-    const unsigned m = __ballot_sync(0xffffffffu, flag != 0u);
-    if (lane == 0 && m) atomicOr(&p2f[bd.p2f_off + ((size_t)g * 2 + s) * N + r], m);
+    __syncthreads();
+    // (strand, word) pairs, one warp each; lane = instance
+    for (int sw = warp; sw < 2 * W; sw += 8) {
+      const int s = sw / W, w = sw % W;
+      const int sh = s ? 2 : 0;
+      const int npos = min(16, L - 16 * w);
+      const unsigned char* rb = s_row + lane * pitch + shift;
+      const int* c0 = s_c0[s] + 16 * w;
+      unsigned word = 0u, flag = 0u;
+#pragma unroll 4
+      for (int t = 0; t < npos; t++) {
+        const unsigned b = rb[c0[t]];
+        word |= ((b >> sh) & 3u) << (2 * t);
+        flag |= b;
+      }
+      p2[bd.p2_off + ((((size_t)g * 2 + s) * N + r) * W + w) * 32 + lane] = word;
+      const unsigned m = __ballot_sync(0xffffffffu, (flag & (CLS_N | CLS_X)) != 0u);
+      if (lane == 0 && m) atomicOr(&p2f[bd.p2f_off + ((size_t)g * 2 + s) * N + r], m);
+    }
   }
 }
 

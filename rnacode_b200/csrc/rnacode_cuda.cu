@@ -287,6 +287,7 @@ struct rc_batch {
   unsigned char *d_raw = nullptr, *d_cls = nullptr;
   unsigned *d_p2 = nullptr, *d_p2f = nullptr;  // packed rows (k_pack2) and their flag words, for the blocks scored by k_dp_smpf
   size_t p2_words = 0, p2f_words = 0;
+  int max_n_inst = 1, max_fused_N = 1;
   PairTables ptab2{};             // PairTables indexed by packed codons (first position in the low bits)
   PairTables* d_ptab2 = nullptr;
   int* d_cols0 = nullptr;
@@ -618,6 +619,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     bd.L = L;
     bd.NK = d.N - 1;
     bd.n_inst = 1 + d.n_samples;
+    b->max_n_inst = std::max(b->max_n_inst, bd.n_inst);
     bd.inst_stride = (int)align_up((size_t)d.N * d.cols, 16);
     bd.fNK = (float)bd.NK;
     bd.rcpNK = 1.0f / bd.fNK;
@@ -676,9 +678,10 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       const size_t sm_bytes = (size_t)228 * 1024;
       const bool two_fused = 2 * (smpf_smem_bytes(bd, layout) + (size_t)SMP_MAX_WARPS * 64 * sizeof(RowRec) + 1024) <= sm_bytes;
       const bool two_unfused = 2 * (smp_smem_bytes(bd, 0, layout, 0) + (size_t)SMP_WARPS * 64 * sizeof(RowRec) + 1024) <= sm_bytes;
-      if ((layout == 2 || layout == 5) && !seg && !ctx->no_fused && !ctx->force_dense && (two_fused || !two_unfused) &&
+      if ((layout == 2 || layout == 5) && !seg && !ctx->no_fused && !ctx->force_dense && (two_fused || !two_unfused) && bd.cols <= P2_MAX_COLS &&
           smpf_smem_bytes(bd, layout) + (size_t)SMP_WARPS * 64 * sizeof(RowRec) <= (size_t)ctx->smem_optin) {
         bd.smp_fused = 1;
+        b->max_fused_N = std::max(b->max_fused_N, bd.N);
         bd.p2_words = (bd.L + 15) / 16;
         const size_t groups = (size_t)(bd.n_inst + 31) / 32;
         bd.p2_off = (long long)b->p2_words;
@@ -1492,7 +1495,8 @@ extern "C" int rc_batch_run(rc_batch* b) {
     RC_CUDA(cudaGetLastError());
     if (b->p2_words > 0) {  // packed rows for the blocks whose DP kernel builds its own sigma table (needs cols0)
       RC_CUDA(cudaMemsetAsync(b->d_p2f, 0, sizeof(unsigned) * b->p2f_words, st));
-      k_pack2<<<g, 256, 0, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_p2, b->d_p2f);
+      dim3 g2((unsigned)b->n_blocks, (unsigned)std::min(256, ((b->max_n_inst + 31) / 32) * b->max_fused_N));
+      k_pack2<<<g2, 256, 0, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_p2, b->d_p2f);
       RC_CUDA(cudaGetLastError());
       b->stats.launches++;
     }
