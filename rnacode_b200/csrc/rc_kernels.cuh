@@ -122,17 +122,19 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDev* __restrict__ block
 constexpr int P2_MAX_COLS = 1020;  // longest row k_pack2 stages (blocks scored by k_dp_smpf are far shorter: their sigma table fits smem)
 
 __global__ void __launch_bounds__(256) k_pack2(const BlockDev* __restrict__ blocks, const unsigned char* __restrict__ cls,
-                                               const int* __restrict__ cols0, unsigned* __restrict__ p2, unsigned* __restrict__ p2f) {
-  __shared__ __align__(16) unsigned char s_row[32 * (P2_MAX_COLS + 16)];
-  __shared__ int s_c0[2][P2_MAX_COLS];
+                                               const int* __restrict__ cols0, unsigned* __restrict__ p2, unsigned* __restrict__ p2f,
+                                               int max_L) {
+  extern __shared__ __align__(16) unsigned char p2_smem[];  // s_c0[2][max_L] ints | s_row[32 * max pitch] (sized by the host)
   const BlockDev bd = blocks[blockIdx.x];
   if (!bd.smp_fused) return;
+  int* s_c0base = reinterpret_cast<int*>(p2_smem);
+  unsigned char* s_row = p2_smem + (size_t)2 * max_L * sizeof(int);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = bd.N, L = bd.L, W = bd.p2_words, cols = bd.cols;
   const int groups = (bd.n_inst + 31) >> 5;
   int pitch = (cols + 6 + 3) / 4 * 4;
   if (((pitch / 4) & 1) == 0) pitch += 4;  // odd word count: the 32 instances' bytes of a column sit in 32 banks
-  for (int t = threadIdx.x; t < 2 * L; t += blockDim.x) s_c0[t / L][t % L] = cols0[bd.cols0_off + (size_t)(t / L) * (L + 1) + 1 + t % L];
+  for (int t = threadIdx.x; t < 2 * L; t += blockDim.x) s_c0base[(t / L) * max_L + t % L] = cols0[bd.cols0_off + (size_t)(t / L) * (L + 1) + 1 + t % L];
   for (int gr = blockIdx.y; gr < groups * N; gr += gridDim.y) {
     const int g = gr / N, r = gr % N;
     __syncthreads();  // s_c0 written; the previous pass is done with s_row
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256) k_pack2(const BlockDev* __restrict__ bloc
       const int sh = s ? 2 : 0;
       const int npos = min(16, L - 16 * w);
       const unsigned char* rb = s_row + lane * pitch + shift;
-      const int* c0 = s_c0[s] + 16 * w;
+      const int* c0 = s_c0base + s * max_L + 16 * w;
       unsigned word = 0u, flag = 0u;
 #pragma unroll 4
       for (int t = 0; t < npos; t++) {

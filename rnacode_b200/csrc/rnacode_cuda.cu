@@ -287,7 +287,7 @@ struct rc_batch {
   unsigned char *d_raw = nullptr, *d_cls = nullptr;
   unsigned *d_p2 = nullptr, *d_p2f = nullptr;  // packed rows (k_pack2) and their flag words, for the blocks scored by k_dp_smpf
   size_t p2_words = 0, p2f_words = 0;
-  int max_n_inst = 1, max_fused_N = 1;
+  int max_n_inst = 1, max_fused_N = 1, max_fused_cols = 1;
   PairTables ptab2{};             // PairTables indexed by packed codons (first position in the low bits)
   PairTables* d_ptab2 = nullptr;
   int* d_cols0 = nullptr;
@@ -682,6 +682,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
           smpf_smem_bytes(bd, layout) + (size_t)SMP_WARPS * 64 * sizeof(RowRec) <= (size_t)ctx->smem_optin) {
         bd.smp_fused = 1;
         b->max_fused_N = std::max(b->max_fused_N, bd.N);
+        b->max_fused_cols = std::max(b->max_fused_cols, bd.cols);
         bd.p2_words = (bd.L + 15) / 16;
         const size_t groups = (size_t)(bd.n_inst + 31) / 32;
         bd.p2_off = (long long)b->p2_words;
@@ -1496,7 +1497,10 @@ extern "C" int rc_batch_run(rc_batch* b) {
     if (b->p2_words > 0) {  // packed rows for the blocks whose DP kernel builds its own sigma table (needs cols0)
       RC_CUDA(cudaMemsetAsync(b->d_p2f, 0, sizeof(unsigned) * b->p2f_words, st));
       dim3 g2((unsigned)b->n_blocks, (unsigned)std::min(256, ((b->max_n_inst + 31) / 32) * b->max_fused_N));
-      k_pack2<<<g2, 256, 0, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_p2, b->d_p2f);
+      const int max_L = (b->max_fused_cols + 3) / 4 * 4;
+      const size_t p2_smem = (size_t)2 * max_L * sizeof(int) + (size_t)32 * (b->max_fused_cols + 16);
+      RC_CUDA(cudaFuncSetAttribute(k_pack2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem));
+      k_pack2<<<g2, 256, p2_smem, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_p2, b->d_p2f, max_L);
       RC_CUDA(cudaGetLastError());
       b->stats.launches++;
     }
