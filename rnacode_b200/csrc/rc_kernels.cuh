@@ -2844,83 +2844,100 @@ __device__ __forceinline__ unsigned philox_draw(unsigned seed, unsigned node, un
 
 constexpr int EVO_WARPS = 4;
 #ifndef RC_EVO_SPW
-#define RC_EVO_SPW 2
+#define RC_EVO_SPW 8
 #endif
-constexpr int EVO_SPW = RC_EVO_SPW;  // samples per warp: their MT19937 states are seeded side by side, one lane each (more: fewer
-                                     // seeding passes per sample, but 2.5 KB of shared memory per sample limit the resident warps)
-constexpr int EVO_MT_PITCH = 625;   // words per state in shared memory (odd: the seeding lanes hit distinct banks)
-constexpr int EVO_SMEM = EVO_WARPS * EVO_SPW * EVO_MT_PITCH * 4;
+constexpr int EVO_SPW = RC_EVO_SPW;  // samples per task: their MT19937 states are seeded side by side, one lane each
 
+// Persistent warps: warp `wg` of the grid works through the tasks wg, wg + n_warps, ...; a task is EVO_SPW consecutive
+// samples of one block (evo_task0: prefix sums of the tasks per block).  The states of a task are seeded by EVO_SPW lanes in
+// parallel into the warp's private slot of a global scratch (init_genrand is a serial chain of 624 steps: seeding one state
+// per warp wastes 31 lanes, seeding 32 per warp in shared memory would leave room for two warps per SM); each sample then
+// loads its state into the warp's 2.5 KB of shared memory and is drawn with all 32 lanes.
 __global__ void __launch_bounds__(EVO_WARPS * 32)
-    k_evolve(const BlockDev* __restrict__ blocks, const EvoDev* __restrict__ evos, const int* __restrict__ nodes,
-             const unsigned* __restrict__ thr, const unsigned* __restrict__ seeds, unsigned char* __restrict__ seqs,
-             unsigned char* __restrict__ raw, int evo0) {
-  extern __shared__ unsigned s_mt[];  // [EVO_WARPS][EVO_SPW][EVO_MT_PITCH]
+    k_evolve(const BlockDev* __restrict__ blocks, const EvoDev* __restrict__ evos, const int* __restrict__ evo_task0, int n_evos,
+             const int* __restrict__ nodes, const unsigned* __restrict__ thr, const unsigned* __restrict__ seeds,
+             unsigned char* __restrict__ seqs, unsigned char* __restrict__ raw, unsigned* __restrict__ mt_scratch) {
+  __shared__ unsigned s_mt[EVO_WARPS][624];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const EvoDev ev = evos[evo0 + blockIdx.y];
-  const BlockDev& bd = blocks[ev.block];
-  const int n_samp = bd.n_inst - 1;
-  const int s_base = (blockIdx.x * EVO_WARPS + warp) * EVO_SPW;  // the warp draws samples s_base .. s_base + EVO_SPW - 1, one after the other
-  if (s_base >= n_samp) return;
-  const int n_mine = min(EVO_SPW, n_samp - s_base);
-  const int cols = bd.cols;
-  const int* nd = nodes + ev.node_off;
-  const unsigned* th = thr + ev.thr_off;
-  unsigned* wmt = s_mt + warp * (EVO_SPW * EVO_MT_PITCH);
-  if (ev.rng == 0) {
-    // init_genrand (seqgen/twister.c:73-86) is a serial recurrence of 624 steps: lane q runs it for sample s_base + q, so
-    // the warp seeds its EVO_SPW generators in the time of one
-    if (lane < n_mine) {
-      unsigned x = seeds[ev.seed_off + s_base + lane];
-      unsigned* m = wmt + lane * EVO_MT_PITCH;
-      for (int i = 0; i < 624; i++) {
-        m[i] = x;
-        x = 1812433253u * (x ^ (x >> 30)) + (unsigned)(i + 1);
-      }
-    }
-    __syncwarp();
-  }
+  const int wg = blockIdx.x * EVO_WARPS + warp, n_warps = gridDim.x * EVO_WARPS;
+  const int total_tasks = evo_task0[n_evos];
+  unsigned* mt = s_mt[warp];
+  unsigned* slot = mt_scratch + (size_t)wg * EVO_SPW * 624;
 #pragma unroll 1
-  for (int q = 0; q < n_mine; q++) {
-    const int sample = s_base + q;
-    const unsigned seed = seeds[ev.seed_off + sample];
-    unsigned char* myseq = seqs + ev.seq_off + (size_t)sample * ev.n_internal * cols;
-    unsigned char* myraw = raw + bd.raw_off + (size_t)sample * bd.N * cols;
-    unsigned* mt = wmt + q * EVO_MT_PITCH;
-    int pos = 624;  // next unread word of the current 624-word batch
-    for (int n = 0; n < ev.n_nodes; n++) {
-      const int parent = nd[4 * n], row = nd[4 * n + 1], slot = nd[4 * n + 2];
-      const unsigned char* pseq = parent >= 0 ? myseq + (size_t)nd[4 * parent + 2] * cols : nullptr;
-      const unsigned* tn = th + (size_t)n * 16;
-      for (int c0 = 0; c0 < cols; c0 += 32) {
-        const int site = c0 + lane;
-        const int cnt = min(32, cols - c0);  // draws consumed by this chunk
-        unsigned u;
-        if (ev.rng == 0) {
-          // lanes 0..cnt-1 take the next cnt outputs of the generator, in order
-          int idx = pos + lane;
-          unsigned v = 0;
-          if (lane < cnt && idx < 624) v = mt[idx];
-          if (pos + cnt > 624) {  // the chunk crosses a batch boundary (warp-uniform)
-            __syncwarp();
-            mt_twist(mt, lane);
-            if (lane < cnt && idx >= 624) v = mt[idx - 624];
-            pos -= 624;
-          }
-          pos += cnt;
-          u = mt_temper(v);
-        } else {
-          u = philox_draw(seed, (unsigned)n, (unsigned)site);
-        }
-        if (site < cols) {
-          const int ps = parent >= 0 ? (int)pseq[site] : 0;  // root: row 0 of its table holds the cumulative frequencies
-          const unsigned* t = tn + ps * 4;
-          const int state = (u > t[0]) + (u > t[1]) + (u > t[2]);
-          if (slot >= 0) myseq[(size_t)slot * cols + site] = (unsigned char)state;
-          if (row >= 0) myraw[(size_t)row * cols + site] = (unsigned char)("ACGT"[state]);
+  for (int task = wg; task < total_tasks; task += n_warps) {
+    int lo = 0, hi = n_evos - 1;  // the block of the task: largest e with evo_task0[e] <= task
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (evo_task0[mid] <= task) lo = mid;
+      else hi = mid - 1;
+    }
+    const EvoDev ev = evos[lo];
+    const BlockDev& bd = blocks[ev.block];
+    const int n_samp = bd.n_inst - 1;
+    const int s_base = (task - evo_task0[lo]) * EVO_SPW;
+    const int n_mine = min(EVO_SPW, n_samp - s_base);
+    const int cols = bd.cols;
+    const int* nd = nodes + ev.node_off;
+    const unsigned* th = thr + ev.thr_off;
+    if (ev.rng == 0) {
+      // init_genrand (seqgen/twister.c:73-86): lane q seeds the state of sample s_base + q
+      if (lane < n_mine) {
+        unsigned x = seeds[ev.seed_off + s_base + lane];
+        unsigned* m = slot + (size_t)lane * 624;
+        for (int i = 0; i < 624; i++) {
+          m[i] = x;
+          x = 1812433253u * (x ^ (x >> 30)) + (unsigned)(i + 1);
         }
       }
-      __syncwarp();  // a child reads its parent's sequence written by other lanes
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int q = 0; q < n_mine; q++) {
+      const int sample = s_base + q;
+      const unsigned seed = seeds[ev.seed_off + sample];
+      unsigned char* myseq = seqs + ev.seq_off + (size_t)sample * ev.n_internal * cols;
+      unsigned char* myraw = raw + bd.raw_off + (size_t)sample * bd.N * cols;
+      if (ev.rng == 0) {
+        for (int i = lane; i < 624; i += 32) mt[i] = slot[(size_t)q * 624 + i];
+        __syncwarp();
+      }
+      int pos = 624;  // next unread word of the current 624-word batch
+      for (int n = 0; n < ev.n_nodes; n++) {
+        const int parent = nd[4 * n], row = nd[4 * n + 1], slot_n = nd[4 * n + 2];
+        const unsigned char* pseq = parent >= 0 ? myseq + (size_t)nd[4 * parent + 2] * cols : nullptr;
+        const unsigned tv = th[(size_t)n * 16 + (lane & 15)];  // the node's 16 thresholds, one per lane; fetched by shuffle below
+        for (int c0 = 0; c0 < cols; c0 += 32) {
+          const int site = c0 + lane;
+          const int cnt = min(32, cols - c0);  // draws consumed by this chunk
+          unsigned u;
+          if (ev.rng == 0) {
+            // lanes 0..cnt-1 take the next cnt outputs of the generator, in order
+            int idx = pos + lane;
+            unsigned v = 0;
+            if (lane < cnt && idx < 624) v = mt[idx];
+            if (pos + cnt > 624) {  // the chunk crosses a batch boundary (warp-uniform)
+              __syncwarp();
+              mt_twist(mt, lane);
+              if (lane < cnt && idx >= 624) v = mt[idx - 624];
+              pos -= 624;
+            }
+            pos += cnt;
+            u = mt_temper(v);
+          } else {
+            u = philox_draw(seed, (unsigned)n, (unsigned)site);
+          }
+          const int ps = (parent >= 0 && site < cols) ? (int)pseq[site] : 0;  // root: row 0 of its table holds the cumulative frequencies
+          const unsigned t0 = __shfl_sync(0xffffffffu, tv, ps * 4), t1 = __shfl_sync(0xffffffffu, tv, ps * 4 + 1),
+                         t2 = __shfl_sync(0xffffffffu, tv, ps * 4 + 2);
+          if (site < cols) {
+            const int state = (u > t0) + (u > t1) + (u > t2);
+            if (slot_n >= 0) myseq[(size_t)slot_n * cols + site] = (unsigned char)state;
+            if (row >= 0) myraw[(size_t)row * cols + site] = (unsigned char)("ACGT"[state]);
+          }
+        }
+        __syncwarp();  // a child reads its parent's sequence written by other lanes
+      }
+      __syncwarp();  // the state in shared memory is free for the next sample
     }
   }
 }

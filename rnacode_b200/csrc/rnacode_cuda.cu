@@ -309,6 +309,10 @@ struct rc_batch {
   int* d_evo_nodes = nullptr;
   unsigned *d_evo_thr = nullptr, *d_evo_seeds = nullptr;
   unsigned char* d_evo_seq = nullptr;
+  std::vector<int> evo_task0;   // prefix sums of the k_evolve tasks (EVO_SPW samples each) per simulated block
+  int* d_evo_task0 = nullptr;
+  unsigned* d_evo_mt = nullptr;  // seeded generator states, one slot of EVO_SPW states per persistent warp of k_evolve
+  size_t evo_mt_bytes = 0;
   int evo_max_samples = 0;
   // device, scratch
   float* d_sigma = nullptr;
@@ -515,7 +519,7 @@ static void free_batch_device(rc_batch* b) {
   rc_ctx* ctx = b->ctx;
   void* ptrs[] = {b->d_blocks, b->d_items, b->d_ctas, b->d_raw, b->d_cls, b->d_cols0, b->d_scores, b->d_z, b->d_res,
                   b->d_hss, b->d_hsscnt, b->d_ovf, b->d_tables, b->d_ptab, b->d_sigma, b->d_recs, b->d_dense, b->d_partial, b->d_p2, b->d_p2f, b->d_ptab2,
-                  b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq};
+                  b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq, b->d_evo_task0, b->d_evo_mt};
   for (void* p : ptrs) ctx_free(ctx, p);
   for (auto& e : b->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   b->events.clear();
@@ -1041,14 +1045,18 @@ extern "C" int rc_batch_upload(rc_batch* b) {
   RC_CUDA(cudaMemcpyAsync(b->d_ptab, &b->ptab, sizeof(PairTables), cudaMemcpyHostToDevice, st));
   if (b->d_ptab2) RC_CUDA(cudaMemcpyAsync(b->d_ptab2, &b->ptab2, sizeof(PairTables), cudaMemcpyHostToDevice, st));
   if (!b->evos.empty()) {
-    void* ptrs[] = {b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq};
+    void* ptrs[] = {b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq, b->d_evo_task0};
     for (void* p : ptrs) ctx_free(ctx, p);
+    b->evo_task0.assign(1, 0);
+    for (const EvoDev& e : b->evos)
+      b->evo_task0.push_back(b->evo_task0.back() + (b->blocks[e.block].n_inst - 1 + EVO_SPW - 1) / EVO_SPW);
+    b->d_evo_task0 = (int*)ctx_alloc(ctx, sizeof(int) * b->evo_task0.size());
     b->d_evos = (EvoDev*)ctx_alloc(ctx, sizeof(EvoDev) * b->evos.size());
     b->d_evo_nodes = (int*)ctx_alloc(ctx, sizeof(int) * b->evo_nodes.size());
     b->d_evo_thr = (unsigned*)ctx_alloc(ctx, sizeof(unsigned) * b->evo_thr.size());
     b->d_evo_seeds = (unsigned*)ctx_alloc(ctx, sizeof(unsigned) * b->evo_seeds.size());
     b->d_evo_seq = (unsigned char*)ctx_alloc(ctx, b->evo_seq_bytes);
-    if (!b->d_evos || !b->d_evo_nodes || !b->d_evo_thr || !b->d_evo_seeds || !b->d_evo_seq) {
+    if (!b->d_evos || !b->d_evo_nodes || !b->d_evo_thr || !b->d_evo_seeds || !b->d_evo_seq || !b->d_evo_task0) {
       ctx_fail(ctx, "device allocation failed (evolve tables)");
       return RC_ERR_NOMEM;
     }
@@ -1056,6 +1064,7 @@ extern "C" int rc_batch_upload(rc_batch* b) {
     RC_CUDA(cudaMemcpyAsync(b->d_evo_nodes, b->evo_nodes.data(), sizeof(int) * b->evo_nodes.size(), cudaMemcpyHostToDevice, st));
     RC_CUDA(cudaMemcpyAsync(b->d_evo_thr, b->evo_thr.data(), sizeof(unsigned) * b->evo_thr.size(), cudaMemcpyHostToDevice, st));
     RC_CUDA(cudaMemcpyAsync(b->d_evo_seeds, b->evo_seeds.data(), sizeof(unsigned) * b->evo_seeds.size(), cudaMemcpyHostToDevice, st));
+    RC_CUDA(cudaMemcpyAsync(b->d_evo_task0, b->evo_task0.data(), sizeof(int) * b->evo_task0.size(), cudaMemcpyHostToDevice, st));
     h2d += sizeof(EvoDev) * b->evos.size() + sizeof(int) * b->evo_nodes.size() +
            sizeof(unsigned) * (b->evo_thr.size() + b->evo_seeds.size());
   }
@@ -1476,15 +1485,20 @@ extern "C" int rc_batch_run(rc_batch* b) {
   for (const BlockDev& bd : b->blocks) maxchunks = std::max(maxchunks, (int)(((size_t)bd.inst_stride >> 4) * bd.n_inst / 256 + 1));
   int ev = ev_begin(b, 0);
   if (!b->evos.empty()) {
-    RC_CUDA(cudaFuncSetAttribute(k_evolve, cudaFuncAttributeMaxDynamicSharedMemorySize, EVO_SMEM));
-    const unsigned gx = (unsigned)((b->evo_max_samples + EVO_WARPS * EVO_SPW - 1) / (EVO_WARPS * EVO_SPW));
-    for (size_t e0 = 0; e0 < b->evos.size(); e0 += 65535) {  // gridDim.y is limited to 65535
-      dim3 ge(gx, (unsigned)std::min<size_t>(65535, b->evos.size() - e0));
-      k_evolve<<<ge, EVO_WARPS * 32, EVO_SMEM, st>>>(b->d_blocks, b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds,
-                                                    b->d_evo_seq, b->d_raw, (int)e0);
-      RC_CUDA(cudaGetLastError());
-      b->stats.launches++;
+    const int total_tasks = b->evo_task0.back();
+    const int want = (total_tasks + EVO_WARPS - 1) / EVO_WARPS;
+    const int gx = std::max(1, std::min(want, ctx->sm_count * 16));  // persistent warps: 16 CTAs of 4 warps per SM at most
+    const size_t need = (size_t)gx * EVO_WARPS * EVO_SPW * 624 * sizeof(unsigned);
+    if (need > b->evo_mt_bytes) {
+      ctx_free(ctx, b->d_evo_mt);
+      b->d_evo_mt = (unsigned*)ctx_alloc(ctx, need);
+      if (!b->d_evo_mt) { ctx_fail(ctx, "device allocation failed (generator states)"); return RC_ERR_NOMEM; }
+      b->evo_mt_bytes = need;
     }
+    k_evolve<<<gx, EVO_WARPS * 32, 0, st>>>(b->d_blocks, b->d_evos, b->d_evo_task0, (int)b->evos.size(), b->d_evo_nodes,
+                                            b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq, b->d_raw, b->d_evo_mt);
+    RC_CUDA(cudaGetLastError());
+    b->stats.launches++;
   }
   {
     dim3 g((unsigned)b->n_blocks, (unsigned)std::min(maxchunks, 2048));
