@@ -2333,7 +2333,7 @@ __device__ __forceinline__ unsigned p2_codon(const unsigned char* row, int p0) {
 }
 
 template <int NK, bool CHAINED>
-__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps per SM: at most 128 registers
     k_dp_smpf(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
               const unsigned* __restrict__ p2, const unsigned* __restrict__ p2f, const unsigned char* __restrict__ cls,
               const int* __restrict__ cols0, const float* __restrict__ scores, const PairTables* __restrict__ tables,
@@ -2351,8 +2351,19 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
   const int strand = cd.sf / 3, frame = cd.sf % 3;
   const int sites = bd.sites[frame];
   const int group = cd.task0;  // group of 32 instances inside the item
-  const int inst_l = group * 32 + lane;
-  const bool valid = inst_l < it.ninst;
+  // Folded group: a group with at most 16 instances (the last one of a block with 101 = 3 * 32 + 5 of them, RNAcode's default
+  // -n 100) does not leave its other lanes idle: the lanes are cut into R = 32 / m replicas of m >= #instances lanes, lane l
+  // works for instance l % m, and replica l / m takes its own start-codon pair -- R pairs side by side.  The rows of the
+  // replicas start 2 codons apart; until the last one has started the steps are masked per lane (reg_update_diag).
+  const int ninst_g = min(32, it.ninst - group * 32);
+  int fold_m = 32;
+  if (!CHAINED && bd.smp_fold && ninst_g <= 16) {
+    fold_m = 1;
+    while (fold_m < ninst_g) fold_m <<= 1;
+  }
+  const int R = 32 / fold_m, il = lane & (fold_m - 1), rep = lane / fold_m;
+  const int inst_l = group * 32 + il;
+  const bool valid = il < ninst_g;
   const bool first = !CHAINED || chunk == 0, last = !CHAINED || chunk == bd.nchunk - 1;
   const int N = bd.N, cols = bd.cols, L = bd.L, W = bd.p2_words;
 
@@ -2403,8 +2414,8 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
   __syncthreads();  // barrier initialised; s_sc, s_flag, s_col written
   mbar_wait(bar, 0);
   {
-    const unsigned char* rr = s_ref + lane * 4;
-    const unsigned lane_bit = 1u << lane;
+    const unsigned char* rr = s_ref + il * 4;
+    const unsigned lane_bit = 1u << il;
     const unsigned fl_ref = s_flag[0];
     // class bytes of this lane's instance, for codons of rows with 'N' / 'X' (rare)
     const unsigned char* cbase = cls + bd.cls_off + (size_t)(it.inst0 + (valid ? inst_l : 0)) * bd.inst_stride;
@@ -2424,7 +2435,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
         for (int kk = 0; kk < 4; kk++) {
           float v = 0.0f;
           if (4 * kq + kk < n_real) {  // warp-uniform
-            const unsigned qb = p2_codon(s_sp + (size_t)(4 * kq + kk) * prow + lane * 4, p0);
+            const unsigned qb = p2_codon(s_sp + (size_t)(4 * kq + kk) * prow + il * 4, p0);
             const unsigned e = trow[qb];
             v = s_tab.val[e & 0x3ffu] - s_sc[(4 * kq + kk) * 4 + (e >> 10)];  // observed - expected (src/score.c:422-425), or constant - 0
           }
@@ -2465,12 +2476,16 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
     const size_t per_group = ((size_t)npairs * sites - (size_t)npairs * (npairs - 1)) * 32;
     part = partial + it.part_off[strand][frame] + (size_t)group * per_group + lane;
   }
+  const int nsuper = (npairs + R - 1) / R;  // start-codon pairs taken R at a time (R = 1: one pair per warp and turn)
 #pragma unroll 1
   for (int turn = 0;; turn++) {
-    const int p = (turn & 1) ? (turn + 1) * nw - 1 - warp : turn * nw + warp;  // boustrophedon, see k_dp_smp
-    if (turn * nw >= npairs) break;
-    if (p >= npairs) continue;
-    const int r0 = 2 * p;
+    const int sp = (turn & 1) ? (turn + 1) * nw - 1 - warp : turn * nw + warp;  // boustrophedon, see k_dp_smp
+    if (turn * nw >= nsuper) break;
+    if (sp >= nsuper) continue;
+    const int p = sp * R + rep;            // this lane's pair (may lie past the end for the last replicas)
+    const int r0 = 2 * p;                  // its first row
+    const int r_first = 2 * sp * R;        // first row of the warp
+    const int j_steady = r_first + 2 * R;  // from here on both rows of every lane have started
     RowRec* rec0 = srec + (warp * 32 + lane) * 2;
     float2* pp = CHAINED ? part + ((size_t)p * sites - (size_t)p * (p - 1) - r0) * 32 : nullptr;
     float2 S0[NK], S1[NK], S2[NK];
@@ -2479,13 +2494,21 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
     RowFoldS fx, fy;
     folds_init(fx, foldB);
     folds_init(fy, foldB);
-    int j = r0;
+    int j = r_first;
 #pragma unroll 1
     while (j < sites) {
       float svA[RS];
       const unsigned zA = zs[j];
       smp_load_row<NK>(sig_a + j * ROW_BYTES, zA, svA);
-      if (j >= r0 + 2 && j + 1 < sites) {
+      if (R > 1 && j < j_steady) {
+        // folded group, rows still starting: one end codon at a time, every addend masked per lane until its row starts
+        // (the state stays exactly (0,0,0), the sums 0, and the fold ignores a sum of 0)
+        const float2 sum = reg_update_diag<NK>(S0, S1, S2, svA, j >= r0, j >= r0 + 1, Delta, Omega, omega);
+        folds_single(fx, fy, sum, j, true, fNK, rcpNK, rec0, band_slots);
+        j += 1;
+        continue;
+      }
+      if (j >= j_steady && j + 1 < sites) {
         const unsigned zB = zs[j + 1];
         if ((zA | zB) == 0u) {
           float svB[RS];
@@ -2516,7 +2539,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
       }
       j += 1;
     }
-    if (valid && last) {
+    if (valid && last && r0 < sites) {
       folds_store(fx, rec_inst + r0, rec0, fNK, rcpNK);
       if (r0 + 1 < sites) folds_store(fy, rec_inst + r0 + 1, rec0 + 1, fNK, rcpNK);
     }

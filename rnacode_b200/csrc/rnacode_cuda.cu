@@ -45,6 +45,7 @@ struct rc_ctx {
   long reg_max_nk = 12;  // row-major alignments with more scored species take k_dp_chain (k_dp_reg<13..16> spills: 17x3000 14.7 vs 11.1 ms)
   long no_smps = 0;          // never stream the sigma table in segments (k_dp_smps)
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
+  long no_fold = 0;           // 1: a last group of at most 16 instances is scored like a full one (k_dp_smpf)
   long no_fused = 0;          // 1: never build the sigma table inside the sample-major DP kernel (k_dp_smpf)
   long tail_max = 0;          // a sample-major block whose instance count leaves 1..tail_max instances in its last group of 32 scores
                               // those instances row-major (lanes = rows) instead of in a warp with that many live lanes (0: never)
@@ -404,6 +405,7 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   if (const char* e = getenv("RNACODE_CUDA_SMP_WARPS")) ctx->smp_warps_forced = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_HSS_THR_TASKS")) ctx->hss_thr_tasks = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_NO_FUSED")) ctx->no_fused = atol(e) ? 1 : 0;
+  if (const char* e = getenv("RNACODE_CUDA_NO_FOLD")) ctx->no_fold = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_TAIL_MAX")) ctx->tail_max = std::max(0L, std::min(31L, atol(e)));
   if (const char* e = getenv("RNACODE_CUDA_REG_MAX_NK")) ctx->reg_max_nk = std::max(12L, std::min<long>(REG_MAX_NK, atol(e)));
   unsigned char lut[256];
@@ -470,6 +472,8 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->smps_max_sites = value;
   } else if (k == "smpc_max_sites") {
     ctx->smpc_max_sites = value;
+  } else if (k == "no_fold") {
+    ctx->no_fold = value ? 1 : 0;
   } else if (k == "no_fused") {
     ctx->no_fused = value ? 1 : 0;
   } else if (k == "tail_max") {
@@ -683,8 +687,10 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       const bool two_fused = 2 * (smpf_smem_bytes(bd, layout) + (size_t)SMP_MAX_WARPS * 64 * sizeof(RowRec) + 1024) <= sm_bytes;
       const bool two_unfused = 2 * (smp_smem_bytes(bd, 0, layout, 0) + (size_t)SMP_WARPS * 64 * sizeof(RowRec) + 1024) <= sm_bytes;
       if ((layout == 2 || layout == 5) && !seg && !ctx->no_fused && !ctx->force_dense && (two_fused || !two_unfused) && bd.cols <= P2_MAX_COLS &&
+          (layout == 5 || bd.NK <= 12) &&  // k_dp_smpf<13..16> would spill at the 128 registers two CTAs per SM allow
           smpf_smem_bytes(bd, layout) + (size_t)SMP_WARPS * 64 * sizeof(RowRec) <= (size_t)ctx->smem_optin) {
         bd.smp_fused = 1;
+        bd.smp_fold = ctx->no_fold ? 0 : 1;
         b->max_fused_N = std::max(b->max_fused_N, bd.N);
         b->max_fused_cols = std::max(b->max_fused_cols, bd.cols);
         bd.p2_words = (bd.L + 15) / 16;

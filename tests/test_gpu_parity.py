@@ -191,18 +191,22 @@ def test_config5_mixed_lengths_vs_oracle(rc_ctx, oracle):
     bt.close()
 
 
-@pytest.mark.parametrize("opts", [{"no_fused": 0}, {"tail_max": 12}, {"no_fused": 0, "tail_max": 12}],
+@pytest.mark.parametrize("opts", [{"no_fused": 0}, {"no_fused": 1}, {"no_fold": 1}, {"tail_max": 12}, {"no_fused": 0, "tail_max": 12}],
                          ids=lambda o: "+".join("%s%d" % kv for kv in sorted(o.items())))
 def test_optional_sample_major_routes_vs_oracle(oracle, opts):
-    """Two routes that are off by default: k_dp_smpf (the DP CTA builds its sigma table itself, plain and chunked) and the tail
-    split (the last 1..12 instances of a sample-major block scored row-major).  Same answers as the oracle, bit for bit."""
+    """The routes of the sample-major family, each switched on and off: k_dp_smpf (the DP CTA builds its sigma table itself from
+    the packed rows of k_pack2; default where it keeps two CTAs per SM) against k_sigma_smp + k_dp_smp, its folded last group
+    (several start-codon pairs side by side when at most 16 instances are left), and the tail split (the last 1..12 instances
+    of a block scored row-major; off by default).  Same answers as the oracle, bit for bit."""
     from rnacode_b200 import synth
     capi = _capi()
     ctx = capi.Context(0)
     for k, v in opts.items():
         ctx.set_option(k, v)
     try:
-        shapes = [(10, 120, 100), (10, 121, 69), (4, 45, 70), (17, 150, 33), (6, 250, 40), (26, 150, 40), (100, 96, 36), (50, 130, 75)]
+        # instance counts that leave 1, 5, 8, 13 and 16 instances in the last group (folded: 32, 4, 4, 2 and 2 pairs side by side)
+        shapes = [(10, 120, 100), (10, 121, 69), (4, 45, 70), (17, 150, 33), (6, 250, 40), (26, 150, 40), (100, 96, 36), (50, 130, 75),
+                  (10, 120, 32), (9, 118, 44), (12, 33, 79), (3, 7, 47), (5, 200, 16)]
         blocks, data = [], []
         for idx, (N, cols, n) in enumerate(shapes):
             rows = synth.synth_block(8, idx, N, cols, gap_rate=0.02)
