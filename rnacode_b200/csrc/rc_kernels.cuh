@@ -114,17 +114,19 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDev* __restrict__ block
 // (code 0, ntMap), and the reverse strand complements upper-case ACGTU only (revAln) -- all of which the class byte already
 // encodes.  'N' / 'X' (src/score.c:394-404) cannot be expressed in two bits: rows that hold one at a reference position are
 // marked per lane in a flag word, their codons take the byte-wise path.
-// One CTA pass per (group, row): the class bytes of the row of the group's 32 instances are staged in shared memory with
-// coalesced word loads (odd word pitch), then every thread packs the sixteen positions of one (strand, word, instance) from
-// its instance's staged bytes -- lane = instance, so the 128-byte lines of the output are written whole.
-// grid = (x: block, y: grid-stride over (group, row)).  cols0 must exist (k_prep<1>).  0.5 byte per character and strand.
+// One CTA per group: the class bytes of as many rows of the group's 32 instances as fit are staged in shared memory with
+// coalesced word loads (odd word pitch, many loads in flight), then every thread packs the sixteen positions of one
+// (strand, row, word, instance) from its instance's staged bytes -- lane = instance, so the 128-byte lines of the output are
+// written whole.  grid = (x: block, y: grid-stride over groups).  cols0 must exist (k_prep<1>).
+// 0.5 byte per character and strand.
 // ---------------------------------------------------------------------------------------------
-constexpr int P2_MAX_COLS = 1020;  // longest row k_pack2 stages (blocks scored by k_dp_smpf are far shorter: their sigma table fits smem)
+constexpr int P2_MAX_COLS = 1020;         // longest row k_pack2 stages (blocks scored by k_dp_smpf are far shorter: their sigma table fits smem)
+constexpr int P2_STAGE_BYTES = 64 * 1024;  // staging budget: rows per pass = P2_STAGE_BYTES / (32 * pitch)
 
 __global__ void __launch_bounds__(256) k_pack2(const BlockDev* __restrict__ blocks, const unsigned char* __restrict__ cls,
                                                const int* __restrict__ cols0, unsigned* __restrict__ p2, unsigned* __restrict__ p2f,
-                                               int max_L) {
-  extern __shared__ __align__(16) unsigned char p2_smem[];  // s_c0[2][max_L] ints | s_row[32 * max pitch] (sized by the host)
+                                               int max_L, int stage_bytes) {
+  extern __shared__ __align__(16) unsigned char p2_smem[];  // s_c0[2][max_L] ints | s_row[rows per pass][32][pitch]
   const BlockDev bd = blocks[blockIdx.x];
   if (!bd.smp_fused) return;
   int* s_c0base = reinterpret_cast<int*>(p2_smem);
@@ -134,37 +136,42 @@ __global__ void __launch_bounds__(256) k_pack2(const BlockDev* __restrict__ bloc
   const int groups = (bd.n_inst + 31) >> 5;
   int pitch = (cols + 6 + 3) / 4 * 4;
   if (((pitch / 4) & 1) == 0) pitch += 4;  // odd word count: the 32 instances' bytes of a column sit in 32 banks
+  const int rpp = max(1, min(N, stage_bytes / (32 * pitch)));  // rows per pass
   for (int t = threadIdx.x; t < 2 * L; t += blockDim.x) s_c0base[(t / L) * max_L + t % L] = cols0[bd.cols0_off + (size_t)(t / L) * (L + 1) + 1 + t % L];
-  for (int gr = blockIdx.y; gr < groups * N; gr += gridDim.y) {
-    const int g = gr / N, r = gr % N;
-    __syncthreads();  // s_c0 written; the previous pass is done with s_row
-    // stage row r of the 32 instances: one warp per instance, aligned word copies; column c of instance li at s_row[li*pitch + shift + c]
-    const size_t roff = (size_t)r * cols;
-    const unsigned shift = (unsigned)roff & 3u;
-    for (int li = warp; li < 32; li += 8) {
-      const int inst = g * 32 + li;
-      const unsigned* src4 = reinterpret_cast<const unsigned*>(cls + bd.cls_off + (size_t)(inst < bd.n_inst ? inst : 0) * bd.inst_stride + roff - shift);
-      unsigned* dst4 = reinterpret_cast<unsigned*>(s_row + li * pitch);
-      for (int w = lane; w < (int)(shift + cols + 3) / 4; w += 32) dst4[w] = inst < bd.n_inst ? src4[w] : 0u;
-    }
-    __syncthreads();
-    // (strand, word) pairs, one warp each; lane = instance
-    for (int sw = warp; sw < 2 * W; sw += 8) {
-      const int s = sw / W, w = sw % W;
-      const int sh = s ? 2 : 0;
-      const int npos = min(16, L - 16 * w);
-      const unsigned char* rb = s_row + lane * pitch + shift;
-      const int* c0 = s_c0base + s * max_L + 16 * w;
-      unsigned word = 0u, flag = 0u;
-#pragma unroll 4
-      for (int t = 0; t < npos; t++) {
-        const unsigned b = rb[c0[t]];
-        word |= ((b >> sh) & 3u) << (2 * t);
-        flag |= b;
+  for (int g = blockIdx.y; g < groups; g += gridDim.y) {
+    for (int r0 = 0; r0 < N; r0 += rpp) {
+      const int nr = min(rpp, N - r0);
+      __syncthreads();  // s_c0 written; the previous pass is done with s_row
+      // stage rows r0 .. r0+nr-1 of the 32 instances: one warp per (row, instance), aligned word copies;
+      // column c of (row rr, instance li) at s_row[(rr*32 + li)*pitch + shift(rr) + c]
+      for (int pr = warp; pr < nr * 32; pr += 8) {
+        const int rr = pr >> 5, li = pr & 31, inst = g * 32 + li;
+        const size_t roff = (size_t)(r0 + rr) * cols;
+        const unsigned shift = (unsigned)roff & 3u;
+        const unsigned* src4 = reinterpret_cast<const unsigned*>(cls + bd.cls_off + (size_t)(inst < bd.n_inst ? inst : 0) * bd.inst_stride + roff - shift);
+        unsigned* dst4 = reinterpret_cast<unsigned*>(s_row + (size_t)pr * pitch);
+        for (int w = lane; w < (int)(shift + cols + 3) / 4; w += 32) dst4[w] = inst < bd.n_inst ? src4[w] : 0u;
       }
-      p2[bd.p2_off + ((((size_t)g * 2 + s) * N + r) * W + w) * 32 + lane] = word;
-      const unsigned m = __ballot_sync(0xffffffffu, (flag & (CLS_N | CLS_X)) != 0u);
-      if (lane == 0 && m) atomicOr(&p2f[bd.p2f_off + ((size_t)g * 2 + s) * N + r], m);
+      __syncthreads();
+      // (strand, row, word) triples, one warp each; lane = instance
+      for (int task = warp; task < 2 * nr * W; task += 8) {
+        const int w = task % W, rr = (task / W) % nr, s = task / (W * nr);
+        const int r = r0 + rr;
+        const int sh = s ? 2 : 0;
+        const int npos = min(16, L - 16 * w);
+        const unsigned char* rb = s_row + (size_t)(rr * 32 + lane) * pitch + (((size_t)r * cols) & 3u);
+        const int* c0 = s_c0base + s * max_L + 16 * w;
+        unsigned word = 0u, flag = 0u;
+#pragma unroll 4
+        for (int t = 0; t < npos; t++) {
+          const unsigned b = rb[c0[t]];
+          word |= ((b >> sh) & 3u) << (2 * t);
+          flag |= b;
+        }
+        p2[bd.p2_off + ((((size_t)g * 2 + s) * N + r) * W + w) * 32 + lane] = word;
+        const unsigned m = __ballot_sync(0xffffffffu, (flag & (CLS_N | CLS_X)) != 0u);
+        if (lane == 0 && m) atomicOr(&p2f[bd.p2f_off + ((size_t)g * 2 + s) * N + r], m);
+      }
     }
   }
 }
@@ -2323,13 +2330,28 @@ struct SmpfCfg {
   }
 };
 
-// six adjacent bits of a packed row: the codon whose first position is p0 (see k_pack2); row = shared address of the lane's
-// word 0, words 128 bytes apart
-__device__ __forceinline__ unsigned p2_codon(const unsigned char* row, int p0) {
-  const int w = p0 >> 4, sh = 2 * (p0 & 15);
-  const unsigned lo = *reinterpret_cast<const unsigned*>(row + (size_t)w * 128);
-  const unsigned hi = *reinterpret_cast<const unsigned*>(row + (size_t)(w + 1) * 128);  // the staged rows have one word of slack
-  return __funnelshift_r(lo, hi, sh) & 63u;
+// shared-memory loads by 32-bit shared address (the table phase of k_dp_smpf does all its addressing in 32 bits)
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+// six adjacent bits of a packed row (see k_pack2): the codon whose first position sits at bit `sh` of the word at shared
+// address `a`; two: the codon runs over into the next word (128 bytes on).  sh and two are warp-uniform.
+__device__ __forceinline__ unsigned p2_codon(unsigned a, unsigned sh, bool two) {
+  const unsigned lo = lds_u32(a);
+  if (!two) return (lo >> sh) & 63u;
+  return __funnelshift_r(lo, lds_u32(a + 128), sh) & 63u;
 }
 
 template <int NK, bool CHAINED>
@@ -2414,35 +2436,45 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
   __syncthreads();  // barrier initialised; s_sc, s_flag, s_col written
   mbar_wait(bar, 0);
   {
-    const unsigned char* rr = s_ref + il * 4;
     const unsigned lane_bit = 1u << il;
-    const unsigned fl_ref = s_flag[0];
     // class bytes of this lane's instance, for codons of rows with 'N' / 'X' (rare)
     const unsigned char* cbase = cls + bd.cls_off + (size_t)(it.inst0 + (valid ? inst_l : 0)) * bd.inst_stride;
-    const int sh = strand ? 2 : 0;
-    for (int kq = 0; kq < q_count; kq++) {
-      unsigned fl_any = fl_ref;
+    const unsigned ref_a = smem_u32(s_ref) + il * 4, sp_a = smem_u32(s_sp) + il * 4, prow32 = (unsigned)prow;
+    const unsigned tab_t = smem_u32(&s_tab.t[0]), tab_v = smem_u32(&s_tab.val[0]), sc_a = smem_u32(s_sc);
+    const unsigned out_a = smem_u32(smem) + lane * 16;
+    unsigned fl_all = s_flag[0];  // flag words of the reference row and of all species rows of the launch
+    for (int k = 0; k < n_real; k++) fl_all |= s_flag[1 + k];
+    const bool slow_warp = fl_all != 0u;  // warp-uniform (every lane reads the same words)
+    constexpr int NQ = CHAINED ? 3 : RSB / 4;
+    for (int j = warp; j < sites; j += nw) {
+      const int p0 = 3 * j + frame;
+      const unsigned woff = (unsigned)(p0 >> 4) * 128u, sh = 2u * (unsigned)(p0 & 15);
+      const bool two = sh > 26u;
+      const unsigned qa = p2_codon(ref_a + woff, sh, two);
+      const unsigned trow = tab_t + (qa << 7);  // 64 entries of 2 bytes per reference codon
+      unsigned ka = sp_a + woff;                // the codon's word in species row 0 of the launch, then row by row
 #pragma unroll
-      for (int kk = 0; kk < 4; kk++) fl_any |= s_flag[1 + 4 * kq + kk];
-      const bool slow_lane = (fl_any & lane_bit) != 0u;
-      const bool slow_warp = fl_any != 0u;  // warp-uniform (every lane reads the same words)
-      for (int j = warp; j < sites; j += nw) {
-        const int p0 = 3 * j + frame;
-        const unsigned qa = p2_codon(rr, p0);
-        const unsigned short* trow = s_tab.t + (qa << 6);
+      for (int kq = 0; kq < NQ; kq++) {
+        if (CHAINED && kq >= q_count) break;
         float v4[4];
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
+          const int k = 4 * kq + kk;
           float v = 0.0f;
-          if (4 * kq + kk < n_real) {  // warp-uniform
-            const unsigned qb = p2_codon(s_sp + (size_t)(4 * kq + kk) * prow + il * 4, p0);
-            const unsigned e = trow[qb];
-            v = s_tab.val[e & 0x3ffu] - s_sc[(4 * kq + kk) * 4 + (e >> 10)];  // observed - expected (src/score.c:422-425), or constant - 0
+          if (CHAINED ? (k < n_real) : (k < NK)) {  // compile-time for the plain kernel, warp-uniform otherwise
+            const unsigned qb = p2_codon(ka, sh, two);
+            const unsigned e = lds_u16(trow + 2u * qb);
+            // observed - expected (src/score.c:422-425), or constant - 0
+            v = lds_f32(tab_v + 4u * (e & 0x3ffu)) - lds_f32(sc_a + 16u * (unsigned)k + 4u * (e >> 10));
+            ka += prow32;
           }
           v4[kk] = v;
         }
         if (slow_warp) {  // some lane's rows hold an 'N' or 'X': those lanes test the six characters (src/score.c:394-404)
-          if (slow_lane && valid) {
+          unsigned fl_q = s_flag[0];
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) fl_q |= s_flag[1 + 4 * kq + kk];
+          if ((fl_q & lane_bit) != 0u && valid) {
             const int i1 = s_col[3 * j], i2 = s_col[3 * j + 1], i3 = s_col[3 * j + 2];
             const unsigned a1 = cbase[i1], a2 = cbase[i2], a3 = cbase[i3];
             const unsigned nA = (a1 | a2 | a3) & CLS_N;
@@ -2455,10 +2487,11 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
               }
           }
         }
-        *reinterpret_cast<float4*>(smem + (size_t)j * ROW_BYTES + kq * 512 + lane * 16) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(out_a + (unsigned)j * ROW_BYTES + kq * 512), "f"(v4[0]),
+                     "f"(v4[1]), "f"(v4[2]), "f"(v4[3])
+                     : "memory");
       }
     }
-    (void)sh;
   }
   __syncthreads();  // the table is complete
 

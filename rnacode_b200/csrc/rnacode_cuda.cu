@@ -1516,11 +1516,13 @@ extern "C" int rc_batch_run(rc_batch* b) {
     RC_CUDA(cudaGetLastError());
     if (b->p2_words > 0) {  // packed rows for the blocks whose DP kernel builds its own sigma table (needs cols0)
       RC_CUDA(cudaMemsetAsync(b->d_p2f, 0, sizeof(unsigned) * b->p2f_words, st));
-      dim3 g2((unsigned)b->n_blocks, (unsigned)std::min(256, ((b->max_n_inst + 31) / 32) * b->max_fused_N));
+      dim3 g2((unsigned)b->n_blocks, (unsigned)std::min(64, (b->max_n_inst + 31) / 32));
       const int max_L = (b->max_fused_cols + 3) / 4 * 4;
-      const size_t p2_smem = (size_t)2 * max_L * sizeof(int) + (size_t)32 * (b->max_fused_cols + 16);
+      const int pitch_max = b->max_fused_cols + 16;
+      const int stage = std::max(32 * pitch_max, std::min(P2_STAGE_BYTES, 32 * pitch_max * b->max_fused_N));
+      const size_t p2_smem = (size_t)2 * max_L * sizeof(int) + (size_t)stage;
       RC_CUDA(cudaFuncSetAttribute(k_pack2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem));
-      k_pack2<<<g2, 256, p2_smem, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_p2, b->d_p2f, max_L);
+      k_pack2<<<g2, 256, p2_smem, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_p2, b->d_p2f, max_L, stage);
       RC_CUDA(cudaGetLastError());
       b->stats.launches++;
     }
