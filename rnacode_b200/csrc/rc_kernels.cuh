@@ -159,17 +159,42 @@ __global__ void __launch_bounds__(256) k_pack2(const BlockDev* __restrict__ bloc
         const int r = r0 + rr;
         const int sh = s ? 2 : 0;
         const int npos = min(16, L - 16 * w);
-        const unsigned char* rb = s_row + (size_t)(rr * 32 + lane) * pitch + (((size_t)r * cols) & 3u);
+        const unsigned rbase = (unsigned)(rr * 32 + lane) * (unsigned)pitch + (unsigned)(((size_t)r * cols) & 3u);  // byte offset of column 0
+        const unsigned char* rb = s_row + rbase;
         const int* c0 = s_c0base + s * max_L + 16 * w;
         unsigned word = 0u, flag = 0u;
+        const int cfirst = c0[0], clast = c0[npos - 1];
+        if (npos == 16 && (clast - cfirst == 15 || cfirst - clast == 15)) {
+          // the sixteen positions are sixteen adjacent columns (no gap of the reference inside): four words of class bytes,
+          // classified four characters at a time (SIMD in a register), instead of sixteen byte loads.  clo = lowest column.
+          const unsigned clo = (unsigned)min(cfirst, clast);
+          const unsigned boff = rbase + clo, al = boff & ~3u, fs = (boff & 3u) * 8u;  // warp-uniform alignment
+          const unsigned* wp = reinterpret_cast<const unsigned*>(s_row + al);
+          const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = fs ? wp[4] : 0u;
+          const unsigned q[4] = {__funnelshift_r(w0, w1, fs), __funnelshift_r(w1, w2, fs), __funnelshift_r(w2, w3, fs),
+                                 __funnelshift_r(w3, w4, fs)};
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            unsigned x = (q[i] >> sh) & 0x03030303u;  // 2-bit code of each of the four bytes
+            x |= x >> 6;                              // bytes 0,1 -> bits 0-3 ; bytes 2,3 -> bits 16-19
+            x = (x | (x >> 12)) & 0xffu;              // four codes in eight bits, lowest column first
+            word |= x << (8 * i);
+            flag |= q[i];
+          }
+          if (clast < cfirst) {  // reverse strand: position t is column clo + 15 - t -- reverse the order of the 2-bit fields
+            word = __brev(word);
+            word = ((word & 0x55555555u) << 1) | ((word >> 1) & 0x55555555u);
+          }
+        } else {
 #pragma unroll 4
-        for (int t = 0; t < npos; t++) {
-          const unsigned b = rb[c0[t]];
-          word |= ((b >> sh) & 3u) << (2 * t);
-          flag |= b;
+          for (int t = 0; t < npos; t++) {
+            const unsigned b = rb[c0[t]];
+            word |= ((b >> sh) & 3u) << (2 * t);
+            flag |= b;
+          }
         }
         p2[bd.p2_off + ((((size_t)g * 2 + s) * N + r) * W + w) * 32 + lane] = word;
-        const unsigned m = __ballot_sync(0xffffffffu, (flag & (CLS_N | CLS_X)) != 0u);
+        const unsigned m = __ballot_sync(0xffffffffu, (flag & ((CLS_N | CLS_X) * 0x01010101u)) != 0u);  // any of up to four bytes
         if (lane == 0 && m) atomicOr(&p2f[bd.p2f_off + ((size_t)g * 2 + s) * N + r], m);
       }
     }
@@ -2914,6 +2939,7 @@ __global__ void __launch_bounds__(EVO_WARPS * 32)
              const int* __restrict__ nodes, const unsigned* __restrict__ thr, const unsigned* __restrict__ seeds,
              unsigned char* __restrict__ seqs, unsigned char* __restrict__ raw, unsigned* __restrict__ mt_scratch) {
   __shared__ unsigned s_mt[EVO_WARPS][624];
+  __shared__ uint4 s_thr[EVO_WARPS][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = blockIdx.x * EVO_WARPS + warp, n_warps = gridDim.x * EVO_WARPS;
   const int total_tasks = evo_task0[n_evos];
@@ -2951,7 +2977,8 @@ __global__ void __launch_bounds__(EVO_WARPS * 32)
     for (int q = 0; q < n_mine; q++) {
       const int sample = s_base + q;
       const unsigned seed = seeds[ev.seed_off + sample];
-      unsigned char* myseq = seqs + ev.seq_off + (size_t)sample * ev.n_internal * cols;
+      const int cols4 = (cols + 3) & ~3;  // internal-node sequences: one byte per site (the state 0..3), rows padded to words
+      unsigned char* myseq = seqs + ev.seq_off + (size_t)sample * ev.n_internal * cols4;
       unsigned char* myraw = raw + bd.raw_off + (size_t)sample * bd.N * cols;
       if (ev.rng == 0) {
         for (int i = lane; i < 624; i += 32) mt[i] = slot[(size_t)q * 624 + i];
@@ -2960,38 +2987,61 @@ __global__ void __launch_bounds__(EVO_WARPS * 32)
       int pos = 624;  // next unread word of the current 624-word batch
       for (int n = 0; n < ev.n_nodes; n++) {
         const int parent = nd[4 * n], row = nd[4 * n + 1], slot_n = nd[4 * n + 2];
-        const unsigned char* pseq = parent >= 0 ? myseq + (size_t)nd[4 * parent + 2] * cols : nullptr;
-        const unsigned tv = th[(size_t)n * 16 + (lane & 15)];  // the node's 16 thresholds, one per lane; fetched by shuffle below
-        for (int c0 = 0; c0 < cols; c0 += 32) {
-          const int site = c0 + lane;
-          const int cnt = min(32, cols - c0);  // draws consumed by this chunk
-          unsigned u;
+        const unsigned* pseq = parent >= 0 ? reinterpret_cast<const unsigned*>(myseq + (size_t)nd[4 * parent + 2] * cols4) : nullptr;
+        unsigned* oseq = slot_n >= 0 ? reinterpret_cast<unsigned*>(myseq + (size_t)slot_n * cols4) : nullptr;
+        unsigned char* orow = row >= 0 ? myraw + (size_t)row * cols : nullptr;
+        const bool row_aligned = (reinterpret_cast<size_t>(orow) & 3) == 0;  // warp-uniform
+        // the node's thresholds [parent state][4] in shared memory: one 16-byte load per site below
+        if (lane < 16) reinterpret_cast<unsigned*>(&s_thr[warp][0])[lane] = th[(size_t)n * 16 + lane];
+        __syncwarp();
+        // four consecutive sites per lane, 128 sites per pass: the draws of a pass are the next cnt outputs of the generator
+        for (int c0 = 0; c0 < cols; c0 += 128) {
+          const int cnt = min(128, cols - c0);
+          const int off = 4 * lane, site0 = c0 + off;
+          unsigned u[4];
           if (ev.rng == 0) {
-            // lanes 0..cnt-1 take the next cnt outputs of the generator, in order
-            int idx = pos + lane;
-            unsigned v = 0;
-            if (lane < cnt && idx < 624) v = mt[idx];
-            if (pos + cnt > 624) {  // the chunk crosses a batch boundary (warp-uniform)
+            const int idx = pos + off;
+            unsigned v[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) v[t] = (off + t < cnt && idx + t < 624) ? mt[idx + t] : 0u;
+            if (pos + cnt > 624) {  // the pass crosses a batch boundary (warp-uniform)
               __syncwarp();
               mt_twist(mt, lane);
-              if (lane < cnt && idx >= 624) v = mt[idx - 624];
+#pragma unroll
+              for (int t = 0; t < 4; t++)
+                if (off + t < cnt && idx + t >= 624) v[t] = mt[idx + t - 624];
               pos -= 624;
             }
             pos += cnt;
-            u = mt_temper(v);
+#pragma unroll
+            for (int t = 0; t < 4; t++) u[t] = mt_temper(v[t]);
           } else {
-            u = philox_draw(seed, (unsigned)n, (unsigned)site);
+#pragma unroll
+            for (int t = 0; t < 4; t++) u[t] = philox_draw(seed, (unsigned)n, (unsigned)(site0 + t));
           }
-          const int ps = (parent >= 0 && site < cols) ? (int)pseq[site] : 0;  // root: row 0 of its table holds the cumulative frequencies
-          const unsigned t0 = __shfl_sync(0xffffffffu, tv, ps * 4), t1 = __shfl_sync(0xffffffffu, tv, ps * 4 + 1),
-                         t2 = __shfl_sync(0xffffffffu, tv, ps * 4 + 2);
-          if (site < cols) {
-            const int state = (u > t0) + (u > t1) + (u > t2);
-            if (slot_n >= 0) myseq[(size_t)slot_n * cols + site] = (unsigned char)state;
-            if (row >= 0) myraw[(size_t)row * cols + site] = (unsigned char)("ACGT"[state]);
+          if (off < cnt) {
+            const unsigned pw = pseq ? pseq[site0 >> 2] : 0u;  // parent states of the four sites; the root draws from row 0 of its table
+            unsigned st = 0u, ch = 0u;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+              const uint4 tt = s_thr[warp][(pw >> (8 * t)) & 3u];
+              const unsigned state = (u[t] > tt.x) + (u[t] > tt.y) + (u[t] > tt.z);
+              st |= state << (8 * t);
+              ch |= ((0x54474341u >> (8 * state)) & 0xffu) << (8 * t);  // "ACGT"[state]
+            }
+            if (oseq) oseq[site0 >> 2] = st;  // (the padding bytes of the last word are never read as sites)
+            if (orow) {
+              if (row_aligned && off + 3 < cnt) {
+                *reinterpret_cast<unsigned*>(orow + site0) = ch;
+              } else {
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                  if (off + t < cnt) orow[site0 + t] = (unsigned char)(ch >> (8 * t));
+              }
+            }
           }
         }
-        __syncwarp();  // a child reads its parent's sequence written by other lanes
+        __syncwarp();  // a child reads its parent's sequence written by other lanes; s_thr is rewritten for the next node
       }
       __syncwarp();  // the state in shared memory is free for the next sample
     }

@@ -989,7 +989,7 @@ extern "C" int rc_batch_set_evolve(rc_batch* b, int block, const rc_tree_desc* t
   ev.n_internal = n_internal;
   for (int i = 0; i < n_samples; i++) b->evo_seeds.push_back(seeds[i]);
   ev.seq_off = (long long)b->evo_seq_bytes;
-  b->evo_seq_bytes += (size_t)n_samples * n_internal * bd.cols;
+  b->evo_seq_bytes += (size_t)n_samples * n_internal * ((bd.cols + 3) & ~3);  // rows of the internal nodes padded to words
   b->evo_max_samples = std::max(b->evo_max_samples, n_samples);
   b->evo_of_block[block] = (int)b->evos.size();
   b->evos.push_back(ev);
