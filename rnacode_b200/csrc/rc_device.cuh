@@ -65,7 +65,6 @@ struct BlockDev {
   int smp_seg;              // layouts 2 / 5: 1 = the frame's sigma table does not fit shared memory, streamed in segments (k_dp_smps)
   int smp_fused;            // layouts 2 / 5, resident table: 1 = the DP kernel builds its sigma table itself from class bytes
                             // (k_dp_smpf; no sigma scratch, no k_sigma_smp launch for this block)
-  int hss_inkernel;         // 1 = k_dp_smpf runs the sequential part of getHSS itself (k_hss / k_hss_thr skip the block)
   int smp_fold;             // k_dp_smpf: 1 = a last group of at most 16 instances runs several start-codon pairs side by side
   int p2_words;             // k_dp_smpf: 32-bit words per packed row = ceil(L / 16)
   long long p2_off;         // k_dp_smpf: u32 offset of the block's packed rows (k_pack2):

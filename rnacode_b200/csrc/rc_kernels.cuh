@@ -1892,19 +1892,6 @@ __device__ __forceinline__ void folds_store(const RowFoldS& f, RowRec* grec, con
   }
 }
 
-// final record of a row for the in-kernel scan of k_dp_smpf: 8 bytes in shared memory -- the quotient of the row maximum (or
-// -inf: no positive entry), its end codon and a flag; a complex row also leaves its full record in global memory
-__device__ __forceinline__ void folds_store_c(const RowFoldS& f, uint2* c, RowRec* grec, const RowRec* srec, float fNK, float rcpNK) {
-  if (f.Ms == INFINITY) {
-    rec_copy(grec, srec);
-    *c = make_uint2(__float_as_uint(srec->Emax), (unsigned)srec->jF | (1u << 16));
-  } else if (f.Ms > 0.0f) {
-    *c = make_uint2(__float_as_uint(quot_nk(f.Ms, fNK, rcpNK)), (unsigned)f.jF);
-  } else {
-    *c = make_uint2(__float_as_uint(-INFINITY), 0u);
-  }
-}
-
 #ifndef RC_FOLD_GATE
 #define RC_FOLD_GATE 0  // 1: skip the fold of a step pair when no lane has a sum above its row's lower bound
 #endif
@@ -2360,10 +2347,8 @@ struct SmpfCfg {
   static __host__ __device__ size_t off_col(int sites, int row_bytes, int nsp) { return off_flag(sites, row_bytes, nsp) + align16((size_t)(nsp + 1) * 4); }
   static __host__ __device__ size_t off_ref(int sites, int row_bytes, int nsp) { return off_col(sites, row_bytes, nsp) + align16((size_t)3 * sites * 4); }
   static __host__ __device__ size_t off_sp(int sites, int row_bytes, int nsp, int words) { return off_ref(sites, row_bytes, nsp) + (size_t)(words + 1) * 128; }
-  // (after the table phase the two staging areas hold the rows' compact getHSS records, [row][instance] 8 bytes each)
   static __host__ __device__ size_t off_rec(int sites, int row_bytes, int nsp, int words) {
-    const size_t staged = (size_t)(words + 1) * 128 + ((size_t)nsp * words + 1) * 128, crec = (size_t)sites * 256;
-    return off_ref(sites, row_bytes, nsp) + (staged > crec ? staged : crec);
+    return off_sp(sites, row_bytes, nsp, words) + ((size_t)nsp * words + 1) * 128;
   }
   static __host__ __device__ size_t total(int sites, int row_bytes, int nsp, int words, int nw) {
     return off_rec(sites, row_bytes, nsp, words) + (size_t)nw * 64 * sizeof(RowRec);
@@ -2400,8 +2385,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
               const unsigned* __restrict__ p2, const unsigned* __restrict__ p2f, const unsigned char* __restrict__ cls,
               const int* __restrict__ cols0, const float* __restrict__ scores, const PairTables* __restrict__ tables,
               const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm, int band_slots, int chunk,
-              float2* __restrict__ partial, float* __restrict__ res, HssDev* __restrict__ hss, int* __restrict__ hsscnt,
-              int* __restrict__ ovf_counter) {
+              float2* __restrict__ partial) {
   constexpr int RS = RegCfg<NK>::RS;
   constexpr int RSB = (NK + 3) / 4 * 4;
   constexpr int ROW_BYTES = (CHAINED ? 12 : RSB) * 32 * 4;  // one end codon, 32 lanes (chained: always room for three quads)
@@ -2449,7 +2433,6 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
   unsigned char* s_ref = smem + Cfg::off_ref(sites, ROW_BYTES, NSP);                    // packed reference row [word][lane]
   unsigned char* s_sp = smem + Cfg::off_sp(sites, ROW_BYTES, NSP, W);                   // packed species rows [species][word][lane]
   RowRec* srec = reinterpret_cast<RowRec*>(smem + Cfg::off_rec(sites, ROW_BYTES, NSP, W));
-  uint2* crec = reinterpret_cast<uint2*>(s_ref);  // compact records [row][instance], written once the staged rows are dead
 
   // ---- table phase: kernel (b) for this CTA's (instances, strand, frame, species of the launch) ------------------------
   const size_t z_bytes = Cfg::align16((size_t)sites * 4);
@@ -2615,95 +2598,8 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
       j += 1;
     }
     if (valid && last && r0 < sites) {
-      if (!CHAINED && bd.hss_inkernel) {
-        folds_store_c(fx, crec + (size_t)r0 * 32 + il, rec_inst + r0, rec0, fNK, rcpNK);
-        if (r0 + 1 < sites) folds_store_c(fy, crec + (size_t)(r0 + 1) * 32 + il, rec_inst + r0 + 1, rec0 + 1, fNK, rcpNK);
-      } else {
-        folds_store(fx, rec_inst + r0, rec0, fNK, rcpNK);
-        if (r0 + 1 < sites) folds_store(fy, rec_inst + r0 + 1, rec0 + 1, fNK, rcpNK);
-      }
-    }
-  }
-  if (CHAINED || !bd.hss_inkernel) return;
-
-  // ---- scan phase: the sequential part of getHSS (src/score.c:888-961, see k_hss_thr) over the compact records of the CTA's
-  // 32 instances, one lane each; rows of a complex fold are read from their full record in global memory
-  __syncthreads();  // every row of the frame has its record (global writes of this CTA are visible to it after the barrier)
-  if (warp != 0) return;
-  {
-    const bool have = lane < ninst_g;
-    const int inst = it.inst0 + group * 32 + lane;
-    const RowRec* grec = recs + it.rec_off[strand][frame] + (size_t)(group * 32 + (have ? lane : 0)) * sites;
-    HssDev* out = hss + bd.hss_off[strand][frame];
-    int nout = 0;
-    float best = -1.0f, cur = 0.0f;
-    bool overflow = false;
-    int segS = -1, segE = -1;
-    for (int i = 0; i + 1 < sites; i++) {  // the last row only holds the frame's final entry, which never survives (:893-900)
-      const uint2 c = crec[(size_t)i * 32 + lane];
-      const float e = __uint_as_float(c.x);
-      if (!have || !(e > 0.0f)) continue;  // no positive entry in this row
-      const int jF = (int)(c.y & 0xffffu);
-      const bool cplx = (c.y >> 16) != 0u;
-      // a simple row: maximum e at jF, nothing accepted after it -- Emax = vF = the single band entry
-      float Emax = e, vF = e, be0 = e, be1 = 0.0f, be2 = 0.0f;
-      int rjF = jF, bj0 = jF, bj1 = 0, bj2 = 0, nb = 1;
-      if (cplx) {  // RowRec: w0 = {Emax, vF, be0, be1}, w1 = {be2, jF | n << 16, bj0 | bj1 << 16, bj2 | pad << 16}
-        const uint4 w0 = reinterpret_cast<const uint4*>(grec + i)[0], w1 = reinterpret_cast<const uint4*>(grec + i)[1];
-        Emax = __uint_as_float(w0.x);
-        vF = __uint_as_float(w0.y);
-        be0 = __uint_as_float(w0.z);
-        be1 = __uint_as_float(w0.w);
-        be2 = __uint_as_float(w1.x);
-        rjF = (int)(w1.y & 0xffffu);
-        nb = (int)((w1.y >> 16) & 0xffu);
-        if ((w1.y >> 16) & 0x8000u) overflow = true;
-        bj0 = (int)(w1.z & 0xffffu);
-        bj1 = (int)(w1.z >> 16);
-        bj2 = (int)(w1.w & 0xffffu);
-      }
-      bool take;
-      if (cur > 0.0f && segE < i) {  // flush (:897-949)
-        if (segE - segS >= 2) {
-          if (inst == 0) {
-            out[nout].startSite = segS;
-            out[nout].endSite = segE;
-            out[nout].score = cur;
-          }
-          nout++;
-          best = fmaxf(best, cur);
-        }
-        take = true;
-      } else {  // overlap with the current segment (:953-959)
-        const int len = segE - segS;
-        const float d0 = be0 - cur, d1 = be1 - cur, d2 = be2 - cur;
-        take = Emax > cur;
-        take = take || (nb > 0 && d0 >= -0.0001f && d0 <= 0.0001f && bj0 - i >= len);
-        take = take || (nb > 1 && d1 >= -0.0001f && d1 <= 0.0001f && bj1 - i >= len);
-        take = take || (nb > 2 && d2 >= -0.0001f && d2 <= 0.0001f && bj2 - i >= len);
-      }
-      if (take) {
-        cur = vF;
-        segS = i;
-        segE = rjF;
-      }
-    }
-    if (have) {
-      if (sites > 0 && segE - segS >= 2) {  // forced flush on the frame's last entry
-        if (inst == 0) {
-          out[nout].startSite = segS;
-          out[nout].endSite = segE;
-          out[nout].score = cur;
-        }
-        nout++;
-        best = fmaxf(best, cur);
-      }
-      if (overflow) {
-        best = -2.0f;
-        atomicAdd(ovf_counter, 1);
-      }
-      res[bd.res_off + (size_t)inst * 6 + cd.sf] = best;
-      if (inst == 0) hsscnt[bd.hsscnt_off + cd.sf] = overflow ? -1 : nout;
+      folds_store(fx, rec_inst + r0, rec0, fNK, rcpNK);
+      if (r0 + 1 < sites) folds_store(fy, rec_inst + r0 + 1, rec0 + 1, fNK, rcpNK);
     }
   }
 }
@@ -2725,7 +2621,7 @@ __global__ void __launch_bounds__(HSS_WARPS * 32)
   const BlockDev& bd = blocks[it.block];
   const int lane = threadIdx.x & 31;
   const int idx = blockIdx.y * HSS_WARPS + (threadIdx.x >> 5);
-  if (idx >= it.ninst * 6 || !bd.hss_warp || bd.hss_inkernel) return;
+  if (idx >= it.ninst * 6 || !bd.hss_warp) return;
   const int inst_l = idx / 6, sf = idx % 6;
   const int strand = sf / 3, frame = sf % 3;
   const int sites = bd.sites[frame];
@@ -2833,7 +2729,7 @@ __global__ void __launch_bounds__(128)
   const Item it = items[blockIdx.x];
   const BlockDev& bd = blocks[it.block];
   const int idx = blockIdx.y * blockDim.x + threadIdx.x;
-  if (idx >= it.ninst * 6 || bd.hss_warp || bd.hss_inkernel) return;
+  if (idx >= it.ninst * 6 || bd.hss_warp) return;
   const int inst_l = idx / 6, sf = idx % 6;
   const int strand = sf / 3, frame = sf % 3;
   const int sites = bd.sites[frame];

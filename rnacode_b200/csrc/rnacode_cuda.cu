@@ -45,7 +45,6 @@ struct rc_ctx {
   long reg_max_nk = 12;  // row-major alignments with more scored species take k_dp_chain (k_dp_reg<13..16> spills: 17x3000 14.7 vs 11.1 ms)
   long no_smps = 0;          // never stream the sigma table in segments (k_dp_smps)
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
-  long no_inkernel_scan = 0;  // 1: k_dp_smpf leaves the sequential part of getHSS to k_hss_thr
   long no_fold = 0;           // 1: a last group of at most 16 instances is scored like a full one (k_dp_smpf)
   long no_fused = 0;          // 1: never build the sigma table inside the sample-major DP kernel (k_dp_smpf)
   long tail_max = 0;          // a sample-major block whose instance count leaves 1..tail_max instances in its last group of 32 scores
@@ -149,7 +148,6 @@ struct Chunk {
   int max_smp_quads = 0;  // most species quads of a sample-major item (k_sigma_smp spreads them over gridDim.z)
   int max_smp_npos = 0;   // most reference positions of a sample-major item (k_sigma_smp: chunks of SIG_PCH positions)
   int hss_warp_items = 0;  // items whose frames are long enough for the warp-per-task k_hss
-  int hss_inkernel_items = 0;  // items whose DP kernel runs the scan itself
 };
 
 struct EventPair {
@@ -407,7 +405,6 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   if (const char* e = getenv("RNACODE_CUDA_SMP_WARPS")) ctx->smp_warps_forced = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_HSS_THR_TASKS")) ctx->hss_thr_tasks = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_NO_FUSED")) ctx->no_fused = atol(e) ? 1 : 0;
-  if (const char* e = getenv("RNACODE_CUDA_NO_INKERNEL_SCAN")) ctx->no_inkernel_scan = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_NO_FOLD")) ctx->no_fold = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_TAIL_MAX")) ctx->tail_max = std::max(0L, std::min(31L, atol(e)));
   if (const char* e = getenv("RNACODE_CUDA_REG_MAX_NK")) ctx->reg_max_nk = std::max(12L, std::min<long>(REG_MAX_NK, atol(e)));
@@ -475,8 +472,6 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->smps_max_sites = value;
   } else if (k == "smpc_max_sites") {
     ctx->smpc_max_sites = value;
-  } else if (k == "no_inkernel_scan") {
-    ctx->no_inkernel_scan = value ? 1 : 0;
   } else if (k == "no_fold") {
     ctx->no_fold = value ? 1 : 0;
   } else if (k == "no_fused") {
@@ -696,7 +691,6 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
           smpf_smem_bytes(bd, layout) + (size_t)SMP_WARPS * 64 * sizeof(RowRec) <= (size_t)ctx->smem_optin) {
         bd.smp_fused = 1;
         bd.smp_fold = ctx->no_fold ? 0 : 1;
-        bd.hss_inkernel = (layout == 2 && !ctx->no_inkernel_scan) ? 1 : 0;
         b->max_fused_N = std::max(b->max_fused_N, bd.N);
         b->max_fused_cols = std::max(b->max_fused_cols, bd.cols);
         bd.p2_words = (bd.L + 15) / 16;
@@ -852,8 +846,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       if (bd.layout != 2 && bd.layout != 5)  // grid of k_sigma / k_sigma_rows (sample-major items have kernels of their own)
         cur.max_sigma_work = std::max(cur.max_sigma_work, (long long)take * 2 * (bd.L - 2 + 3 * RC_REG_TILE));
       cur.max_ninst = std::max(cur.max_ninst, take);
-      if (bd.hss_inkernel) cur.hss_inkernel_items++;
-      else if (bd.hss_warp) cur.hss_warp_items++;
+      if (bd.hss_warp) cur.hss_warp_items++;
       cur.n_layout[bd.layout]++;
       b->items.push_back(it);
       cur.nitems++;
@@ -1277,8 +1270,7 @@ static int launch_dp_smpf_nk(rc_batch* b, int chunk, bool last, const CtaDesc* d
   RC_CUDA(cudaFuncSetAttribute(k_dp_smpf<NK, CHAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_dp_smpf<NK, CHAINED><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_p2, b->d_p2f, b->d_cls,
                                                                          b->d_cols0, b->d_scores, b->d_ptab2, b->d_z, b->d_recs,
-                                                                         b->prm, (int)ctx->band_slots, chunk, b->d_partial, b->d_res,
-                                                                         b->d_hss, b->d_hsscnt, b->d_ovf);
+                                                                         b->prm, (int)ctx->band_slots, chunk, b->d_partial);
   RC_CUDA(cudaGetLastError());
   b->stats.launches++;
   b->stats.dp_launches++;
@@ -1629,7 +1621,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
         RC_CUDA(cudaGetLastError());
         b->stats.launches++;
       }
-      if (ch.hss_warp_items + ch.hss_inkernel_items < (int)ch.nitems) {
+      if (ch.hss_warp_items < (int)ch.nitems) {
         dim3 g((unsigned)ch.nitems, (unsigned)((ch.max_ninst * 6 + 127) / 128));
         k_hss_thr<<<g, 128, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_recs, b->d_res, b->d_hss, b->d_hsscnt, b->d_ovf);
         RC_CUDA(cudaGetLastError());
@@ -1651,8 +1643,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
       if (bd.L < 3) continue;
       for (int inst = 0; inst < bd.n_inst; inst++) {
         bool hit = false;
-        for (int sf = 0; sf < 6; sf++)
-          if (bd.sites[sf % 3] > 0) hit |= b->h_res[bd.res_off + (size_t)inst * 6 + sf] == -2.0f;  // (frames without a codon are never scanned)
+        for (int sf = 0; sf < 6; sf++) hit |= b->h_res[bd.res_off + (size_t)inst * 6 + sf] == -2.0f;
         if (hit) {
           Item s;
           memset(&s, 0, sizeof(s));
@@ -1747,8 +1738,7 @@ extern "C" int rc_batch_max_scores(rc_batch* b, int block, double* max_scores) {
   for (int inst = 1; inst < bd.n_inst; inst++) {
     float best = -1.0f;  // results[0].score of an empty list (src/score.c:1129-1134, :1044)
     if (bd.L >= 3)
-      for (int sf = 0; sf < 6; sf++)
-        if (bd.sites[sf % 3] > 0) best = std::max(best, b->h_res[bd.res_off + (size_t)inst * 6 + sf]);  // a frame without a codon has no entry
+      for (int sf = 0; sf < 6; sf++) best = std::max(best, b->h_res[bd.res_off + (size_t)inst * 6 + sf]);
     max_scores[inst - 1] = (double)best;
   }
   return RC_OK;
