@@ -1643,7 +1643,8 @@ extern "C" int rc_batch_run(rc_batch* b) {
       if (bd.L < 3) continue;
       for (int inst = 0; inst < bd.n_inst; inst++) {
         bool hit = false;
-        for (int sf = 0; sf < 6; sf++) hit |= b->h_res[bd.res_off + (size_t)inst * 6 + sf] == -2.0f;
+        for (int sf = 0; sf < 6; sf++)
+          if (bd.sites[sf % 3] > 0) hit |= b->h_res[bd.res_off + (size_t)inst * 6 + sf] == -2.0f;
         if (hit) {
           Item s;
           memset(&s, 0, sizeof(s));
@@ -1738,7 +1739,8 @@ extern "C" int rc_batch_max_scores(rc_batch* b, int block, double* max_scores) {
   for (int inst = 1; inst < bd.n_inst; inst++) {
     float best = -1.0f;  // results[0].score of an empty list (src/score.c:1129-1134, :1044)
     if (bd.L >= 3)
-      for (int sf = 0; sf < 6; sf++) best = std::max(best, b->h_res[bd.res_off + (size_t)inst * 6 + sf]);
+      for (int sf = 0; sf < 6; sf++)
+        if (bd.sites[sf % 3] > 0) best = std::max(best, b->h_res[bd.res_off + (size_t)inst * 6 + sf]);
     max_scores[inst - 1] = (double)best;
   }
   return RC_OK;
