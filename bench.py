@@ -461,11 +461,13 @@ class Bench:
         else:  # null alignments drawn on the GPU (kernel d), the CLIs' default
             blocks = [capi.Block(rows, sf, sr, None, n_samples=n) for rows, sf, sr, _ in blocks_np]
 
+        descs = capi.Batch.block_descs(blocks)                      # the caller's descriptor array and tree tables exist
+        plan = None if host_samples else capi.Batch.evolve_plan(trees, seeds)  # before the step, like the rows themselves
+
         def make_batch():
-            bt = self.ctx.batch(blocks, self.prm, self.blosum)
+            bt = self.ctx.batch(blocks, self.prm, self.blosum, descs)
             if not host_samples:
-                for i in range(len(blocks)):
-                    bt.set_evolve(i, trees[i], seeds[i], capi.RC_RNG_MT19937)
+                bt.set_evolve_many(plan, capi.RC_RNG_MT19937)
             return bt
 
         # device-resident leg
@@ -507,7 +509,7 @@ class Bench:
             b2.run()
             b2.download()
             s2 = b2.stats()
-            _ = [b2.max_scores(i) for i in range(len(blocks))]
+            _ = b2.max_scores_all()
             b2.close()
             return s2
         for _ in range(2):

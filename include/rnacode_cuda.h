@@ -142,11 +142,17 @@ int rc_batch_create(rc_ctx *ctx, const rc_block_desc *blocks, int n_blocks, cons
 /* Draw the block's n_samples null alignments on the GPU instead of taking them from desc.samples (which may
  * then be NULL).  seeds: one per sample (what SetSeed() would receive, low 32 bits).  Call before rc_batch_upload. */
 int rc_batch_set_evolve(rc_batch *batch, int block, const rc_tree_desc *tree, const unsigned int *seeds, int rng);
+/* The same for n consecutive blocks first .. first+n-1 in one call (a window of thousands of short blocks: the batched CLI
+ * and the benchmark set every block's tree): trees[i] and seeds[i] (n_samples of that block) belong to block first+i. */
+int rc_batch_set_evolve_many(rc_batch *batch, int first, int n, const rc_tree_desc *trees, const unsigned int *const *seeds,
+                             int rng);
 int rc_batch_upload(rc_batch *batch);   /* host -> device copies of rows, samples and score tables */
 int rc_batch_run(rc_batch *batch);      /* all kernels; inputs and outputs stay in HBM */
 int rc_batch_download(rc_batch *batch); /* device -> host copy of HSS records and per-sample maxima; synchronises */
 int rc_batch_native_hss(rc_batch *batch, int block, rc_hss *out, int max_hss, int *n_hss);
 int rc_batch_max_scores(rc_batch *batch, int block, double *max_scores /* n_samples of that block */);
+/* maxScores of every block, block after block; n_out must be the sum of the blocks' n_samples */
+int rc_batch_max_scores_all(rc_batch *batch, double *max_scores, size_t n_out);
 void rc_batch_destroy(rc_batch *batch);
 
 /* -- introspection for benchmarks and tests ------------------------------------------------------- */

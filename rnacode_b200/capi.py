@@ -63,7 +63,7 @@ EXPORTS = [
     "rc_score_aln", "rc_score_samples", "rc_batch_create", "rc_batch_upload", "rc_batch_run", "rc_batch_download",
     "rc_batch_native_hss", "rc_batch_max_scores", "rc_batch_destroy", "rc_batch_get_stats", "rc_version",
     "rc_calibrate_issue", "rc_batch_set_evolve", "rc_score_samples_evolve", "rc_batch_get_sample_rows", "rc_device_count",
-    "rc_pair_rows",
+    "rc_pair_rows", "rc_batch_set_evolve_many", "rc_batch_max_scores_all",
 ]
 
 _lib = None
@@ -106,6 +106,8 @@ def load():
     lib.rc_score_samples_evolve.argtypes = [vp, C.POINTER(rc_block_desc), C.POINTER(rc_tree_desc), vp, i,
                                             C.POINTER(rc_params), vp, vp]
     lib.rc_batch_get_sample_rows.argtypes = [vp, i, i, vp]
+    lib.rc_batch_set_evolve_many.argtypes = [vp, i, i, vp, vp, i]
+    lib.rc_batch_max_scores_all.argtypes = [vp, vp, C.c_size_t]
     _lib = lib
     return lib
 
@@ -225,25 +227,48 @@ class Context:
         self._check(self.lib.rc_calibrate_issue(self.h, C.byref(v)))
         return v.value
 
-    def batch(self, blocks, params, blosum):
-        return Batch(self, blocks, params, blosum)
+    def batch(self, blocks, params, blosum, descs=None):
+        return Batch(self, blocks, params, blosum, descs)
 
 
 class Batch:
-    def __init__(self, ctx, blocks, params, blosum):
+    def __init__(self, ctx, blocks, params, blosum, descs=None):
         self.ctx = ctx
         self.blocks = list(blocks)
-        self._descs = (rc_block_desc * len(self.blocks))(*[b.desc() for b in self.blocks])
+        # descs: a ctypes array built earlier with Batch.block_descs(blocks) (thousands of blocks: not rebuilt per batch)
+        self._descs = descs if descs is not None else Batch.block_descs(self.blocks)
         self._blosum = _blosum_arr(blosum)
         self.h = C.c_void_p()
         ctx._check(ctx.lib.rc_batch_create(ctx.h, self._descs, len(self.blocks), C.byref(params), self._blosum.ctypes.data,
                                            C.byref(self.h)))
+
+    @staticmethod
+    def block_descs(blocks):
+        return (rc_block_desc * len(blocks))(*[b.desc() for b in blocks])
 
     def set_evolve(self, i, tree, seeds, rng=RC_RNG_MT19937):
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
         d = tree.desc()
         self._keep = getattr(self, "_keep", []) + [tree, seeds]
         self.ctx._check(self.ctx.lib.rc_batch_set_evolve(self.h, i, C.byref(d), seeds.ctypes.data, rng))
+
+    @staticmethod
+    def evolve_plan(trees, seeds):
+        """ctypes arrays for set_evolve_many, built once for a list of trees / per-block seed arrays (kept alive by the plan)."""
+        seeds = [np.ascontiguousarray(s, dtype=np.uint32) for s in seeds]
+        descs = (rc_tree_desc * len(trees))(*[t.desc() for t in trees])
+        ptrs = (C.c_void_p * len(seeds))(*[s.ctypes.data for s in seeds])
+        return {"descs": descs, "ptrs": ptrs, "keep": (trees, seeds), "n": len(trees)}
+
+    def set_evolve_many(self, plan, rng=RC_RNG_MT19937, first=0):
+        self._keep = getattr(self, "_keep", []) + [plan]
+        self.ctx._check(self.ctx.lib.rc_batch_set_evolve_many(self.h, first, plan["n"], plan["descs"], plan["ptrs"], rng))
+
+    def max_scores_all(self):
+        n = sum(b.n_samples for b in self.blocks)
+        res = np.zeros(n, dtype=np.float64)
+        self.ctx._check(self.ctx.lib.rc_batch_max_scores_all(self.h, res.ctypes.data, n))
+        return res
 
     def sample_rows(self, i, sample):
         b = self.blocks[i]

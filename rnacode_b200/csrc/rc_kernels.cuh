@@ -1969,7 +1969,7 @@ __device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv
 // CHAINED: two CTAs of 8 warps per SM need at most 128 registers per thread (the 12-species chunk with partial sums coming in
 // and the fold state would take 138)
 template <int NK, bool CHAINED>
-__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 : 1)
     k_dp_smp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
              const float* __restrict__ sigma, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm,
              int band_slots, int chunk, float2* __restrict__ partial) {
@@ -1984,8 +1984,20 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
   const int strand = cd.sf / 3, frame = cd.sf % 3;
   const int sites = bd.sites[frame];
   const int group = cd.task0;  // group of 32 instances inside the item
-  const int inst_l = group * 32 + lane;
-  const bool valid = inst_l < it.ninst;
+  // Folded group: a group with at most 16 instances (the last one of a block with 101 = 3 * 32 + 5 of them, RNAcode's default
+  // -n 100) does not leave its other lanes idle: the lanes are cut into R = 32 / m replicas of m >= #instances lanes, lane l
+  // works for instance l % m (it reads that instance's column of the sigma table), and replica l / m takes its own start-codon
+  // pair -- R pairs side by side.  The rows of the replicas start 2 codons apart; until the last one has started the steps are
+  // masked per lane (reg_update_diag).
+  const int ninst_g = min(32, it.ninst - group * 32);
+  int fold_m = 32;
+  if (bd.smp_fold && ninst_g <= 16) {
+    fold_m = 1;
+    while (fold_m < ninst_g) fold_m <<= 1;
+  }
+  const int R = 32 / fold_m, il = lane & (fold_m - 1), rep = lane / fold_m;
+  const int inst_l = group * 32 + il;
+  const bool valid = il < ninst_g;
   const bool first = !CHAINED || chunk == 0, last = !CHAINED || chunk == bd.nchunk - 1;
   const int ngrp = (it.ninst + 31) / 32;
 
@@ -1993,7 +2005,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
   const size_t z_bytes = ((size_t)sites * 4 + 15) / 16 * 16;
   unsigned* zs = reinterpret_cast<unsigned*>(smem + sig_bytes);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sig_bytes + z_bytes);
-  // fold state of the getHSS digest, two records per lane and warp (only the launch that owns the digest has room for it)
+  // records of rows whose fold went complex, two per lane and warp (only the launch that owns the digest has room for them)
   RowRec* srec = reinterpret_cast<RowRec*>(smem + sig_bytes + z_bytes + 16);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
@@ -2006,12 +2018,12 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
   __syncthreads();
   mbar_wait(bar, 0);
 
-  unsigned sig_a = smem_u32(smem) + lane * 16;
+  unsigned sig_a = smem_u32(smem) + il * 16;
   asm volatile("" : "+r"(sig_a));
   const float Delta = prm.Delta, Omega = prm.Omega;
   float omega = prm.omega;
   asm volatile("" : "+f"(omega));
-  const float fNK = bd.fNK, rcpNK = bd.rcpNK;
+  const float fNK = bd.fNK, rcpNK = bd.rcpNK, foldB = bd.fold_B;
   RowRec* rec_inst = recs + it.rec_off[strand][frame] + (size_t)(valid ? inst_l : 0) * sites;
   // partial sums of this (item, strand, frame, group): [pair][end codon from the pair's first row on][lane]
   const int npairs = (sites + 1) / 2;
@@ -2021,107 +2033,87 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, CHAINED ? 2 : 1)
     part = partial + it.part_off[strand][frame] + (size_t)group * per_group + lane;
   }
 
-  // boustrophedon assignment of start-codon pairs to warps: w, 2W-1-w, 2W+w, 4W-1-w, ... (rows get shorter
+  // boustrophedon assignment of start-codon pairs (R at a time) to warps: w, 2W-1-w, 2W+w, 4W-1-w, ... (rows get shorter
   // with the pair index, so every warp receives a similar total length)
+  const int nsuper = (npairs + R - 1) / R;
 #pragma unroll 1
   for (int turn = 0;; turn++) {
-    const int p = (turn & 1) ? (turn + 1) * nw - 1 - warp : turn * nw + warp;
-    if (turn * nw >= npairs) break;
-    if (p >= npairs) continue;
-    const int r0 = 2 * p;
+    const int sp = (turn & 1) ? (turn + 1) * nw - 1 - warp : turn * nw + warp;
+    if (turn * nw >= nsuper) break;
+    if (sp >= nsuper) continue;
+    const int p = sp * R + rep;            // this lane's pair (may lie past the end for the last replicas)
+    const int r0 = 2 * p;                  // its first row
+    const int r_first = 2 * sp * R;        // first row of the warp
+    const int j_steady = r_first + 2 * R;  // from here on both rows of every lane have started
+    const bool live = p < npairs;
     RowRec* rec0 = srec + (warp * 32 + lane) * 2;
-#if !RC_SMP_FOLDS
-    if (last) {
-      rec_init(rec0);
-      rec_init(rec0 + 1);
-    }
-#endif
-    float2* pp = CHAINED ? part + ((size_t)p * sites - (size_t)p * (p - 1) - r0) * 32 : nullptr;  // pp[j * 32] = entry of end codon j
+    // pp[j * 32] = entry of end codon j of this lane's pair (a lane without a pair never touches it)
+    float2* pp = (CHAINED && live) ? part + ((size_t)p * sites - (size_t)p * (p - 1) - r0) * 32 : nullptr;
     float2 S0[NK], S1[NK], S2[NK];
 #pragma unroll
     for (int k = 0; k < NK; k++) S0[k] = S1[k] = S2[k] = make_float2(0.0f, 0.0f);
-#if RC_SMP_FOLDS
     RowFoldS sx, sy;
-    folds_init(sx, bd.fold_B);
-    folds_init(sy, bd.fold_B);
-#else
-    RowFold fx, fy;
-    fold_init(fx);
-    fold_init(fy);
-#endif
-    int j = r0;
+    folds_init(sx, foldB);
+    folds_init(sy, foldB);
+    int j = r_first;
 #pragma unroll 1
     while (j < sites) {
       float svA[RS];
       const unsigned zA = zs[j];
       smp_load_row<NK>(sig_a + j * ROW_BYTES, zA, svA);
-      if ((j >= r0 + 2 || (RC_SMP_DIAG_PAIR && j == r0)) && j + 1 < sites) {
+      if (R > 1 && j < j_steady) {
+        // folded group, rows still starting: one end codon at a time, every addend masked per lane until its row starts
+        // (the state stays exactly (0,0,0), the sums 0, and the fold ignores a sum of 0)
+        const bool mx = j >= r0, my = j >= r0 + 1;
+        float2 sin = make_float2(0.0f, 0.0f);
+        if (CHAINED && !first && mx) sin = pp[(size_t)j * 32];
+        if (CHAINED && !first && !my) sin.y = 0.0f;
+        const float2 sum = reg_update_diag<NK, CHAINED>(S0, S1, S2, svA, mx, my, Delta, Omega, omega, sin);
+        if (CHAINED && !last) {
+          if (mx) pp[(size_t)j * 32] = sum;
+        } else {
+          folds_single(sx, sy, sum, j, true, fNK, rcpNK, rec0, band_slots);
+        }
+        j += 1;
+        continue;
+      }
+      if (j >= j_steady && j + 1 < sites) {
         const unsigned zB = zs[j + 1];
         if ((zA | zB) == 0u) {
           float svB[RS];
           smp_load_row<NK>(sig_a + (j + 1) * ROW_BYTES, zB, svB);
           float2 sumA, sumB, sinA = make_float2(0.0f, 0.0f), sinB = make_float2(0.0f, 0.0f);
-          if (CHAINED && !first) {
+          if (CHAINED && !first && live) {
             sinA = pp[(size_t)j * 32];
             sinB = pp[(size_t)(j + 1) * 32];
           }
-          // the pair's first two end codons: row r0 starts at j, row r0+1 at j+1 (masked straight-line block, see reg_pair_diag)
-          if (RC_SMP_DIAG_PAIR && j == r0) reg_pair_diag<NK, CHAINED>(S0, S1, S2, svA, svB, omega, true, false, sumA, sumB, sinA, sinB);
-          else reg_pair_fast<NK, CHAINED>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
+          reg_pair_fast<NK, CHAINED>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
           if (CHAINED && !last) {
-            pp[(size_t)j * 32] = sumA;
-            pp[(size_t)(j + 1) * 32] = sumB;
-          }
-#if RC_SMP_FOLDS
-          else {
+            if (live) {
+              pp[(size_t)j * 32] = sumA;
+              pp[(size_t)(j + 1) * 32] = sumB;
+            }
+          } else {
             folds_pair(sx, sy, sumA, sumB, j, fNK, rcpNK, rec0, band_slots);
           }
-#else
-          else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f && valid) {
-            fold_entry(sumA.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
-            fold_entry(sumA.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
-            fold_entry(sumB.x, j + 1, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
-            fold_entry(sumB.y, j + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
-          }
-#endif
           j += 2;
           continue;
         }
       }
       float2 sin = make_float2(0.0f, 0.0f);
-      if (CHAINED && !first) sin = pp[(size_t)j * 32];
+      if (CHAINED && !first && live) sin = pp[(size_t)j * 32];
       const float2 sum = reg_update<NK, CHAINED>(S0, S1, S2, svA, j < r0 + 2, j, r0, Delta, Omega, omega, sin);
       if (CHAINED && !last) {
-        pp[(size_t)j * 32] = sum;
-      }
-#if RC_SMP_FOLDS
-      else {
+        if (live) pp[(size_t)j * 32] = sum;
+      } else {
         folds_single(sx, sy, sum, j, j > r0, fNK, rcpNK, rec0, band_slots);
       }
-#else
-      else if (fmaxf(sum.x, sum.y) > 0.0f && valid) {
-        fold_entry(sum.x, j, r0, sites, fNK, rcpNK, rec0, band_slots, fx);
-        if (r0 + 1 < sites) fold_entry(sum.y, j, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, fy);
-      }
-#endif
       j += 1;
     }
-#if RC_SMP_FOLDS
-    if (valid && last) {
+    if (valid && last && r0 < sites) {
       folds_store(sx, rec_inst + r0, rec0, fNK, rcpNK);
       if (r0 + 1 < sites) folds_store(sy, rec_inst + r0 + 1, rec0 + 1, fNK, rcpNK);
     }
-#else
-    if (valid && last) {
-#pragma unroll
-      for (int t = 0; t < 2; t++)
-        if (r0 + t < sites) {
-          const RowFold& f = t ? fy : fx;
-          if (f.jF >= 0) fold_flush(rec0 + t, f.M, f.jF);
-          rec_copy(rec_inst + r0 + t, rec0 + t);
-        }
-    }
-#endif
   }
 }
 
@@ -2927,7 +2919,8 @@ constexpr int EVO_WARPS = 4;
 #ifndef RC_EVO_SPW
 #define RC_EVO_SPW 8
 #endif
-constexpr int EVO_SPW = RC_EVO_SPW;  // samples per task: their MT19937 states are seeded side by side, one lane each
+constexpr int EVO_SPW = RC_EVO_SPW;  // most samples per task: their MT19937 states are seeded side by side, one lane each (the host
+                                     // takes fewer per task when a batch has too few samples to fill the GPU with tasks of eight)
 
 // Persistent warps: warp `wg` of the grid works through the tasks wg, wg + n_warps, ...; a task is EVO_SPW consecutive
 // samples of one block (evo_task0: prefix sums of the tasks per block).  The states of a task are seeded by EVO_SPW lanes in
@@ -2937,14 +2930,14 @@ constexpr int EVO_SPW = RC_EVO_SPW;  // samples per task: their MT19937 states a
 __global__ void __launch_bounds__(EVO_WARPS * 32)
     k_evolve(const BlockDev* __restrict__ blocks, const EvoDev* __restrict__ evos, const int* __restrict__ evo_task0, int n_evos,
              const int* __restrict__ nodes, const unsigned* __restrict__ thr, const unsigned* __restrict__ seeds,
-             unsigned char* __restrict__ seqs, unsigned char* __restrict__ raw, unsigned* __restrict__ mt_scratch) {
+             unsigned char* __restrict__ seqs, unsigned char* __restrict__ raw, unsigned* __restrict__ mt_scratch, int spw) {
   __shared__ unsigned s_mt[EVO_WARPS][624];
   __shared__ uint4 s_thr[EVO_WARPS][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = blockIdx.x * EVO_WARPS + warp, n_warps = gridDim.x * EVO_WARPS;
   const int total_tasks = evo_task0[n_evos];
   unsigned* mt = s_mt[warp];
-  unsigned* slot = mt_scratch + (size_t)wg * EVO_SPW * 624;
+  unsigned* slot = mt_scratch + (size_t)wg * spw * 624;
 #pragma unroll 1
   for (int task = wg; task < total_tasks; task += n_warps) {
     int lo = 0, hi = n_evos - 1;  // the block of the task: largest e with evo_task0[e] <= task
@@ -2956,8 +2949,8 @@ __global__ void __launch_bounds__(EVO_WARPS * 32)
     const EvoDev ev = evos[lo];
     const BlockDev& bd = blocks[ev.block];
     const int n_samp = bd.n_inst - 1;
-    const int s_base = (task - evo_task0[lo]) * EVO_SPW;
-    const int n_mine = min(EVO_SPW, n_samp - s_base);
+    const int s_base = (task - evo_task0[lo]) * spw;
+    const int n_mine = min(spw, n_samp - s_base);
     const int cols = bd.cols;
     const int* nd = nodes + ev.node_off;
     const unsigned* th = thr + ev.thr_off;

@@ -310,6 +310,7 @@ struct rc_batch {
   int* d_evo_nodes = nullptr;
   unsigned *d_evo_thr = nullptr, *d_evo_seeds = nullptr;
   unsigned char* d_evo_seq = nullptr;
+  int evo_spw = EVO_SPW;        // samples per k_evolve task in this batch
   std::vector<int> evo_task0;   // prefix sums of the k_evolve tasks (EVO_SPW samples each) per simulated block
   int* d_evo_task0 = nullptr;
   unsigned* d_evo_mt = nullptr;  // seeded generator states, one slot of EVO_SPW states per persistent warp of k_evolve
@@ -700,6 +701,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
         bd.p2f_off = (long long)b->p2f_words;
         b->p2f_words += groups * 2 * bd.N;
       }
+      if ((layout == 2 || layout == 5) && !seg) bd.smp_fold = ctx->no_fold ? 0 : 1;  // resident-table kernels fold a short last group
       if (layout == 2 || layout == 5) {
         // B of RowFoldS: (N-1) * 1.0002e-4 for the tolerance of getHSS's tie rule plus 2^-21 of the largest species sum a
         // row can reach (per end codon and species at most the largest sigma -- BLOSUM entry or stop penalty minus the
@@ -996,6 +998,20 @@ extern "C" int rc_batch_set_evolve(rc_batch* b, int block, const rc_tree_desc* t
   return RC_OK;
 }
 
+extern "C" int rc_batch_set_evolve_many(rc_batch* b, int first, int n, const rc_tree_desc* trees, const unsigned int* const* seeds,
+                                        int rng) {
+  if (!b) return RC_ERR_ARG;
+  if (first < 0 || n < 0 || first + n > b->n_blocks || (n > 0 && (!trees || !seeds))) {
+    ctx_fail(b->ctx, "rc_batch_set_evolve_many: bad argument");
+    return RC_ERR_ARG;
+  }
+  for (int i = 0; i < n; i++) {
+    const int r = rc_batch_set_evolve(b, first + i, &trees[i], seeds[i], rng);
+    if (r != RC_OK) return r;
+  }
+  return RC_OK;
+}
+
 extern "C" int rc_batch_get_sample_rows(rc_batch* b, int block, int sample, char* rows) {
   if (!b || block < 0 || block >= b->n_blocks || !rows) return RC_ERR_ARG;
   rc_ctx* ctx = b->ctx;
@@ -1053,9 +1069,14 @@ extern "C" int rc_batch_upload(rc_batch* b) {
   if (!b->evos.empty()) {
     void* ptrs[] = {b->d_evos, b->d_evo_nodes, b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq, b->d_evo_task0};
     for (void* p : ptrs) ctx_free(ctx, p);
+    // samples per task of k_evolve: eight (their generators are seeded side by side) unless the batch has so few samples that
+    // tasks of eight would leave most of the GPU's warps without work
+    long long total_samples = 0;
+    for (const EvoDev& e : b->evos) total_samples += b->blocks[e.block].n_inst - 1;
+    b->evo_spw = (int)std::max<long long>(1, std::min<long long>(EVO_SPW, total_samples / ((long long)ctx->sm_count * 32)));
     b->evo_task0.assign(1, 0);
     for (const EvoDev& e : b->evos)
-      b->evo_task0.push_back(b->evo_task0.back() + (b->blocks[e.block].n_inst - 1 + EVO_SPW - 1) / EVO_SPW);
+      b->evo_task0.push_back(b->evo_task0.back() + (b->blocks[e.block].n_inst - 1 + b->evo_spw - 1) / b->evo_spw);
     b->d_evo_task0 = (int*)ctx_alloc(ctx, sizeof(int) * b->evo_task0.size());
     b->d_evos = (EvoDev*)ctx_alloc(ctx, sizeof(EvoDev) * b->evos.size());
     b->d_evo_nodes = (int*)ctx_alloc(ctx, sizeof(int) * b->evo_nodes.size());
@@ -1494,7 +1515,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
     const int total_tasks = b->evo_task0.back();
     const int want = (total_tasks + EVO_WARPS - 1) / EVO_WARPS;
     const int gx = std::max(1, std::min(want, ctx->sm_count * 16));  // persistent warps: 16 CTAs of 4 warps per SM at most
-    const size_t need = (size_t)gx * EVO_WARPS * EVO_SPW * 624 * sizeof(unsigned);
+    const size_t need = (size_t)gx * EVO_WARPS * b->evo_spw * 624 * sizeof(unsigned);
     if (need > b->evo_mt_bytes) {
       ctx_free(ctx, b->d_evo_mt);
       b->d_evo_mt = (unsigned*)ctx_alloc(ctx, need);
@@ -1502,7 +1523,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
       b->evo_mt_bytes = need;
     }
     k_evolve<<<gx, EVO_WARPS * 32, 0, st>>>(b->d_blocks, b->d_evos, b->d_evo_task0, (int)b->evos.size(), b->d_evo_nodes,
-                                            b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq, b->d_raw, b->d_evo_mt);
+                                            b->d_evo_thr, b->d_evo_seeds, b->d_evo_seq, b->d_raw, b->d_evo_mt, b->evo_spw);
     RC_CUDA(cudaGetLastError());
     b->stats.launches++;
   }
@@ -1742,6 +1763,23 @@ extern "C" int rc_batch_max_scores(rc_batch* b, int block, double* max_scores) {
       for (int sf = 0; sf < 6; sf++)
         if (bd.sites[sf % 3] > 0) best = std::max(best, b->h_res[bd.res_off + (size_t)inst * 6 + sf]);
     max_scores[inst - 1] = (double)best;
+  }
+  return RC_OK;
+}
+
+extern "C" int rc_batch_max_scores_all(rc_batch* b, double* max_scores, size_t n_out) {
+  if (!b || !max_scores) return RC_ERR_ARG;
+  size_t need = 0;
+  for (int i = 0; i < b->n_blocks; i++) need += (size_t)b->blocks[i].n_inst - 1;
+  if (need != n_out) {
+    ctx_fail(b->ctx, "rc_batch_max_scores_all: n_out must be the sum of the blocks' n_samples");
+    return RC_ERR_ARG;
+  }
+  size_t pos = 0;
+  for (int i = 0; i < b->n_blocks; i++) {
+    const int r = rc_batch_max_scores(b, i, max_scores + pos);
+    if (r != RC_OK) return r;
+    pos += (size_t)b->blocks[i].n_inst - 1;
   }
   return RC_OK;
 }

@@ -151,3 +151,25 @@ def test_set_evolve_rejects_bad_trees(rc_ctx):
     with pytest.raises(capi.RcError):
         bt.upload()  # samples missing and no tree
     bt.close()
+
+
+def test_bulk_calls_match_per_block_calls(rc_ctx):
+    """rc_batch_set_evolve_many / rc_batch_max_scores_all (one call for a window of blocks) give what the per-block calls give."""
+    from rnacode_b200 import capi
+    doc = op.golden("genomic_pre_maf")
+    prm = capi.make_params(**op.golden_params(doc))
+    blks = [b for b in doc["blocks"] if not b.get("skipped")][:12]
+    blocks = [capi.Block(*op.block_arrays(doc, b)[:3], None, n_samples=24 + (i % 5)) for i, b in enumerate(blks)]
+    trees = [_tree(capi, b) for b in blks]
+    seeds = [np.arange(100 * i + 1, 100 * i + 1 + blocks[i].n_samples, dtype=np.uint32) for i in range(len(blks))]
+    one = rc_ctx.batch(blocks, prm, doc["blosum"])
+    for i in range(len(blocks)):
+        one.set_evolve(i, trees[i], seeds[i], capi.RC_RNG_MT19937)
+    one.upload(); one.run(); one.download()
+    many = rc_ctx.batch(blocks, prm, doc["blosum"], capi.Batch.block_descs(blocks))
+    many.set_evolve_many(capi.Batch.evolve_plan(trees, seeds), capi.RC_RNG_MT19937)
+    many.upload(); many.run(); many.download()
+    assert np.array_equal(many.max_scores_all(), np.concatenate([one.max_scores(i) for i in range(len(blocks))]))
+    for i in range(len(blocks)):
+        assert many.native_hss(i) == one.native_hss(i) == op.expected_hss(blks[i])
+    one.close(); many.close()
