@@ -1438,6 +1438,9 @@ __device__ __forceinline__ void rec_copy(RowRec* dst, const RowRec* src) {
 #ifndef RC_REG_DIAG_MASKED
 #define RC_REG_DIAG_MASKED 1
 #endif
+#ifndef RC_REG_SINGLE
+#define RC_REG_SINGLE 0
+#endif
 template <int NK>
 __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
     k_dp_reg(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
@@ -1554,6 +1557,32 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
       float svA[RS], svB[RS];
       reg_load_row<NK>(a0, svA);
       reg_load_row<NK>(a0 + RS * 4, svB);
+#if RC_REG_SINGLE
+      // A codon with a frameshift of some species is taken alone and the loop goes on from the next codon, so that the kernel
+      // holds ONE copy of the branchy general update (instruction-cache footprint of the steady loop)
+      int c = 0;
+#pragma unroll 1
+      while (c < tsteps) {
+        float2 sumA, sumB = make_float2(0.0f, 0.0f);
+        const int jc = j0 + c;
+        const bool pair = c + 1 < tsteps && (__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u;
+        if (pair) {
+          reg_pair_fast<NK>(S0, S1, S2, svA, svB, omega, sumA, sumB);
+          c += 2;
+        } else {
+          sumA = reg_update<NK>(S0, S1, S2, svA, false, jc, r0, Delta, Omega, omega);
+          c += 1;
+        }
+        reg_load_row<NK>(a0 + c * RS * 4, svA);
+        reg_load_row<NK>(a0 + (c + 1) * RS * 4, svB);
+        if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
+          if (sumA.x > 0.0f) lb.x = RC_REG_CHECK(sumA.x, jc, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumA.y > 0.0f) lb.y = RC_REG_CHECK(sumA.y, jc, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          if (sumB.x > 0.0f) lb.x = RC_REG_CHECK(sumB.x, jc + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumB.y > 0.0f) lb.y = RC_REG_CHECK(sumB.y, jc + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+        }
+      }
+#else
 #pragma unroll 1
       for (int c = 0; c < tsteps; c += 2) {
         float2 sumA, sumB;
@@ -1573,6 +1602,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
           if (sumB.y > 0.0f) lb.y = RC_REG_CHECK(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
         }
       }
+#endif
     }
     __syncwarp();
     if (lane == 0 && tile + 2 < ntiles) {
