@@ -1663,6 +1663,9 @@ struct ChainCfg {
 #ifndef RC_CHAIN_MAXREG
 #define RC_CHAIN_MAXREG 128
 #endif
+#ifndef RC_CHAIN_SINGLE
+#define RC_CHAIN_SINGLE 0
+#endif
 template <int NK, bool MULTI>
 __global__ void
 #if RC_CHAIN_MAXREG < 128
@@ -1776,6 +1779,54 @@ __global__ void
     mbar_wait(&bars[s], parity);
     if (!first) mbar_wait(&full_in[hs], hround & 1u);                           // partial sums of this tile have arrived
     if (!last && hround > 0) mbar_wait(&empty_out[hs], (hround & 1u) ^ 1u);     // the next warp is done with this stage
+#if RC_CHAIN_SINGLE
+    {
+      // One copy of each update in the loop (instruction-cache footprint: the five warps of a CTA are in different phases of
+      // it): a codon with a frameshift, and every codon of a tile in which rows start, is taken alone.
+      float svA[RS], svB[RS];
+      reg_load_row<NK>(a0, svA);
+      reg_load_row<NK>(a0 + RS * 4, svB);
+      int c = 0;
+#pragma unroll 1
+      while (c < TILE) {
+        const int c0 = c;
+        float2 sumA, sumB = make_float2(0.0f, 0.0f);
+        float2 sinA = make_float2(0.0f, 0.0f), sinB = make_float2(0.0f, 0.0f);
+        const bool pair = !diag && c + 1 < TILE && (__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u;
+        if (!first) {
+          sinA = lds_f2(hin + c * 256);
+          if (pair) sinB = lds_f2(hin + (c + 1) * 256);
+        } else if (MULTI && !gfirst) {
+          sinA = gp[((size_t)tile * TILE + c) * 32];
+          if (pair) sinB = gp[((size_t)tile * TILE + c + 1) * 32];
+        }
+        if (pair) {
+          reg_pair_fast<NK, true>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
+          c += 2;
+        } else if (!diag) {
+          sumA = reg_update<NK, true>(S0, S1, S2, svA, false, j0 + c, r0, Delta, Omega, omega, sinA);
+          c += 1;
+        } else {
+          sumA = reg_update_diag<NK, true>(S0, S1, S2, svA, j0 + c >= r0, j0 + c > r0, Delta, Omega, omega, sinA);
+          c += 1;
+        }
+        reg_load_row<NK>(a0 + c * RS * 4, svA);
+        reg_load_row<NK>(a0 + (c + 1) * RS * 4, svB);
+        if (!last) {
+          sts_f2(hout + c0 * 256, sumA);
+          if (pair) sts_f2(hout + (c0 + 1) * 256, sumB);
+        } else if (MULTI && !glast) {
+          gp[((size_t)tile * TILE + c0) * 32] = sumA;
+          if (pair) gp[((size_t)tile * TILE + c0 + 1) * 32] = sumB;
+        } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
+          if (sumA.x > 0.0f) lb.x = RC_REG_CHECK(sumA.x, j0 + c0, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumA.y > 0.0f) lb.y = RC_REG_CHECK(sumA.y, j0 + c0, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+          if (sumB.x > 0.0f) lb.x = RC_REG_CHECK(sumB.x, j0 + c0 + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+          if (sumB.y > 0.0f) lb.y = RC_REG_CHECK(sumB.y, j0 + c0 + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+        }
+      }
+    }
+#else
     {
       float svA[RS], svB[RS];
       reg_load_row<NK>(a0, svA);
@@ -1824,6 +1875,7 @@ __global__ void
         }
       }
     }
+#endif
     __syncwarp();
     if (lane == 0) {
       if (tile + 2 < ntiles) {
