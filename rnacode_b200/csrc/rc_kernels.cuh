@@ -2050,6 +2050,21 @@ __device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv
 #endif
 // CHAINED: two CTAs of 8 warps per SM need at most 128 registers per thread (the 12-species chunk with partial sums coming in
 // and the fold state would take 138)
+// CHAINED: the partial sums a lane continues come from global memory (they were written by the launch of the preceding
+// chunk), one float2 per end codon.  Waiting for them was the kernel's largest stall (long_scoreboard 4.1 per issue,
+// profiles/r02_k_dp_smp_chunked.md), so every lane requests them SMP_PF end codons ahead with cp.async into a ring slot of
+// its own in shared memory (no registers held while the copy is in flight): one commit group per end codon.
+constexpr int SMP_PF = 4;                                   // end codons in flight per lane
+constexpr int SMP_PF_BYTES = SMP_MAX_WARPS * SMP_PF * 256;  // ring of a CTA: [warp][slot][lane] float2
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <int NK, bool CHAINED>
 __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 : 1)
     k_dp_smp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
@@ -2088,7 +2103,10 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
   unsigned* zs = reinterpret_cast<unsigned*>(smem + sig_bytes);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sig_bytes + z_bytes);
   // records of rows whose fold went complex, two per lane and warp (only the launch that owns the digest has room for them)
-  RowRec* srec = reinterpret_cast<RowRec*>(smem + sig_bytes + z_bytes + 16);
+  RowRec* srec = reinterpret_cast<RowRec*>(smem + sig_bytes + z_bytes + 16 + (CHAINED ? SMP_PF_BYTES : 0));
+  // CHAINED: this lane's slot 0 of the prefetch ring for incoming partial sums
+  unsigned pf_a = smem_u32(smem + sig_bytes + z_bytes + 16) + (unsigned)(warp * (SMP_PF * 256) + lane * 8);
+  asm volatile("" : "+r"(pf_a));
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
@@ -2138,8 +2156,29 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
     folds_init(sx, foldB);
     folds_init(sy, foldB);
     int j = r_first;
+    const bool pf = CHAINED && !first && live;  // this lane continues partial sums of the preceding chunk
+    int jreq = r0;                              // next end codon whose partial sum this lane has to request
+    // One request = one commit group; a request past the last end codon re-reads the last entry into a slot nobody reads, so
+    // that "at most two groups pending" always means "the entries of j and j + 1 have arrived".
+    auto pf_issue = [&](int jtop) {
+      if (jreq < jtop + SMP_PF) {
+        cp_async8(pf_a + (unsigned)(jreq & (SMP_PF - 1)) * 256u, pp + (size_t)min(jreq, sites - 1) * 32);
+        cp_async_commit();
+        jreq++;
+      }
+    };
+    if (pf) {
+      pf_issue(j);
+      pf_issue(j);
+    }
 #pragma unroll 1
     while (j < sites) {
+      if (pf) {
+        // top-up: an iteration consumes one or two end codons, two requests keep SMP_PF of them in flight
+        pf_issue(j);
+        pf_issue(j);
+        cp_async_wait<SMP_PF - 2>();
+      }
       float svA[RS];
       const unsigned zA = zs[j];
       smp_load_row<NK>(sig_a + j * ROW_BYTES, zA, svA);
@@ -2148,7 +2187,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
         // (the state stays exactly (0,0,0), the sums 0, and the fold ignores a sum of 0)
         const bool mx = j >= r0, my = j >= r0 + 1;
         float2 sin = make_float2(0.0f, 0.0f);
-        if (CHAINED && !first && mx) sin = pp[(size_t)j * 32];
+        if (pf && mx) sin = lds_f2(pf_a + (unsigned)(j & (SMP_PF - 1)) * 256u);
         if (CHAINED && !first && !my) sin.y = 0.0f;
         const float2 sum = reg_update_diag<NK, CHAINED>(S0, S1, S2, svA, mx, my, Delta, Omega, omega, sin);
         if (CHAINED && !last) {
@@ -2165,9 +2204,9 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
           float svB[RS];
           smp_load_row<NK>(sig_a + (j + 1) * ROW_BYTES, zB, svB);
           float2 sumA, sumB, sinA = make_float2(0.0f, 0.0f), sinB = make_float2(0.0f, 0.0f);
-          if (CHAINED && !first && live) {
-            sinA = pp[(size_t)j * 32];
-            sinB = pp[(size_t)(j + 1) * 32];
+          if (pf) {
+            sinA = lds_f2(pf_a + (unsigned)(j & (SMP_PF - 1)) * 256u);
+            sinB = lds_f2(pf_a + (unsigned)((j + 1) & (SMP_PF - 1)) * 256u);
           }
           reg_pair_fast<NK, CHAINED>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
           if (CHAINED && !last) {
@@ -2183,7 +2222,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
         }
       }
       float2 sin = make_float2(0.0f, 0.0f);
-      if (CHAINED && !first && live) sin = pp[(size_t)j * 32];
+      if (pf) sin = lds_f2(pf_a + (unsigned)(j & (SMP_PF - 1)) * 256u);
       const float2 sum = reg_update<NK, CHAINED>(S0, S1, S2, svA, j < r0 + 2, j, r0, Delta, Omega, omega, sin);
       if (CHAINED && !last) {
         if (live) pp[(size_t)j * 32] = sum;

@@ -1202,6 +1202,7 @@ static int smp_warps(rc_ctx* ctx, size_t smem_table, bool with_fold) {
 template <int NK>
 static int launch_dp_smpc_nk(rc_batch* b, int chunk, bool last, bool seg, const CtaDesc* d_ctas, size_t ncta, size_t smem) {
   rc_ctx* ctx = b->ctx;
+  if (!seg) smem += SMP_PF_BYTES;  // prefetch ring of the incoming partial sums (k_dp_smp<., true>)
   const int nw = smp_warps(ctx, smem, last);
   if (last) smem += (size_t)nw * 64 * sizeof(RowRec);
   if (seg) {
