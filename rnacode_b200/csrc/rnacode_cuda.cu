@@ -64,6 +64,18 @@ static void ctx_fail(rc_ctx* ctx, const std::string& msg) {
   if (ctx) ctx->err = msg;
 }
 
+// Dynamic shared memory above 48 KB has to be allowed per kernel.  The attribute belongs to the (device, function) pair, not to
+// the caller: two host threads that run batches on the same device must not race between "allow my size" and "launch", so
+// every kernel is always allowed the device's opt-in maximum (less its static shared memory) -- the same value from every
+// thread.
+template <class K>
+static cudaError_t allow_max_smem(rc_ctx* ctx, K kernel) {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - (int)fa.sharedSizeBytes);
+}
+
 static void* ctx_alloc(rc_ctx* ctx, size_t bytes) {
   bytes = (std::max<size_t>(bytes, 256) + 255) / 256 * 256;
   // best fit among cached blocks that are not wastefully large
@@ -1137,7 +1149,7 @@ static int launch_dp(rc_batch* b, const CtaDesc* d_ctas, size_t ncta, int maxNK,
     return RC_ERR_ARG;
   }
   const size_t smem = nw * per_warp;
-  RC_CUDA(cudaFuncSetAttribute(k_dp<R, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RC_CUDA(allow_max_smem(ctx, k_dp<R, DENSE>));
   k_dp<R, DENSE><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
                                                                       b->d_recs, b->d_dense, b->prm, (int)ctx->band_slots,
                                                                       maxNK, maxZs, nst);
@@ -1206,12 +1218,12 @@ static int launch_dp_smpc_nk(rc_batch* b, int chunk, bool last, bool seg, const 
   const int nw = smp_warps(ctx, smem, last);
   if (last) smem += (size_t)nw * 64 * sizeof(RowRec);
   if (seg) {
-    RC_CUDA(cudaFuncSetAttribute(k_dp_smps<NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RC_CUDA(allow_max_smem(ctx, k_dp_smps<NK, true>));
     k_dp_smps<NK, true><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
                                                                              b->d_recs, b->prm, (int)ctx->band_slots, chunk,
                                                                              b->d_partial);
   } else {
-    RC_CUDA(cudaFuncSetAttribute(k_dp_smp<NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RC_CUDA(allow_max_smem(ctx, k_dp_smp<NK, true>));
     k_dp_smp<NK, true><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
                                                                             b->d_recs, b->prm, (int)ctx->band_slots, chunk,
                                                                             b->d_partial);
@@ -1245,11 +1257,11 @@ static int launch_dp_smp_nk(rc_batch* b, bool seg, const CtaDesc* d_ctas, size_t
   const int nw = smp_warps(ctx, smem, true);
   smem += (size_t)nw * 64 * sizeof(RowRec);
   if (seg) {
-    RC_CUDA(cudaFuncSetAttribute(k_dp_smps<NK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RC_CUDA(allow_max_smem(ctx, k_dp_smps<NK, false>));
     k_dp_smps<NK, false><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
                                                                               b->d_recs, b->prm, (int)ctx->band_slots, 0, nullptr);
   } else {
-    RC_CUDA(cudaFuncSetAttribute(k_dp_smp<NK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RC_CUDA(allow_max_smem(ctx, k_dp_smp<NK, false>));
     k_dp_smp<NK, false><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
                                                                            b->d_recs, b->prm, (int)ctx->band_slots, 0, nullptr);
   }
@@ -1289,7 +1301,7 @@ static int launch_dp_smpf_nk(rc_batch* b, int chunk, bool last, const CtaDesc* d
   (void)last;
   const int nw = smp_warps(ctx, smem, true);
   smem += (size_t)nw * 64 * sizeof(RowRec);  // the carve-up always has the records at the end (SmpfCfg::off_rec)
-  RC_CUDA(cudaFuncSetAttribute(k_dp_smpf<NK, CHAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RC_CUDA(allow_max_smem(ctx, k_dp_smpf<NK, CHAINED>));
   k_dp_smpf<NK, CHAINED><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_p2, b->d_p2f, b->d_cls,
                                                                          b->d_cols0, b->d_scores, b->d_ptab2, b->d_z, b->d_recs,
                                                                          b->prm, (int)ctx->band_slots, chunk, b->d_partial);
@@ -1354,11 +1366,11 @@ static int launch_dp_chain_nk(rc_batch* b, int W, const CtaDesc* d_ctas, size_t 
       return RC_ERR_STATE;
     }
     if (np == 1) {
-      RC_CUDA(cudaFuncSetAttribute(k_dp_chain<NKW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RC_CUDA(allow_max_smem(ctx, k_dp_chain<NKW, false>));
       k_dp_chain<NKW, false><<<(unsigned)ncta, wp * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_recs,
                                                                             b->prm, (int)ctx->band_slots, 0, nullptr);
     } else {
-      RC_CUDA(cudaFuncSetAttribute(k_dp_chain<NKW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RC_CUDA(allow_max_smem(ctx, k_dp_chain<NKW, true>));
       k_dp_chain<NKW, true><<<(unsigned)ncta, wp * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_recs,
                                                                            b->prm, (int)ctx->band_slots, c_lo, b->d_partial);
     }
@@ -1543,7 +1555,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
       const int pitch_max = b->max_fused_cols + 16;
       const int stage = std::max(32 * pitch_max, std::min(P2_STAGE_BYTES, 32 * pitch_max * b->max_fused_N));
       const size_t p2_smem = (size_t)2 * max_L * sizeof(int) + (size_t)stage;
-      RC_CUDA(cudaFuncSetAttribute(k_pack2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem));
+      RC_CUDA(allow_max_smem(ctx, k_pack2));
       k_pack2<<<g2, 256, p2_smem, st>>>(b->d_blocks, b->d_cls, b->d_cols0, b->d_p2, b->d_p2f, max_L, stage);
       RC_CUDA(cudaGetLastError());
       b->stats.launches++;
@@ -1599,7 +1611,7 @@ extern "C" int rc_batch_run(rc_batch* b) {
         const int npc = (ch.max_smp_npos + SIG_PCH - 1) / SIG_PCH;
         dim3 g2((unsigned)ch.nitems, (unsigned)((ch.max_ninst + 31) / 32), (unsigned)(npc * 2 * nqz));
         constexpr int SIGMA_SMP_DYN_SMEM = 4 * 32 * SIG_PITCH;  // species staging; static + dynamic exceed 48 KB
-        RC_CUDA(cudaFuncSetAttribute(k_sigma_smp, cudaFuncAttributeMaxDynamicSharedMemorySize, SIGMA_SMP_DYN_SMEM));
+        RC_CUDA(allow_max_smem(ctx, k_sigma_smp));
         k_sigma_smp<<<g2, 256, SIGMA_SMP_DYN_SMEM, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores,
                                                          b->d_ptab, b->d_sigma, nqz);
         RC_CUDA(cudaGetLastError());
