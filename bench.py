@@ -840,7 +840,7 @@ def ours(args):
         side = {}
         for name in SIDE_WORKLOADS:
             try:
-                s = B.measure(name, steps=5, warmup=3, host_samples=False, e2e_steps=3)
+                s = B.measure(name, steps=5, warmup=3, host_samples=False, e2e_steps=4, pipelined=True)
                 r = B.roofline(s, nominal_peak, issue_measured, sm_count, sm_max)
                 ms = s["total_ms"] / s["steps"]
                 side[name] = {"workload": s["desc"], "blocks": len(s["blocks"]), "n_samples": s["n"], "cells_per_step": s["cells"],
@@ -848,10 +848,13 @@ def ours(args):
                               "blocks_per_s": len(s["blocks"]) / (ms * 1e-3), "stage_ms_per_step": s["stage_ms"],
                               "roofline_frac": r["frac"], "roofline_frac_blended": r["frac_blended"],
                               "frameshift_fraction_g": r["frameshift_fraction_g"], "gpu_launches": int(s["launches"]),
-                              "e2e": {"value": s["cells"] / (s["e2e_ms"] / s["e2e_steps"] * 1e-3), "unit": UNIT,
-                                      "ms_per_step": s["e2e_ms"] / s["e2e_steps"], "h2d_bytes_per_step": s["h2d"],
+                              "e2e": {"value": s["cells"] / (s["e2e_pipe_ms"] / s["e2e_steps"] * 1e-3), "unit": UNIT,
+                                      "ms_per_step": s["e2e_pipe_ms"] / s["e2e_steps"], "h2d_bytes_per_step": s["h2d"],
                                       "d2h_bytes_per_step": s["d2h"],
-                                      "note": "C ABI from host buffers: native rows, score tables, trees, seeds; null alignments drawn on the GPU"},
+                                      "note": "C ABI from host buffers: native rows, score tables, trees, seeds; null alignments drawn "
+                                              "on the GPU; two host threads / contexts take the steps alternately (as in the headline's e2e)",
+                                      "serial": {"value": s["cells"] / (s["e2e_ms"] / s["e2e_steps"] * 1e-3),
+                                                 "ms_per_step": s["e2e_ms"] / s["e2e_steps"]}},
                               "null_alignments": "drawn on the GPU inside the step (k_evolve, exact MT19937 mode)"}
                 del s
             except Exception as e:  # a side workload must not take the headline down

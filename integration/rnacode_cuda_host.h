@@ -80,17 +80,42 @@ static rc_params current_params(void) {
   return p;
 }
 
+/* Row of the sorted null alignment each tree tip ends up in.  tree2aln (src/treeSimulate.c:254-283) lists the simulated rows in
+ * tip order under the names of the tree, and sortAln (src/misc.c:150-171) brings them into input order with a double loop of
+ * swaps that never stops at the first match -- for the usual one-to-one names that is the permutation "tip -> row of that name",
+ * and for duplicate or unmatched names it still leaves SOME arrangement, which is what the reference then scores.  The same
+ * swaps on (name, tip index) pairs reproduce that arrangement for every input.  row_of_tip has tree->numTips entries. */
+static void sorted_rows_of_tips(TTree *tree, const struct aln *alignment[], int N, int *row_of_tip) {
+  const int T = tree->numTips;
+  const char **nm = (const char **)malloc(sizeof(char *) * (size_t)(T > 0 ? T : 1));
+  int *src = (int *)malloc(sizeof(int) * (size_t)(T > 0 ? T : 1));
+  int i, j;
+  for (j = 0; j < T; j++) {
+    nm[j] = tree->names[j];
+    src[j] = j;
+  }
+  for (i = 0; i < N && i < T; i++)
+    for (j = 0; j < T; j++)
+      if (strcmp(alignment[i]->name, nm[j]) == 0) {
+        const char *tn = nm[j];
+        const int ts = src[j];
+        nm[j] = nm[i];
+        src[j] = src[i];
+        nm[i] = tn;
+        src[i] = ts;
+      }
+  for (i = 0; i < T; i++) row_of_tip[src[i]] = i < N ? i : -1;
+  free(nm);
+  free(src);
+}
+
 /* The tree flattened in the order EvolveSequences visits its nodes (seqgen/evolve.c:400-433): root, subtree of
  * branch1, of branch2 and, for the unrooted trees PhyML writes, of branch0.  cum = what MutateSequence would pass to
  * SetState for the branch above the node (SetMatrix(matrix[0], length0 * 1.0), NoRates, seqgen/evolve.c:291-292). */
-static void flatten_node(TTree *tree, TNode *node, int parent, const struct aln *alignment[], int N, int *n, int *par,
-                         int *row, double *cum) {
+static void flatten_rec(TTree *tree, TNode *node, int parent, const int *row_of_tip, int *n, int *par, int *row, double *cum) {
   int me = (*n)++, k;
   par[me] = parent;
-  row[me] = -1;
-  if (node->tipNo != -1)
-    for (k = 0; k < N; k++)
-      if (strcmp(alignment[k]->name, tree->names[node->tipNo]) == 0) row[me] = k; /* sortAln, src/misc.c:150-171 */
+  row[me] = node->tipNo != -1 ? row_of_tip[node->tipNo] : -1;
   if (parent < 0) {
     for (k = 0; k < 16; k++) cum[k] = 0.0;
     for (k = 0; k < 4; k++) cum[k] = addFreq[k]; /* RandomSequence draws from the cumulative frequencies */
@@ -98,10 +123,17 @@ static void flatten_node(TTree *tree, TNode *node, int parent, const struct aln 
     SetMatrix(cum + (size_t)me * 16, node->length0 * 1.0);
   }
   if (node->tipNo == -1) {
-    flatten_node(tree, node->branch1, me, alignment, N, n, par, row, cum);
-    flatten_node(tree, node->branch2, me, alignment, N, n, par, row, cum);
-    if (parent < 0 && !tree->rooted) flatten_node(tree, node->branch0, me, alignment, N, n, par, row, cum);
+    flatten_rec(tree, node->branch1, me, row_of_tip, n, par, row, cum);
+    flatten_rec(tree, node->branch2, me, row_of_tip, n, par, row, cum);
+    if (parent < 0 && !tree->rooted) flatten_rec(tree, node->branch0, me, row_of_tip, n, par, row, cum);
   }
+}
+static void flatten_node(TTree *tree, TNode *node, int parent, const struct aln *alignment[], int N, int *n, int *par,
+                         int *row, double *cum) {
+  int *row_of_tip = (int *)malloc(sizeof(int) * (size_t)(tree->numTips > 0 ? tree->numTips : 1));
+  sorted_rows_of_tips(tree, alignment, N, row_of_tip);
+  flatten_rec(tree, node, parent, row_of_tip, n, par, row, cum);
+  free(row_of_tip);
 }
 
 /* seq-gen's model set-up as simulateTree does it before evolving (src/treeSimulate.c:59-93), without evolving */

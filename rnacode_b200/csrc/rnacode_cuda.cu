@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rc_kernels.cuh"
@@ -168,6 +169,7 @@ struct EventPair {
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr size_t MAX_ITEM_INST = 32768;  // instances per item (a multiple of 32): -n 100000 on tiny blocks must not overflow gridDim.y
 
 int class_of(const BlockDev& bd) {
   if (bd.layout == 3) return CHAIN_CLASS0 + (bd.nchunk - 2) * CHAIN_NKW_SPAN + (bd.nkw - CHAIN_NKW_MIN);
@@ -815,6 +817,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     int inst = sg.inst0;
     while (inst < sg.inst1) {
       size_t room = budget > cur_bytes ? (budget - cur_bytes) / bytes_per_inst : 0;
+      room = std::min<size_t>(room, MAX_ITEM_INST);  // grids carry (instances of an item) * 6 / warps in gridDim.y (<= 65535)
       if (room == 0) {
         if (cur.nitems == 0) room = 1;  // a single instance always goes through
         else { close_chunk(); continue; }
@@ -953,7 +956,18 @@ static unsigned threshold_of(double P) {
   return (unsigned)u;
 }
 
+// deferred: (offset into evo_thr, cumulative probabilities, count) of thresholds still to be computed -- rc_batch_set_evolve_many
+// converts the tables of all its blocks on several host threads
+struct ThrJob { size_t off; const double* cum; size_t n; };
+static int set_evolve_impl(rc_batch* b, int block, const rc_tree_desc* tree, const unsigned int* seeds, int rng,
+                           std::vector<ThrJob>* deferred);
+
 extern "C" int rc_batch_set_evolve(rc_batch* b, int block, const rc_tree_desc* tree, const unsigned int* seeds, int rng) {
+  return set_evolve_impl(b, block, tree, seeds, rng, nullptr);
+}
+
+static int set_evolve_impl(rc_batch* b, int block, const rc_tree_desc* tree, const unsigned int* seeds, int rng,
+                           std::vector<ThrJob>* deferred) {
   if (!b) return RC_ERR_ARG;
   rc_ctx* ctx = b->ctx;
   if (block < 0 || block >= b->n_blocks || !tree || !seeds || tree->n_nodes < 2 || !tree->parent || !tree->row || !tree->cum ||
@@ -993,7 +1007,12 @@ extern "C" int rc_batch_set_evolve(rc_batch* b, int block, const rc_tree_desc* t
     b->evo_nodes.push_back(row);
     b->evo_nodes.push_back(row >= 0 ? -1 : n_internal++);
     b->evo_nodes.push_back(0);
-    for (int k = 0; k < 16; k++) b->evo_thr.push_back(threshold_of(tree->cum[(size_t)n * 16 + k]));
+    if (!deferred)
+      for (int k = 0; k < 16; k++) b->evo_thr.push_back(threshold_of(tree->cum[(size_t)n * 16 + k]));
+  }
+  if (deferred) {
+    deferred->push_back(ThrJob{b->evo_thr.size(), tree->cum, (size_t)tree->n_nodes * 16});
+    b->evo_thr.resize(b->evo_thr.size() + (size_t)tree->n_nodes * 16);
   }
   for (int r = 0; r < bd.N; r++)
     if (!seen[r]) {
@@ -1017,9 +1036,29 @@ extern "C" int rc_batch_set_evolve_many(rc_batch* b, int first, int n, const rc_
     ctx_fail(b->ctx, "rc_batch_set_evolve_many: bad argument");
     return RC_ERR_ARG;
   }
+  std::vector<ThrJob> jobs;
+  jobs.reserve(n);
   for (int i = 0; i < n; i++) {
-    const int r = rc_batch_set_evolve(b, first + i, &trees[i], seeds[i], rng);
+    const int r = set_evolve_impl(b, first + i, &trees[i], seeds[i], rng, &jobs);
     if (r != RC_OK) return r;
+  }
+  // the integer thresholds of all branches (16 per node, a few double operations each): 3 M of them for 10 000 ten-species blocks,
+  // spread over the host's cores
+  size_t total = 0;
+  for (const ThrJob& j : jobs) total += j.n;
+  unsigned* thr = b->evo_thr.data();
+  auto work = [&](size_t j0, size_t j1) {
+    for (size_t q = j0; q < j1; q++)
+      for (size_t k = 0; k < jobs[q].n; k++) thr[jobs[q].off + k] = threshold_of(jobs[q].cum[k]);
+  };
+  const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  const size_t nt = total >= 65536 ? std::min<size_t>(hw, jobs.size()) : 1;
+  if (nt <= 1) {
+    work(0, jobs.size());
+  } else {
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++) th.emplace_back(work, jobs.size() * t / nt, jobs.size() * (t + 1) / nt);
+    for (std::thread& t : th) t.join();
   }
   return RC_OK;
 }

@@ -79,6 +79,20 @@ EPS_CASES = (("coding.aln", ["--tabular"]), ("coding.maf", ["--gtf"]),
              ("genomic-preprocessed.maf", ["--tabular", "-n", "20", "--eps-cutoff", "0.9"]))
 
 
+def dupnames_maf(ex, path):
+    """examples/coding.maf with its second row renamed to the first row's name: the reference still scores such a block
+    (sortAln's swaps, src/misc.c:150-171, leave an arrangement of the simulated rows), and so must the drop-ins."""
+    lines = open(os.path.join(ex, "coding.maf")).read().split("\n")
+    srows = [i for i, ln in enumerate(lines) if ln.startswith("s ")]
+    first = lines[srows[0]].split()[1]
+    second = lines[srows[1]].split()[1]
+    lines[srows[1]] = lines[srows[1]].replace(second, first.ljust(len(second)), 1) if len(first) <= len(second) else \
+        lines[srows[1]].replace(second, first, 1)
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines))
+    return path
+
+
 def eps_golden(ex):
     """--eps plots of the unmodified reference (deterministic seeds): stdout and the SHA-256 of every hss-<n>.eps."""
     import hashlib
@@ -172,6 +186,9 @@ def main():
     env = dict(os.environ, RNACODE_SEED="1")
     cli["synthetic:mixed --tabular -n 30"] = subprocess.run([DET, "--tabular", "-n", "30", p], check=True, capture_output=True,
                                                             env=env).stdout.decode()
+    p = dupnames_maf(ex, os.path.join(TMP, "dupnames.maf"))
+    cli["synthetic:dupnames --tabular -n 20"] = subprocess.run([DET, "--tabular", "-n", "20", p], check=True, capture_output=True,
+                                                               env=env).stdout.decode()
     long_cases(ex, cli)
     save("cli_outputs", cli)
     save("eps_outputs", eps_golden(ex))

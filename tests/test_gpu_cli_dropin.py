@@ -30,6 +30,11 @@ def _input(fname, tmp_path):
         p = os.path.join(str(tmp_path), "synth_mixed.maf")
         synth.to_maf(make_golden.mixed_blocks(), p)
         return p
+    if fname == "synthetic:dupnames":
+        import sys
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import make_golden
+        return make_golden.dupnames_maf(EXAMPLES, os.path.join(str(tmp_path), "dupnames.maf"))
     return os.path.join(EXAMPLES, fname)
 
 
