@@ -2029,6 +2029,22 @@ __device__ __forceinline__ void folds_single(RowFoldS& fx, RowFoldS& fy, float2 
 // share it and walk the start-codon pairs (long and short rows paired up for balance).  State handling,
 // packed FADD2 arithmetic, float order and the getHSS digest are those of k_dp_reg.
 // ---------------------------------------------------------------------------------------------
+// shared-memory loads by 32-bit shared address (the table phase of k_dp_smpf does all its addressing in 32 bits)
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
 template <int NK>
 __device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv)[RegCfg<NK>::RS]) {
   constexpr int RSB = (NK + 3) / 4 * 4;
@@ -2118,8 +2134,8 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
   __syncthreads();
   mbar_wait(bar, 0);
 
-  unsigned sig_a = smem_u32(smem) + il * 16;
-  asm volatile("" : "+r"(sig_a));
+  unsigned sig_a = smem_u32(smem) + il * 16, zs_a = smem_u32(zs);
+  asm volatile("" : "+r"(sig_a), "+r"(zs_a));
   const float Delta = prm.Delta, Omega = prm.Omega;
   float omega = prm.omega;
   asm volatile("" : "+f"(omega));
@@ -2180,7 +2196,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
         cp_async_wait<SMP_PF - 2>();
       }
       float svA[RS];
-      const unsigned zA = zs[j];
+      const unsigned zA = lds_u32(zs_a + 4u * (unsigned)j);
       smp_load_row<NK>(sig_a + j * ROW_BYTES, zA, svA);
       if (R > 1 && j < j_steady) {
         // folded group, rows still starting: one end codon at a time, every addend masked per lane until its row starts
@@ -2199,7 +2215,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
         continue;
       }
       if (j >= j_steady && j + 1 < sites) {
-        const unsigned zB = zs[j + 1];
+        const unsigned zB = lds_u32(zs_a + 4u * (unsigned)j + 4u);
         if ((zA | zB) == 0u) {
           float svB[RS];
           smp_load_row<NK>(sig_a + (j + 1) * ROW_BYTES, zB, svB);
@@ -2468,22 +2484,6 @@ struct SmpfCfg {
   }
 };
 
-// shared-memory loads by 32-bit shared address (the table phase of k_dp_smpf does all its addressing in 32 bits)
-__device__ __forceinline__ unsigned lds_u32(unsigned a) {
-  unsigned v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ unsigned lds_u16(unsigned a) {
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ float lds_f32(unsigned a) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-  return v;
-}
 // six adjacent bits of a packed row (see k_pack2): the codon whose first position sits at bit `sh` of the word at shared
 // address `a`; two: the codon runs over into the next word (128 bytes on).  sh and two are warp-uniform.
 __device__ __forceinline__ unsigned p2_codon(unsigned a, unsigned sh, bool two) {
@@ -2634,8 +2634,8 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
   __syncthreads();  // the table is complete
 
   // ---- DP phase: k_dp_smp's loop with the fold in species-sum space ------------------------------------------------------
-  unsigned sig_a = smem_u32(smem) + lane * 16;
-  asm volatile("" : "+r"(sig_a));
+  unsigned sig_a = smem_u32(smem) + lane * 16, zs_a = smem_u32(zs);
+  asm volatile("" : "+r"(sig_a), "+r"(zs_a));
   const float Delta = prm.Delta, Omega = prm.Omega;
   float omega = prm.omega;
   asm volatile("" : "+f"(omega));
@@ -2669,7 +2669,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
 #pragma unroll 1
     while (j < sites) {
       float svA[RS];
-      const unsigned zA = zs[j];
+      const unsigned zA = lds_u32(zs_a + 4u * (unsigned)j);
       smp_load_row<NK>(sig_a + j * ROW_BYTES, zA, svA);
       if (R > 1 && j < j_steady) {
         // folded group, rows still starting: one end codon at a time, every addend masked per lane until its row starts
@@ -2680,7 +2680,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
         continue;
       }
       if (j >= j_steady && j + 1 < sites) {
-        const unsigned zB = zs[j + 1];
+        const unsigned zB = lds_u32(zs_a + 4u * (unsigned)j + 4u);
         if ((zA | zB) == 0u) {
           float svB[RS];
           smp_load_row<NK>(sig_a + (j + 1) * ROW_BYTES, zB, svB);
@@ -2996,9 +2996,11 @@ __device__ __forceinline__ unsigned mt_temper(unsigned y) {
   return y;
 }
 
-__device__ __forceinline__ void mt_twist(unsigned* mt, int lane) {
+// need: how many words of the new batch will ever be read (the sample's last batch is only regenerated that far: word kk of the
+// new batch depends on the OLD words kk, kk+1, kk+397 or the new word kk-227 -- never on a later new word)
+__device__ __forceinline__ void mt_twist(unsigned* mt, int lane, int need = 624) {
 #pragma unroll 1
-  for (int base = 0; base < 624; base += 32) {
+  for (int base = 0; base < need; base += 32) {
     const int kk = base + lane;
     unsigned a = 0, b = 0, c = 0;
     if (kk < 624) {
@@ -3043,17 +3045,103 @@ constexpr int EVO_WARPS = 4;
 constexpr int EVO_SPW = RC_EVO_SPW;  // most samples per task: their MT19937 states are seeded side by side, one lane each (the host
                                      // takes fewer per task when a batch has too few samples to fill the GPU with tasks of eight)
 
+// The next `cnt` (<= 128) outputs of the sample's generator, four consecutive ones per lane (lane l: outputs 4l .. 4l+3 of the
+// pass); the state is regenerated when the pass crosses the end of the current 624-word batch (warp-uniform).
+// left: outputs the sample still needs from the batches not yet generated.
+__device__ __forceinline__ void evo_draw4(unsigned* mt, int& pos, int& left, int cnt, int lane, unsigned (&u)[4]) {
+  const int off = 4 * lane, idx = pos + off;
+  unsigned v[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) v[t] = (off + t < cnt && idx + t < 624) ? mt[idx + t] : 0u;
+  if (pos + cnt > 624) {  // the pass crosses a batch boundary (warp-uniform)
+    __syncwarp();
+    mt_twist(mt, lane, min(624, left));
+    left -= 624;
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+      if (off + t < cnt && idx + t >= 624) v[t] = mt[idx + t - 624];
+    pos -= 624;
+  }
+  pos += cnt;
+#pragma unroll
+  for (int t = 0; t < 4; t++) u[t] = mt_temper(v[t]);
+}
+
+// One null alignment of a SMALL problem: at most 32 tree nodes and 128 * P columns (the production regime: blocks of a dozen
+// species cut to ~200 columns).  A site's states along the tree never leave the lane that owns the site: the states of all
+// nodes of a site are two bits each in one 64-bit register (a child looks its parent's up with a shift), the thresholds of
+// ALL nodes sit in shared memory for the whole task, and nothing is exchanged between lanes except inside the generator --
+// no sequence of an internal node is written anywhere, no per-node table reload, no per-node warp barrier.  The generator's
+// outputs are consumed exactly as in the general path: node by node in evolution order, one per site.
+// s_nd[n] = (parent + 1) | (row + 1) << 8; s_th[n * 4 + parent state] = the node's three thresholds (+ unused fourth).
+constexpr int EVO_SMALL_NODES = 32;
+template <int P>
+__device__ __forceinline__ void evo_sample_small(int rng, int n_nodes, int cols, unsigned* mt, const unsigned* s_nd,
+                                                 const uint4* s_th, unsigned seed, unsigned char* myraw, int lane) {
+  unsigned long long sb[P][4];
+#pragma unroll
+  for (int p = 0; p < P; p++)
+#pragma unroll
+    for (int t = 0; t < 4; t++) sb[p][t] = 0ull;
+  int pos = 624, left = n_nodes * cols;
+  const int off = 4 * lane;
+#pragma unroll 1
+  for (int n = 0; n < n_nodes; n++) {
+    const unsigned ndw = s_nd[n];
+    const int parent = (int)(ndw & 0xffu) - 1, row = (int)(ndw >> 8) - 1;
+    unsigned char* orow = row >= 0 ? myraw + (size_t)row * cols : nullptr;
+    const bool row_aligned = (reinterpret_cast<size_t>(orow) & 3) == 0;  // warp-uniform
+    const unsigned psh = parent >= 0 ? 2u * (unsigned)parent : 0u;
+    const uint4* tn = s_th + 4 * n;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      const int c0 = 128 * p;
+      if (P > 1 && c0 >= cols) break;
+      const int cnt = min(128, cols - c0), site0 = c0 + off;
+      unsigned u[4];
+      if (rng == 0) {
+        evo_draw4(mt, pos, left, cnt, lane, u);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; t++) u[t] = philox_draw(seed, (unsigned)n, (unsigned)(site0 + t));
+      }
+      if (off < cnt) {
+        unsigned ch = 0u;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const unsigned ps = parent >= 0 ? (unsigned)(sb[p][t] >> psh) & 3u : 0u;  // the root draws from row 0 of its table
+          const uint4 tt = tn[ps];
+          const unsigned state = (u[t] > tt.x) + (u[t] > tt.y) + (u[t] > tt.z);
+          sb[p][t] |= (unsigned long long)state << (2 * n);
+          ch |= ((0x54474341u >> (8 * state)) & 0xffu) << (8 * t);  // "ACGT"[state]
+        }
+        if (orow) {
+          if (row_aligned && off + 3 < cnt) {
+            *reinterpret_cast<unsigned*>(orow + site0) = ch;
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+              if (off + t < cnt) orow[site0 + t] = (unsigned char)(ch >> (8 * t));
+          }
+        }
+      }
+    }
+  }
+}
+
 // Persistent warps: warp `wg` of the grid works through the tasks wg, wg + n_warps, ...; a task is EVO_SPW consecutive
 // samples of one block (evo_task0: prefix sums of the tasks per block).  The states of a task are seeded by EVO_SPW lanes in
 // parallel into the warp's private slot of a global scratch (init_genrand is a serial chain of 624 steps: seeding one state
 // per warp wastes 31 lanes, seeding 32 per warp in shared memory would leave room for two warps per SM); each sample then
 // loads its state into the warp's 2.5 KB of shared memory and is drawn with all 32 lanes.
-__global__ void __launch_bounds__(EVO_WARPS * 32)
+__global__ void __launch_bounds__(EVO_WARPS * 32, 4)
     k_evolve(const BlockDev* __restrict__ blocks, const EvoDev* __restrict__ evos, const int* __restrict__ evo_task0, int n_evos,
              const int* __restrict__ nodes, const unsigned* __restrict__ thr, const unsigned* __restrict__ seeds,
              unsigned char* __restrict__ seqs, unsigned char* __restrict__ raw, unsigned* __restrict__ mt_scratch, int spw) {
   __shared__ unsigned s_mt[EVO_WARPS][624];
   __shared__ uint4 s_thr[EVO_WARPS][4];
+  __shared__ uint4 s_tha[EVO_WARPS][EVO_SMALL_NODES * 4];  // small problems: thresholds of all nodes
+  __shared__ unsigned s_nda[EVO_WARPS][EVO_SMALL_NODES];   // ... and their (parent, row)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = blockIdx.x * EVO_WARPS + warp, n_warps = gridDim.x * EVO_WARPS;
   const int total_tasks = evo_task0[n_evos];
@@ -3075,6 +3163,13 @@ __global__ void __launch_bounds__(EVO_WARPS * 32)
     const int cols = bd.cols;
     const int* nd = nodes + ev.node_off;
     const unsigned* th = thr + ev.thr_off;
+    const bool small = ev.n_nodes <= EVO_SMALL_NODES && cols <= 256 && bd.N <= 255;  // warp-uniform (evo_sample_small)
+    if (small) {
+      __syncwarp();  // the previous task's samples are done with the tables
+      for (int i = lane; i < ev.n_nodes * 16; i += 32) reinterpret_cast<unsigned*>(&s_tha[warp][0])[i] = th[i];
+      if (lane < ev.n_nodes) s_nda[warp][lane] = (unsigned)(nd[4 * lane] + 1) | ((unsigned)(nd[4 * lane + 1] + 1) << 8);
+      __syncwarp();
+    }
     if (ev.rng == 0) {
       // init_genrand (seqgen/twister.c:73-86): lane q seeds the state of sample s_base + q
       if (lane < n_mine) {
@@ -3098,7 +3193,14 @@ __global__ void __launch_bounds__(EVO_WARPS * 32)
         for (int i = lane; i < 624; i += 32) mt[i] = slot[(size_t)q * 624 + i];
         __syncwarp();
       }
+      if (small) {
+        if (cols <= 128) evo_sample_small<1>(ev.rng, ev.n_nodes, cols, mt, s_nda[warp], s_tha[warp], seed, myraw, lane);
+        else evo_sample_small<2>(ev.rng, ev.n_nodes, cols, mt, s_nda[warp], s_tha[warp], seed, myraw, lane);
+        __syncwarp();  // the state in shared memory is free for the next sample
+        continue;
+      }
       int pos = 624;  // next unread word of the current 624-word batch
+      int left = ev.n_nodes * cols;  // outputs still to come from batches not yet generated
       for (int n = 0; n < ev.n_nodes; n++) {
         const int parent = nd[4 * n], row = nd[4 * n + 1], slot_n = nd[4 * n + 2];
         const unsigned* pseq = parent >= 0 ? reinterpret_cast<const unsigned*>(myseq + (size_t)nd[4 * parent + 2] * cols4) : nullptr;
@@ -3114,21 +3216,7 @@ __global__ void __launch_bounds__(EVO_WARPS * 32)
           const int off = 4 * lane, site0 = c0 + off;
           unsigned u[4];
           if (ev.rng == 0) {
-            const int idx = pos + off;
-            unsigned v[4];
-#pragma unroll
-            for (int t = 0; t < 4; t++) v[t] = (off + t < cnt && idx + t < 624) ? mt[idx + t] : 0u;
-            if (pos + cnt > 624) {  // the pass crosses a batch boundary (warp-uniform)
-              __syncwarp();
-              mt_twist(mt, lane);
-#pragma unroll
-              for (int t = 0; t < 4; t++)
-                if (off + t < cnt && idx + t >= 624) v[t] = mt[idx + t - 624];
-              pos -= 624;
-            }
-            pos += cnt;
-#pragma unroll
-            for (int t = 0; t < 4; t++) u[t] = mt_temper(v[t]);
+            evo_draw4(mt, pos, left, cnt, lane, u);
           } else {
 #pragma unroll
             for (int t = 0; t < 4; t++) u[t] = philox_draw(seed, (unsigned)n, (unsigned)(site0 + t));
