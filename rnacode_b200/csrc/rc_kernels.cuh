@@ -48,6 +48,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void cp_async4(unsigned dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ float max3f(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -150,8 +164,14 @@ __global__ void __launch_bounds__(256) k_pack2(const BlockDev* __restrict__ bloc
         const unsigned shift = (unsigned)roff & 3u;
         const unsigned* src4 = reinterpret_cast<const unsigned*>(cls + bd.cls_off + (size_t)(inst < bd.n_inst ? inst : 0) * bd.inst_stride + roff - shift);
         unsigned* dst4 = reinterpret_cast<unsigned*>(s_row + (size_t)pr * pitch);
-        for (int w = lane; w < (int)(shift + cols + 3) / 4; w += 32) dst4[w] = inst < bd.n_inst ? src4[w] : 0u;
+        // asynchronous word copies (LDGSTS): nothing waits between the (row, instance) runs of a warp, all of a pass's loads
+        // are in flight together (with ordinary loads every run cost a round trip to memory: 2.5 ms for 10 000 blocks of 10 x 120)
+        for (int w = lane; w < (int)(shift + cols + 3) / 4; w += 32) {
+          if (inst < bd.n_inst) cp_async4(smem_u32(dst4 + w), src4 + w);
+          else dst4[w] = 0u;
+        }
       }
+      cp_async_wait_all();
       __syncthreads();
       // (strand, row, word) triples, one warp each; lane = instance
       for (int task = warp; task < 2 * nr * W; task += 8) {
@@ -2072,15 +2092,6 @@ __device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv
 // its own in shared memory (no registers held while the copy is in flight): one commit group per end codon.
 constexpr int SMP_PF = 4;                                   // end codons in flight per lane
 constexpr int SMP_PF_BYTES = SMP_MAX_WARPS * SMP_PF * 256;  // ring of a CTA: [warp][slot][lane] float2
-__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 template <int NK, bool CHAINED>
 __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 : 1)
     k_dp_smp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
@@ -2997,7 +3008,9 @@ __device__ __forceinline__ unsigned mt_temper(unsigned y) {
 }
 
 // need: how many words of the new batch will ever be read (the sample's last batch is only regenerated that far: word kk of the
-// new batch depends on the OLD words kk, kk+1, kk+397 or the new word kk-227 -- never on a later new word)
+// new batch depends on the OLD words kk, kk+1, kk+397 or the new word kk-227 -- never on a later new word).
+// (Measured and rejected: three chunks of 224 independent words, seven per lane, two barriers per chunk instead of two per 32
+// words -- 10.6 against 9.1 ms of pack + evolve on 10 000 blocks of 10 x 120.)
 __device__ __forceinline__ void mt_twist(unsigned* mt, int lane, int need = 624) {
 #pragma unroll 1
   for (int base = 0; base < need; base += 32) {
