@@ -174,8 +174,17 @@ __global__ void __launch_bounds__(256) k_pack2(const BlockDev* __restrict__ bloc
       cp_async_wait_all();
       __syncthreads();
       // (strand, row, word) triples, one warp each; lane = instance
-      for (int task = warp; task < 2 * nr * W; task += 8) {
-        const int w = task % W, rr = (task / W) % nr, s = task / (W * nr);
+      // (the triple of a task is carried along instead of divided out: the divisions were a third of the kernel's instructions)
+      int w = warp, rr = 0, s = 0;
+      while (w >= W) {
+        w -= W;
+        if (++rr == nr) { rr = 0; s++; }
+      }
+      for (int task = warp; task < 2 * nr * W; task += 8, w += 8) {
+        while (w >= W) {
+          w -= W;
+          if (++rr == nr) { rr = 0; s++; }
+        }
         const int r = r0 + rr;
         const int sh = s ? 2 : 0;
         const int npos = min(16, L - 16 * w);
