@@ -1695,6 +1695,9 @@ struct ChainCfg {
 #ifndef RC_CHAIN_SINGLE
 #define RC_CHAIN_SINGLE 0
 #endif
+#ifndef RC_CHAIN_MERGE
+#define RC_CHAIN_MERGE 0
+#endif
 template <int NK, bool MULTI>
 __global__ void
 #if RC_CHAIN_MAXREG < 128
@@ -1872,6 +1875,27 @@ __global__ void
           sinB = gp[((size_t)tile * TILE + c + 1) * 32];
         }
         const bool clean = (__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u;
+#if RC_CHAIN_MERGE
+        // One copy of the general update for codons with a frameshift, in diagonal tiles or not (outside them the per-row
+        // masks are simply true), taken twice in a loop: the kernel shrinks from 47 KB to about 32 KB of SASS -- the five warps
+        // of a CTA are in different phases of the loop and `no_instruction` was its largest stall.
+        if (!clean) {
+          const bool P = !diag || j0 + c >= r0, Q = !diag || j0 + c > r0;
+#pragma unroll 1
+          for (int h = 0; h < 2; h++) {
+            float sv[RS];
+#pragma unroll
+            for (int q = 0; q < RS; q++) sv[q] = h ? svB[q] : svA[q];
+            const float2 sum = reg_update_diag<NK, true>(S0, S1, S2, sv, P, h ? P : Q, Delta, Omega, omega, h ? sinB : sinA);
+            if (h) sumB = sum;
+            else sumA = sum;
+          }
+        } else if (!diag) {
+          reg_pair_fast<NK, true>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
+        } else {
+          reg_pair_diag<NK, true>(S0, S1, S2, svA, svB, omega, j0 + c >= r0, j0 + c > r0, sumA, sumB, sinA, sinB);
+        }
+#else
         if (!diag) {
           if (clean) {
             reg_pair_fast<NK, true>(S0, S1, S2, svA, svB, omega, sumA, sumB, sinA, sinB);
@@ -1888,6 +1912,7 @@ __global__ void
             sumB = reg_update_diag<NK, true>(S0, S1, S2, svB, P, P, Delta, Omega, omega, sinB);
           }
         }
+#endif
         reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
         reg_load_row<NK>(a0 + (c + 3) * RS * 4, svB);
         if (!last) {
