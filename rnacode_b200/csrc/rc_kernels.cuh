@@ -2179,8 +2179,8 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
   __syncthreads();
   mbar_wait(bar, 0);
 
-  unsigned sig_a = smem_u32(smem) + il * 16, zs_a = smem_u32(zs);
-  asm volatile("" : "+r"(sig_a), "+r"(zs_a));
+  unsigned sig_a = smem_u32(smem) + il * 16;
+  asm volatile("" : "+r"(sig_a));
   const float Delta = prm.Delta, Omega = prm.Omega;
   float omega = prm.omega;
   asm volatile("" : "+f"(omega));
@@ -2241,7 +2241,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
         cp_async_wait<SMP_PF - 2>();
       }
       float svA[RS];
-      const unsigned zA = lds_u32(zs_a + 4u * (unsigned)j);
+      const unsigned zA = zs[j];
       smp_load_row<NK>(sig_a + j * ROW_BYTES, zA, svA);
       if (R > 1 && j < j_steady) {
         // folded group, rows still starting: one end codon at a time, every addend masked per lane until its row starts
@@ -2260,7 +2260,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
         continue;
       }
       if (j >= j_steady && j + 1 < sites) {
-        const unsigned zB = lds_u32(zs_a + 4u * (unsigned)j + 4u);
+        const unsigned zB = zs[j + 1];
         if ((zA | zB) == 0u) {
           float svB[RS];
           smp_load_row<NK>(sig_a + (j + 1) * ROW_BYTES, zB, svB);
