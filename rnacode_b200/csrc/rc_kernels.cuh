@@ -2126,7 +2126,10 @@ __device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv
 // its own in shared memory (no registers held while the copy is in flight): one commit group per end codon.
 constexpr int SMP_PF = 4;                                   // end codons in flight per lane
 constexpr int SMP_PF_BYTES = SMP_MAX_WARPS * SMP_PF * 256;  // ring of a CTA: [warp][slot][lane] float2
-template <int NK, bool CHAINED>
+// LASTC (chained launches only): the launch of the last chunk, the one that owns the getHSS fold.  A compile-time flag: the
+// launches of the other chunks carry no fold state, which is what keeps the 12-species chunk within the 128 registers that
+// two resident CTAs allow (the kernel is very sensitive to spills in its step loop: one more live register cost 7 %).
+template <int NK, bool CHAINED, bool LASTC = true>
 __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 : 1)
     k_dp_smp(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
              const float* __restrict__ sigma, const unsigned* __restrict__ ztiles, RowRec* __restrict__ recs, Params prm,
@@ -2156,7 +2159,8 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
   const int R = 32 / fold_m, il = lane & (fold_m - 1), rep = lane / fold_m;
   const int inst_l = group * 32 + il;
   const bool valid = il < ninst_g;
-  const bool first = !CHAINED || chunk == 0, last = !CHAINED || chunk == bd.nchunk - 1;
+  const bool first = !CHAINED || chunk == 0;
+  constexpr bool last = !CHAINED || LASTC;
   const int ngrp = (it.ninst + 31) / 32;
 
   const size_t sig_bytes = (size_t)sites * ROW_BYTES;

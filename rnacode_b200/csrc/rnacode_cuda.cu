@@ -1262,10 +1262,17 @@ static int launch_dp_smpc_nk(rc_batch* b, int chunk, bool last, bool seg, const 
                                                                              b->d_recs, b->prm, (int)ctx->band_slots, chunk,
                                                                              b->d_partial);
   } else {
-    RC_CUDA(allow_max_smem(ctx, k_dp_smp<NK, true>));
-    k_dp_smp<NK, true><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
-                                                                            b->d_recs, b->prm, (int)ctx->band_slots, chunk,
-                                                                            b->d_partial);
+    if (last) {
+      RC_CUDA(allow_max_smem(ctx, k_dp_smp<NK, true, true>));
+      k_dp_smp<NK, true, true><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+                                                                                    b->d_recs, b->prm, (int)ctx->band_slots, chunk,
+                                                                                    b->d_partial);
+    } else {
+      RC_CUDA(allow_max_smem(ctx, k_dp_smp<NK, true, false>));
+      k_dp_smp<NK, true, false><<<(unsigned)ncta, nw * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_z,
+                                                                                     b->d_recs, b->prm, (int)ctx->band_slots, chunk,
+                                                                                     b->d_partial);
+    }
   }
   RC_CUDA(cudaGetLastError());
   b->stats.launches++;

@@ -63,10 +63,12 @@ def plan_units(per_aln, blocks, s0, ns, world_size, want_native=True):
     order = sorted(range(len(units)), key=lambda k: (-units[k].cost, k))  # stable: equal costs keep input order
     shards = [[] for _ in range(G)]
     load = [0.0] * G
+    heap = [(0.0, r) for r in range(G)]  # (work so far, device): the least loaded device, lowest index on ties
     for k in order:
-        d = min(range(G), key=lambda r: (load[r], r))
+        _, d = heapq.heappop(heap)
         shards[d].append(units[k])
         load[d] += units[k].cost
+        heapq.heappush(heap, (load[d], d))
     return shards, load
 
 
