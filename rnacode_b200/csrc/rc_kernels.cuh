@@ -1698,7 +1698,11 @@ struct ChainCfg {
 #ifndef RC_CHAIN_MERGE
 #define RC_CHAIN_MERGE 0
 #endif
-template <int NK, bool MULTI>
+// PF / PL (compile-time, per launch): this launch is the FIRST / LAST pass of the alignment's species chunks.  Only the first
+// warp of a later pass reads partial sums from global memory, only the last warp of an earlier pass writes them, only the last
+// warp of the last pass owns the getHSS fold: a pass compiled without the paths it can never take needs fewer registers (the
+// step loop spilled at the 128 that three resident CTAs allow).  MULTI = false: a single pass, PF = PL = true.
+template <int NK, bool MULTI, bool PF = true, bool PL = true>
 __global__ void
 #if RC_CHAIN_MAXREG < 128
     __maxnreg__(RC_CHAIN_MAXREG)
@@ -1729,7 +1733,7 @@ __global__ void
   // resident per SM: the warps of a launch own the chunks c_lo .. c_lo + W - 1, the first warp of a later pass continues
   // the partial sums the previous pass left in global memory, the last warp of an earlier pass leaves them there.
   const int chunk = c_lo + warp;
-  const bool gfirst = !MULTI || chunk == 0, glast = !MULTI || chunk == bd.nchunk - 1;  // ends of the whole species chain
+  const bool gfirst = first && PF, glast = last && PL;  // ends of the whole species chain (chunk == 0 / == bd.nchunk - 1)
   // (MULTI = false: single-pass launch, first == gfirst and last == glast, the global hand-over code compiles away)
 
   unsigned char* ring = smem + (size_t)warp * RING_BYTES;
@@ -1778,7 +1782,7 @@ __global__ void
   const int t_last_diag = (row_base + 32 * R - 1) / TILE;
   // partial sums between passes: [instance][row group][tile from the group's first][end codon][lane] float2
   float2* gp = nullptr;
-  if (MULTI && ((first && !gfirst) || (last && !glast))) {
+  if (MULTI && ((first && !PF) || (last && !PL))) {
     const size_t per_inst = (size_t)ngroups * ntiles - 2 * (size_t)ngroups * (ngroups - 1);  // tiles
     gp = partial + it.part_off[strand][frame] +
          ((size_t)inst_l * per_inst + (size_t)g * ntiles - 2 * (size_t)g * (g - 1) - t0) * (TILE * 32) + lane;  // + tile * TILE * 32
@@ -1790,7 +1794,7 @@ __global__ void
       bulk_g2s(ring + sq * STAGE_BYTES, sig_src + (size_t)(t0 + q) * tile_stride, STAGE_BYTES, &bars[sq]);
     }
   }
-  if (last && glast) {
+  if (PL && last) {
     rec_init(rec0);
     rec_init(rec0 + 1);
     __syncwarp();
@@ -1828,7 +1832,7 @@ __global__ void
         if (!first) {
           sinA = lds_f2(hin + c * 256);
           if (pair) sinB = lds_f2(hin + (c + 1) * 256);
-        } else if (MULTI && !gfirst) {
+        } else if (MULTI && !PF) {
           sinA = gp[((size_t)tile * TILE + c) * 32];
           if (pair) sinB = gp[((size_t)tile * TILE + c + 1) * 32];
         }
@@ -1847,10 +1851,10 @@ __global__ void
         if (!last) {
           sts_f2(hout + c0 * 256, sumA);
           if (pair) sts_f2(hout + (c0 + 1) * 256, sumB);
-        } else if (MULTI && !glast) {
+        } else if (MULTI && !PL) {
           gp[((size_t)tile * TILE + c0) * 32] = sumA;
           if (pair) gp[((size_t)tile * TILE + c0 + 1) * 32] = sumB;
-        } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
+        } else if (PL && fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
           if (sumA.x > 0.0f) lb.x = RC_REG_CHECK(sumA.x, j0 + c0, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
           if (sumA.y > 0.0f) lb.y = RC_REG_CHECK(sumA.y, j0 + c0, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
           if (sumB.x > 0.0f) lb.x = RC_REG_CHECK(sumB.x, j0 + c0 + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
@@ -1870,7 +1874,7 @@ __global__ void
         if (!first) {
           sinA = lds_f2(hin + c * 256);
           sinB = lds_f2(hin + (c + 1) * 256);
-        } else if (MULTI && !gfirst) {
+        } else if (MULTI && !PF) {
           sinA = gp[((size_t)tile * TILE + c) * 32];
           sinB = gp[((size_t)tile * TILE + c + 1) * 32];
         }
@@ -1918,10 +1922,10 @@ __global__ void
         if (!last) {
           sts_f2(hout + c * 256, sumA);
           sts_f2(hout + (c + 1) * 256, sumB);
-        } else if (MULTI && !glast) {
+        } else if (MULTI && !PL) {
           gp[((size_t)tile * TILE + c) * 32] = sumA;
           gp[((size_t)tile * TILE + c + 1) * 32] = sumB;
-        } else if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
+        } else if (PL && fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
           if (sumA.x > 0.0f) lb.x = RC_REG_CHECK(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
           if (sumA.y > 0.0f) lb.y = RC_REG_CHECK(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
           if (sumB.x > 0.0f) lb.x = RC_REG_CHECK(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
@@ -1944,7 +1948,7 @@ __global__ void
       hround++;
     }
   }
-  if (last && glast) {
+  if (PL && last) {
     RowRec* grec = recs + it.rec_off[strand][frame] + (size_t)inst_l * sites + r0;
 #pragma unroll
     for (int t = 0; t < R; t++)

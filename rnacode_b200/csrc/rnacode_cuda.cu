@@ -1411,15 +1411,18 @@ static int launch_dp_chain_nk(rc_batch* b, int W, const CtaDesc* d_ctas, size_t 
       ctx_fail(ctx, "internal: k_dp_chain shared memory exceeds the device limit");
       return RC_ERR_STATE;
     }
-    if (np == 1) {
-      RC_CUDA(allow_max_smem(ctx, k_dp_chain<NKW, false>));
-      k_dp_chain<NKW, false><<<(unsigned)ncta, wp * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_recs,
-                                                                            b->prm, (int)ctx->band_slots, 0, nullptr);
-    } else {
-      RC_CUDA(allow_max_smem(ctx, k_dp_chain<NKW, true>));
-      k_dp_chain<NKW, true><<<(unsigned)ncta, wp * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_recs,
-                                                                           b->prm, (int)ctx->band_slots, c_lo, b->d_partial);
-    }
+#define RC_LAUNCH_CHAIN(...)                                                                                              \
+  do {                                                                                                                    \
+    RC_CUDA(allow_max_smem(ctx, k_dp_chain<__VA_ARGS__>));                                                                \
+    k_dp_chain<__VA_ARGS__><<<(unsigned)ncta, wp * 32, smem, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma,  \
+                                                                            b->d_recs, b->prm, (int)ctx->band_slots, c_lo, \
+                                                                            np == 1 ? nullptr : b->d_partial);            \
+  } while (0)
+    if (np == 1) RC_LAUNCH_CHAIN(NKW, false, true, true);
+    else if (pass == 0) RC_LAUNCH_CHAIN(NKW, true, true, false);
+    else if (pass == np - 1) RC_LAUNCH_CHAIN(NKW, true, false, true);
+    else RC_LAUNCH_CHAIN(NKW, true, false, false);
+#undef RC_LAUNCH_CHAIN
     RC_CUDA(cudaGetLastError());
     b->stats.launches++;
     b->stats.dp_launches++;
