@@ -3053,7 +3053,40 @@ __device__ __forceinline__ unsigned mt_temper(unsigned y) {
 // new batch depends on the OLD words kk, kk+1, kk+397 or the new word kk-227 -- never on a later new word).
 // (Measured and rejected: three chunks of 224 independent words, seven per lane, two barriers per chunk instead of two per 32
 // words -- 10.6 against 9.1 ms of pack + evolve on 10 000 blocks of 10 x 120.)
+#ifndef RC_EVO_TWIST_ROWS
+#define RC_EVO_TWIST_ROWS 1
+#endif
 __device__ __forceinline__ void mt_twist(unsigned* mt, int lane, int need = 624) {
+#if RC_EVO_TWIST_ROWS > 1
+  // U rows of 32 words per turn (U * 32 < 227 consecutive words are independent of each other): one pair of barriers per turn
+  constexpr int U = RC_EVO_TWIST_ROWS;
+  const unsigned ma = smem_u32(mt);
+  const int lim = min(624, (need + 31) & ~31);
+#pragma unroll 1
+  for (int base = 0; base < lim; base += 32 * U) {
+    unsigned a[U], b[U], c[U];
+#pragma unroll
+    for (int i = 0; i < U; i++) {
+      const int kk = base + 32 * i + lane;
+      if (kk < lim) {
+        a[i] = lds_u32(ma + 4u * (unsigned)kk);
+        b[i] = lds_u32(ma + 4u * (unsigned)(kk == 623 ? 0 : kk + 1));
+        c[i] = lds_u32(ma + 4u * (unsigned)(kk < 227 ? kk + 397 : kk - 227));
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < U; i++) {
+      const int kk = base + 32 * i + lane;
+      if (kk < lim) {
+        const unsigned y = (a[i] & 0x80000000u) | (b[i] & 0x7fffffffu);
+        const unsigned v = c[i] ^ (y >> 1) ^ ((0u - (b[i] & 1u)) & 0x9908b0dfu);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ma + 4u * (unsigned)kk), "r"(v) : "memory");
+      }
+    }
+    __syncwarp();
+  }
+#else
 #pragma unroll 1
   for (int base = 0; base < need; base += 32) {
     const int kk = base + lane;
@@ -3070,6 +3103,7 @@ __device__ __forceinline__ void mt_twist(unsigned* mt, int lane, int need = 624)
     }
     __syncwarp();
   }
+#endif
 }
 
 __device__ __forceinline__ void philox_round(unsigned (&c)[4], unsigned k0, unsigned k1) {

@@ -25,7 +25,9 @@ rows=list(csv.reader(sys.stdin)); d=dict(zip(rows[0],rows[2]))
 def b(k):
     v=float(d[k]); u=dict(zip(rows[0],rows[1]))[k]
     return v*{'byte':1,'Kbyte':1e3,'Mbyte':1e6,'Gbyte':1e9}.get(u,1)
-print('  \"$1\": {\"workload\": \"$2\", \"dram_bytes_per_launch\": %d, \"ms\": %s},'%(b('dram__bytes_read.sum')+b('dram__bytes_write.sum'), d['gpu__time_duration.sum']))" >> $OUT/traffic.json
+tu=dict(zip(rows[0],rows[1]))['gpu__time_duration.sum']
+ms=float(d['gpu__time_duration.sum'])*{'ns':1e-6,'us':1e-3,'usecond':1e-3,'ms':1.0,'msecond':1.0,'s':1e3,'second':1e3,'nsecond':1e-6}.get(tu,1.0)
+print('  \"$1\": {\"workload\": \"$2\", \"dram_bytes_per_launch\": %d, \"ms\": %.6f},'%(b('dram__bytes_read.sum')+b('dram__bytes_write.sum'), ms))" >> $OUT/traffic.json
   else
     echo "capture of $1 failed" >> $OUT/errors.txt
   fi
