@@ -1659,7 +1659,10 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
 // sigma layout 3: [instance][tile][chunk][step][RS] (RS = NK sigma values + the chunk's z word, padded to 16 B).
 // ---------------------------------------------------------------------------------------------
 constexpr int CHAIN_MAX_WARPS = 16;   // warps of one k_dp_chain CTA (launch bound)
-constexpr int CHAIN_PASS_WARPS = 5;   // chunks per pass when an alignment has more (see k_dp_chain)
+#ifndef RC_CHAIN_PASS_WARPS
+#define RC_CHAIN_PASS_WARPS 5
+#endif
+constexpr int CHAIN_PASS_WARPS = RC_CHAIN_PASS_WARPS;   // chunks per pass when an alignment has more (see k_dp_chain)
 constexpr int CHAIN_MAX_TASKS = 8;  // upper bound of BlockDev.chain_tasks
 #ifndef RC_CHAIN_STAGES
 #define RC_CHAIN_STAGES 3
@@ -1733,8 +1736,8 @@ __global__ void
   // resident per SM: the warps of a launch own the chunks c_lo .. c_lo + W - 1, the first warp of a later pass continues
   // the partial sums the previous pass left in global memory, the last warp of an earlier pass leaves them there.
   const int chunk = c_lo + warp;
-  const bool gfirst = first && PF, glast = last && PL;  // ends of the whole species chain (chunk == 0 / == bd.nchunk - 1)
-  // (MULTI = false: single-pass launch, first == gfirst and last == glast, the global hand-over code compiles away)
+  // ends of the whole species chain: chunk == 0 <=> first && PF, chunk == bd.nchunk - 1 <=> last && PL
+  // (MULTI = false: single-pass launch, PF = PL = true, the global hand-over code compiles away)
 
   unsigned char* ring = smem + (size_t)warp * RING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * STAGE_BYTES);
@@ -2300,6 +2303,9 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, (CHAINED || NK <= 12) ? 2 
       }
       j += 1;
     }
+    // the requests past the last end codon are still in flight: they must have landed before the next row pair's requests
+    // reuse their slots (two asynchronous copies to one address are not ordered among themselves)
+    if (pf) cp_async_wait<0>();
     if (valid && last && r0 < sites) {
       folds_store(sx, rec_inst + r0, rec0, fNK, rcpNK);
       if (r0 + 1 < sites) folds_store(sy, rec_inst + r0 + 1, rec0 + 1, fNK, rcpNK);
@@ -3054,7 +3060,7 @@ __device__ __forceinline__ unsigned mt_temper(unsigned y) {
 // (Measured and rejected: three chunks of 224 independent words, seven per lane, two barriers per chunk instead of two per 32
 // words -- 10.6 against 9.1 ms of pack + evolve on 10 000 blocks of 10 x 120.)
 #ifndef RC_EVO_TWIST_ROWS
-#define RC_EVO_TWIST_ROWS 1
+#define RC_EVO_TWIST_ROWS 2  // rows of 32 words per turn of the regeneration (measured: 1 -> 8.37, 2 -> 8.14, 3 -> 8.16, 7 -> 10.6 ms of pack + evolve on 10 000 x 10x120)
 #endif
 __device__ __forceinline__ void mt_twist(unsigned* mt, int lane, int need = 624) {
 #if RC_EVO_TWIST_ROWS > 1
