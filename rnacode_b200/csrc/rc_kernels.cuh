@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_pack2(const BlockDev* __restrict__ bloc
                                                int max_L, int stage_bytes) {
   extern __shared__ __align__(16) unsigned char p2_smem[];  // s_c0[2][max_L] ints | s_row[rows per pass][32][pitch]
   const BlockDev bd = blocks[blockIdx.x];
-  if (!bd.smp_fused) return;
+  if (bd.p2_words == 0) return;  // only blocks whose sigma values are formed from packed rows (k_dp_smpf, k_sigma_p2)
   int* s_c0base = reinterpret_cast<int*>(p2_smem);
   unsigned char* s_row = p2_smem + (size_t)2 * max_L * sizeof(int);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(256)
   const Item it = items[blockIdx.x];
   const BlockDev bd = blocks[it.block];
   const int group = blockIdx.y;
-  if ((bd.layout != 2 && bd.layout != 5) || bd.smp_fused || group * 32 >= it.ninst) return;  // fused: k_dp_smpf builds its own table
+  if ((bd.layout != 2 && bd.layout != 5) || bd.smp_fused || bd.sig_p2 || group * 32 >= it.ninst) return;  // fused: k_dp_smpf builds its own table; sig_p2: k_sigma_p2
   // blockIdx.z = ((position chunk * 2) + strand) * nqz + quad share
   const int qz = blockIdx.z % nqz, s_cta = (blockIdx.z / nqz) & 1, pc = blockIdx.z / (2 * nqz);
   const int L = bd.L, N = bd.N, NK = bd.NK, cols = bd.cols;
@@ -2772,6 +2772,139 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
     if (valid && last && r0 < sites) {
       folds_store(fx, rec_inst + r0, rec0, fNK, rcpNK);
       if (r0 + 1 < sites) folds_store(fy, rec_inst + r0 + 1, rec0 + 1, fNK, rcpNK);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (b) k_sigma_p2: the sigma tables of the sample-major layouts 2 / 5 that live in HBM (k_dp_smp, k_dp_smps), built from
+// k_pack2's packed rows exactly as k_dp_smpf's table phase builds its own -- a codon is six adjacent bits of a packed word,
+// sigma = val[t[codonA][codonB] & 0x3ff] - expected[k][t >> 10] (calculateSigma, src/score.c:375-426, through PairTables), rows
+// with an 'N' / 'X' at a reference position take the byte-wise test per lane -- instead of k_sigma_smp's three byte loads and
+// shifts per character (43 instructions per sigma value there, about 10 here).
+// One CTA per (item, group of 32 instances, strand, species chunk): the packed reference row and the chunk's species rows arrive
+// by TMA bulk copies and serve all three frames; lane = instance, a warp writes the 512 bytes of one (end codon, species quad)
+// with one float4 store per lane.  grid = (item, group * 2 + strand, chunk).
+// Dynamic shared memory: PairTables | expected scores [16][4] | flag words [17] | barrier | reference row | species rows.
+// ---------------------------------------------------------------------------------------------
+struct SigP2Cfg {
+  static __host__ __device__ size_t off_sc() { return sizeof(PairTables); }
+  static __host__ __device__ size_t off_flag() { return off_sc() + 16 * 4 * sizeof(float); }
+  static __host__ __device__ size_t off_bar() { return off_flag() + 32 * sizeof(unsigned); }
+  static __host__ __device__ size_t off_ref() { return off_bar() + 16; }
+  static __host__ __device__ size_t off_sp(int words) { return off_ref() + (size_t)(words + 1) * 128; }
+  static __host__ __device__ size_t total(int words, int nsp) { return off_sp(words) + ((size_t)nsp * words + 1) * 128; }
+};
+
+__global__ void __launch_bounds__(256)
+    k_sigma_p2(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned* __restrict__ p2,
+               const unsigned* __restrict__ p2f, const unsigned char* __restrict__ cls, const int* __restrict__ cols0,
+               const float* __restrict__ scores, const PairTables* __restrict__ tables, float* __restrict__ sigma) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Item& it = items[blockIdx.x];
+  const BlockDev& bd = blocks[it.block];
+  if (!bd.sig_p2) return;
+  const int group = blockIdx.y >> 1, strand = blockIdx.y & 1, chunk = blockIdx.z;
+  const bool chained = bd.layout == 5;
+  if (group * 32 >= it.ninst || chunk >= (chained ? bd.nchunk : 1)) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int N = bd.N, cols = bd.cols, L = bd.L, W = bd.p2_words, NK = bd.NK;
+  const int rsb = (NK + 3) / 4 * 4;
+  int q_first = 0, q_count = rsb / 4;
+  if (chained) {
+    q_first = chunk * bd.chunk_base + min(chunk, bd.chunk_rem);
+    q_count = bd.chunk_base + (chunk < bd.chunk_rem ? 1 : 0);
+  }
+  const int k_first = 4 * q_first;
+  const int n_real = min(4 * q_count, NK - k_first);         // species rows of this CTA that exist
+  const unsigned ROW_BYTES = (chained ? 12u : (unsigned)rsb) * 128u;  // one end codon of the table: quads x 32 lanes x 16 B
+  const int ninst_g = min(32, it.ninst - group * 32);
+  const bool valid = lane < ninst_g;
+  const int ngrp = (it.ninst + 31) / 32;
+  const size_t grp_index = chained ? (size_t)chunk * ngrp + group : (size_t)group;
+
+  const PairTables& s_tab = *reinterpret_cast<const PairTables*>(smem);
+  float* s_sc = reinterpret_cast<float*>(smem + SigP2Cfg::off_sc());
+  unsigned* s_flag = reinterpret_cast<unsigned*>(smem + SigP2Cfg::off_flag());
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SigP2Cfg::off_bar());
+  unsigned char* s_ref = smem + SigP2Cfg::off_ref();
+  unsigned char* s_sp = smem + SigP2Cfg::off_sp(W);
+
+  const size_t prow = (size_t)W * 128;  // bytes of one packed row of 32 instances
+  const size_t grp = (size_t)(it.inst0 >> 5) + group;
+  const unsigned* gp2 = p2 + bd.p2_off + ((grp * 2 + strand) * N) * (size_t)W * 32;
+  const unsigned* gfl = p2f + bd.p2f_off + (grp * 2 + strand) * N;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(bar, (unsigned)(sizeof(PairTables) + prow + (size_t)n_real * prow));
+    bulk_g2s(smem, tables, (unsigned)sizeof(PairTables), bar);
+    bulk_g2s(s_ref, gp2, (unsigned)prow, bar);
+    bulk_g2s(s_sp, gp2 + (size_t)(1 + k_first) * W * 32, (unsigned)((size_t)n_real * prow), bar);
+  }
+  for (int t = threadIdx.x; t < 64; t += blockDim.x) {
+    const int kk = t >> 2, h = t & 3, row = 1 + k_first + kk;
+    s_sc[t] = (h > 0 && kk < n_real) ? scores[bd.scores_off + ((size_t)strand * N + row) * 4 + h] : 0.0f;
+  }
+  for (int t = threadIdx.x; t <= 16; t += blockDim.x) s_flag[t] = t == 0 ? gfl[0] : (t - 1 < n_real ? gfl[k_first + t] : 0u);
+  __syncthreads();  // barrier initialised; s_sc, s_flag written
+  mbar_wait(bar, 0);
+
+  const unsigned lane_bit = 1u << lane;
+  const unsigned char* cbase = cls + bd.cls_off + (size_t)(it.inst0 + group * 32 + (valid ? lane : 0)) * bd.inst_stride;
+  const unsigned ref_a = smem_u32(s_ref) + lane * 4, sp_a = smem_u32(s_sp) + lane * 4, prow32 = (unsigned)prow;
+  const unsigned tab_t = smem_u32(&s_tab.t[0]), tab_v = smem_u32(&s_tab.val[0]), sc_a = smem_u32(s_sc);
+  unsigned fl_all = s_flag[0];
+  for (int k = 0; k < n_real; k++) fl_all |= s_flag[1 + k];
+  const bool slow_warp = fl_all != 0u;  // warp-uniform
+  // codon of site j of frame f: reference positions x-2 .. x with x = 3j + 3 + f, i.e. entries f+1+3j .. f+3+3j of cols0
+  const int* c0s = cols0 + bd.cols0_off + (size_t)strand * (L + 1);
+#pragma unroll 1
+  for (int frame = 0; frame < 3; frame++) {
+    const int sites = bd.sites[frame];
+    float* outg = sigma + it.sigma_off[strand][frame] + grp_index * sites * (ROW_BYTES / 4) + lane * 4;
+#pragma unroll 1
+    for (int j = warp; j < sites; j += nw) {
+      const int p0 = 3 * j + frame;
+      const unsigned woff = (unsigned)(p0 >> 4) * 128u, sh = 2u * (unsigned)(p0 & 15);
+      const bool two = sh > 26u;
+      const unsigned qa = p2_codon(ref_a + woff, sh, two);
+      const unsigned trow = tab_t + (qa << 7);  // 64 entries of 2 bytes per reference codon
+      unsigned ka = sp_a + woff;                // the codon's word in species row 0 of the CTA, then row by row
+#pragma unroll 1
+      for (int kq = 0; kq < q_count; kq++) {
+        float v4[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          const int k = 4 * kq + kk;
+          float v = 0.0f;
+          if (k < n_real) {  // warp-uniform
+            const unsigned qb = p2_codon(ka, sh, two);
+            const unsigned e = lds_u16(trow + 2u * qb);
+            v = lds_f32(tab_v + 4u * (e & 0x3ffu)) - lds_f32(sc_a + 16u * (unsigned)k + 4u * (e >> 10));  // src/score.c:422-425
+            ka += prow32;
+          }
+          v4[kk] = v;
+        }
+        if (slow_warp) {  // some lane's rows hold an 'N' or 'X': those lanes test the six characters (src/score.c:394-404)
+          unsigned fl_q = s_flag[0];
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) fl_q |= s_flag[1 + 4 * kq + kk];
+          if ((fl_q & lane_bit) != 0u && valid) {
+            const int i1 = c0s[frame + 1 + 3 * j], i2 = c0s[frame + 2 + 3 * j], i3 = c0s[frame + 3 + 3 * j];
+            const unsigned a1 = cbase[i1], a2 = cbase[i2], a3 = cbase[i3];
+            const unsigned nA = (a1 | a2 | a3) & CLS_N;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++)
+              if (4 * kq + kk < n_real) {
+                const unsigned char* rk = cbase + (size_t)(1 + k_first + 4 * kq + kk) * cols;
+                const unsigned b1 = rk[i1], b2 = rk[i2], b3 = rk[i3];
+                if (nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X)) v4[kk] = 0.0f;
+              }
+          }
+        }
+        *reinterpret_cast<float4*>(outg + ((size_t)j * ROW_BYTES + (size_t)kq * 512) / 4) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+      }
     }
   }
 }

@@ -48,6 +48,7 @@ struct rc_ctx {
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
   long no_fold = 0;           // 1: a last group of at most 16 instances is scored like a full one (k_dp_smpf)
   long no_fused = 0;          // 1: never build the sigma table inside the sample-major DP kernel (k_dp_smpf)
+  long no_sig_p2 = 0;         // 1: sigma tables of the sample-major layouts always from class bytes (k_sigma_smp), never from packed rows
   long tail_max = 0;          // a sample-major block whose instance count leaves 1..tail_max instances in its last group of 32 scores
                               // those instances row-major (lanes = rows) instead of in a warp with that many live lanes (0: never)
   long smpc_max_sites = 0;    // longest frame (codons) for the STREAMED chunked sample-major route of wide alignments
@@ -155,6 +156,9 @@ struct Chunk {
   size_t sigma_floats = 0, rec_count = 0, part_count = 0, max_smp_smem = 0, max_smps_smem = 0;
   size_t max_smpf_smem = 0;  // k_dp_smpf: shared memory of a CTA without the fold records
   int n_smp_unfused = 0;     // sample-major items that still need k_sigma_smp
+  int n_sig_p2 = 0;          // ... of which k_sigma_p2 serves this many (packed rows); its grid and shared memory:
+  int max_p2_chunks = 1;
+  size_t max_p2_smem = 0;
   long long max_sigma_work = 0;  // largest ninst*2*(L-2) of an item, for the k_sigma grid
   int max_ninst = 0;
   int n_layout[6] = {0, 0, 0, 0, 0, 0};  // items per sigma layout
@@ -420,6 +424,7 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   if (const char* e = getenv("RNACODE_CUDA_SMP_WARPS")) ctx->smp_warps_forced = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_HSS_THR_TASKS")) ctx->hss_thr_tasks = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_NO_FUSED")) ctx->no_fused = atol(e) ? 1 : 0;
+  if (const char* e = getenv("RNACODE_CUDA_NO_SIG_P2")) ctx->no_sig_p2 = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_NO_FOLD")) ctx->no_fold = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_TAIL_MAX")) ctx->tail_max = std::max(0L, std::min(31L, atol(e)));
   if (const char* e = getenv("RNACODE_CUDA_REG_MAX_NK")) ctx->reg_max_nk = std::max(12L, std::min<long>(REG_MAX_NK, atol(e)));
@@ -491,6 +496,8 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->no_fold = value ? 1 : 0;
   } else if (k == "no_fused") {
     ctx->no_fused = value ? 1 : 0;
+  } else if (k == "no_sig_p2") {
+    ctx->no_sig_p2 = value ? 1 : 0;
   } else if (k == "tail_max") {
     if (value < 0 || value > 31) { ctx_fail(ctx, "tail_max must be 0..31"); return RC_ERR_ARG; }
     ctx->tail_max = value;
@@ -715,6 +722,20 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
         bd.p2f_off = (long long)b->p2f_words;
         b->p2f_words += groups * 2 * bd.N;
       }
+      // the other sample-major blocks keep their sigma table in HBM; it is built from the same packed rows (k_sigma_p2) when the
+      // rows of a species chunk fit shared memory twice per SM, from class bytes (k_sigma_smp) otherwise
+      if ((layout == 2 || layout == 5) && !bd.smp_fused && !ctx->no_sig_p2 && !ctx->force_dense && bd.cols <= P2_MAX_COLS && bd.L >= 3 &&
+          SigP2Cfg::total((bd.L + 15) / 16, layout == 5 ? 12 : (bd.NK + 3) / 4 * 4) <= (size_t)100 * 1024) {
+        bd.sig_p2 = 1;
+        b->max_fused_N = std::max(b->max_fused_N, bd.N);
+        b->max_fused_cols = std::max(b->max_fused_cols, bd.cols);
+        bd.p2_words = (bd.L + 15) / 16;
+        const size_t groups = (size_t)(bd.n_inst + 31) / 32;
+        bd.p2_off = (long long)b->p2_words;
+        b->p2_words += groups * 2 * bd.N * bd.p2_words * 32 + 64;
+        bd.p2f_off = (long long)b->p2f_words;
+        b->p2f_words += groups * 2 * bd.N;
+      }
       if ((layout == 2 || layout == 5) && !seg) bd.smp_fold = ctx->no_fold ? 0 : 1;  // resident-table kernels fold a short last group
       if (layout == 2 || layout == 5) {
         // B of RowFoldS: (N-1) * 1.0002e-4 for the tolerance of getHSS's tie rule plus 2^-21 of the largest species sum a
@@ -854,6 +875,11 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
         cur.max_smpf_smem = std::max(cur.max_smpf_smem, smpf_smem_bytes(bd, bd.layout));
       } else if (bd.layout == 2 || bd.layout == 5) {
         cur.n_smp_unfused++;
+        if (bd.sig_p2) {
+          cur.n_sig_p2++;
+          cur.max_p2_chunks = std::max(cur.max_p2_chunks, bd.layout == 5 ? bd.nchunk : 1);
+          cur.max_p2_smem = std::max(cur.max_p2_smem, SigP2Cfg::total(bd.p2_words, bd.layout == 5 ? 12 : (bd.NK + 3) / 4 * 4));
+        }
         if (!bd.smp_seg) cur.max_smp_smem = std::max(cur.max_smp_smem, smp_smem_bytes(bd, 0, bd.layout, 0));
         if (bd.smp_seg) cur.max_smps_smem = std::max(cur.max_smps_smem, smp_smem_bytes(bd, 0, bd.layout, 1));
         cur.max_smp_quads = std::max(cur.max_smp_quads, (bd.NK + 3) / 4);
@@ -1655,7 +1681,15 @@ extern "C" int rc_batch_run(rc_batch* b) {
         RC_CUDA(cudaGetLastError());
         b->stats.launches++;
       }
-      if (ch.n_smp_unfused > 0) {  // some items use the sample-major layouts with a sigma table in HBM
+      if (ch.n_sig_p2 > 0) {  // sample-major sigma tables built from the packed rows
+        dim3 g3((unsigned)ch.nitems, (unsigned)((ch.max_ninst + 31) / 32) * 2, (unsigned)ch.max_p2_chunks);
+        RC_CUDA(allow_max_smem(ctx, k_sigma_p2));
+        k_sigma_p2<<<g3, 256, ch.max_p2_smem, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_p2, b->d_p2f, b->d_cls, b->d_cols0,
+                                                    b->d_scores, b->d_ptab2, b->d_sigma);
+        RC_CUDA(cudaGetLastError());
+        b->stats.launches++;
+      }
+      if (ch.n_smp_unfused > ch.n_sig_p2) {  // ... and those built from class bytes
         const int nqz = std::min(16, std::max(1, ch.max_smp_quads / 3));
         const int npc = (ch.max_smp_npos + SIG_PCH - 1) / SIG_PCH;
         dim3 g2((unsigned)ch.nitems, (unsigned)((ch.max_ninst + 31) / 32), (unsigned)(npc * 2 * nqz));
