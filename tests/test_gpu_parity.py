@@ -191,11 +191,13 @@ def test_config5_mixed_lengths_vs_oracle(rc_ctx, oracle):
     bt.close()
 
 
-@pytest.mark.parametrize("opts", [{"no_fused": 0}, {"no_fused": 1}, {"no_fold": 1}, {"tail_max": 12}, {"no_fused": 0, "tail_max": 12}],
+@pytest.mark.parametrize("opts", [{"no_fused": 0}, {"no_fused": 1}, {"no_fold": 1}, {"tail_max": 12}, {"no_fused": 0, "tail_max": 12},
+                                  {"no_sig_p2": 1}, {"no_fused": 1, "no_sig_p2": 1}],
                          ids=lambda o: "+".join("%s%d" % kv for kv in sorted(o.items())))
 def test_optional_sample_major_routes_vs_oracle(oracle, opts):
     """The routes of the sample-major family, each switched on and off: k_dp_smpf (the DP CTA builds its sigma table itself from
-    the packed rows of k_pack2; default where it keeps two CTAs per SM) against k_sigma_smp + k_dp_smp, its folded last group
+    the packed rows of k_pack2; default where it keeps two CTAs per SM) against k_sigma_p2 / k_sigma_smp + k_dp_smp (sigma tables
+    in HBM, built from the packed rows or -- no_sig_p2 -- from class bytes), its folded last group
     (several start-codon pairs side by side when at most 16 instances are left), and the tail split (the last 1..12 instances
     of a block scored row-major; off by default).  Same answers as the oracle, bit for bit."""
     from rnacode_b200 import synth
