@@ -74,7 +74,7 @@ WORKLOADS = {
     "genomic_lowgap": (GENOMIC_SHAPES, 1000, 2, "genomic.maf block shapes, gap rate 0.0005 (frameshift density of the real file), -n 1000", 0.0005),
     "genomic_gapfree": (GENOMIC_SHAPES, 1000, 2, "genomic.maf block shapes, gap-free (the 6-op cell of SURVEY 8(d)), -n 1000", 0.0),
 }
-SIDE_WORKLOADS = ["short", "wide_n1000", "hundred", "hundred_short"]  # reported under "workloads" at N = 1
+SIDE_WORKLOADS = ["short", "wide_n1000", "hundred", "hundred_short", "genomic_lowgap"]  # reported under "workloads" at N = 1
 METRIC = "codon_dp_cells_per_s"
 UNIT = "cells/s"
 OPS_PER_CELL = 6.0    # 3 FADD + MAX3 (2 FMNMX) + 1 FADD for a cell without frameshift

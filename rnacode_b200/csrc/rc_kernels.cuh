@@ -62,6 +62,31 @@ __device__ __forceinline__ void cp_async4(unsigned dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// shared-memory loads by 32-bit shared address (the table phase of k_dp_smpf does all its addressing in 32 bits)
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(unsigned a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f2(unsigned a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+
 __device__ __forceinline__ float max3f(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -1647,6 +1672,260 @@ __global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
 }
 
 // ---------------------------------------------------------------------------------------------
+// (c) k_dp_regtu: k_dp_reg with THREE instead of four additions per cell.
+// Without a frameshift a step adds sigma to S0 and the SAME constant omega to S1 and S2 (src/score.c:506-510), and the cell only
+// needs max3(S0, S1, S2).  Rounding to nearest is monotone, so max(S1 (+) omega, S2 (+) omega) == max(S1, S2) (+) omega bit for
+// bit: the kernel carries T = max(S1, S2) -- one addition per step -- and takes max(S0, T).  The smaller of the two, U, and which
+// of them is S1 are only needed at the next frameshift of that species (src/score.c:512-533 mixes the three states): U is
+// brought up to date there, n deferred additions of omega at once.  n roundings collapse because omega is -2^k (the default
+// -2.0; the host sends every other value to k_dp_reg): a sum stays exactly representable while its magnitude does not leave
+// the binade of the value the deferred run started from, so whole runs are one FMA, and a run that crosses a binade boundary
+// is cut there -- one FMA up to and including the first rounded step, then on from the rounded value (catch_up; checked on
+// the host against the step-by-step loop, bit for bit, on 2*10^7 random (value, k, n); tools/catch_up_check.c).
+// Rows that started after the species' previous frameshift have S1 == S2 == T, no catching up.
+// Everything else -- task shape, TMA ring, masked diagonal tiles, species sum in k order, getHSS fold -- is k_dp_reg's.
+// ---------------------------------------------------------------------------------------------
+// u (+) w, n times, w = -2^k (k = kexp).  See above; returns exactly what the loop `for (i < n) u = u + w` returns.
+__device__ __forceinline__ float catch_up(float u, float w, int kexp, int n) {
+  while (n > 0) {
+    const unsigned bits = __float_as_uint(u);
+    const int expf = (int)((bits >> 23) & 0xffu);
+    const int shift = kexp + 150 - expf;  // log2(|w| / ulp(u))
+    if (expf == 0 || shift < 0) {         // zero / denormal, or w finer than u's grid (every step rounds): one plain step
+      u = u + w;
+      n--;
+      continue;
+    }
+    const float B = __uint_as_float((bits & 0x7f800000u) + 0x00800000u);  // top of u's binade: all multiples of ulp(u) up to B exist
+    const float r = __fmaf_rn(w, (float)n, u);
+    if (fabsf(r) <= B) return r;  // the run never leaves the binade (or ends on its first rounded step): exact
+    const int m = (int)((bits & 0x7fffffu) | 0x800000u);
+    const int num = ((bits >> 31) ? -m : m) + (1 << 24);  // (u + B) / ulp(u)
+    const int J = shift >= 25 ? 0 : (num >> shift);       // steps that stay exact
+    u = __fmaf_rn(w, (float)(J + 1), u);                  // ... and the first rounded one
+    n -= J + 1;
+  }
+  return u;
+}
+
+struct TuEvent {
+  float2 s0, t, u;
+  unsigned bits;  // bit 0: row x has S1 >= S2 (S1 is T), bit 1: the same for row y
+};
+// Frameshift of one species at one end codon (src/score.c:512-533) on the (S0, T, U) form.  n: clean steps since U was last
+// current (warp-uniform); fx / fy: the row started after that point (S1 == S2 == T); D2 / O2: Delta / Omega per row, +0 for a row
+// that has not started yet (the state stays (0,0,0), see reg_pair_diag).
+__device__ __noinline__ TuEvent tu_event(float2 s0, float2 t, float2 u, unsigned bits, bool neg, int n, bool fx, bool fy, float2 D2,
+                                         float2 O2, float omega, int kexp) {
+  u.x = fx ? t.x : catch_up(u.x, omega, kexp, n);
+  u.y = fy ? t.y : catch_up(u.y, omega, kexp, n);
+  const bool bx = (bits & 1u) != 0u, by = (bits & 2u) != 0u;
+  float2 a0 = s0;
+  float2 a1 = make_float2(bx ? t.x : u.x, by ? t.y : u.y);
+  float2 a2 = make_float2(bx ? u.x : t.x, by ? u.y : t.y);
+  reg_shift2(neg, D2, O2, a0, a1, a2);
+  TuEvent e;
+  e.s0 = a0;
+  e.t = make_float2(fmaxf(a1.x, a2.x), fmaxf(a1.y, a2.y));
+  e.u = make_float2(fminf(a1.x, a2.x), fminf(a1.y, a2.y));
+  e.bits = (a1.x >= a2.x ? 1u : 0u) | (a1.y >= a2.y ? 2u : 0u);
+  return e;
+}
+
+// two frameshift-free end codons, all rows live
+template <int NK>
+__device__ __forceinline__ void tu_pair_fast(float2 (&S0)[NK], float2 (&T)[NK], const float (&svA)[RegCfg<NK>::RS],
+                                             const float (&svB)[RegCfg<NK>::RS], float omega, float2& sumA, float2& sumB) {
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    S0[k] = add2s(S0[k], svA[k]);
+    T[k] = add2s(T[k], omega);
+    const float2 m = make_float2(fmaxf(S0[k].x, T[k].x), fmaxf(S0[k].y, T[k].y));
+    sumA = (k == 0) ? m : add2(sumA, m);
+  }
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    S0[k] = add2s(S0[k], svB[k]);
+    T[k] = add2s(T[k], omega);
+    const float2 m = make_float2(fmaxf(S0[k].x, T[k].x), fmaxf(S0[k].y, T[k].y));
+    sumB = (k == 0) ? m : add2(sumB, m);
+  }
+}
+// the same in a tile in which rows start (masks as in reg_pair_diag)
+template <int NK>
+__device__ __forceinline__ void tu_pair_diag(float2 (&S0)[NK], float2 (&T)[NK], const float (&svA)[RegCfg<NK>::RS],
+                                             const float (&svB)[RegCfg<NK>::RS], float omega, bool P, bool Q, float2& sumA,
+                                             float2& sumB) {
+  const float2 omA = make_float2(P ? omega : 0.0f, Q ? omega : 0.0f);
+  const float omB = P ? omega : 0.0f;
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    S0[k] = add2(S0[k], make_float2(P ? svA[k] : 0.0f, Q ? svA[k] : 0.0f));
+    T[k] = add2(T[k], omA);
+    const float2 m = make_float2(fmaxf(S0[k].x, T[k].x), fmaxf(S0[k].y, T[k].y));
+    sumA = (k == 0) ? m : add2(sumA, m);
+  }
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    S0[k] = add2s(S0[k], P ? svB[k] : 0.0f);
+    T[k] = add2s(T[k], omB);
+    const float2 m = make_float2(fmaxf(S0[k].x, T[k].x), fmaxf(S0[k].y, T[k].y));
+    sumB = (k == 0) ? m : add2(sumB, m);
+  }
+}
+// one end codon, any frameshift pattern; mx / my: the lane's rows are live at this codon (both true outside diagonal tiles)
+// U_a: shared address of this lane's U of species 0 ([species][lane] float2, 256 bytes per species); tU_a: of the warp's
+// tU[0] -- both only touched at a frameshift, so they stay out of the registers of the step loop
+template <int NK>
+__device__ __forceinline__ float2 tu_update(float2 (&S0)[NK], float2 (&T)[NK], unsigned U_a, unsigned& bx, unsigned& by,
+                                            unsigned tU_a, const float (&sv)[RegCfg<NK>::RS], bool mx, bool my, int j, int r0,
+                                            float Delta, float Omega, float omega, int kexp) {
+  const unsigned zw = __float_as_uint(sv[NK]);
+  const float2 om2 = make_float2(mx ? omega : 0.0f, my ? omega : 0.0f);
+  float2 sum;
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    const unsigned z2 = (zw >> (2 * k)) & 3u;
+    if (z2 == 0u) {
+      S0[k] = add2(S0[k], make_float2(mx ? sv[k] : 0.0f, my ? sv[k] : 0.0f));
+      T[k] = add2(T[k], om2);
+    } else {
+      const float2 D2 = make_float2(mx ? Delta : 0.0f, my ? Delta : 0.0f);
+      const float2 O2 = make_float2(mx ? Omega : 0.0f, my ? Omega : 0.0f);
+      const int tk = (int)lds_u32(tU_a + 4u * k);
+      const TuEvent e = tu_event(S0[k], T[k], lds_f2(U_a + 256u * k), ((bx >> k) & 1u) | (((by >> k) & 1u) << 1), (z2 & 2u) != 0u,
+                                 j - 1 - tk, r0 > tk, r0 + 1 > tk, D2, O2, omega, kexp);
+      S0[k] = e.s0;
+      T[k] = e.t;
+      sts_f2(U_a + 256u * k, e.u);
+      bx = (bx & ~(1u << k)) | ((e.bits & 1u) << k);
+      by = (by & ~(1u << k)) | (((e.bits >> 1) & 1u) << k);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(tU_a + 4u * k), "r"(j) : "memory");  // every lane writes the same value
+    }
+    const float2 m = make_float2(fmaxf(S0[k].x, T[k].x), fmaxf(S0[k].y, T[k].y));
+    sum = (k == 0) ? m : add2(sum, m);
+  }
+  return sum;
+}
+
+template <int NK>
+__global__ void __launch_bounds__(DP_WARPS * 32, RC_REG_MINB)
+    k_dp_regtu(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const CtaDesc* __restrict__ ctas,
+               const float* __restrict__ sigma, RowRec* __restrict__ recs, Params prm, int band_slots) {
+  constexpr int R = 2;
+  constexpr int RS = RegCfg<NK>::RS;
+  constexpr int RT = RC_REG_TILE;
+  constexpr int STAGE_BYTES = RT * RS * 4;
+  __shared__ __align__(128) unsigned char smem[DP_WARPS][2 * STAGE_BYTES + 16 + 2 * RS * 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const CtaDesc cd = ctas[blockIdx.x];
+  const Item& it = items[cd.item];
+  const BlockDev& bd = blocks[it.block];
+  const int strand = cd.sf / 3, frame = cd.sf % 3;
+  const int sites = bd.sites[frame];
+  const int nsteps = bd.ntiles[frame] * TILE;
+  const int ntiles = nsteps / RT;
+  const int ngroups = (sites + 32 * R - 1) / (32 * R);
+  const int task = cd.task0 + warp;
+  if (task >= it.ninst * ngroups) return;
+  const int inst_l = task / ngroups, g = task % ngroups;
+  const int row_base = g * 32 * R;
+  const int r0 = row_base + lane * R;
+
+  unsigned char* ring = smem[warp];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * STAGE_BYTES);
+  unsigned ring_a = smem_u32(ring);
+  asm volatile("" : "+r"(ring_a));
+  const float* sig_src = sigma + it.sigma_off[strand][frame] + (size_t)inst_l * nsteps * RS;
+  const int t0 = row_base / RT;
+  const int t_last_diag = (row_base + 32 * R - 1) / RT;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+    for (int s = 0; s < 2 && t0 + s < ntiles; s++) {
+      mbar_expect_tx(&bars[s], STAGE_BYTES);
+      bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(t0 + s) * RT * RS, STAGE_BYTES, &bars[s]);
+    }
+  }
+  __shared__ __align__(16) RowRec srec[DP_WARPS][R * 32];
+  RowRec* rec0 = &srec[warp][lane * R];
+  rec_init(rec0);
+  rec_init(rec0 + 1);
+  __syncwarp();
+
+  // U per (species, lane) and tU per species (end codon of the species' last frameshift seen by this warp; -1: none yet)
+  __shared__ __align__(16) float2 s_U[DP_WARPS][NK][32];
+  __shared__ int s_tU[DP_WARPS][NK];
+  float2 S0[NK], T[NK];
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    S0[k] = T[k] = make_float2(0.0f, 0.0f);
+    s_U[warp][k][lane] = make_float2(0.0f, 0.0f);
+    s_tU[warp][k] = -1;
+  }
+  unsigned U_a = smem_u32(&s_U[warp][0][lane]), tU_a = smem_u32(&s_tU[warp][0]);
+  asm volatile("" : "+r"(U_a), "+r"(tU_a));
+  __syncwarp();
+  unsigned bx = 0u, by = 0u;
+  float2 lb = make_float2(-INFINITY, -INFINITY);
+  const float Delta = prm.Delta, Omega = prm.Omega;
+  float omega = prm.omega;
+  asm volatile("" : "+f"(omega));
+  const int kexp = (int)((__float_as_uint(prm.omega) >> 23) & 0xffu) - 127;
+  const float fNK = bd.fNK, rcpNK = bd.rcpNK;
+
+#pragma unroll 1
+  for (int tile = t0; tile < ntiles; tile++) {
+    const int s = (tile - t0) & 1;
+    const unsigned parity = ((tile - t0) >> 1) & 1;
+    const unsigned a0 = ring_a + s * STAGE_BYTES;
+    const int j0 = tile * RT;
+    const bool diag = tile <= t_last_diag;  // rows start inside this tile
+    mbar_wait(&bars[s], parity);
+    float svA[RS], svB[RS];
+    reg_load_row<NK>(a0, svA);
+    reg_load_row<NK>(a0 + RS * 4, svB);
+#pragma unroll 1
+    for (int c = 0; c < RT; c += 2) {
+      float2 sumA, sumB;
+      const bool clean = (__float_as_uint(svA[NK]) | __float_as_uint(svB[NK])) == 0u;
+      if (diag) {
+        const bool P = j0 + c >= r0, Q = j0 + c > r0;
+        if (clean) {
+          tu_pair_diag<NK>(S0, T, svA, svB, omega, P, Q, sumA, sumB);
+        } else {
+          sumA = tu_update<NK>(S0, T, U_a, bx, by, tU_a, svA, P, Q, j0 + c, r0, Delta, Omega, omega, kexp);
+          sumB = tu_update<NK>(S0, T, U_a, bx, by, tU_a, svB, P, P, j0 + c + 1, r0, Delta, Omega, omega, kexp);
+        }
+      } else if (clean) {
+        tu_pair_fast<NK>(S0, T, svA, svB, omega, sumA, sumB);
+      } else {
+        sumA = tu_update<NK>(S0, T, U_a, bx, by, tU_a, svA, true, true, j0 + c, r0, Delta, Omega, omega, kexp);
+        sumB = tu_update<NK>(S0, T, U_a, bx, by, tU_a, svB, true, true, j0 + c + 1, r0, Delta, Omega, omega, kexp);
+      }
+      reg_load_row<NK>(a0 + (c + 2) * RS * 4, svA);
+      reg_load_row<NK>(a0 + (c + 3) * RS * 4, svB);
+      if (fmaxf(fmaxf(sumA.x, sumA.y), fmaxf(sumB.x, sumB.y)) > 0.0f) {
+        if (sumA.x > 0.0f) lb.x = RC_REG_CHECK(sumA.x, j0 + c, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+        if (sumA.y > 0.0f) lb.y = RC_REG_CHECK(sumA.y, j0 + c, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+        if (sumB.x > 0.0f) lb.x = RC_REG_CHECK(sumB.x, j0 + c + 1, r0, sites, fNK, rcpNK, rec0, band_slots, lb.x);
+        if (sumB.y > 0.0f) lb.y = RC_REG_CHECK(sumB.y, j0 + c + 1, r0 + 1, sites, fNK, rcpNK, rec0 + 1, band_slots, lb.y);
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && tile + 2 < ntiles) {
+      mbar_expect_tx(&bars[s], STAGE_BYTES);
+      bulk_g2s(ring + s * STAGE_BYTES, sig_src + (size_t)(tile + 2) * RT * RS, STAGE_BYTES, &bars[s]);
+    }
+  }
+  RowRec* grec = recs + it.rec_off[strand][frame] + (size_t)inst_l * sites + r0;
+#pragma unroll
+  for (int t = 0; t < R; t++)
+    if (r0 + t < sites) rec_copy(grec + t, rec0 + t);
+}
+
+// ---------------------------------------------------------------------------------------------
 // (c) k_dp_chain: the register-resident DP for WIDE alignments (N-1 > 16).  The species are cut into W chunks
 // of at most NK species; the CTA has W warps that all work on the same task (instance, strand, frame, 64 start
 // codons), warp g owning chunk g with its 3*NK float2 states in registers exactly like k_dp_reg.  The species
@@ -1671,15 +1950,6 @@ constexpr int CHAIN_MAX_TASKS = 8;  // upper bound of BlockDev.chain_tasks
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ float2 lds_f2(unsigned a) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts_f2(unsigned a, float2 v) {
-  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
-}
-
 template <int NK>
 struct ChainCfg {
   static constexpr int RS = RegCfg<NK>::RS;
@@ -2090,22 +2360,6 @@ __device__ __forceinline__ void folds_single(RowFoldS& fx, RowFoldS& fy, float2 
 // share it and walk the start-codon pairs (long and short rows paired up for balance).  State handling,
 // packed FADD2 arithmetic, float order and the getHSS digest are those of k_dp_reg.
 // ---------------------------------------------------------------------------------------------
-// shared-memory loads by 32-bit shared address (the table phase of k_dp_smpf does all its addressing in 32 bits)
-__device__ __forceinline__ unsigned lds_u32(unsigned a) {
-  unsigned v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ unsigned lds_u16(unsigned a) {
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ float lds_f32(unsigned a) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-  return v;
-}
 template <int NK>
 __device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv)[RegCfg<NK>::RS]) {
   constexpr int RSB = (NK + 3) / 4 * 4;

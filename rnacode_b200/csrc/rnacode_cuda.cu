@@ -48,6 +48,8 @@ struct rc_ctx {
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
   long no_fold = 0;           // 1: a last group of at most 16 instances is scored like a full one (k_dp_smpf)
   long no_fused = 0;          // 1: never build the sigma table inside the sample-major DP kernel (k_dp_smpf)
+  long reg_tu = -1;           // k_dp_regtu (three additions per cell, needs omega = -2^k): -1 = where the batch's frameshift density
+                              // makes it the faster kernel, 0 = never, 1 = always
   long no_sig_p2 = 0;         // 1: sigma tables of the sample-major layouts always from class bytes (k_sigma_smp), never from packed rows
   long tail_max = 0;          // a sample-major block whose instance count leaves 1..tail_max instances in its last group of 32 scores
                               // those instances row-major (lanes = rows) instead of in a warp with that many live lanes (0: never)
@@ -288,6 +290,8 @@ void finish_layout(BlockDev& bd) {
 
 struct rc_batch {
   rc_ctx* ctx = nullptr;
+  double fs_events = 0.0, fs_cells = 0.0;  // row-major register-kernel blocks: estimated (species, codon) pairs with a frameshift / all
+  bool use_tu = false;                      // k_dp_regtu instead of k_dp_reg (decided per batch in rc_batch_create)
   int n_blocks = 0;  // blocks of the caller; b->blocks may hold "tail" blocks after them (see rc_batch_create)
   std::vector<int> tail_of;   // per caller block: index of its tail block in `blocks`, or -1
   std::vector<int> main_inst; // per caller block: instances [0, main_inst) use the block's own layout, the rest the tail block's
@@ -425,6 +429,7 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   if (const char* e = getenv("RNACODE_CUDA_HSS_THR_TASKS")) ctx->hss_thr_tasks = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_NO_FUSED")) ctx->no_fused = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_NO_SIG_P2")) ctx->no_sig_p2 = atol(e) ? 1 : 0;
+  if (const char* e = getenv("RNACODE_CUDA_REG_TU")) ctx->reg_tu = std::max(-1L, std::min(1L, atol(e)));
   if (const char* e = getenv("RNACODE_CUDA_NO_FOLD")) ctx->no_fold = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_TAIL_MAX")) ctx->tail_max = std::max(0L, std::min(31L, atol(e)));
   if (const char* e = getenv("RNACODE_CUDA_REG_MAX_NK")) ctx->reg_max_nk = std::max(12L, std::min<long>(REG_MAX_NK, atol(e)));
@@ -498,6 +503,8 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->no_fused = value ? 1 : 0;
   } else if (k == "no_sig_p2") {
     ctx->no_sig_p2 = value ? 1 : 0;
+  } else if (k == "reg_tu") {
+    ctx->reg_tu = std::max(-1L, std::min(1L, value));
   } else if (k == "tail_max") {
     if (value < 0 || value > 31) { ctx_fail(ctx, "tail_max must be 0..31"); return RC_ERR_ARG; }
     ctx->tail_max = value;
@@ -702,6 +709,23 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
       set_layout(bd, layout);
       bd.smp_seg = seg;
       finish_layout(bd);
+      if (layout == 1) {
+        // Frameshift density of the block, estimated from its gap runs: a run whose length is not a multiple of three shifts the
+        // frame of one codon of its species (of every species when it sits in the reference row).  k_dp_regtu pays for every
+        // frameshift, k_dp_reg for every cell.
+        double ev = 0.0;
+        for (int r = 0; r < d.N; r++) {
+          const char* row = d.rows + (size_t)r * d.cols;
+          int run = 0;
+          for (int c = 0; c <= d.cols; c++) {
+            if (c < d.cols && row[c] == '-') { run++; continue; }
+            if (run % 3 != 0) ev += r == 0 ? (double)bd.NK : 1.0;
+            run = 0;
+          }
+        }
+        b->fs_events += ev * bd.n_inst;
+        b->fs_cells += (double)bd.NK * (L / 3.0) * bd.n_inst;
+      }
       // resident-table sample-major blocks build their sigma table inside the DP kernel when the staged rows fit as well
       // ... unless that costs a resident CTA (two CTAs of 8 warps per SM need <= 113 KB each): wide alignments in chunks have
       // a 100 KB table already and stay with k_sigma_smp + k_dp_smp
@@ -766,6 +790,15 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
     b->res_floats += (size_t)bd.n_inst * 6;
     bd.hsscnt_off = (long long)b->hsscnt_ints;
     b->hsscnt_ints += 6;
+  }
+  {
+    // k_dp_regtu (three additions per cell, deferred S1 / S2 bookkeeping at frameshifts) wins below about 0.6 % of the
+    // (species, codon) pairs with a frameshift -- the real examples/genomic.maf has 0.17 %, SURVEY 8(d)'s generator 3 % -- and
+    // needs omega = -2^k
+    int ex = 0;
+    const bool pow2 = params->omega < 0.0f && std::frexp(-params->omega, &ex) == 0.5f && ex >= -20 && ex <= 20;
+    const double g = b->fs_cells > 0 ? b->fs_events / b->fs_cells : 1.0;
+    b->use_tu = pow2 && (ctx->reg_tu == 1 || (ctx->reg_tu < 0 && g < 0.006));
   }
   b->stats.cells = cells;
   // Tail blocks.  The sample-major kernels put 32 instances into a warp; a block with 101 instances (RNAcode's default -n 100)
@@ -1227,8 +1260,13 @@ static int launch_dp(rc_batch* b, const CtaDesc* d_ctas, size_t ncta, int maxNK,
 template <int NK>
 static int launch_dp_reg_nk(rc_batch* b, const CtaDesc* d_ctas, size_t ncta) {
   rc_ctx* ctx = b->ctx;
-  k_dp_reg<NK><<<(unsigned)ncta, DP_WARPS * 32, 0, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_recs,
-                                                                 b->prm, (int)ctx->band_slots);
+  // k_dp_regtu: the three-addition form with deferred S1 / S2 bookkeeping, chosen per batch (rc_batch_create)
+  if (b->use_tu && NK <= 12)
+    k_dp_regtu<(NK <= 12 ? NK : 1)><<<(unsigned)ncta, DP_WARPS * 32, 0, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma,
+                                                                                     b->d_recs, b->prm, (int)ctx->band_slots);
+  else
+    k_dp_reg<NK><<<(unsigned)ncta, DP_WARPS * 32, 0, ctx->stream>>>(b->d_blocks, b->d_items, d_ctas, b->d_sigma, b->d_recs,
+                                                                   b->prm, (int)ctx->band_slots);
   RC_CUDA(cudaGetLastError());
   b->stats.launches++;
   b->stats.dp_launches++;

@@ -227,6 +227,39 @@ def test_optional_sample_major_routes_vs_oracle(oracle, opts):
         ctx.close()
 
 
+@pytest.mark.parametrize("omega", [-2.0, -4.0, -0.5, -1.5], ids=lambda w: "omega%g" % w)
+@pytest.mark.parametrize("reg_tu", [1, 0, -1], ids=lambda v: "reg_tu%d" % v)
+def test_three_addition_kernel_vs_oracle(oracle, reg_tu, omega):
+    """k_dp_regtu carries max(S1, S2) instead of S1 and S2 and brings the smaller one up to date at a frameshift -- n deferred
+    additions of omega collapsed into one FMA per binade (needs omega = -2^k; -1.5 must fall back to k_dp_reg).  Forced on,
+    forced off and on its own choice, on row-major blocks from gap-free to very gappy (several frameshifts per species and
+    row, rows that start between two frameshifts, sums that cross many binades): the oracle's answers, bit for bit."""
+    from rnacode_b200 import synth
+    capi = _capi()
+    ctx = capi.Context(0)
+    ctx.set_option("reg_tu", reg_tu)
+    kw = dict(omega=omega)
+    try:
+        shapes = [(8, 1000, 2, 0.0067), (10, 600, 4, 0.02), (10, 2400, 2, 0.0005), (5, 900, 2, 0.08), (12, 700, 3, 0.02),
+                  (3, 300, 2, 0.05), (10, 1500, 1, 0.0), (2, 2000, 3, 0.03), (13, 500, 2, 0.01)]
+        blocks, data = [], []
+        for idx, (N, cols, n, gr) in enumerate(shapes):
+            rows = synth.synth_block(77, idx, N, cols, gap_rate=gr)
+            sf, sr = synth.synth_scores(77, idx, N)
+            smp = synth.synth_samples(77, idx, n, N, cols)
+            blocks.append(_block(rows, sf, sr, smp))
+            data.append((rows, sf, sr, smp))
+        bt = ctx.batch(blocks, capi.make_params(**kw), oracle.blosum62)
+        bt.upload(); bt.run(); bt.download()
+        for i, (rows, sf, sr, smp) in enumerate(data):
+            assert bt.native_hss(i) == oracle.score_aln(rows, sf, sr, oracle.params(**kw)), (reg_tu, omega, shapes[i])
+            exp = oracle.sample_maxima(rows, smp, sf, sr, oracle.params(**kw)).astype(np.float32)
+            assert np.array_equal(bt.max_scores(i).astype(np.float32), exp), (reg_tu, omega, shapes[i])
+        bt.close()
+    finally:
+        ctx.close()
+
+
 def test_near_ties_after_the_row_maximum(rc_ctx, oracle):
     """The species-sum fold of the sample-major kernels treats a positive sum just below a row's maximum exactly (folds_exact).
     Alignments made of a few repeated columns give rows full of exact ties and of near ties (sums that differ by rounding
