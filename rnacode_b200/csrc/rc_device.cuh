@@ -66,6 +66,7 @@ struct BlockDev {
   int smp_fused;            // layouts 2 / 5, resident table: 1 = the DP kernel builds its sigma table itself from class bytes
                             // (k_dp_smpf; no sigma scratch, no k_sigma_smp launch for this block)
   int smp_fold;             // k_dp_smpf: 1 = a last group of at most 16 instances runs several start-codon pairs side by side
+  int smpf_allf;            // k_dp_smpf: 1 = one CTA per (strand, group) takes the three frames in turn (CtaDesc.sf = 6 + strand)
   int sig_p2;               // layouts 2 / 5 with a sigma table in HBM: 1 = the table is built from k_pack2's packed rows (k_sigma_p2)
                             // instead of class bytes (k_sigma_smp)
   int p2_words;             // k_dp_smpf: 32-bit words per packed row = ceil(L / 16)

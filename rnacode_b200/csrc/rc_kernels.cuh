@@ -2385,7 +2385,10 @@ __device__ __forceinline__ void smp_load_row(unsigned a, unsigned zw, float (&sv
 // chunk), one float2 per end codon.  Waiting for them was the kernel's largest stall (long_scoreboard 4.1 per issue,
 // profiles/r02_k_dp_smp_chunked.md), so every lane requests them SMP_PF end codons ahead with cp.async into a ring slot of
 // its own in shared memory (no registers held while the copy is in flight): one commit group per end codon.
-constexpr int SMP_PF = 4;                                   // end codons in flight per lane
+#ifndef RC_SMP_PF
+#define RC_SMP_PF 4
+#endif
+constexpr int SMP_PF = RC_SMP_PF;                                   // end codons in flight per lane
 constexpr int SMP_PF_BYTES = SMP_MAX_WARPS * SMP_PF * 256;  // ring of a CTA: [warp][slot][lane] float2
 // LASTC (chained launches only): the launch of the last chunk, the one that owns the getHSS fold.  A compile-time flag: the
 // launches of the other chunks carry no fold state, which is what keeps the 12-species chunk within the 128 registers that
@@ -2821,8 +2824,12 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
   const CtaDesc cd = ctas[blockIdx.x];
   const Item& it = items[cd.item];
   const BlockDev& bd = blocks[it.block];
-  const int strand = cd.sf / 3, frame = cd.sf % 3;
-  const int sites = bd.sites[frame];
+  // cd.sf = strand * 3 + frame, or 6 + strand: ONE CTA for the three frames of the strand -- they share the tables and the packed
+  // rows, only the z words, the sigma table and the DP differ (a third of the CTAs, a third of the set-up latency)
+  const bool allf = !CHAINED && cd.sf >= 6;
+  const int strand = allf ? cd.sf - 6 : cd.sf / 3;
+  const int f_lo = allf ? 0 : cd.sf % 3, f_hi = allf ? 3 : f_lo + 1;
+  const int sites_c = bd.sites[f_lo];  // the carve-up of shared memory follows the CTA's first (= longest) frame
   const int group = cd.task0;  // group of 32 instances inside the item
   // Folded group: a group with at most 16 instances (the last one of a block with 101 = 3 * 32 + 5 of them, RNAcode's default
   // -n 100) does not leave its other lanes idle: the lanes are cut into R = 32 / m replicas of m >= #instances lanes, lane l
@@ -2850,18 +2857,17 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
   const int k_first = 4 * q_first;                         // first scored species (0-based) of the launch
   const int n_real = min(4 * q_count, bd.NK - k_first);    // species rows that exist
 
-  unsigned* zs = reinterpret_cast<unsigned*>(smem + Cfg::off_z(sites, ROW_BYTES));
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::off_bar(sites, ROW_BYTES));
-  const PairTables& s_tab = *reinterpret_cast<const PairTables*>(smem + Cfg::off_tab(sites, ROW_BYTES));
-  float* s_sc = reinterpret_cast<float*>(smem + Cfg::off_sc(sites, ROW_BYTES));            // [species of the launch][h], h = 0 -> 0
-  unsigned* s_flag = reinterpret_cast<unsigned*>(smem + Cfg::off_flag(sites, ROW_BYTES, NSP));  // [0]: reference row, [1 + k]: species
-  int* s_col = reinterpret_cast<int*>(smem + Cfg::off_col(sites, ROW_BYTES, NSP));      // columns of the frame's codons (byte-wise path)
-  unsigned char* s_ref = smem + Cfg::off_ref(sites, ROW_BYTES, NSP);                    // packed reference row [word][lane]
-  unsigned char* s_sp = smem + Cfg::off_sp(sites, ROW_BYTES, NSP, W);                   // packed species rows [species][word][lane]
-  RowRec* srec = reinterpret_cast<RowRec*>(smem + Cfg::off_rec(sites, ROW_BYTES, NSP, W));
+  unsigned* zs = reinterpret_cast<unsigned*>(smem + Cfg::off_z(sites_c, ROW_BYTES));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::off_bar(sites_c, ROW_BYTES));
+  const PairTables& s_tab = *reinterpret_cast<const PairTables*>(smem + Cfg::off_tab(sites_c, ROW_BYTES));
+  float* s_sc = reinterpret_cast<float*>(smem + Cfg::off_sc(sites_c, ROW_BYTES));            // [species of the launch][h], h = 0 -> 0
+  unsigned* s_flag = reinterpret_cast<unsigned*>(smem + Cfg::off_flag(sites_c, ROW_BYTES, NSP));  // [0]: reference row, [1 + k]: species
+  int* s_col = reinterpret_cast<int*>(smem + Cfg::off_col(sites_c, ROW_BYTES, NSP));      // columns of the frame's codons (byte-wise path)
+  unsigned char* s_ref = smem + Cfg::off_ref(sites_c, ROW_BYTES, NSP);                    // packed reference row [word][lane]
+  unsigned char* s_sp = smem + Cfg::off_sp(sites_c, ROW_BYTES, NSP, W);                   // packed species rows [species][word][lane]
+  RowRec* srec = reinterpret_cast<RowRec*>(smem + Cfg::off_rec(sites_c, ROW_BYTES, NSP, W));
 
   // ---- table phase: kernel (b) for this CTA's (instances, strand, frame, species of the launch) ------------------------
-  const size_t z_bytes = Cfg::align16((size_t)sites * 4);
   const size_t prow = (size_t)W * 128;  // bytes of one packed row of 32 instances
   const size_t grp = (size_t)(it.inst0 >> 5) + group;
   const unsigned* gp2 = p2 + bd.p2_off + ((grp * 2 + strand) * N) * (size_t)W * 32;
@@ -2869,9 +2875,8 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
-    mbar_expect_tx(bar, (unsigned)(sizeof(PairTables) + z_bytes + prow + (size_t)n_real * prow));
-    bulk_g2s(smem + Cfg::off_tab(sites, ROW_BYTES), tables, (unsigned)sizeof(PairTables), bar);
-    bulk_g2s(zs, ztiles + bd.z_off[strand][frame] + (CHAINED ? (size_t)chunk * bd.ntiles[frame] * TILE : 0), (unsigned)z_bytes, bar);
+    mbar_expect_tx(bar, (unsigned)(sizeof(PairTables) + prow + (size_t)n_real * prow));
+    bulk_g2s(smem + Cfg::off_tab(sites_c, ROW_BYTES), tables, (unsigned)sizeof(PairTables), bar);
     bulk_g2s(s_ref, gp2, (unsigned)prow, bar);
     bulk_g2s(s_sp, gp2 + (size_t)(1 + k_first) * W * 32, (unsigned)((size_t)n_real * prow), bar);
   }
@@ -2881,11 +2886,18 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
     s_sc[t] = (h > 0 && kk < n_real) ? scores[bd.scores_off + ((size_t)strand * N + row) * 4 + h] : 0.0f;
   }
   for (int t = threadIdx.x; t <= NSP; t += blockDim.x) s_flag[t] = t == 0 ? gfl[0] : (t - 1 < n_real ? gfl[k_first + t] : 0u);
+#pragma unroll 1
+  for (int frame = f_lo; frame < f_hi; frame++) {
+  const int sites = bd.sites[frame];
+  if (sites <= 0) continue;  // (uniform)
+  // z words of the frame (one per end codon; a few hundred bytes: plain loads, in flight while the bulk copies arrive)
+  const unsigned* zg = ztiles + bd.z_off[strand][frame] + (CHAINED ? (size_t)chunk * bd.ntiles[frame] * TILE : 0);
+  for (int t = threadIdx.x; t < sites; t += blockDim.x) zs[t] = zg[t];
   // codon of site j: reference positions x-2 .. x with x = 3j + 3 + frame, i.e. entries frame+1+3j .. frame+3+3j of cols0
   const int* c0 = cols0 + bd.cols0_off + (size_t)strand * (L + 1) + frame + 1;
   for (int t = threadIdx.x; t < 3 * sites; t += blockDim.x) s_col[t] = c0[t];
-  __syncthreads();  // barrier initialised; s_sc, s_flag, s_col written
-  mbar_wait(bar, 0);
+  __syncthreads();  // barrier initialised; s_sc, s_flag, zs, s_col written
+  if (frame == f_lo) mbar_wait(bar, 0);
   {
     const unsigned lane_bit = 1u << il;
     // class bytes of this lane's instance, for codons of rows with 'N' / 'X' (rare)
@@ -3027,6 +3039,8 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2)  // two CTAs of 8 warps
       folds_store(fx, rec_inst + r0, rec0, fNK, rcpNK);
       if (r0 + 1 < sites) folds_store(fy, rec_inst + r0 + 1, rec0 + 1, fNK, rcpNK);
     }
+  }
+  __syncthreads();  // every warp is done with the frame's table and z words before the next frame overwrites them
   }
 }
 

@@ -48,6 +48,7 @@ struct rc_ctx {
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
   long no_fold = 0;           // 1: a last group of at most 16 instances is scored like a full one (k_dp_smpf)
   long no_fused = 0;          // 1: never build the sigma table inside the sample-major DP kernel (k_dp_smpf)
+  long no_allf = 0;           // 1: k_dp_smpf with one CTA per frame instead of one per strand (three frames in turn)
   long reg_tu = -1;           // k_dp_regtu (three additions per cell, needs omega = -2^k): -1 = where the batch's frameshift density
                               // makes it the faster kernel, 0 = never, 1 = always
   long no_sig_p2 = 0;         // 1: sigma tables of the sample-major layouts always from class bytes (k_sigma_smp), never from packed rows
@@ -429,6 +430,7 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   if (const char* e = getenv("RNACODE_CUDA_HSS_THR_TASKS")) ctx->hss_thr_tasks = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_NO_FUSED")) ctx->no_fused = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_NO_SIG_P2")) ctx->no_sig_p2 = atol(e) ? 1 : 0;
+  if (const char* e = getenv("RNACODE_CUDA_NO_ALLF")) ctx->no_allf = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_REG_TU")) ctx->reg_tu = std::max(-1L, std::min(1L, atol(e)));
   if (const char* e = getenv("RNACODE_CUDA_NO_FOLD")) ctx->no_fold = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_TAIL_MAX")) ctx->tail_max = std::max(0L, std::min(31L, atol(e)));
@@ -503,6 +505,8 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->no_fused = value ? 1 : 0;
   } else if (k == "no_sig_p2") {
     ctx->no_sig_p2 = value ? 1 : 0;
+  } else if (k == "no_allf") {
+    ctx->no_allf = value ? 1 : 0;
   } else if (k == "reg_tu") {
     ctx->reg_tu = std::max(-1L, std::min(1L, value));
   } else if (k == "tail_max") {
@@ -565,6 +569,13 @@ static void build_ctas(const std::vector<BlockDev>& blocks, const std::vector<It
     const Item& it = items[i];
     const BlockDev& bd = blocks[it.block];
     if (want_class >= 0 && class_of(bd) != want_class) continue;
+    if (bd.layout == 2 && bd.smp_fused && bd.smpf_allf && want_class >= 0) {
+      // k_dp_smpf: one CTA per (strand, group) works through the three frames (they share the tables and the packed rows)
+      if (bd.sites[0] > 0)
+        for (int strand = 0; strand < 2; strand++)
+          for (int g = 0; g < (it.ninst + 31) / 32; g++) out.push_back(CtaDesc{(int)i, 6 + strand, g});
+      continue;
+    }
     if ((bd.layout == 2 || bd.layout == 5) && want_class >= 0) {
       for (int sf = 0; sf < 6; sf++) {
         if (bd.sites[sf % 3] <= 0) continue;
@@ -736,6 +747,7 @@ extern "C" int rc_batch_create(rc_ctx* ctx, const rc_block_desc* descs, int n_bl
           (layout == 5 || bd.NK <= 12) &&  // k_dp_smpf<13..16> would spill at the 128 registers two CTAs per SM allow
           smpf_smem_bytes(bd, layout) + (size_t)SMP_WARPS * 64 * sizeof(RowRec) <= (size_t)ctx->smem_optin) {
         bd.smp_fused = 1;
+        bd.smpf_allf = (layout == 2 && !ctx->no_allf) ? 1 : 0;
         bd.smp_fold = ctx->no_fold ? 0 : 1;
         b->max_fused_N = std::max(b->max_fused_N, bd.N);
         b->max_fused_cols = std::max(b->max_fused_cols, bd.cols);
