@@ -106,7 +106,7 @@ int rc_set_stream(rc_ctx *ctx, void *cuda_stream);
 /* Tunables / test hooks: "force_dense" (0/1: route every alignment through the dense-S fallback),
  * "band_slots" (1..3: tie-band slots per row record before the dense fallback is taken),
  * "scratch_mb" (device scratch budget per chunk), and switches that only choose between kernels with identical results
- * (DESIGN.md section 4): "no_smp", "no_smps", "no_chain", "no_fused", "no_fold", "no_sig_p2" (0/1), "reg_tu" (-1 auto / 0 / 1), "tail_max" (0..31),
+ * (DESIGN.md section 4): "no_smp", "no_smps", "no_chain", "no_fused", "no_fold", "no_sig_p2", "no_sig_rows3", "no_allf" (0/1), "reg_tu" (-1 auto / 0 / 1), "tail_max" (0..31),
  * "reg_max_nk" (12..16), "smps_max_sites", "smpc_max_sites", "hss_thr_tasks".  Unknown keys are an error. */
 int rc_set_option(rc_ctx *ctx, const char *key, long value);
 

@@ -391,7 +391,7 @@ __host__ __device__ inline unsigned pt_swap(unsigned q) { return ((q & 3u) << 4)
 __global__ void __launch_bounds__(256)
     k_sigma(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned char* __restrict__ cls,
             const int* __restrict__ cols0, const float* __restrict__ scores, const SigmaTables* __restrict__ tables,
-            const unsigned* __restrict__ ztiles, float* __restrict__ sigma, Params prm) {
+            const unsigned* __restrict__ ztiles, float* __restrict__ sigma, Params prm, int skip3) {
   __shared__ SigmaTables s_tab;
   __shared__ __align__(8) uint64_t s_bar;
   if (threadIdx.x == 0) {
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256)
 
   const Item it = items[blockIdx.x];
   const BlockDev bd = blocks[it.block];
-  if (bd.layout == 2 || bd.layout == 1) return;  // served by k_sigma_smp / k_sigma_rows
+  if (bd.layout == 2 || bd.layout == 1 || (skip3 && bd.layout == 3)) return;  // served by k_sigma_smp / k_sigma_rows / k_sigma_rows3
   const int L = bd.L, N = bd.N, NK = bd.NK, cols = bd.cols;
   const int npos = L - 2;
   const long long total = (long long)it.ninst * 2 * npos;
@@ -597,6 +597,101 @@ __global__ void __launch_bounds__(256)
         v4[t] = v;
       }
       out[q] = make_float4(v4[0], v4[1], v4[2], v4[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (b) k_sigma_rows3: the same for layout 3 (k_dp_chain): one thread per (instance, strand, frame, end codon) writes the step's
+// rows of ALL species chunks -- per chunk its sigma values, dummy species (+0), the chunk's z word and the padding -- as float4,
+// so that a warp (32 consecutive end codons = two tiles) stores 768 contiguous bytes per chunk and tile.  (k_sigma wrote these
+// rows value by value with threads running over reference positions, i.e. over the three frames' arrays in turn.)
+// Tile layout: [chunk][step][rs3], rs3 = roundup(nkw + 1, 4); rows of the last tile past the frame's end are zero.
+// ---------------------------------------------------------------------------------------------
+constexpr int SIG3_MAX_N = 501;  // rows of the reference's largest alignment (MAX_NUM_NAMES, src/rnaz_utils.h:7) + 1
+__global__ void __launch_bounds__(256)
+    k_sigma_rows3(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned char* __restrict__ cls,
+                  const int* __restrict__ cols0, const float* __restrict__ scores, const PairTables* __restrict__ tables,
+                  const unsigned* __restrict__ ztiles, float* __restrict__ sigma) {
+  __shared__ PairTables s_tab;
+  __shared__ float s_sc[2 * SIG3_MAX_N * 4];  // expected scores [strand][row][h], h = 0 -> 0 (see PairTables)
+  __shared__ __align__(8) uint64_t s_bar;
+  const Item it = items[blockIdx.x];
+  const BlockDev bd = blocks[it.block];
+  if (bd.layout != 3) return;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&s_bar, (unsigned)sizeof(PairTables));
+    bulk_g2s(&s_tab, tables, (unsigned)sizeof(PairTables), &s_bar);
+  }
+  for (int t = threadIdx.x; t < 2 * bd.N * 4; t += blockDim.x) s_sc[t] = (t & 3) ? scores[bd.scores_off + t] : 0.0f;
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+  const int L = bd.L, N = bd.N, cols = bd.cols;
+  const int nkw = bd.nkw, rs3 = (nkw + 1 + 3) / 4 * 4;
+  const int st0 = bd.ntiles[0] * TILE, st1 = bd.ntiles[1] * TILE, st2 = bd.ntiles[2] * TILE;  // padded steps per frame
+  const int per_is = st0 + st1 + st2;
+  const long long total = (long long)it.ninst * 2 * per_is;
+  for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.y * blockDim.x) {
+    int r = (int)(idx % per_is);
+    const int is = (int)(idx / per_is);
+    const int s = is & 1, inst_l = is >> 1;
+    int f = 0;
+    if (r >= st0) { r -= st0; f = 1; }
+    if (f == 1 && r >= st1) { r -= st1; f = 2; }
+    const int j = r, tile = j / TILE, c = j % TILE;
+    float* out0 = sigma + it.sigma_off[s][f] + ((size_t)inst_l * bd.ntiles[f] + tile) * bd.sig_tile + (size_t)c * rs3;
+    if (j >= bd.sites[f]) {  // padding rows of the last tile: sigma = 0, no frameshift
+      for (int g = 0; g < bd.nchunk; g++)
+        for (int q = 0; q < rs3 / 4; q++)
+          reinterpret_cast<float4*>(out0 + (size_t)g * TILE * rs3)[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      continue;
+    }
+    const int x = 3 * j + 3 + f;
+    const int* c0 = cols0 + bd.cols0_off + (size_t)s * (L + 1);
+    const int c1 = c0[x - 2], c2 = c0[x - 1], c3 = c0[x];
+    const unsigned char* base = cls + bd.cls_off + (size_t)(it.inst0 + inst_l) * bd.inst_stride;
+    const unsigned a1 = base[c1], a2 = base[c2], a3 = base[c3];
+    const int sh = s ? 2 : 0;
+    const unsigned qa = (((a1 >> sh) & 3u) << 4) | (((a2 >> sh) & 3u) << 2) | ((a3 >> sh) & 3u);
+    const unsigned nA = (a1 | a2 | a3) & CLS_N;
+    const unsigned short* trow = s_tab.t + (qa << 6);
+    const float* sc = s_sc + s * N * 4;
+    const unsigned* z3 = ztiles + bd.z_off[s][f] + (size_t)tile * bd.zstride + c;  // + chunk * TILE
+    int cfirst = 0;
+    for (int g = 0; g < bd.nchunk; g++) {
+      const int csize = bd.chunk_base + (g < bd.chunk_rem ? 1 : 0);
+      const unsigned zword = z3[(size_t)g * TILE];
+      float4* out = reinterpret_cast<float4*>(out0 + (size_t)g * TILE * rs3);
+      for (int q = 0; q < rs3 / 4; q++) {
+        unsigned bb[4][3];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const int kk = 4 * q + t;
+          const unsigned char* rowk = base + (size_t)(kk < csize ? cfirst + kk + 1 : 0) * cols;
+          bb[t][0] = rowk[c1];
+          bb[t][1] = rowk[c2];
+          bb[t][2] = rowk[c3];
+        }
+        float v4[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const int kk = 4 * q + t;
+          const unsigned b1 = bb[t][0], b2 = bb[t][1], b3 = bb[t][2];
+          const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
+          const unsigned e = trow[qb];
+          // src/score.c:394-425 through PairTables; entries of a species with a frameshift are never read by the recurrence: +0
+          float v = s_tab.val[e & 0x3ffu] - sc[(kk < csize ? cfirst + kk + 1 : 0) * 4 + (e >> 10)];
+          const unsigned zero = nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X) | ((zword >> (2 * (kk & 15))) & 1u);
+          if (zero || kk >= csize) v = 0.0f;            // dummy species and padding: +0
+          if (kk == nkw) v = __uint_as_float(zword);    // the chunk's z word rides behind its nkw species slots
+          v4[t] = v;
+        }
+        out[q] = make_float4(v4[0], v4[1], v4[2], v4[3]);
+      }
+      cfirst += csize;
     }
   }
 }

@@ -48,6 +48,7 @@ struct rc_ctx {
   long smps_max_sites = 420;  // longest frame (codons) for k_dp_smps; beyond, the row-major k_dp_reg is faster (break-even ~1200 columns)
   long no_fold = 0;           // 1: a last group of at most 16 instances is scored like a full one (k_dp_smpf)
   long no_fused = 0;          // 1: never build the sigma table inside the sample-major DP kernel (k_dp_smpf)
+  long no_sig_rows3 = 0;      // 1: layout-3 sigma tiles by the generic k_sigma instead of k_sigma_rows3
   long no_allf = 0;           // 1: k_dp_smpf with one CTA per frame instead of one per strand (three frames in turn)
   long reg_tu = -1;           // k_dp_regtu (three additions per cell, needs omega = -2^k): -1 = where the batch's frameshift density
                               // makes it the faster kernel, 0 = never, 1 = always
@@ -430,6 +431,7 @@ extern "C" int rc_create(rc_ctx** out, int device) {
   if (const char* e = getenv("RNACODE_CUDA_HSS_THR_TASKS")) ctx->hss_thr_tasks = atol(e);
   if (const char* e = getenv("RNACODE_CUDA_NO_FUSED")) ctx->no_fused = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_NO_SIG_P2")) ctx->no_sig_p2 = atol(e) ? 1 : 0;
+  if (const char* e = getenv("RNACODE_CUDA_NO_SIG_ROWS3")) ctx->no_sig_rows3 = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_NO_ALLF")) ctx->no_allf = atol(e) ? 1 : 0;
   if (const char* e = getenv("RNACODE_CUDA_REG_TU")) ctx->reg_tu = std::max(-1L, std::min(1L, atol(e)));
   if (const char* e = getenv("RNACODE_CUDA_NO_FOLD")) ctx->no_fold = atol(e) ? 1 : 0;
@@ -505,6 +507,8 @@ extern "C" int rc_set_option(rc_ctx* ctx, const char* key, long value) {
     ctx->no_fused = value ? 1 : 0;
   } else if (k == "no_sig_p2") {
     ctx->no_sig_p2 = value ? 1 : 0;
+  } else if (k == "no_sig_rows3") {
+    ctx->no_sig_rows3 = value ? 1 : 0;
   } else if (k == "no_allf") {
     ctx->no_allf = value ? 1 : 0;
   } else if (k == "reg_tu") {
@@ -1602,7 +1606,7 @@ static int run_dense_items(rc_batch* b, const std::vector<Item>& src_items) {
     RC_CUDA_D(cudaGetLastError());
     const long long work = (long long)it.ninst * 2 * (bd.L - 2);
     dim3 gs(1, (unsigned)std::min<long long>((work + 255) / 256, 4096));
-    k_sigma<<<gs, 256, 0, st>>>(d_blk, d_item, b->d_cls, b->d_cols0, b->d_scores, b->d_tables, d_zs, b->d_sigma, b->prm);
+    k_sigma<<<gs, 256, 0, st>>>(d_blk, d_item, b->d_cls, b->d_cols0, b->d_scores, b->d_tables, d_zs, b->d_sigma, b->prm, 0);
     RC_CUDA_D(cudaGetLastError());
     // the DP kernel reads blocks / items / z through the batch pointers: point them at the private copies
     BlockDev* saved_blocks = b->d_blocks;
@@ -1719,9 +1723,15 @@ extern "C" int rc_batch_run(rc_batch* b) {
     ev = ev_begin(b, 1);
     {
       dim3 g((unsigned)ch.nitems, (unsigned)std::min<long long>((ch.max_sigma_work + 255) / 256, 8192));
-      if (ch.n_layout[0] + ch.n_layout[3] > 0) {
+      if (ch.n_layout[3] > 0 && !ctx->no_sig_rows3) {  // layout 3: whole step rows per thread
+        k_sigma_rows3<<<g, 256, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores, b->d_ptab, b->d_z,
+                                         b->d_sigma);
+        RC_CUDA(cudaGetLastError());
+        b->stats.launches++;
+      }
+      if (ch.n_layout[0] + (ctx->no_sig_rows3 ? ch.n_layout[3] : 0) > 0) {
         k_sigma<<<g, 256, 0, st>>>(b->d_blocks, b->d_items + ch.item0, b->d_cls, b->d_cols0, b->d_scores, b->d_tables,
-                                   b->d_z, b->d_sigma, b->prm);
+                                   b->d_z, b->d_sigma, b->prm, ctx->no_sig_rows3 ? 0 : 1);
         RC_CUDA(cudaGetLastError());
         b->stats.launches++;
       }
