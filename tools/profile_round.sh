@@ -38,6 +38,7 @@ cap k_dp_smp_chunked hundred_short '^k_dp_smp$' '--evolve'
 cap k_dp_chain hundred '^k_dp_chain$' '--evolve'
 cap k_dp_smps mid5 '^k_dp_smps$' '--evolve'
 cap k_sigma_p2 hundred_short '^k_sigma_p2$' '--evolve'
+cap k_sigma_rows3 hundred '^k_sigma_rows3$' '--evolve'
 cap k_dp_regtu genomic_lowgap '^k_dp_regtu$' ''
 cap k_pack short2k '^k_pack$' '--evolve'
 cap k_pack2 short2k '^k_pack2$' '--evolve'
