@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(256)
 // writes 32 consecutive rows (fully coalesced 128-bit stores; k_sigma's position-major mapping scatters 4-byte
 // stores over the three frames).  Steps past the end of the frame in the last tile get all-zero rows.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
     k_sigma_rows(const BlockDev* __restrict__ blocks, const Item* __restrict__ items, const unsigned char* __restrict__ cls,
                  const int* __restrict__ cols0, const float* __restrict__ scores, const PairTables* __restrict__ tables,
                  const unsigned* __restrict__ ztiles, float* __restrict__ sigma, Params prm) {
@@ -571,40 +571,32 @@ __global__ void __launch_bounds__(256, 3)
     const unsigned short* trow = s_tab.t + (qa << 6);
     const float* sc = s_sc + s * N * 4;
     const unsigned zword = ztiles[bd.z_off[s][f] + j];  // zstride == TILE: one word per step
-    // all codon bytes of the row first (up to 48 independent loads in flight, three bytes packed per register), then the
-    // arithmetic: the kernel is bound by the latency of these loads
-    constexpr int MAXQ = (REG_MAX_NK + 1 + 3) / 4;
-    unsigned bp[4 * MAXQ];
+    for (int q = 0; q < rs / 4; q++) {
+      // the twelve bytes of the quad's codons first (independent loads in flight), then the arithmetic
+      unsigned bb[4][3];
 #pragma unroll
-    for (int q = 0; q < MAXQ; q++) {
-      if (q < rs / 4) {
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-          const int k = 4 * q + t;
-          const unsigned char* rowk = base + (size_t)(k < NK ? k + 1 : 0) * cols;
-          bp[4 * q + t] = (unsigned)rowk[c1] | ((unsigned)rowk[c2] << 8) | ((unsigned)rowk[c3] << 16);
-        }
+      for (int t = 0; t < 4; t++) {
+        const int k = 4 * q + t;
+        const unsigned char* rowk = base + (size_t)(k < NK ? k + 1 : 0) * cols;
+        bb[t][0] = rowk[c1];
+        bb[t][1] = rowk[c2];
+        bb[t][2] = rowk[c3];
       }
-    }
+      float v4[4];
 #pragma unroll
-    for (int q = 0; q < MAXQ; q++) {
-      if (q < rs / 4) {
-        float v4[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-          const int k = 4 * q + t;
-          const unsigned b1 = bp[4 * q + t] & 0xffu, b2 = (bp[4 * q + t] >> 8) & 0xffu, b3 = bp[4 * q + t] >> 16;
-          const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
-          const unsigned e = trow[qb];
-          // src/score.c:394-425 through PairTables, see k_sigma_smp; entries with a frameshift are never read by the recurrence: +0
-          float v = s_tab.val[e & 0x3ffu] - sc[(k < NK ? k + 1 : 0) * 4 + (e >> 10)];
-          const unsigned zero = nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X) | ((zword >> (2 * (k & 15))) & 1u);
-          if (zero || k > NK) v = 0.0f;
-          if (k == NK) v = __uint_as_float(zword);
-          v4[t] = v;
-        }
-        out[q] = make_float4(v4[0], v4[1], v4[2], v4[3]);
+      for (int t = 0; t < 4; t++) {
+        const int k = 4 * q + t;
+        const unsigned b1 = bb[t][0], b2 = bb[t][1], b3 = bb[t][2];
+        const unsigned qb = (((b1 >> sh) & 3u) << 4) | (((b2 >> sh) & 3u) << 2) | ((b3 >> sh) & 3u);
+        const unsigned e = trow[qb];
+        // src/score.c:394-425 through PairTables, see k_sigma_smp; entries with a frameshift are never read by the recurrence: +0
+        float v = s_tab.val[e & 0x3ffu] - sc[(k < NK ? k + 1 : 0) * 4 + (e >> 10)];
+        const unsigned zero = nA | ((b1 | b2 | b3) & CLS_N) | (b1 & b2 & b3 & CLS_X) | ((zword >> (2 * (k & 15))) & 1u);
+        if (zero || k > NK) v = 0.0f;
+        if (k == NK) v = __uint_as_float(zword);
+        v4[t] = v;
       }
+      out[q] = make_float4(v4[0], v4[1], v4[2], v4[3]);
     }
   }
 }
