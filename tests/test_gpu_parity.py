@@ -192,7 +192,7 @@ def test_config5_mixed_lengths_vs_oracle(rc_ctx, oracle):
 
 
 @pytest.mark.parametrize("opts", [{"no_fused": 0}, {"no_fused": 1}, {"no_fold": 1}, {"tail_max": 12}, {"no_fused": 0, "tail_max": 12},
-                                  {"no_sig_p2": 1}, {"no_fused": 1, "no_sig_p2": 1}],
+                                  {"no_sig_p2": 1}, {"no_fused": 1, "no_sig_p2": 1}, {"no_allf": 1}],
                          ids=lambda o: "+".join("%s%d" % kv for kv in sorted(o.items())))
 def test_optional_sample_major_routes_vs_oracle(oracle, opts):
     """The routes of the sample-major family, each switched on and off: k_dp_smpf (the DP CTA builds its sigma table itself from
@@ -331,17 +331,18 @@ def test_chain_kernel_equals_generic_kernel(oracle):
     sf, sr = synth.synth_scores(33, 2, 31)
     smp = synth.synth_samples(33, 2, 3, 31, 900)
     res = []
-    for no_chain in (0, 1):
+    for no_chain, no_rows3 in ((0, 0), (1, 0), (0, 1)):  # (0, 1): the chain kernel on sigma tiles written by the generic k_sigma
         ctx = capi.Context(0)
         ctx.set_option("no_chain", no_chain)
+        ctx.set_option("no_sig_rows3", no_rows3)
         try:
             b = _block(rows, sf, sr, smp)
             res.append((ctx.score_aln(b, capi.make_params(), oracle.blosum62),
                         ctx.score_samples(b, capi.make_params(), oracle.blosum62).astype(np.float32)))
         finally:
             ctx.close()
-    assert res[0][0] == res[1][0] == oracle.score_aln(rows, sf, sr, oracle.params())
-    assert np.array_equal(res[0][1], res[1][1])
+    assert res[0][0] == res[1][0] == res[2][0] == oracle.score_aln(rows, sf, sr, oracle.params())
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][1], res[2][1])
     kw = dict(Delta=-6.0, Omega=-3.0, omega=0.25, stopPenalty_0=-100.0, stopPenalty_k=-5.0)
     ctx = capi.Context(0)
     try:
