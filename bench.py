@@ -654,14 +654,20 @@ class Bench:
             def scorer(units):
                 blks = [capi.Block(block(u.block)[0], block(u.block)[1], block(u.block)[2], None, n_samples=u.ns) for u in units]
                 bt = ctx.batch(blks, self.prm, self.blosum)
-                for k, u in enumerate(units):
-                    if u.ns > 0:
-                        bt.set_evolve(k, block(u.block)[3], block(u.block)[4][u.s0:u.s0 + u.ns], capi.RC_RNG_MT19937)
+                if all(u.ns > 0 for u in units):  # one call: the trees' tables are converted on several host threads
+                    bt.set_evolve_many(capi.Batch.evolve_plan([block(u.block)[3] for u in units],
+                                                              [block(u.block)[4][u.s0:u.s0 + u.ns] for u in units]),
+                                       capi.RC_RNG_MT19937)
+                else:
+                    for k, u in enumerate(units):
+                        if u.ns > 0:
+                            bt.set_evolve(k, block(u.block)[3], block(u.block)[4][u.s0:u.s0 + u.ns], capi.RC_RNG_MT19937)
                 bt.upload(); bt.run(); bt.download()
-                res = {}
+                allmax = bt.max_scores_all()
+                res, pos = {}, 0
                 for k, u in enumerate(units):
-                    res[(u.block, u.s0)] = (bt.native_hss(k) if u.want_native else None,
-                                            bt.max_scores(k) if u.ns > 0 else np.zeros(0))
+                    res[(u.block, u.s0)] = (bt.native_hss(k) if u.want_native else None, allmax[pos:pos + u.ns].copy())
+                    pos += u.ns
                 bt.close()
                 return res
             return scorer
