@@ -29,11 +29,14 @@ static float catchup(float u, float w, int k, int n, int *iters) {
   }
   return u;
 }
-int main(){
+/* tools/catch_up_check.c [cases]: the closed form of k_dp_regtu's catch_up (rnacode_b200/csrc/rc_kernels.cuh -- the same statements
+ * in C) against the step-by-step loop `u = u + w`, bit for bit, on random (value, k, n).  gcc -O2 -ffp-contract=off ... -lm */
+int main(int argc, char **argv){
+  const long cases = argc > 1 ? atol(argv[1]) : 20000000;
   srand48(12345);
   long bad=0, tot=0, it=0, maxit=0;
   const int ks[]={1,2,0,-1,3,-3,5};
-  for (long t=0;t<20000000;t++){
+  for (long t=0;t<cases;t++){
     int k=ks[lrand48()%7]; float w=-ldexpf(1.0f,k);
     int mode=lrand48()%6; float u;
     if(mode==0) u=(float)((drand48()-0.5)*20000.0);
